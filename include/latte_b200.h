@@ -1,0 +1,129 @@
+/* latte_b200 — C ABI of the B200-native Latte denoiser hot path (liblatte_b200.so).
+ *
+ * Drop-in boundary: the reference's hot path is `Latte.forward` /
+ * `Latte.forward_with_cfg` (Vchitect/Latte models/latte.py:314-398), a PyTorch nn.Module.  A binding
+ * (ctypes here) hands this library raw DEVICE pointers owned by the caller plus the
+ * caller's CUDA stream.  Rules:
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every function enqueues work on `stream` and returns; it never synchronises, never allocates
+ *     device memory and keeps no pointer past the call;
+ *   - return value 0 = ok, negative B200_ERR_* otherwise; text via b200_last_error() (thread-local);
+ *   - sm_100 only: any other device returns B200_ERR_ARCH. There is no CPU fallback.
+ * All matrices are row-major.  "16-bit" means IEEE fp16 (dtype = B200_FP16) or bfloat16 (B200_BF16).
+ */
+#ifndef LATTE_B200_H
+#define LATTE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+enum {
+  B200_OK = 0,
+  B200_ERR_SHAPE = -1,
+  B200_ERR_DTYPE = -2,
+  B200_ERR_ALIGN = -3,
+  B200_ERR_ARCH = -4,
+  B200_ERR_WORKSPACE = -5,
+  B200_ERR_CUDA = -6,
+  B200_ERR_UNSUPPORTED = -7
+};
+enum { B200_FP16 = 0, B200_BF16 = 1 };
+enum { B200_EPI_BIAS = 0, B200_EPI_BIAS_GELU = 1, B200_EPI_GATE_RESIDUAL = 2 };
+
+/* Model geometry: the ctor arguments of reference `Latte` (models/latte.py:208-223). */
+typedef struct B200LatteShape {
+  int32_t depth;        /* number of TransformerBlocks; even = spatial, odd = temporal (latte.py:345-346) */
+  int32_t hidden;       /* D */
+  int32_t heads;        /* H; head_dim = D / H must be 64 or in (64, 80] */
+  int32_t mlp_hidden;   /* int(D * mlp_ratio) */
+  int32_t patch;        /* p (only 2 is built) */
+  int32_t in_channels;  /* C */
+  int32_t out_channels; /* 2C if learn_sigma else C */
+  int32_t input_size;   /* latent H = W */
+  int32_t frames;       /* F */
+  int32_t num_embed;    /* rows of the label table (num_classes + 1); 0 when extras != 2 */
+  int32_t dtype;        /* B200_FP16 / B200_BF16: tensor-core operand type of the packed weights */
+} B200LatteShape;
+
+/* Packed weights (device pointers, torch-owned).  fp32 unless noted.  `*_w16` are 16-bit copies in
+ * `shape.dtype`, stacked over blocks in block order.  Names follow the reference state_dict. */
+typedef struct B200LatteWeights {
+  const float* patch_w;    /* x_embedder.proj.weight      [D, C*p*p]                      */
+  const float* patch_b;    /* x_embedder.proj.bias        [D]                             */
+  const float* pos_embed;  /* pos_embed                   [N, D]                          */
+  const float* temp_embed; /* temp_embed                  [F, D]                          */
+  const float* t_w0;       /* t_embedder.mlp.0.weight     [D, 256]                        */
+  const float* t_b0;       /* t_embedder.mlp.0.bias       [D]                             */
+  const float* t_w2;       /* t_embedder.mlp.2.weight     [D, D]                          */
+  const float* t_b2;       /* t_embedder.mlp.2.bias       [D]                             */
+  const float* y_table;    /* y_embedder.embedding_table.weight [num_embed, D] or NULL    */
+  const void* ada_w16;     /* blocks.*.adaLN_modulation.1.weight then final_layer's: [depth*6D + 2D, D] 16-bit */
+  const float* ada_b;      /* matching biases             [depth*6D + 2D]                 */
+  const void* qkv_w16;     /* blocks.*.attn.qkv.weight    [depth][3D, D] 16-bit           */
+  const float* qkv_b;      /*                             [depth][3D]                     */
+  const void* proj_w16;    /* blocks.*.attn.proj.weight   [depth][D, D] 16-bit            */
+  const float* proj_b;     /*                             [depth][D]                      */
+  const void* fc1_w16;     /* blocks.*.mlp.fc1.weight     [depth][4D, D] 16-bit           */
+  const float* fc1_b;      /*                             [depth][4D]                     */
+  const void* fc2_w16;     /* blocks.*.mlp.fc2.weight     [depth][D, 4D] 16-bit           */
+  const float* fc2_b;      /*                             [depth][D]                      */
+  const float* final_w;    /* final_layer.linear.weight   [p*p*out_channels, D]           */
+  const float* final_b;    /* final_layer.linear.bias     [p*p*out_channels]              */
+} B200LatteWeights;
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+B200_API const char* b200_last_error(void);
+B200_API int b200_abi_version(void);
+
+/* Bytes of scratch `b200_latte_forward` needs for `batch` videos (0 on invalid shape; see b200_last_error). */
+B200_API size_t b200_latte_workspace_bytes(const B200LatteShape* shape, int batch);
+
+/* Whole denoiser forward — replaces Latte.forward (models/latte.py:314-377) and, when use_cfg != 0,
+ * Latte.forward_with_cfg (latte.py:379-398: rows [0, batch/2) are the conditional half, x rows
+ * [batch/2, batch) are ignored and replaced by a copy of the first half; eps channels [0, in_channels)
+ * of BOTH halves become uncond + cfg_scale * (cond - uncond)).
+ *   x   [batch, F, C, S, S] fp32        t [batch] int64        y [batch] int64 or NULL (extras != 2)
+ *   out [batch, F, out_channels, S, S] fp32
+ *   workspace: >= b200_latte_workspace_bytes(shape, batch) bytes, 1024-byte aligned.             */
+B200_API int b200_latte_forward(const B200LatteShape* shape, const B200LatteWeights* w, const float* x, const int64_t* t,
+                       const int64_t* y, int batch, int use_cfg, float cfg_scale, float* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* out = epilogue(A @ W^T + bias) on tcgen05 tensor cores — replaces the nn.Linear calls of the block
+ * (latte.py:50 qkv, :75 proj, timm Mlp fc1/fc2 via :171).  A [M,K], W [N,K] 16-bit; bias [N] fp32 or NULL.
+ *   B200_EPI_BIAS           out16[M,N] = acc + bias
+ *   B200_EPI_BIAS_GELU      out16[M,N] = gelu_tanh(acc + bias)                     (latte.py:169)
+ *   B200_EPI_GATE_RESIDUAL  resid[M,N] (fp32, in place) += gate[row / rows_per_batch][col] * (acc + bias)
+ *                           (latte.py:179-180); gate row stride = gate_batch_stride floats.
+ * K % 64 == 0, N % 32 == 0 required; M arbitrary.                                                  */
+B200_API int b200_linear(const void* A, const void* W, const float* bias, int M, int N, int K, int dtype, int epilogue,
+                void* out16, float* resid, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
+                int block_n, void* stream);
+
+/* softmax(q k^T / sqrt(hd)) v per head — replaces Attention.forward 'math' mode between the qkv and
+ * proj Linears (latte.py:50-70).  qkv [T, 3*heads*head_dim] 16-bit with T = batch*frames*tokens rows in
+ * (b, f, n) order; out [T, heads*head_dim] 16-bit.  temporal = 0: one sequence per (b, f) over n
+ * (latte.py:353); temporal = 1: one sequence per (b, n) over f (latte.py:355-367) — no transpose pass. */
+B200_API int b200_attention(const void* qkv, void* out, int batch, int frames, int tokens, int heads, int head_dim,
+                   int dtype, int temporal, void* stream);
+
+/* out16[r, :] = LayerNorm(x[r, :]; no affine, eps 1e-6) * (1 + scale[b]) + shift[b], b = r / rows_per_batch
+ * — replaces norm1/norm2 + modulate (latte.py:28-29, 166-168, 179-180). x fp32 [rows, dim].          */
+B200_API int b200_ln_modulate(const float* x, const float* shift, const float* scale, int64_t mod_batch_stride,
+                     int rows_per_batch, void* out16, int rows, int dim, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATTE_B200_H */

@@ -1,0 +1,88 @@
+"""ctypes binding of liblatte_b200.so (the C ABI in include/latte_b200.h).
+
+There is no fallback: if the library is missing it is built with nvcc; if that fails, importing
+raises.  Nothing here touches torch — the wrappers above pass raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+ABI_VERSION = 1
+OK = 0
+FP16, BF16 = 0, 1
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL = 0, 1, 2
+ERR_NAMES = {-1: "SHAPE", -2: "DTYPE", -3: "ALIGN", -4: "ARCH", -5: "WORKSPACE", -6: "CUDA", -7: "UNSUPPORTED"}
+
+
+class LatteShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "depth", "hidden", "heads", "mlp_hidden", "patch", "in_channels", "out_channels", "input_size",
+        "frames", "num_embed", "dtype")]
+
+
+WEIGHT_FIELDS = (
+    "patch_w", "patch_b", "pos_embed", "temp_embed", "t_w0", "t_b0", "t_w2", "t_b2", "y_table",
+    "ada_w16", "ada_b", "qkv_w16", "qkv_b", "proj_w16", "proj_b", "fc1_w16", "fc1_b", "fc2_w16", "fc2_b",
+    "final_w", "final_b")
+
+
+class LatteWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+
+
+EXPORTS = {
+    "b200_last_error": (C.c_char_p, []),
+    "b200_abi_version": (C.c_int, []),
+    "b200_latte_workspace_bytes": (C.c_size_t, [C.POINTER(LatteShape), C.c_int]),
+    "b200_latte_forward": (C.c_int, [C.POINTER(LatteShape), C.POINTER(LatteWeights), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]),
+    "b200_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "b200_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p]),
+    "b200_ln_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(rebuild_if_stale: bool = True):
+    """Load (building first if needed) and type the library.  Raises on any failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path) or (rebuild_if_stale and os.environ.get("LATTE_B200_NO_BUILD") != "1"):
+        try:
+            _build.build_library()
+        except Exception as e:  # a prebuilt .so that travelled to a box without nvcc is still usable
+            if not os.path.exists(path):
+                raise RuntimeError(f"liblatte_b200.so is missing and could not be built: {e}") from e
+    lib = C.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.b200_abi_version()
+    if v != ABI_VERSION:
+        raise RuntimeError(f"liblatte_b200.so ABI version {v} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().b200_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RuntimeError(f"{what} failed: B200_ERR_{ERR_NAMES.get(rc, rc)}: {last_error()}")

@@ -1,0 +1,196 @@
+// extern "C" surface of liblatte_b200.so (declared in include/latte_b200.h) and the forward orchestration.
+#include "common.h"
+
+namespace b200 {
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  float* x;          // [T, D]   fp32 residual stream, rows (b, f, n)
+  uint16_t* h;       // [T, D]   16-bit: LN+modulate output, then attention output
+  uint16_t* qkv;     // [T, 3D]  16-bit
+  uint16_t* g;       // [T, 4D]  16-bit MLP hidden
+  float* tfreq;      // [B, 256]
+  float* th;         // [B, D]   SiLU(Linear(256, D))
+  float* c;          // [B, D]   t_emb (+ y_emb)
+  float* mod;        // [B, depth*6D + 2D]
+  size_t bytes;
+};
+
+int shape_ok(const B200LatteShape* s, int batch) {
+  B200_REQUIRE(s != nullptr, B200_ERR_SHAPE, "shape is NULL");
+  B200_REQUIRE(batch > 0, B200_ERR_SHAPE, "batch %d must be positive", batch);
+  B200_REQUIRE(s->depth > 0 && s->depth % 2 == 0, B200_ERR_SHAPE, "depth %d must be even (spatial/temporal pairs)", s->depth);
+  B200_REQUIRE(s->heads > 0 && s->hidden % s->heads == 0, B200_ERR_SHAPE, "hidden %d not divisible by heads %d", s->hidden, s->heads);
+  const int hd = s->hidden / s->heads;
+  B200_REQUIRE(hd == 64 || hd == 72 || hd == 80, B200_ERR_UNSUPPORTED, "head_dim %d unsupported", hd);
+  B200_REQUIRE(s->hidden % 64 == 0 && s->mlp_hidden % 64 == 0, B200_ERR_UNSUPPORTED,
+               "hidden %d and mlp_hidden %d must be multiples of 64 (GEMM K tile)", s->hidden, s->mlp_hidden);
+  B200_REQUIRE(s->patch == 2, B200_ERR_UNSUPPORTED, "patch size %d not built (only 2)", s->patch);
+  B200_REQUIRE(s->input_size % s->patch == 0, B200_ERR_SHAPE, "input_size %d not divisible by patch", s->input_size);
+  B200_REQUIRE(s->dtype == B200_FP16 || s->dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", s->dtype);
+  B200_REQUIRE(s->out_channels * s->patch * s->patch <= 32, B200_ERR_UNSUPPORTED, "p*p*out_channels > 32");
+  return B200_OK;
+}
+
+void carve(const B200LatteShape* s, int batch, void* base, Workspace* ws) {
+  const size_t grid = s->input_size / s->patch;
+  const size_t T = static_cast<size_t>(batch) * s->frames * grid * grid;
+  const size_t D = s->hidden;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  ws->x = static_cast<float*>(take(T * D * 4));
+  ws->h = static_cast<uint16_t*>(take(T * D * 2));
+  ws->qkv = static_cast<uint16_t*>(take(T * 3 * D * 2));
+  ws->g = static_cast<uint16_t*>(take(T * static_cast<size_t>(s->mlp_hidden) * 2));
+  ws->tfreq = static_cast<float*>(take(static_cast<size_t>(batch) * 256 * 4));
+  ws->th = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
+  ws->c = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
+  ws->mod = static_cast<float*>(take(static_cast<size_t>(batch) * (static_cast<size_t>(s->depth) * 6 * D + 2 * D) * 4));
+  ws->bytes = off;
+}
+
+int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, const int64_t* t, const int64_t* y,
+            int batch, int use_cfg, float cfg_scale, float* out, void* workspace, size_t workspace_bytes,
+            cudaStream_t stream) {
+  B200_TRY(shape_ok(s, batch));
+  B200_REQUIRE(w && x && t && out && workspace, B200_ERR_SHAPE, "NULL argument");
+  B200_REQUIRE((s->num_embed > 0) == (y != nullptr && w->y_table != nullptr), B200_ERR_SHAPE,
+               "labels y and y_table must be given iff num_embed > 0 (extras == 2)");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, B200_ERR_ALIGN, "workspace must be 1024-byte aligned");
+  const bool cfg = use_cfg != 0;
+  B200_REQUIRE(!cfg || batch % 2 == 0, B200_ERR_SHAPE, "classifier-free guidance needs an even batch (got %d)", batch);
+  B200_TRY(check_arch());
+  Workspace ws;
+  carve(s, batch, workspace, &ws);
+  B200_REQUIRE(ws.bytes <= workspace_bytes, B200_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes,
+               workspace_bytes);
+
+  const int D = s->hidden, H = s->heads, hd = D / H, F = s->frames, depth = s->depth;
+  const int grid = s->input_size / s->patch, N = grid * grid;
+  const int T = batch * F * N;
+  const int rows_per_batch = F * N;
+  const int bf16 = s->dtype == B200_BF16;
+  const long long mod_bs = static_cast<long long>(depth) * 6 * D + 2 * D;
+  const int HID = s->mlp_hidden;
+
+  // ---- conditioning, once per SAMPLE (latte.py:332-339): c = t_embedder(t) (+ y_embedder(y)); mod = adaLN(SiLU(c)) for all blocks
+  B200_TRY(launch_timestep_freq(reinterpret_cast<const long long*>(t), ws.tfreq, batch, stream));
+  B200_TRY(launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, stream));
+  B200_TRY(launch_gemv(w->t_w2, 32, 0, w->t_b2, ws.th, ws.c, batch, D, D, 0, 0, s->num_embed > 0 ? w->y_table : nullptr,
+                       reinterpret_cast<const long long*>(y), stream));
+  B200_TRY(launch_gemv(w->ada_w16, 16, bf16, w->ada_b, ws.c, ws.mod, batch, static_cast<int>(mod_bs), D, 1, 0, nullptr,
+                       nullptr, stream));
+
+  // ---- patch embedding + pos_embed -> fp32 residual stream (latte.py:330-331)
+  B200_TRY(launch_patch_embed(x, cfg ? batch / 2 : batch, w->patch_w, w->patch_b, w->pos_embed, ws.x, batch, F,
+                              s->in_channels, s->input_size, s->patch, D, stream));
+
+  // ---- blocks (latte.py:345-368); rows stay in (b, f, n) order for all of them
+  for (int i = 0; i < depth; ++i) {
+    const float* m = ws.mod + static_cast<size_t>(i) * 6 * D;  // [shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp]
+    const uint16_t* qkv_w = static_cast<const uint16_t*>(w->qkv_w16) + static_cast<size_t>(i) * 3 * D * D;
+    const uint16_t* proj_w = static_cast<const uint16_t*>(w->proj_w16) + static_cast<size_t>(i) * D * D;
+    const uint16_t* fc1_w = static_cast<const uint16_t*>(w->fc1_w16) + static_cast<size_t>(i) * HID * D;
+    const uint16_t* fc2_w = static_cast<const uint16_t*>(w->fc2_w16) + static_cast<size_t>(i) * D * HID;
+
+    B200_TRY(launch_ln_modulate(ws.x, m + 0 * D, m + 1 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    GemmArgs ga{};
+    ga.A = ws.h; ga.W = qkv_w; ga.bias = w->qkv_b + static_cast<size_t>(i) * 3 * D;
+    ga.M = T; ga.N = 3 * D; ga.K = D; ga.bf16 = bf16; ga.epilogue = B200_EPI_BIAS; ga.out16 = ws.qkv;
+    B200_TRY(launch_gemm(ga, stream));
+
+    AttnArgs aa{};
+    aa.qkv = ws.qkv; aa.out = ws.h; aa.batch = batch; aa.frames = F; aa.tokens = N; aa.heads = H; aa.head_dim = hd;
+    aa.bf16 = bf16; aa.temporal = i & 1;
+    B200_TRY(launch_attention(aa, stream));
+
+    GemmArgs gp{};
+    gp.A = ws.h; gp.W = proj_w; gp.bias = w->proj_b + static_cast<size_t>(i) * D;
+    gp.M = T; gp.N = D; gp.K = D; gp.bf16 = bf16; gp.epilogue = B200_EPI_GATE_RESIDUAL; gp.resid = ws.x;
+    gp.gate = m + 2 * D; gp.gate_batch_stride = mod_bs; gp.rows_per_batch = rows_per_batch;
+    B200_TRY(launch_gemm(gp, stream));
+
+    B200_TRY(launch_ln_modulate(ws.x, m + 3 * D, m + 4 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    GemmArgs g1{};
+    g1.A = ws.h; g1.W = fc1_w; g1.bias = w->fc1_b + static_cast<size_t>(i) * HID;
+    g1.M = T; g1.N = HID; g1.K = D; g1.bf16 = bf16; g1.epilogue = B200_EPI_BIAS_GELU; g1.out16 = ws.g;
+    B200_TRY(launch_gemm(g1, stream));
+
+    GemmArgs g2{};
+    g2.A = ws.g; g2.W = fc2_w; g2.bias = w->fc2_b + static_cast<size_t>(i) * D;
+    g2.M = T; g2.N = D; g2.K = HID; g2.bf16 = bf16; g2.epilogue = B200_EPI_GATE_RESIDUAL; g2.resid = ws.x;
+    g2.gate = m + 5 * D; g2.gate_batch_stride = mod_bs; g2.rows_per_batch = rows_per_batch;
+    if (i == 0) {  // x = x + temp_embed before the first temporal block (latte.py:357-358), folded into block 0's last epilogue
+      g2.row_add = w->temp_embed; g2.row_add_div = N; g2.row_add_period = F;
+    }
+    B200_TRY(launch_gemm(g2, stream));
+  }
+
+  // ---- final layer + unpatchify (latte.py:374-376), then guidance (latte.py:394-398)
+  const float* mf = ws.mod + static_cast<size_t>(depth) * 6 * D;  // [shift, scale]
+  B200_TRY(launch_final_layer(ws.x, mf, mf + D, mod_bs, w->final_w, w->final_b, out, batch, F, grid, s->patch,
+                              s->out_channels, D, stream));
+  if (cfg) {
+    const long long per_sample = static_cast<long long>(F) * s->out_channels * s->input_size * s->input_size;
+    B200_TRY(launch_cfg_combine(out, batch, per_sample, F, s->out_channels, s->in_channels, s->input_size * s->input_size,
+                                cfg_scale, stream));
+  }
+  return B200_OK;
+}
+
+}  // namespace
+}  // namespace b200
+
+extern "C" {
+
+B200_API const char* b200_last_error(void) { return b200::get_error(); }
+B200_API int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+B200_API size_t b200_latte_workspace_bytes(const B200LatteShape* shape, int batch) {
+  if (b200::shape_ok(shape, batch) != B200_OK) return 0;
+  b200::Workspace ws;
+  b200::carve(shape, batch, nullptr, &ws);
+  return ws.bytes;
+}
+
+B200_API int b200_latte_forward(const B200LatteShape* shape, const B200LatteWeights* w, const float* x, const int64_t* t,
+                       const int64_t* y, int batch, int use_cfg, float cfg_scale, float* out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return b200::forward(shape, w, x, t, y, batch, use_cfg, cfg_scale, out, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+B200_API int b200_linear(const void* A, const void* W, const float* bias, int M, int N, int K, int dtype, int epilogue,
+                void* out16, float* resid, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
+                int block_n, void* stream) {
+  B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype);
+  b200::GemmArgs a{};
+  a.A = A; a.W = W; a.bias = bias; a.M = M; a.N = N; a.K = K; a.bf16 = dtype == B200_BF16; a.epilogue = epilogue;
+  a.out16 = out16; a.resid = resid; a.gate = gate; a.gate_batch_stride = gate_batch_stride;
+  a.rows_per_batch = rows_per_batch; a.block_n = block_n;
+  return b200::launch_gemm(a, static_cast<cudaStream_t>(stream));
+}
+
+B200_API int b200_attention(const void* qkv, void* out, int batch, int frames, int tokens, int heads, int head_dim, int dtype,
+                   int temporal, void* stream) {
+  B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype);
+  b200::AttnArgs a{};
+  a.qkv = qkv; a.out = out; a.batch = batch; a.frames = frames; a.tokens = tokens; a.heads = heads;
+  a.head_dim = head_dim; a.bf16 = dtype == B200_BF16; a.temporal = temporal;
+  return b200::launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+B200_API int b200_ln_modulate(const float* x, const float* shift, const float* scale, int64_t mod_batch_stride,
+                     int rows_per_batch, void* out16, int rows, int dim, int dtype, void* stream) {
+  B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype);
+  return b200::launch_ln_modulate(x, shift, scale, mod_batch_stride, rows_per_batch, out16, rows, dim,
+                                  dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// Fused spatial / temporal attention on tcgen05:  out = softmax(q k^T / sqrt(hd)) v  per head.
+//
+// Replaces the 'math' branch of Attention.forward between its two Linears (reference models/latte.py:50-70:
+// reshape/permute/.contiguous(), q@k^T, *scale, softmax, @v, transpose/reshape) AND the two einops
+// rearranges that regroup tokens between spatial and temporal blocks (latte.py:355,368).  The hidden state and
+// the qkv buffer stay in ONE layout, rows = (b, f, n); the regrouping is done by the TMA box that fetches a tile:
+//   spatial  (temporal=0): a tile is 128 consecutive tokens of one frame; keys = the frame's N tokens.
+//            3-D map {hd, 3H, T}; Q box {64|16, 1, 128}, K/V box {64|16, 1, N}.
+//            N < 128: 128/N whole sequences are packed per tile with a block-diagonal mask (r/N == c/N).
+//   temporal (temporal=1): a tile is G = 128/F neighbouring tokens x all F frames, fetched with a 4-D map
+//            {hd, 3H, N, B*F} and box {64|16, 1, G, F} -> tile row r = f*G + g; the G sequences are masked
+//            block-diagonally (r % G == c % G).  Wasted tensor FLOPs (x G) are free; HBM traffic is minimal:
+//            every q/k/v element is read once, every output written once, no transpose pass.
+// head_dim 72 (XL) is not a multiple of the UMMA K=16 / N=16 granules: the first 64 dims use 128B-swizzled
+// tiles, dims [64,80) a second 32B-swizzled tile whose out-of-range columns TMA zero-fills.
+//
+// CTA = 160 threads: warps 0-3 softmax/epilogue (thread = tile row = TMEM lane), warp 4 = TMA + MMA issuer.
+//   S = Q K^T -> TMEM cols [0,Lk)  ->  registers: mask, max, exp2, sum -> P (16-bit) to smem (K-major SW128)
+//   O = P V   -> TMEM cols [256,336) -> registers: * 1/sum -> global.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kThreads = 160;
+constexpr int kTmemCols = 512;
+constexpr int kOCol = 256;
+
+enum { MODE_FULL = 0, MODE_PACKED = 1, MODE_TEMPORAL = 2 };
+
+struct AttnDev {
+  void* out;
+  int T;            // total rows
+  int D;            // heads * head_dim
+  int heads, hd;
+  int tokens;       // N
+  int frames;       // F
+  int group;        // PACKED: N (tokens per sequence); TEMPORAL: G = 128 / F  (power of two)
+  int gshift;       // log2(group)
+  int Lk;           // keys per tile: N (FULL, <= 256) or 128
+  int tiles_per_seq;  // FULL: N / 128; TEMPORAL: N / G
+  float scale_log2; // hd^-0.5 * log2(e)
+};
+
+constexpr int SQ_MAIN = 0;
+constexpr int SK_MAIN = SQ_MAIN + 128 * 128;
+constexpr int SV_MAIN = SK_MAIN + 256 * 128;
+constexpr int SP = SV_MAIN + 256 * 128;
+constexpr int SQ_TAIL = SP + 128 * 256 * 2;
+constexpr int SK_TAIL = SQ_TAIL + 128 * 32;
+constexpr int SV_TAIL = SK_TAIL + 256 * 32;
+constexpr int SBARS = SV_TAIL + 256 * 32;
+constexpr int SMEM_BYTES = SBARS + 128 + 1024;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// group is a power of two: PACKED compares sequence ids (index >> shift), TEMPORAL compares token ids (index & mask)
+template <int MODE>
+__device__ __forceinline__ int row_key(int r, int gshift) {
+  if constexpr (MODE == MODE_PACKED) return r >> gshift;
+  if constexpr (MODE == MODE_TEMPORAL) return r & ((1 << gshift) - 1);
+  return 0;
+}
+template <int MODE>
+__device__ __forceinline__ bool key_valid(int rkey, int col, int gshift) {
+  if constexpr (MODE == MODE_FULL) return true;
+  return row_key<MODE>(col, gshift) == rkey;
+}
+
+template <bool BF16, bool TAIL, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
+            const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt, const AttnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SBARS);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int head = blockIdx.y;
+  const int Lk = p.Lk;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA loads
+      const uint32_t qk_bytes = 128 * 128 + Lk * 128 + (TAIL ? (128 * 32 + Lk * 32) : 0);
+      const uint32_t v_bytes = Lk * 128 + (TAIL ? Lk * 32 : 0);
+      mbar_arrive_expect_tx(bar_qk, qk_bytes);
+      if constexpr (MODE == MODE_TEMPORAL) {
+        const int b = tile / p.tiles_per_seq;
+        const int n0 = (tile % p.tiles_per_seq) * p.group;
+        const int bf0 = b * p.frames;
+        tma_load_4d(smem + SQ_MAIN, &tmQ, bar_qk, 0, head, n0, bf0);
+        tma_load_4d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.heads + head, n0, bf0);
+        if constexpr (TAIL) {
+          tma_load_4d(smem + SQ_TAIL, &tmQt, bar_qk, 64, head, n0, bf0);
+          tma_load_4d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.heads + head, n0, bf0);
+        }
+        mbar_arrive_expect_tx(bar_v, v_bytes);
+        tma_load_4d(smem + SV_MAIN, &tmKV, bar_v, 0, 2 * p.heads + head, n0, bf0);
+        if constexpr (TAIL) tma_load_4d(smem + SV_TAIL, &tmKVt, bar_v, 64, 2 * p.heads + head, n0, bf0);
+      } else {
+        int q_row0, kv_row0;
+        if constexpr (MODE == MODE_FULL) {
+          const int s = tile / p.tiles_per_seq;
+          kv_row0 = s * p.tokens;
+          q_row0 = kv_row0 + (tile % p.tiles_per_seq) * 128;
+        } else {
+          q_row0 = kv_row0 = tile * 128;
+        }
+        tma_load_3d(smem + SQ_MAIN, &tmQ, bar_qk, 0, head, q_row0);
+        tma_load_3d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.heads + head, kv_row0);
+        if constexpr (TAIL) {
+          tma_load_3d(smem + SQ_TAIL, &tmQt, bar_qk, 64, head, q_row0);
+          tma_load_3d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.heads + head, kv_row0);
+        }
+        mbar_arrive_expect_tx(bar_v, v_bytes);
+        tma_load_3d(smem + SV_MAIN, &tmKV, bar_v, 0, 2 * p.heads + head, kv_row0);
+        if constexpr (TAIL) tma_load_3d(smem + SV_TAIL, &tmKVt, bar_v, 64, 2 * p.heads + head, kv_row0);
+      }
+
+      // ---------------------------------------------------------------- S = Q K^T   (M=128, N=Lk, K=hd padded to 16)
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t idesc_s = umma_idesc_f16(BF16, 128, static_cast<uint32_t>(Lk), false, false);
+      const uint64_t dq = umma_smem_desc(smem_u32(smem + SQ_MAIN), 0, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t dk = umma_smem_desc(smem_u32(smem + SK_MAIN), 0, 1024, UMMA_LAYOUT_SW128);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16_ss(tmem_base, umma_desc_advance(dq, k * 32), umma_desc_advance(dk, k * 32), idesc_s, k > 0 ? 1u : 0u);
+      if constexpr (TAIL) {
+        const uint64_t dqt = umma_smem_desc(smem_u32(smem + SQ_TAIL), 0, 256, UMMA_LAYOUT_SW32);
+        const uint64_t dkt = umma_smem_desc(smem_u32(smem + SK_TAIL), 0, 256, UMMA_LAYOUT_SW32);
+        umma_f16_ss(tmem_base, dqt, dkt, idesc_s, 1u);
+      }
+      umma_commit(bar_s);
+
+      // ---------------------------------------------------------------- O = P V   (M=128, N=64 (+16), K=Lk)
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t idesc_o = umma_idesc_f16(BF16, 128, 64, false, true);   // B = V is MN-major ([key][hd] in smem)
+      const uint32_t idesc_ot = umma_idesc_f16(BF16, 128, 16, false, true);
+      const uint64_t dv = umma_smem_desc(smem_u32(smem + SV_MAIN), static_cast<uint32_t>(Lk) * 128, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t dvt = umma_smem_desc(smem_u32(smem + SV_TAIL), static_cast<uint32_t>(Lk) * 32, 256, UMMA_LAYOUT_SW32);
+      const int ksteps = Lk / 16;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t dp = umma_smem_desc(smem_u32(smem + SP + (k >> 2) * (128 * 128)) + (k & 3) * 32, 0, 1024, UMMA_LAYOUT_SW128);
+        umma_f16_ss(tmem_base + kOCol, dp, umma_desc_advance(dv, k * 16 * 128), idesc_o, k > 0 ? 1u : 0u);
+        if constexpr (TAIL)
+          umma_f16_ss(tmem_base + kOCol + 64, dp, umma_desc_advance(dvt, k * 16 * 32), idesc_ot, k > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue: thread = tile row
+    const int r = warp * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int nchunks = Lk / 32;
+    const int rkey = row_key<MODE>(r, p.gshift);
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+
+    float mx = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    const float mscaled = mx * p.scale_log2;
+    float sum = 0.f;
+    uint8_t* prow = smem + SP + r * 128;
+    const int sw = r & 7;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + c * 32, v);
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mscaled));
+        e[j] = key_valid<MODE>(rkey, c * 32 + j, p.gshift) ? x : 0.f;
+        sum += e[j];
+      }
+      uint8_t* atom = prow + (c >> 1) * (128 * 128);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = pack2<BF16>(e[8 * i + 0], e[8 * i + 1]);
+        o.y = pack2<BF16>(e[8 * i + 2], e[8 * i + 3]);
+        o.z = pack2<BF16>(e[8 * i + 4], e[8 * i + 5]);
+        o.w = pack2<BF16>(e[8 * i + 6], e[8 * i + 7]);
+        const int chunk = ((c & 1) * 4 + i) ^ sw;  // 128B swizzle: 16-byte chunk index XOR (row % 8)
+        *reinterpret_cast<uint4*>(atom + chunk * 16) = o;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    // output row of this thread
+    long long out_row;
+    bool row_ok = true;
+    if constexpr (MODE == MODE_TEMPORAL) {
+      const int b = tile / p.tiles_per_seq;
+      const int n0 = (tile % p.tiles_per_seq) * p.group;
+      out_row = (static_cast<long long>(b) * p.frames + r / p.group) * p.tokens + n0 + r % p.group;
+    } else if constexpr (MODE == MODE_FULL) {
+      out_row = static_cast<long long>(tile / p.tiles_per_seq) * p.tokens + (tile % p.tiles_per_seq) * 128 + r;
+    } else {
+      out_row = static_cast<long long>(tile) * 128 + r;
+      row_ok = out_row < p.T;
+    }
+    uint16_t* optr = reinterpret_cast<uint16_t*>(p.out) + out_row * p.D + head * p.hd;
+    const float inv = 1.0f / sum;
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + kOCol + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack2<BF16>(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          o.y = pack2<BF16>(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          o.z = pack2<BF16>(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          o.w = pack2<BF16>(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + c * 32 + i * 8) = o;
+        }
+      }
+    }
+    if constexpr (TAIL) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_row + kOCol + 64, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int tail8 = (p.hd - 64) / 8;  // 1 (hd 72) or 2 (hd 80)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (i >= tail8) break;
+          uint4 o;
+          o.x = pack2<BF16>(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          o.y = pack2<BF16>(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          o.z = pack2<BF16>(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          o.w = pack2<BF16>(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + 64 + i * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <bool BF16, bool TAIL, int MODE>
+int launch_mode(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
+  auto kern = attn_kernel<BF16, TAIL, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, SMEM_BYTES, stream>>>(m[0], m[1], m[2], m[3], p);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <bool BF16, bool TAIL>
+int launch_tail(int mode, const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t s) {
+  switch (mode) {
+    case MODE_FULL: return launch_mode<BF16, TAIL, MODE_FULL>(m, p, grid, s);
+    case MODE_PACKED: return launch_mode<BF16, TAIL, MODE_PACKED>(m, p, grid, s);
+    default: return launch_mode<BF16, TAIL, MODE_TEMPORAL>(m, p, grid, s);
+  }
+}
+
+}  // namespace
+
+int launch_attention(const AttnArgs& a, cudaStream_t stream) {
+  B200_REQUIRE(a.batch > 0 && a.frames > 0 && a.tokens > 0 && a.heads > 0, B200_ERR_SHAPE, "attention: bad shape");
+  B200_REQUIRE(a.head_dim == 64 || a.head_dim == 72 || a.head_dim == 80, B200_ERR_UNSUPPORTED,
+               "attention: head_dim %d unsupported (64, 72, 80)", a.head_dim);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(a.qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
+               B200_ERR_ALIGN, "attention: qkv/out must be 16-byte aligned");
+  B200_TRY(check_arch());
+  const int H = a.heads, hd = a.head_dim, D = H * hd;
+  const long long T = static_cast<long long>(a.batch) * a.frames * a.tokens;
+  const bool tail = hd > 64;
+
+  AttnDev p;
+  p.out = a.out;
+  p.T = static_cast<int>(T);
+  p.D = D;
+  p.heads = H;
+  p.hd = hd;
+  p.tokens = a.tokens;
+  p.frames = a.frames;
+  p.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
+
+  p.group = 1;
+  p.gshift = 0;
+  auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
+
+  CUtensorMap maps[4];
+  int mode;
+  dim3 grid;
+  if (!a.temporal) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(3 * H), static_cast<uint64_t>(T)};
+    const uint64_t str[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(3 * D) * 2};
+    uint32_t kv_rows;
+    if (a.tokens >= 128) {
+      B200_REQUIRE(a.tokens == 128 || a.tokens == 256, B200_ERR_UNSUPPORTED,
+                   "attention: spatial sequence length %d unsupported (<=64 power of two, 128, 256)", a.tokens);
+      mode = MODE_FULL;
+      p.Lk = a.tokens;
+      p.tiles_per_seq = a.tokens / 128;
+      kv_rows = a.tokens;
+      grid = dim3(a.batch * a.frames * p.tiles_per_seq, H);
+    } else {
+      B200_REQUIRE(128 % a.tokens == 0, B200_ERR_UNSUPPORTED, "attention: spatial sequence length %d must divide 128", a.tokens);
+      mode = MODE_PACKED;
+      p.Lk = 128;
+      p.group = a.tokens;
+      p.gshift = ilog2(a.tokens);
+      p.tiles_per_seq = 1;
+      kv_rows = 128;
+      grid = dim3(static_cast<unsigned>((T + 127) / 128), H);
+    }
+    const uint32_t boxQ[3] = {64, 1, 128}, boxQt[3] = {16, 1, 128};
+    const uint32_t boxK[3] = {64, 1, kv_rows}, boxKt[3] = {16, 1, kv_rows};
+    B200_TRY(make_tmap_16bit(&maps[0], a.qkv, 3, dims, str, boxQ, TMAP_SW_128));
+    B200_TRY(make_tmap_16bit(&maps[2], a.qkv, 3, dims, str, boxK, TMAP_SW_128));
+    if (tail) {
+      B200_TRY(make_tmap_16bit(&maps[1], a.qkv, 3, dims, str, boxQt, TMAP_SW_32));
+      B200_TRY(make_tmap_16bit(&maps[3], a.qkv, 3, dims, str, boxKt, TMAP_SW_32));
+    } else {
+      maps[1] = maps[0];
+      maps[3] = maps[2];
+    }
+  } else {
+    const int F = a.frames;
+    B200_REQUIRE(F >= 4 && F <= 128 && 128 % F == 0, B200_ERR_UNSUPPORTED,
+                 "attention: temporal length %d unsupported (power of two in [4,128])", F);
+    const int G = 128 / F;
+    B200_REQUIRE(a.tokens % G == 0, B200_ERR_UNSUPPORTED, "attention: tokens %d must be a multiple of %d", a.tokens, G);
+    mode = MODE_TEMPORAL;
+    p.Lk = 128;
+    p.group = G;
+    p.gshift = ilog2(G);
+    p.tiles_per_seq = a.tokens / G;
+    grid = dim3(a.batch * p.tiles_per_seq, H);
+    const uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(3 * H), static_cast<uint64_t>(a.tokens),
+                              static_cast<uint64_t>(a.batch) * F};
+    const uint64_t str[3] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(3 * D) * 2,
+                             static_cast<uint64_t>(3 * D) * 2 * a.tokens};
+    const uint32_t box[4] = {64, 1, static_cast<uint32_t>(G), static_cast<uint32_t>(F)};
+    const uint32_t boxt[4] = {16, 1, static_cast<uint32_t>(G), static_cast<uint32_t>(F)};
+    B200_TRY(make_tmap_16bit(&maps[0], a.qkv, 4, dims, str, box, TMAP_SW_128));
+    maps[2] = maps[0];
+    if (tail) {
+      B200_TRY(make_tmap_16bit(&maps[1], a.qkv, 4, dims, str, boxt, TMAP_SW_32));
+      maps[3] = maps[1];
+    } else {
+      maps[1] = maps[0];
+      maps[3] = maps[0];
+    }
+  }
+  if (a.bf16) return tail ? launch_tail<true, true>(mode, maps, p, grid, stream) : launch_tail<true, false>(mode, maps, p, grid, stream);
+  return tail ? launch_tail<false, true>(mode, maps, p, grid, stream) : launch_tail<false, false>(mode, maps, p, grid, stream);
+}
+
+}  // namespace b200

@@ -1,0 +1,96 @@
+// Host-side shared declarations for liblatte_b200.so (internal; the public C ABI is include/latte_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/latte_b200.h"
+
+namespace b200 {
+
+// ---- error plumbing (thread-local message; negative enum codes cross the ABI) -----------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define B200_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return B200_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+#define B200_REQUIRE(cond, code, ...)   \
+  do {                                  \
+    if (!(cond)) {                      \
+      b200::set_error(__VA_ARGS__);     \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+#define B200_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != B200_OK) return _rc; \
+  } while (0)
+
+// ---- TMA tensor maps ---------------------------------------------------------------------------
+enum TmapSwizzle { TMAP_SW_NONE = 0, TMAP_SW_32 = 1, TMAP_SW_64 = 2, TMAP_SW_128 = 3 };
+
+// rank-R tiled map over 16-bit elements. dims[0] is the contiguous dimension; strides_bytes[i] is the
+// byte stride of dims[i+1] (R-1 entries). box[i] in elements. OOB elements read as zero.
+int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, TmapSwizzle sw);
+
+// ---- device-property cache ----------------------------------------------------------------------
+int device_sm_count(int* out);
+int check_arch();  // B200_ERR_ARCH unless the current device is sm_100
+
+// ---- kernels (launchers; all enqueue on `stream`, never synchronise) ---------------------------
+struct GemmArgs {
+  const void* A;        // [M, K] 16-bit row-major
+  const void* W;        // [N, K] 16-bit row-major (nn.Linear weight layout)
+  const float* bias;    // [N] fp32 or nullptr
+  int M, N, K;
+  int bf16;             // 0 = fp16 operands, 1 = bf16
+  int epilogue;         // B200_EPI_*
+  void* out16;          // [M, N] 16-bit   (EPI_BIAS / EPI_BIAS_GELU)
+  float* resid;         // [M, N] fp32 in/out (EPI_GATE_RESIDUAL): resid += gate * (acc + bias) (+ row_add)
+  const float* gate;    // gate[(row / rows_per_batch) * gate_batch_stride + col]
+  long long gate_batch_stride;
+  int rows_per_batch;
+  const float* row_add; // optional [period, N] fp32 added to resid rows: row_add[((row / row_add_div) % row_add_period) * N + col]
+  int row_add_div, row_add_period;
+  int block_n;          // 0 = auto
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+struct AttnArgs {
+  const void* qkv;   // [T, 3*heads*head_dim] 16-bit, row = token (b, f, n), cols [q | k | v] each [head][head_dim]
+  void* out;         // [T, heads*head_dim] 16-bit
+  int batch, frames, tokens;  // T = batch*frames*tokens
+  int heads, head_dim;
+  int bf16;
+  int temporal;      // 0: sequences over tokens within a frame; 1: sequences over frames at a fixed token
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
+                       int rows_per_batch, void* out16, int rows, int dim, int bf16, cudaStream_t stream);
+int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const float* b, const float* pos, float* out,
+                       int batch, int frames, int chans, int size, int patch, int dim, cudaStream_t stream);
+// out[b][j] = act_out(W[j,:] . act_in(in[b,:]) + bias[j] (+ add[add_idx[b]][j]));  W fp32 (wbits=32) or 16-bit
+int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const float* in, float* out, int batch, int J,
+                int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx,
+                cudaStream_t stream);
+int launch_timestep_freq(const long long* t, float* out, int batch, cudaStream_t stream);
+int launch_final_layer(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
+                       const float* w, const float* b, float* out, int batch, int frames, int grid, int patch,
+                       int out_ch, int dim, cudaStream_t stream);
+int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, int out_ch, int guided_ch, int hw,
+                       float scale, cudaStream_t stream);
+
+}  // namespace b200

@@ -1,0 +1,399 @@
+// CUDA-core kernels around the tensor-core GEMMs: everything here is HBM- or latency-bound, so the rules are
+// coalesced 16-byte accesses, one pass over the data, fp32 math.
+//   ln_modulate   LayerNorm(no affine, eps 1e-6) + adaLN modulate -> 16-bit GEMM operand   (latte.py:28-29,166-168,179-180)
+//   patch_embed   Conv2d(k=s=p) as a K=C*p*p dot per token + bias + pos_embed -> fp32 residual stream (latte.py:330-331)
+//   timestep_freq sinusoidal features                                                       (latte.py:98-116)
+//   gemv          warp-per-output-row mat-vec for the per-SAMPLE conditioning path: t-MLP (latte.py:118-123),
+//                 label lookup (:148-153) and ONE batched adaLN for all blocks on B rows instead of B*F / B*N
+//                 repeated rows (latte.py:172-178)
+//   final_layer   LN + modulate + Linear(D, p*p*Cout) + unpatchify scatter                   (latte.py:197-201,297-310,374-376)
+//   cfg_combine   classifier-free guidance on eps channels                                   (latte.py:394-398)
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------- ln_modulate
+constexpr int LN_MAXV = 12;  // float4 per lane: dim <= 12*128 = 1536
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, long long mod_bs,
+                                                          int rows_per_batch, uint16_t* __restrict__ out, int rows,
+                                                          int dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = dim >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
+  float4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      v[i] = xr[idx];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(dim);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + 1e-6f);
+  const long long b = row / rows_per_batch;
+  const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_bs);
+  const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
+  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * dim);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 h = __ldg(sh + idx), c = __ldg(sc + idx);
+      const float y0 = fmaf((v[i].x - mean) * rstd, 1.0f + c.x, h.x);
+      const float y1 = fmaf((v[i].y - mean) * rstd, 1.0f + c.y, h.y);
+      const float y2 = fmaf((v[i].z - mean) * rstd, 1.0f + c.z, h.z);
+      const float y3 = fmaf((v[i].w - mean) * rstd, 1.0f + c.w, h.w);
+      orow[idx] = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- patch_embed
+constexpr int PE_TOK = 8;
+constexpr int PE_MAXK = 64;
+
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ x, int x_batch_mod,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          const float* __restrict__ pos, float* __restrict__ out,
+                                                          int total_tokens, int frames, int chans, int size, int patch,
+                                                          int dim) {
+  __shared__ float in[PE_TOK][PE_MAXK];
+  const int grid = size / patch;
+  const int N = grid * grid;
+  const int K = chans * patch * patch;
+  const int tok0 = blockIdx.x * PE_TOK;
+  for (int i = threadIdx.x; i < PE_TOK * K; i += blockDim.x) {
+    const int tl = i / K, k = i % K;
+    const int tok = tok0 + tl;
+    float val = 0.f;
+    if (tok < total_tokens) {
+      const int n = tok % N, bf = tok / N;
+      const int b = bf / frames, f = bf % frames;
+      const int bsrc = b % x_batch_mod;
+      const int gh = n / grid, gw = n % grid;
+      const int c = k / (patch * patch), ij = k % (patch * patch);
+      const int ii = ij / patch, jj = ij % patch;
+      val = x[(((static_cast<size_t>(bsrc) * frames + f) * chans + c) * size + gh * patch + ii) * size + gw * patch + jj];
+    }
+    in[tl][k] = val;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    float wk[PE_MAXK];
+#pragma unroll
+    for (int k = 0; k < PE_MAXK; ++k)
+      if (k < K) wk[k] = __ldg(w + static_cast<size_t>(d) * K + k);
+    const float bd = __ldg(bias + d);
+#pragma unroll
+    for (int tl = 0; tl < PE_TOK; ++tl) {
+      const int tok = tok0 + tl;
+      if (tok >= total_tokens) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < PE_MAXK; ++k)
+        if (k < K) acc = fmaf(in[tl][k], wk[k], acc);
+      out[static_cast<size_t>(tok) * dim + d] = acc + bd + __ldg(pos + static_cast<size_t>(tok % N) * dim + d);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- timestep features
+__global__ void timestep_freq_kernel(const long long* __restrict__ t, float* __restrict__ out, int batch) {
+  const int b = blockIdx.x;
+  const int k = threadIdx.x;  // 0..255
+  if (b >= batch) return;
+  const int half = 128;
+  const int kk = k % half;
+  const float freq = expf(-9.210340371976184f * static_cast<float>(kk) / static_cast<float>(half));  // ln(1e4)
+  const float arg = static_cast<float>(t[b]) * freq;
+  out[b * 256 + k] = (k < half) ? cosf(arg) : sinf(arg);
+}
+
+// ---------------------------------------------------------------------------------- gemv (warp per output row)
+constexpr int GV_MAXB = 8;
+
+template <int WBITS, bool BF16>
+__global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ W, const float* __restrict__ bias,
+                                                   const float* __restrict__ in, float* __restrict__ out, int batch,
+                                                   int J, int K, int silu_in, int silu_out,
+                                                   const float* __restrict__ add_table,
+                                                   const long long* __restrict__ add_idx) {
+  extern __shared__ float sin_[];  // [batch][K]
+  for (int i = threadIdx.x; i < batch * K; i += blockDim.x) {
+    const float v = in[i];
+    sin_[i] = silu_in ? silu(v) : v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < J; j += gridDim.x * warps) {
+    float acc[GV_MAXB];
+#pragma unroll
+    for (int b = 0; b < GV_MAXB; ++b) acc[b] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      float w0, w1, w2, w3;
+      if constexpr (WBITS == 32) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(W) + static_cast<size_t>(j) * K + k));
+        w0 = wv.x; w1 = wv.y; w2 = wv.z; w3 = wv.w;
+      } else {
+        const uint2 wv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(W) + static_cast<size_t>(j) * K + k));
+        const float2 a = unpack2<BF16>(wv.x), c = unpack2<BF16>(wv.y);
+        w0 = a.x; w1 = a.y; w2 = c.x; w3 = c.y;
+      }
+#pragma unroll
+      for (int b = 0; b < GV_MAXB; ++b) {
+        if (b < batch) {
+          const float4 xv = *reinterpret_cast<const float4*>(sin_ + b * K + k);
+          acc[b] = fmaf(w0, xv.x, fmaf(w1, xv.y, fmaf(w2, xv.z, fmaf(w3, xv.w, acc[b]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < GV_MAXB; ++b) {
+      if (b < batch) {
+        float r = warp_sum(acc[b]);
+        if (lane == 0) {
+          if (bias) r += __ldg(bias + j);
+          if (add_table) r += __ldg(add_table + static_cast<size_t>(add_idx[b]) * J + j);
+          out[static_cast<size_t>(b) * J + j] = silu_out ? silu(r) : r;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- final layer
+constexpr int FL_MAXV = 12;
+constexpr int FL_MAXO = 32;
+
+__global__ void __launch_bounds__(512) final_layer_kernel(const float* __restrict__ x, const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, long long mod_bs,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int total_tokens, int frames,
+                                                          int grid, int patch, int out_ch, int dim) {
+  extern __shared__ float sw[];  // [n_out][dim]
+  const int n_out = patch * patch * out_ch;
+  for (int i = threadIdx.x; i < n_out * dim / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int nv = dim >> 2;
+  const int N = grid * grid;
+  const int size = grid * patch;
+  for (int tok = blockIdx.x * warps + (threadIdx.x >> 5); tok < total_tokens; tok += gridDim.x * warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * dim);
+    float4 v[FL_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < FL_MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        v[i] = xr[idx];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(dim);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < FL_MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + 1e-6f);
+    const int n = tok % N, bf = tok / N;
+    const long long b = bf / frames;
+    const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_bs);
+    const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
+#pragma unroll
+    for (int i = 0; i < FL_MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        const float4 h = __ldg(sh + idx), c = __ldg(sc + idx);
+        v[i].x = fmaf((v[i].x - mean) * rstd, 1.0f + c.x, h.x);
+        v[i].y = fmaf((v[i].y - mean) * rstd, 1.0f + c.y, h.y);
+        v[i].z = fmaf((v[i].z - mean) * rstd, 1.0f + c.z, h.z);
+        v[i].w = fmaf((v[i].w - mean) * rstd, 1.0f + c.w, h.w);
+      }
+    }
+    float mine = 0.f;  // lane o keeps output o
+    for (int o = 0; o < n_out; ++o) {
+      const float4* wr = reinterpret_cast<const float4*>(sw + static_cast<size_t>(o) * dim);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < FL_MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nv) {
+          const float4 wv = wr[idx];
+          acc = fmaf(v[i].x, wv.x, fmaf(v[i].y, wv.y, fmaf(v[i].z, wv.z, fmaf(v[i].w, wv.w, acc))));
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == o) mine = acc;
+    }
+    if (lane < n_out) {
+      // unpatchify (latte.py:307-309): o = (pi*patch + qi)*out_ch + c  ->  out[bf][c][gh*patch+pi][gw*patch+qi]
+      const int c = lane % out_ch, pq = lane / out_ch;
+      const int pi = pq / patch, qi = pq % patch;
+      const int gh = n / grid, gw = n % grid;
+      out[((static_cast<size_t>(bf) * out_ch + c) * size + gh * patch + pi) * size + gw * patch + qi] = mine + __ldg(bias + lane);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- cfg combine
+__global__ void cfg_combine_kernel(float* __restrict__ out, int half_batch, long long per_sample, int out_ch,
+                                   int guided_ch, int hw, float scale) {
+  // element (b < half, frame/channel/pixel) with channel < guided_ch:
+  //   e = uncond + scale * (cond - uncond), written to both halves (latte.py:394-398)
+  const long long total = static_cast<long long>(half_batch) * per_sample;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long within = i % per_sample;
+    const int c = static_cast<int>((within / hw) % out_ch);
+    if (c < guided_ch) {
+      const float cond = out[i];
+      const float uncond = out[i + total];
+      const float e = uncond + scale * (cond - uncond);
+      out[i] = e;
+      out[i + total] = e;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
+                       int rows_per_batch, void* out16, int rows, int dim, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAXV * 128, B200_ERR_SHAPE,
+               "ln_modulate: dim %d must be a multiple of 4 and <= %d", dim, LN_MAXV * 128);
+  B200_REQUIRE(rows_per_batch > 0 && mod_batch_stride % 4 == 0, B200_ERR_SHAPE, "ln_modulate: bad batch geometry");
+  B200_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out16) & 7) == 0,
+               B200_ERR_ALIGN, "ln_modulate: pointers must be 16-byte aligned");
+  const int wpb = 8;
+  const int blocks = (rows + wpb - 1) / wpb;
+  if (bf16)
+    ln_modulate_kernel<true><<<blocks, wpb * 32, 0, stream>>>(x, shift, scale, mod_batch_stride, rows_per_batch,
+                                                               reinterpret_cast<uint16_t*>(out16), rows, dim);
+  else
+    ln_modulate_kernel<false><<<blocks, wpb * 32, 0, stream>>>(x, shift, scale, mod_batch_stride, rows_per_batch,
+                                                                reinterpret_cast<uint16_t*>(out16), rows, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const float* b, const float* pos, float* out,
+                       int batch, int frames, int chans, int size, int patch, int dim, cudaStream_t stream) {
+  const int K = chans * patch * patch;
+  B200_REQUIRE(K <= PE_MAXK && size % patch == 0, B200_ERR_SHAPE, "patch_embed: C*p*p = %d exceeds %d", K, PE_MAXK);
+  const int grid = size / patch;
+  const int total = batch * frames * grid * grid;
+  patch_embed_kernel<<<(total + PE_TOK - 1) / PE_TOK, 256, 0, stream>>>(x, x_batch_mod, w, b, pos, out, total, frames,
+                                                                          chans, size, patch, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_timestep_freq(const long long* t, float* out, int batch, cudaStream_t stream) {
+  timestep_freq_kernel<<<batch, 256, 0, stream>>>(t, out, batch);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const float* in, float* out, int batch, int J,
+                int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx,
+                cudaStream_t stream) {
+  B200_REQUIRE(K % 4 == 0 && J > 0, B200_ERR_SHAPE, "gemv: K=%d must be a multiple of 4", K);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, B200_ERR_ALIGN, "gemv: W must be 16-byte aligned");
+  int sms = 0;
+  B200_TRY(device_sm_count(&sms));
+  for (int b0 = 0; b0 < batch; b0 += GV_MAXB) {
+    const int nb = (batch - b0) < GV_MAXB ? (batch - b0) : GV_MAXB;
+    const size_t smem = static_cast<size_t>(nb) * K * sizeof(float);
+    B200_REQUIRE(smem <= 48 * 1024, B200_ERR_SHAPE, "gemv: K=%d too large", K);
+    const int warps = 8;
+    int blocks = (J + warps - 1) / warps;
+    const int cap = sms * 16;
+    if (blocks > cap) blocks = cap;
+    const float* inb = in + static_cast<size_t>(b0) * K;
+    float* outb = out + static_cast<size_t>(b0) * J;
+    const long long* idx = add_idx ? add_idx + b0 : nullptr;
+    if (wbits == 32)
+      gemv_kernel<32, false><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx);
+    else if (bf16)
+      gemv_kernel<16, true><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx);
+    else
+      gemv_kernel<16, false><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+int launch_final_layer(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
+                       const float* w, const float* b, float* out, int batch, int frames, int grid, int patch,
+                       int out_ch, int dim, cudaStream_t stream) {
+  const int n_out = patch * patch * out_ch;
+  B200_REQUIRE(n_out <= FL_MAXO && dim % 4 == 0 && dim <= FL_MAXV * 128, B200_ERR_SHAPE,
+               "final_layer: p*p*Cout = %d must be <= %d, dim %d <= %d", n_out, FL_MAXO, dim, FL_MAXV * 128);
+  const size_t smem = static_cast<size_t>(n_out) * dim * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(final_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  B200_REQUIRE(smem <= 200 * 1024, B200_ERR_SHAPE, "final_layer: weight tile %zu B exceeds shared memory", smem);
+  int sms = 0;
+  B200_TRY(device_sm_count(&sms));
+  const int total = batch * frames * grid * grid;
+  const int warps = 16;
+  int blocks = (total + warps - 1) / warps;
+  if (blocks > sms) blocks = sms;
+  final_layer_kernel<<<blocks, warps * 32, smem, stream>>>(x, shift, scale, mod_batch_stride, w, b, out, total, frames,
+                                                            grid, patch, out_ch, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, int out_ch, int guided_ch, int hw,
+                       float scale, cudaStream_t stream) {
+  (void)frames;
+  B200_REQUIRE(batch % 2 == 0, B200_ERR_SHAPE, "cfg: batch %d must be even", batch);
+  const long long total = static_cast<long long>(batch / 2) * per_sample;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  cfg_combine_kernel<<<blocks, 256, 0, stream>>>(out, batch / 2, per_sample, out_ch, guided_ch, hw, scale);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,332 @@
+// tcgen05 GEMM with fused epilogues: out = epi(A[M,K] @ W[N,K]^T + bias)
+//
+// Replaces the nn.Linear calls inside a Latte TransformerBlock (reference models/latte.py:50 qkv, :75 proj,
+// timm Mlp fc1/fc2 reached from :171,:180) together with the elementwise work that follows them:
+//   EPI_BIAS           qkv projection               -> 16-bit [M,N]
+//   EPI_BIAS_GELU      fc1 + GELU(tanh)             -> 16-bit [M,N]            (latte.py:169)
+//   EPI_GATE_RESIDUAL  proj / fc2 + adaLN gate + residual add, fp32 residual stream in place
+//                      (latte.py:179-180), optionally + temp_embed rows        (latte.py:357-358)
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (128B-swizzled) per pipeline stage
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
+//   warps 2..5  epilogue: tcgen05.ld accumulator rows -> registers -> fused math -> global
+// Two accumulator buffers in TMEM (2*BN columns) let the epilogue of tile i overlap the mainloop of tile i+1.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
+constexpr int kThreads = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
+};
+
+struct GemmDev {
+  int M, N, K;
+  int num_m, num_n;
+  const float* bias;
+  void* out16;
+  float* resid;
+  const float* gate;
+  long long gate_bs;
+  int rows_per_batch;
+  const float* row_add;
+  int row_add_div, row_add_period;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(u)) == x * sigmoid(2u),  u = sqrt(2/pi) (x + 0.044715 x^3)
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+}
+
+template <int BN, int EPI, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m * p.num_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BF16, BM, BN, false, false);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t da = umma_smem_desc(sa, 0, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t db = umma_smem_desc(sa + C::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(d_tmem, umma_desc_advance(da, k * 32), umma_desc_advance(db, k * 32), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const float* gate_row = nullptr;
+      const float* add_row = nullptr;
+      if constexpr (EPI == B200_EPI_GATE_RESIDUAL) {
+        if (row_ok) {
+          gate_row = p.gate + static_cast<long long>(row / p.rows_per_batch) * p.gate_bs;
+          if (p.row_add) add_row = p.row_add + static_cast<size_t>((row / p.row_add_div) % p.row_add_period) * p.N;
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
+          }
+          if constexpr (EPI == B200_EPI_GATE_RESIDUAL) {
+            float4* x4 = reinterpret_cast<float4*>(p.resid + static_cast<size_t>(row) * p.N + col0);
+            const float4* g4 = reinterpret_cast<const float4*>(gate_row + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 xv = x4[j];
+              const float4 g = __ldg(g4 + j);
+              xv.x = fmaf(g.x, f[4 * j + 0], xv.x);
+              xv.y = fmaf(g.y, f[4 * j + 1], xv.y);
+              xv.z = fmaf(g.z, f[4 * j + 2], xv.z);
+              xv.w = fmaf(g.w, f[4 * j + 3], xv.w);
+              if (add_row) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(add_row + col0) + j);
+                xv.x += a.x; xv.y += a.y; xv.z += a.z; xv.w += a.w;
+              }
+              x4[j] = xv;
+            }
+          } else {
+            if constexpr (EPI == B200_EPI_BIAS_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(row) * p.N + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack2<BF16>(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack2<BF16>(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack2<BF16>(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack2<BF16>(f[8 * j + 6], f[8 * j + 7]);
+              o4[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI, bool BF16>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int grid, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = gemm_kernel<BN, EPI, BF16>;
+  static bool attr_set = false;  // per instantiation; benign race (idempotent)
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <int BN, bool BF16>
+int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int grid, cudaStream_t s) {
+  switch (epi) {
+    case B200_EPI_BIAS: return launch_one<BN, B200_EPI_BIAS, BF16>(tmA, tmB, p, grid, s);
+    case B200_EPI_BIAS_GELU: return launch_one<BN, B200_EPI_BIAS_GELU, BF16>(tmA, tmB, p, grid, s);
+    case B200_EPI_GATE_RESIDUAL: return launch_one<BN, B200_EPI_GATE_RESIDUAL, BF16>(tmA, tmB, p, grid, s);
+  }
+  set_error("gemm: unknown epilogue %d", epi);
+  return B200_ERR_UNSUPPORTED;
+}
+
+template <int BN>
+int launch_bn(int bf16, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int grid,
+              cudaStream_t s) {
+  return bf16 ? launch_epi<BN, true>(epi, tmA, tmB, p, grid, s) : launch_epi<BN, false>(epi, tmA, tmB, p, grid, s);
+}
+
+int pick_block_n(int M, int N, int sms) {
+  // minimise (waves x per-tile cost); per-tile cost ~ BN with a small penalty for narrow tiles, whose
+  // smem operand traffic per MMA cycle is higher (128 B/clk at BN=128 vs 96 B/clk at BN=256).
+  const int cand[3] = {256, 192, 128};
+  const double pen[3] = {1.00, 1.03, 1.10};
+  int best = 128;
+  double best_cost = 1e300;
+  for (int i = 0; i < 3; ++i) {
+    const long long tiles = static_cast<long long>((M + BM - 1) / BM) * ((N + cand[i] - 1) / cand[i]);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * cand[i] * pen[i];
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = cand[i]; }
+  }
+  return best;
+}
+
+}  // namespace
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+  B200_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, B200_ERR_SHAPE, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  B200_REQUIRE(a.K % BK == 0, B200_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", a.K, BK);
+  B200_REQUIRE(a.N % 32 == 0, B200_ERR_SHAPE, "gemm: N=%d must be a multiple of 32", a.N);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+               B200_ERR_ALIGN, "gemm: A and W must be 16-byte aligned");
+  if (a.epilogue == B200_EPI_GATE_RESIDUAL) {
+    B200_REQUIRE(a.resid && a.gate && a.rows_per_batch > 0, B200_ERR_SHAPE, "gemm: gated-residual epilogue needs resid, gate, rows_per_batch");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(a.resid) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.gate) & 15) == 0 &&
+                     (a.gate_batch_stride % 4) == 0,
+                 B200_ERR_ALIGN, "gemm: resid/gate must be 16-byte aligned");
+  } else {
+    B200_REQUIRE(a.out16 && (reinterpret_cast<uintptr_t>(a.out16) & 15) == 0, B200_ERR_ALIGN, "gemm: out16 must be 16-byte aligned");
+  }
+  B200_REQUIRE(!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, B200_ERR_ALIGN, "gemm: bias must be 16-byte aligned");
+  B200_TRY(check_arch());
+  int sms = 0;
+  B200_TRY(device_sm_count(&sms));
+
+  int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, sms);
+  B200_REQUIRE(bn == 128 || bn == 192 || bn == 256, B200_ERR_UNSUPPORTED, "gemm: block_n must be 128, 192 or 256 (got %d)", bn);
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dimsA[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.M)};
+    const uint64_t strA[1] = {static_cast<uint64_t>(a.K) * 2};
+    const uint32_t boxA[2] = {BK, BM};
+    B200_TRY(make_tmap_16bit(&tmA, a.A, 2, dimsA, strA, boxA, TMAP_SW_128));
+    const uint64_t dimsB[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N)};
+    const uint64_t strB[1] = {static_cast<uint64_t>(a.K) * 2};
+    const uint32_t boxB[2] = {BK, static_cast<uint32_t>(bn)};
+    B200_TRY(make_tmap_16bit(&tmB, a.W, 2, dimsB, strB, boxB, TMAP_SW_128));
+  }
+  GemmDev p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.num_m = (a.M + BM - 1) / BM;
+  p.num_n = (a.N + bn - 1) / bn;
+  p.bias = a.bias;
+  p.out16 = a.out16;
+  p.resid = a.resid;
+  p.gate = a.gate;
+  p.gate_bs = a.gate_batch_stride;
+  p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
+  p.row_add = a.row_add;
+  p.row_add_div = a.row_add_div > 0 ? a.row_add_div : 1;
+  p.row_add_period = a.row_add_period > 0 ? a.row_add_period : 1;
+  const int tiles = p.num_m * p.num_n;
+  const int grid = tiles < sms ? tiles : sms;
+  switch (bn) {
+    case 128: return launch_bn<128>(a.bf16, a.epilogue, tmA, tmB, p, grid, stream);
+    case 192: return launch_bn<192>(a.bf16, a.epilogue, tmA, tmB, p, grid, stream);
+    default: return launch_bn<256>(a.bf16, a.epilogue, tmA, tmB, p, grid, stream);
+  }
+}
+
+}  // namespace b200

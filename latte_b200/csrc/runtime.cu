@@ -1,0 +1,111 @@
+// Host-side runtime pieces: thread-local error text, TMA tensor-map encoding, device queries.
+#include "common.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace b200 {
+
+namespace {
+thread_local char g_err[512] = {0};
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// cuTensorMapEncodeTiled is a driver-API symbol. The library must load on machines without libcuda
+// (the CPU-only build/test container), so it is resolved at first use through the runtime.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, TmapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  B200_REQUIRE(fn != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the CUDA driver");
+  B200_REQUIRE(rank >= 2 && rank <= 5, B200_ERR_SHAPE, "tensor map rank %d unsupported", rank);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapSwizzle s = CU_TENSOR_MAP_SWIZZLE_NONE;
+  switch (sw) {
+    case TMAP_SW_32: s = CU_TENSOR_MAP_SWIZZLE_32B; break;
+    case TMAP_SW_64: s = CU_TENSOR_MAP_SWIZZLE_64B; break;
+    case TMAP_SW_128: s = CU_TENSOR_MAP_SWIZZLE_128B; break;
+    default: break;
+  }
+  // 16-bit payload: the bit pattern is moved, never interpreted, so one element type serves fp16 and bf16.
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, s, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA,
+               "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu box %u,%u base %p)", static_cast<int>(r),
+               rank, static_cast<unsigned long long>(dims[0]), static_cast<unsigned long long>(dims[1]), box[0], box[1],
+               base);
+  return B200_OK;
+}
+
+namespace {
+struct DevInfo {
+  int valid = 0, major = 0, minor = 0, sms = 0;
+};
+DevInfo g_dev[64];
+std::mutex g_dev_mu;
+
+int dev_info(DevInfo* out) {
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  B200_REQUIRE(dev >= 0 && dev < 64, B200_ERR_CUDA, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!g_dev[dev].valid) {
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&g_dev[dev].major, cudaDevAttrComputeCapabilityMajor, dev));
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&g_dev[dev].minor, cudaDevAttrComputeCapabilityMinor, dev));
+    B200_CHECK_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+    g_dev[dev].valid = 1;
+  }
+  *out = g_dev[dev];
+  return B200_OK;
+}
+}  // namespace
+
+int device_sm_count(int* out) {
+  DevInfo d;
+  B200_TRY(dev_info(&d));
+  *out = d.sms;
+  return B200_OK;
+}
+
+int check_arch() {
+  DevInfo d;
+  B200_TRY(dev_info(&d));
+  B200_REQUIRE(d.major == 10, B200_ERR_ARCH, "latte_b200 kernels are sm_100a only; current device is sm_%d%d", d.major,
+               d.minor);
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -62,7 +62,7 @@ CONFIGS = {
     "Latte-B/2": dict(depth=12, hidden_size=768, num_heads=12),
     "Latte-S/2": dict(depth=12, hidden_size=384, num_heads=6),
     # not in the reference table: a 4-block model with XL's awkward head_dim (72) for fast tests
-    "Latte-tiny72/2": dict(depth=4, hidden_size=288, num_heads=4),
+    "Latte-tiny72/2": dict(depth=4, hidden_size=576, num_heads=8),
     "Latte-tiny64/2": dict(depth=2, hidden_size=128, num_heads=2),
 }
 

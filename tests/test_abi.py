@@ -1,0 +1,78 @@
+"""CPU: the C-ABI library builds, loads without a GPU / libcuda, and exports every symbol the header declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from latte_b200 import _lib
+    return _lib.load()
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "latte_b200.h")).read()
+    return sorted(set(re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    syms = _header_symbols()
+    assert len(syms) >= 7 and "b200_latte_forward" in syms
+    from latte_b200 import _lib
+    assert sorted(_lib.EXPORTS) == syms, "ctypes binding table and include/latte_b200.h disagree"
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported by the .so"
+
+
+def test_no_libcuda_dependency():
+    """The driver API is resolved at run time so the library loads on the CPU-only build box."""
+    import subprocess
+    from latte_b200 import _lib
+    out = subprocess.run(["ldd", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libtorch" not in out and "libc10" not in out, out
+
+
+def test_sass_is_blackwell_native():
+    """The shipped cubin must contain tcgen05 MMA / TMEM / TMA instructions (UTC*MMA, LDTM, UTMALDG) and be sm_100a."""
+    import shutil
+    import subprocess
+    from latte_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert re.search(r"UTC\w*MMA", sass), "no tcgen05.mma in SASS"
+    assert "LDTM" in sass and "UTMALDG" in sass
+    assert not re.search(r"(?<!UTC)HMMA", sass), "legacy mma.sync path present"
+
+
+def test_abi_version_and_error_text(lib):
+    from latte_b200 import _lib
+    assert lib.b200_abi_version() == _lib.ABI_VERSION
+    # host-side validation runs before any CUDA call: a bad shape must come back as an error code + message
+    rc = lib.b200_linear(None, None, None, 128, 128, 65, 0, 0, None, None, None, 0, 1, 0, None)
+    assert rc == -1 and "multiple of 64" in _lib.last_error()
+    rc = lib.b200_linear(None, None, None, 128, 128, 64, 7, 0, None, None, None, 0, 1, 0, None)
+    assert rc == -2
+    rc = lib.b200_attention(None, None, 1, 16, 256, 4, 48, 0, 0, None)
+    assert rc == -7 and "head_dim" in _lib.last_error()
+
+
+def test_workspace_size_formula(lib):
+    from latte_b200 import _lib
+    s = _lib.LatteShape(depth=28, hidden=1152, heads=16, mlp_hidden=4608, patch=2, in_channels=4, out_channels=8,
+                        input_size=32, frames=16, num_embed=102, dtype=_lib.FP16)
+    n = lib.b200_latte_workspace_bytes(C.byref(s), 2)
+    T, D = 2 * 16 * 256, 1152
+    lower = T * D * 4 + T * D * 2 + T * 3 * D * 2 + T * 4 * D * 2
+    assert lower <= n < lower + (1 << 21)
+    s.heads = 10  # 1152/10 not an integer
+    assert lib.b200_latte_workspace_bytes(C.byref(s), 2) == 0 and "heads" in _lib.last_error()
+    s.heads = 16
+    s.patch = 4
+    assert lib.b200_latte_workspace_bytes(C.byref(s), 2) == 0 and "patch" in _lib.last_error()

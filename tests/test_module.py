@@ -1,0 +1,97 @@
+"""CPU: the nn.Module surface mirrors the reference (state_dict contract, factory, deepcopy, loud CPU failure)."""
+import copy
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from latte_b200 import Latte, Latte_models
+from latte_b200.models import get_models
+from oracle import latte_oracle as O
+
+
+def _small():
+    return Latte(input_size=16, hidden_size=128, depth=2, num_heads=2, num_frames=8, num_classes=101, extras=2)
+
+
+def test_state_dict_keys_match_reference_contract():
+    cfg = O.make_config("Latte-tiny64/2", input_size=16, num_frames=8)
+    net = _small()
+    spec = dict(O.state_dict_spec(cfg))
+    sd = net.state_dict()
+    assert set(sd) == set(spec)
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    # frozen tables, trainable everything else
+    grads = {n: p.requires_grad for n, p in net.named_parameters()}
+    assert not grads["pos_embed"] and not grads["temp_embed"]
+    assert all(v for k, v in grads.items() if k not in ("pos_embed", "temp_embed"))
+
+
+def test_reference_checkpoint_roundtrip():
+    cfg = O.make_config("Latte-tiny64/2", input_size=16, num_frames=8)
+    sd = O.make_weights(cfg, 3)
+    net = _small()
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    out = net.state_dict()
+    for k in sd:
+        assert torch.equal(out[k], sd[k]), k
+    ema = copy.deepcopy(net)  # train.py:121
+    assert torch.equal(ema.blocks[1].mlp.fc2.weight, net.blocks[1].mlp.fc2.weight)
+
+
+def test_init_matches_reference_tables_and_zero_init(golden_dir):
+    g = np.load(os.path.join(golden_dir, "subops_tiny72.npz"))
+    net = Latte(input_size=16, hidden_size=576, depth=2, num_heads=8, num_frames=4, num_classes=5, extras=2)
+    assert np.array_equal(net.pos_embed.numpy(), g["fresh_pos_embed"])     # bit-exact sin-cos tables (latte.py:406-457)
+    assert np.array_equal(net.temp_embed.numpy(), g["fresh_temp_embed"])
+    assert float(net.final_layer.linear.weight.abs().max()) == 0.0          # adaLN-Zero (latte.py:286-295)
+    assert all(float(b.adaLN_modulation[1].weight.abs().max()) == 0.0 for b in net.blocks)
+    assert float(net.blocks[0].attn.qkv.bias.abs().max()) == 0.0
+
+
+def test_size_table_and_factory():
+    assert set(Latte_models) == {f"Latte-{s}/{p}" for s in ("XL", "L", "B", "S") for p in (2, 4, 8)}
+    args = SimpleNamespace(model="Latte-S/2", latent_size=32, num_classes=101, num_frames=16, learn_sigma=True, extras=2)
+    net = get_models(args)
+    assert isinstance(net, Latte) and net.hidden_size == 384 and net.depth == 12 and net.num_heads == 6
+    assert net.in_channels == 4 and net.out_channels == 8 and net.learn_sigma and net.num_frames == 16
+    assert sum(p.numel() for p in net.parameters()) == 32_624_288  # reference S/2 parameter count
+    with pytest.raises(NotImplementedError):
+        get_models(SimpleNamespace(model="LatteT2V"))
+
+
+def test_unpatchify_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "subops_tiny72.npz"))
+    net = Latte(input_size=16, hidden_size=128, depth=2, num_heads=2, num_frames=4, num_classes=5, extras=2)
+    x = torch.arange(2 * 64 * 32, dtype=torch.float32).reshape(2, 64, 32)
+    assert np.array_equal(net.unpatchify(x).numpy(), g["unpatchify"])
+
+
+def test_no_cpu_fallback():
+    net = _small().eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.randn(2, 8, 4, 16, 16), torch.tensor([1, 2]), y=torch.tensor([0, 1]))
+    from latte_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.linear(torch.zeros(128, 64, dtype=torch.float16), torch.zeros(128, 64, dtype=torch.float16))
+
+
+def test_unsupported_variants_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        Latte(extras=78)
+    with pytest.raises(NotImplementedError):
+        Latte(attention_mode="flash")
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ (parity claims are void otherwise)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dp, _, files in os.walk(os.path.join(root, "latte_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle." not in text.replace("oracle/", ""), f
