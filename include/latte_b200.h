@@ -123,6 +123,13 @@ B200_API int b200_attention(const void* qkv, void* out, int batch, int frames, i
 B200_API int b200_ln_modulate(const float* x, const float* shift, const float* scale, int64_t mod_batch_stride,
                      int rows_per_batch, void* out16, int rows, int dim, int dtype, void* stream);
 
+/* Measurement hook (bench.py roofline): while enabled, b200_latte_forward brackets every kernel launch with
+ * CUDA events on the launching stream.  b200_profile_collect waits for them and returns, per class
+ * {0 tensor-core GEMM, 1 attention, 2 LN+modulate, 3 other}, the summed device time in ms and the launch count,
+ * then clears the records.  Disabled (default) the forward records nothing.                        */
+B200_API void b200_profile_enable(int on);
+B200_API int b200_profile_collect(double* ms_per_class, int* launches_per_class, int n_classes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ EXPORTS = {
                                  C.c_int, C.c_void_p]),
     "b200_ln_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p]),
+    "b200_profile_enable": (None, [C.c_int]),
+    "b200_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }
 
 _lib = None

@@ -1,8 +1,43 @@
 // extern "C" surface of liblatte_b200.so (declared in include/latte_b200.h) and the forward orchestration.
 #include "common.h"
 
+#include <mutex>
+#include <vector>
+
 namespace b200 {
 namespace {
+
+// ---- optional per-kernel-class timing (bench.py roofline): CUDA events recorded on the launching stream
+// around every launch of b200_latte_forward while enabled. Off by default: zero cost, no events.
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_CLASSES = 4 };
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+struct Profiler {
+  std::mutex mu;
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+} g_prof;
+
+struct ProfScope {
+  cudaStream_t s;
+  cudaEvent_t e1 = nullptr;
+  ProfScope(int cls, cudaStream_t stream) : s(stream) {
+    if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    ProfRec r{cls, g_prof.get(), g_prof.get()};
+    cudaEventRecord(r.e0, s);
+    e1 = r.e1;
+    g_prof.recs.push_back(r);
+  }
+  ~ProfScope() { if (e1) cudaEventRecord(e1, s); }
+};
+#define B200_PROF(cls, expr) do { ProfScope _ps(cls, stream); B200_TRY(expr); } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -80,15 +115,15 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
   const int HID = s->mlp_hidden;
 
   // ---- conditioning, once per SAMPLE (latte.py:332-339): c = t_embedder(t) (+ y_embedder(y)); mod = adaLN(SiLU(c)) for all blocks
-  B200_TRY(launch_timestep_freq(reinterpret_cast<const long long*>(t), ws.tfreq, batch, stream));
-  B200_TRY(launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, stream));
-  B200_TRY(launch_gemv(w->t_w2, 32, 0, w->t_b2, ws.th, ws.c, batch, D, D, 0, 0, s->num_embed > 0 ? w->y_table : nullptr,
+  B200_PROF(PROF_OTHER, launch_timestep_freq(reinterpret_cast<const long long*>(t), ws.tfreq, batch, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w2, 32, 0, w->t_b2, ws.th, ws.c, batch, D, D, 0, 0, s->num_embed > 0 ? w->y_table : nullptr,
                        reinterpret_cast<const long long*>(y), stream));
-  B200_TRY(launch_gemv(w->ada_w16, 16, bf16, w->ada_b, ws.c, ws.mod, batch, static_cast<int>(mod_bs), D, 1, 0, nullptr,
+  B200_PROF(PROF_OTHER, launch_gemv(w->ada_w16, 16, bf16, w->ada_b, ws.c, ws.mod, batch, static_cast<int>(mod_bs), D, 1, 0, nullptr,
                        nullptr, stream));
 
   // ---- patch embedding + pos_embed -> fp32 residual stream (latte.py:330-331)
-  B200_TRY(launch_patch_embed(x, cfg ? batch / 2 : batch, w->patch_w, w->patch_b, w->pos_embed, ws.x, batch, F,
+  B200_PROF(PROF_OTHER, launch_patch_embed(x, cfg ? batch / 2 : batch, w->patch_w, w->patch_b, w->pos_embed, ws.x, batch, F,
                               s->in_channels, s->input_size, s->patch, D, stream));
 
   // ---- blocks (latte.py:345-368); rows stay in (b, f, n) order for all of them
@@ -99,28 +134,28 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
     const uint16_t* fc1_w = static_cast<const uint16_t*>(w->fc1_w16) + static_cast<size_t>(i) * HID * D;
     const uint16_t* fc2_w = static_cast<const uint16_t*>(w->fc2_w16) + static_cast<size_t>(i) * D * HID;
 
-    B200_TRY(launch_ln_modulate(ws.x, m + 0 * D, m + 1 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    B200_PROF(PROF_LN, launch_ln_modulate(ws.x, m + 0 * D, m + 1 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
     GemmArgs ga{};
     ga.A = ws.h; ga.W = qkv_w; ga.bias = w->qkv_b + static_cast<size_t>(i) * 3 * D;
     ga.M = T; ga.N = 3 * D; ga.K = D; ga.bf16 = bf16; ga.epilogue = B200_EPI_BIAS; ga.out16 = ws.qkv;
-    B200_TRY(launch_gemm(ga, stream));
+    B200_PROF(PROF_GEMM, launch_gemm(ga, stream));
 
     AttnArgs aa{};
     aa.qkv = ws.qkv; aa.out = ws.h; aa.batch = batch; aa.frames = F; aa.tokens = N; aa.heads = H; aa.head_dim = hd;
     aa.bf16 = bf16; aa.temporal = i & 1;
-    B200_TRY(launch_attention(aa, stream));
+    B200_PROF(PROF_ATTN, launch_attention(aa, stream));
 
     GemmArgs gp{};
     gp.A = ws.h; gp.W = proj_w; gp.bias = w->proj_b + static_cast<size_t>(i) * D;
     gp.M = T; gp.N = D; gp.K = D; gp.bf16 = bf16; gp.epilogue = B200_EPI_GATE_RESIDUAL; gp.resid = ws.x;
     gp.gate = m + 2 * D; gp.gate_batch_stride = mod_bs; gp.rows_per_batch = rows_per_batch;
-    B200_TRY(launch_gemm(gp, stream));
+    B200_PROF(PROF_GEMM, launch_gemm(gp, stream));
 
-    B200_TRY(launch_ln_modulate(ws.x, m + 3 * D, m + 4 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    B200_PROF(PROF_LN, launch_ln_modulate(ws.x, m + 3 * D, m + 4 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
     GemmArgs g1{};
     g1.A = ws.h; g1.W = fc1_w; g1.bias = w->fc1_b + static_cast<size_t>(i) * HID;
     g1.M = T; g1.N = HID; g1.K = D; g1.bf16 = bf16; g1.epilogue = B200_EPI_BIAS_GELU; g1.out16 = ws.g;
-    B200_TRY(launch_gemm(g1, stream));
+    B200_PROF(PROF_GEMM, launch_gemm(g1, stream));
 
     GemmArgs g2{};
     g2.A = ws.g; g2.W = fc2_w; g2.bias = w->fc2_b + static_cast<size_t>(i) * D;
@@ -129,16 +164,16 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
     if (i == 0) {  // x = x + temp_embed before the first temporal block (latte.py:357-358), folded into block 0's last epilogue
       g2.row_add = w->temp_embed; g2.row_add_div = N; g2.row_add_period = F;
     }
-    B200_TRY(launch_gemm(g2, stream));
+    B200_PROF(PROF_GEMM, launch_gemm(g2, stream));
   }
 
   // ---- final layer + unpatchify (latte.py:374-376), then guidance (latte.py:394-398)
   const float* mf = ws.mod + static_cast<size_t>(depth) * 6 * D;  // [shift, scale]
-  B200_TRY(launch_final_layer(ws.x, mf, mf + D, mod_bs, w->final_w, w->final_b, out, batch, F, grid, s->patch,
+  B200_PROF(PROF_OTHER, launch_final_layer(ws.x, mf, mf + D, mod_bs, w->final_w, w->final_b, out, batch, F, grid, s->patch,
                               s->out_channels, D, stream));
   if (cfg) {
     const long long per_sample = static_cast<long long>(F) * s->out_channels * s->input_size * s->input_size;
-    B200_TRY(launch_cfg_combine(out, batch, per_sample, F, s->out_channels, s->in_channels, s->input_size * s->input_size,
+    B200_PROF(PROF_OTHER, launch_cfg_combine(out, batch, per_sample, F, s->out_channels, s->in_channels, s->input_size * s->input_size,
                                 cfg_scale, stream));
   }
   return B200_OK;
@@ -148,6 +183,27 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
 }  // namespace b200
 
 extern "C" {
+
+B200_API void b200_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(b200::g_prof.mu);
+  b200::g_prof.on = on != 0;
+}
+
+B200_API int b200_profile_collect(double* ms_per_class, int* launches_per_class, int n_classes) {
+  // synchronises on the recorded events, sums elapsed time per class, then clears the records
+  std::lock_guard<std::mutex> lk(b200::g_prof.mu);
+  for (int i = 0; i < n_classes; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+  for (auto& r : b200::g_prof.recs) {
+    B200_CHECK_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    B200_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (r.cls < n_classes) { ms_per_class[r.cls] += ms; launches_per_class[r.cls] += 1; }
+    b200::g_prof.pool.push_back(r.e0);
+    b200::g_prof.pool.push_back(r.e1);
+  }
+  b200::g_prof.recs.clear();
+  return B200_OK;
+}
 
 B200_API const char* b200_last_error(void) { return b200::get_error(); }
 B200_API int b200_abi_version(void) { return B200_ABI_VERSION; }
