@@ -25,8 +25,7 @@ namespace b200 {
 namespace {
 
 constexpr int kThreads = 160;
-constexpr int kTmemCols = 512;
-constexpr int kOCol = 256;
+constexpr int kOCol = 0;  // O (<= 80 columns) reuses the first S columns: S is dead once every row has written its P
 
 enum { MODE_FULL = 0, MODE_PACKED = 1, MODE_TEMPORAL = 2 };
 
@@ -44,15 +43,29 @@ struct AttnDev {
   float scale_log2; // hd^-0.5 * log2(e)
 };
 
-constexpr int SQ_MAIN = 0;
-constexpr int SK_MAIN = SQ_MAIN + 128 * 128;
-constexpr int SV_MAIN = SK_MAIN + 256 * 128;
-constexpr int SP = SV_MAIN + 256 * 128;
-constexpr int SQ_TAIL = SP + 128 * 256 * 2;
-constexpr int SK_TAIL = SQ_TAIL + 128 * 32;
-constexpr int SV_TAIL = SK_TAIL + 256 * 32;
-constexpr int SBARS = SV_TAIL + 256 * 32;
-constexpr int SMEM_BYTES = SBARS + 128 + 1024;
+// Shared-memory plan (bytes, every piece 1 KiB aligned), sized by the key count Lk so that several CTAs fit per SM:
+//   region A: [Q main 128x128B][K main Lk x128B][Q tail 128x32B][K tail Lk x32B]   -- later overwritten by P (128 x Lk 16-bit)
+//   region V: [V main Lk x128B][V tail Lk x32B]
+// Lk=256: 64 KiB + 40 KiB -> 2 CTAs/SM (TMEM 256 cols each); Lk=128: 40 KiB + 20 KiB -> 3 CTAs/SM (TMEM 128 cols each).
+struct SmemPlan {
+  int q_main, k_main, q_tail, k_tail, p, v_main, v_tail, bars, total;
+};
+__host__ __device__ inline SmemPlan make_plan(int Lk, bool tail) {
+  SmemPlan s;
+  s.q_main = 0;
+  s.k_main = 128 * 128;
+  s.q_tail = s.k_main + Lk * 128;
+  s.k_tail = s.q_tail + (tail ? 128 * 32 : 0);
+  const int qk_end = s.k_tail + (tail ? Lk * 32 : 0);
+  const int p_bytes = 128 * Lk * 2;
+  s.p = 0;
+  const int region_a = qk_end > p_bytes ? qk_end : p_bytes;
+  s.v_main = region_a;
+  s.v_tail = s.v_main + Lk * 128;
+  s.bars = s.v_tail + (tail ? Lk * 32 : 0);
+  s.total = s.bars + 128 + 1024;
+  return s;
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -74,12 +87,16 @@ __device__ __forceinline__ bool key_valid(int rkey, int col, int gshift) {
 }
 
 template <bool BF16, bool TAIL, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
             const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SBARS);
+  const SmemPlan sp = make_plan(p.Lk, TAIL);
+  const int SQ_MAIN = sp.q_main, SK_MAIN = sp.k_main, SQ_TAIL = sp.q_tail, SK_TAIL = sp.k_tail, SP = sp.p,
+            SV_MAIN = sp.v_main, SV_TAIL = sp.v_tail;
+  const uint32_t kTmemCols = static_cast<uint32_t>(p.Lk);  // 128 or 256 (power of two >= 32)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_s = bars + 2;
@@ -299,10 +316,11 @@ int launch_mode(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t 
   auto kern = attn_kernel<BF16, TAIL, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, make_plan(256, true).total));
     attr_set = true;
   }
-  kern<<<grid, kThreads, SMEM_BYTES, stream>>>(m[0], m[1], m[2], m[3], p);
+  const int smem_bytes = make_plan(p.Lk, TAIL).total;
+  kern<<<grid, kThreads, smem_bytes, stream>>>(m[0], m[1], m[2], m[3], p);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -25,53 +25,64 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 // ---------------------------------------------------------------------------------- ln_modulate
 constexpr int LN_MAXV = 12;  // float4 per lane: dim <= 12*128 = 1536
 
-template <bool BF16>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
+// One warp per row, the whole row in registers (NV float4 per lane, compile-time so nothing spills and the register
+// count stays low enough for full occupancy), two-pass mean/variance in fp32, one read and one write of the data.
+template <bool BF16, int NV>
+__global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
                                                           const float* __restrict__ scale, long long mod_bs,
                                                           int rows_per_batch, uint16_t* __restrict__ out, int rows,
                                                           int dim) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nv = dim >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
-  float4 v[LN_MAXV];
-  float s = 0.f;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
+    float4 v[NV];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      v[i] = xr[idx];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) v[i] = xr[idx];
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / static_cast<float>(dim);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + 1e-6f);
+    const long long b = row / rows_per_batch;
+    const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_bs);
+    const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * dim);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        const float4 h = __ldg(sh + idx), c = __ldg(sc + idx);
+        const float y0 = fmaf((v[i].x - mean) * rstd, 1.0f + c.x, h.x);
+        const float y1 = fmaf((v[i].y - mean) * rstd, 1.0f + c.y, h.y);
+        const float y2 = fmaf((v[i].z - mean) * rstd, 1.0f + c.z, h.z);
+        const float y3 = fmaf((v[i].w - mean) * rstd, 1.0f + c.w, h.w);
+        orow[idx] = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
+      }
     }
   }
-  const float mean = warp_sum(s) / static_cast<float>(dim);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + 1e-6f);
-  const long long b = row / rows_per_batch;
-  const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_bs);
-  const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
-  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * dim);
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      const float4 h = __ldg(sh + idx), c = __ldg(sc + idx);
-      const float y0 = fmaf((v[i].x - mean) * rstd, 1.0f + c.x, h.x);
-      const float y1 = fmaf((v[i].y - mean) * rstd, 1.0f + c.y, h.y);
-      const float y2 = fmaf((v[i].z - mean) * rstd, 1.0f + c.z, h.z);
-      const float y3 = fmaf((v[i].w - mean) * rstd, 1.0f + c.w, h.w);
-      orow[idx] = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
-    }
-  }
+}
+
+template <bool BF16>
+void ln_dispatch(int nvmax, int blocks, cudaStream_t stream, const float* x, const float* shift, const float* scale,
+                 long long mod_bs, int rpb, uint16_t* out, int rows, int dim) {
+  if (nvmax <= 3) ln_modulate_kernel<BF16, 3><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
+  else if (nvmax <= 6) ln_modulate_kernel<BF16, 6><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
+  else if (nvmax <= 9) ln_modulate_kernel<BF16, 9><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
+  else ln_modulate_kernel<BF16, LN_MAXV><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
 }
 
 // ---------------------------------------------------------------------------------- patch_embed
@@ -300,14 +311,15 @@ int launch_ln_modulate(const float* x, const float* shift, const float* scale, l
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(out16) & 7) == 0,
                B200_ERR_ALIGN, "ln_modulate: pointers must be 16-byte aligned");
-  const int wpb = 8;
-  const int blocks = (rows + wpb - 1) / wpb;
-  if (bf16)
-    ln_modulate_kernel<true><<<blocks, wpb * 32, 0, stream>>>(x, shift, scale, mod_batch_stride, rows_per_batch,
-                                                               reinterpret_cast<uint16_t*>(out16), rows, dim);
-  else
-    ln_modulate_kernel<false><<<blocks, wpb * 32, 0, stream>>>(x, shift, scale, mod_batch_stride, rows_per_batch,
-                                                                reinterpret_cast<uint16_t*>(out16), rows, dim);
+  const int wpb = 4;
+  int sms = 0;
+  B200_TRY(device_sm_count(&sms));
+  int blocks = (rows + wpb - 1) / wpb;
+  const int cap = sms * 12;  // <= 48 resident warps per SM; longer inputs loop (grid-stride) instead of relaunching waves
+  if (blocks > cap) blocks = cap;
+  const int nvmax = (dim / 4 + 31) / 32;
+  if (bf16) ln_dispatch<true>(nvmax, blocks, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim);
+  else ln_dispatch<false>(nvmax, blocks, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -28,10 +28,12 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 4 : 6);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
+  static constexpr int EPI_STAGE_BYTES = 2 * 16384;  // two 128-row x 128-byte staging tiles for the epilogue transpose
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;  // +1024: manual 1 KiB alignment
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
 struct GemmDev {
@@ -97,7 +99,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
+        // n-fastest: the CTAs running concurrently share one A row-panel (the big operand, M >> N here) through L2
+        const int m_blk = tile / p.num_n, n_blk = tile % p.num_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -136,67 +139,121 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
-    const int q = warp & 3;
-    const int row_in_tile = q * 32 + lane;
+    // ------------------------------------------------------------------ epilogue warps
+    // Phase A (thread = accumulator row = TMEM lane): tcgen05.ld a chunk of the row, write it to a 128-byte-per-row
+    //   staging tile in smem with the 16-byte chunks XOR-swizzled by (row % 8) -> conflict-free.
+    // Phase B (8 threads per row): re-read the staging tile so that a quarter-warp covers one full 128-byte row
+    //   segment -> every global access is a whole cache line (4 lines per warp instruction instead of 32).
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int row_a = q * 32 + lane;          // phase-A row
+    const int te = threadIdx.x - 64;          // 0..127
+    const int row_b0 = te >> 3;               // phase-B row within a group of 16
+    const int ch_b = te & 7;                  // phase-B 16-byte chunk within the 128-byte row segment
+    uint8_t* stage_base = smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m, n_blk = tile / p.num_m;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * BM + row_in_tile;
-      const bool row_ok = row < p.M;
+      const int m_blk = tile / p.num_n, n_blk = tile % p.num_n;
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-      const float* gate_row = nullptr;
-      const float* add_row = nullptr;
+
       if constexpr (EPI == B200_EPI_GATE_RESIDUAL) {
-        if (row_ok) {
-          gate_row = p.gate + static_cast<long long>(row / p.rows_per_batch) * p.gate_bs;
-          if (p.row_add) add_row = p.row_add + static_cast<size_t>((row / p.row_add_div) % p.row_add_period) * p.N;
-        }
-      }
+        constexpr int NCH = BN / 32;          // 32 fp32 columns = 128 bytes per row per chunk
+        float4 xr[8];
+        auto prefetch_x = [&](int c) {
+          const int col = n0 + c * 32 + ch_b * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = m0 + it * 16 + row_b0;
+            xr[it] = (row < p.M && col < p.N) ? *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.N + col)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        prefetch_x(0);                         // independent of the accumulator: overlaps the tile's mainloop
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.N) {
-          float f[32];
+        for (int c = 0; c < NCH; ++c) {
+          uint8_t* buf = stage_base + (chunk_ctr & 1) * 16384;
+          ++chunk_ctr;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c == NCH - 1) {                  // all TMEM reads of this tile are done: hand the accumulator back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          uint8_t* srow = buf + row_a * 128;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(srow + ((j ^ (row_a & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int col = n0 + c * 32 + ch_b * 4;
+          if (col < p.N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            for (int it = 0; it < 8; ++it) {
+              const int rl = it * 16 + row_b0;
+              const int row = m0 + rl;
+              if (row < p.M) {
+                const float4 a = *reinterpret_cast<const float4*>(buf + rl * 128 + ((ch_b ^ (rl & 7)) << 4));
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(row / p.rows_per_batch) * p.gate_bs + col));
+                float4 xv = xr[it];
+                xv.x = fmaf(g.x, a.x + b4.x, xv.x);
+                xv.y = fmaf(g.y, a.y + b4.y, xv.y);
+                xv.z = fmaf(g.z, a.z + b4.z, xv.z);
+                xv.w = fmaf(g.w, a.w + b4.w, xv.w);
+                if (p.row_add) {
+                  const float4 ra = __ldg(reinterpret_cast<const float4*>(
+                      p.row_add + static_cast<size_t>((row / p.row_add_div) % p.row_add_period) * p.N + col));
+                  xv.x += ra.x; xv.y += ra.y; xv.z += ra.z; xv.w += ra.w;
+                }
+                *reinterpret_cast<float4*>(p.resid + static_cast<size_t>(row) * p.N + col) = xv;
+              }
             }
           }
-          if constexpr (EPI == B200_EPI_GATE_RESIDUAL) {
-            float4* x4 = reinterpret_cast<float4*>(p.resid + static_cast<size_t>(row) * p.N + col0);
-            const float4* g4 = reinterpret_cast<const float4*>(gate_row + col0);
+          if (c + 1 < NCH) prefetch_x(c + 1);
+        }
+      } else {
+        constexpr int NCH = BN / 64;           // 64 16-bit columns = 128 bytes per row per chunk
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          uint8_t* buf = stage_base + (chunk_ctr & 1) * 16384;
+          ++chunk_ctr;
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(t_row + c * 64, v0);
+          tmem_ld_32x32b_x32(t_row + c * 64 + 32, v1);
+          tmem_ld_wait();
+          if (c == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const int col0 = n0 + c * 64;
+          uint8_t* srow = buf + row_a * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 xv = x4[j];
-              const float4 g = __ldg(g4 + j);
-              xv.x = fmaf(g.x, f[4 * j + 0], xv.x);
-              xv.y = fmaf(g.y, f[4 * j + 1], xv.y);
-              xv.z = fmaf(g.z, f[4 * j + 2], xv.z);
-              xv.w = fmaf(g.w, f[4 * j + 3], xv.w);
-              if (add_row) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(add_row + col0) + j);
-                xv.x += a.x; xv.y += a.y; xv.z += a.z; xv.w += a.w;
+          for (int hh = 0; hh < 2; ++hh) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(hh ? v1[j] : v0[j]);
+            const int cb = col0 + hh * 32;
+            if (p.bias && cb < p.N) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + cb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
               }
-              x4[j] = xv;
             }
-          } else {
             if constexpr (EPI == B200_EPI_BIAS_GELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
             }
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(row) * p.N + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -204,14 +261,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               o.y = pack2<BF16>(f[8 * j + 2], f[8 * j + 3]);
               o.z = pack2<BF16>(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack2<BF16>(f[8 * j + 6], f[8 * j + 7]);
-              o4[j] = o;
+              *reinterpret_cast<uint4*>(srow + (((hh * 4 + j) ^ (row_a & 7)) << 4)) = o;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int col = col0 + ch_b * 8;
+          if (col < p.N) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rl = it * 16 + row_b0;
+              const int row = m0 + rl;
+              if (row < p.M)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(row) * p.N + col) =
+                    *reinterpret_cast<const uint4*>(buf + rl * 128 + ((ch_b ^ (rl & 7)) << 4));
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
