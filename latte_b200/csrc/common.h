@@ -44,6 +44,8 @@ enum TmapSwizzle { TMAP_SW_NONE = 0, TMAP_SW_32 = 1, TMAP_SW_64 = 2, TMAP_SW_128
 // byte stride of dims[i+1] (R-1 entries). box[i] in elements. OOB elements read as zero.
 int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, TmapSwizzle sw);
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle sw);
 
 // ---- device-property cache ----------------------------------------------------------------------
 int device_sm_count(int* out);

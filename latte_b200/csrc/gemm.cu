@@ -7,11 +7,24 @@
 //   EPI_GATE_RESIDUAL  proj / fc2 + adaLN gate + residual add, fp32 residual stream in place
 //                      (latte.py:179-180), optionally + temp_embed rows        (latte.py:357-358)
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// L2 -> SM operand traffic is what bounds this kernel on B200 (a 128xBN tile needs (128+BN)*128 B per 4 MMAs), so CTAs
+// run as clusters of 2 on M-adjacent tiles that share the W tile: each CTA fetches HALF of it and TMA-multicasts that
+// half into both CTAs' shared memory (-33 % L2 reads at BN=256).  MMAs stay cta_group::1; a pipeline slot is reused
+// only after BOTH CTAs' MMAs have drained it (tcgen05.commit multicast to both "empty" barriers, arrival count 2).
+//
+// Structure (one persistent CTA per SM, 224 threads, pair-tiles visited n-fastest so concurrent clusters share A panels in L2):
 //   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (128B-swizzled) per pipeline stage
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
-//   warps 2..5  epilogue: tcgen05.ld accumulator rows -> registers -> fused math -> global
+//   warps 2..5  epilogue (thread = accumulator row = TMEM lane)
+//   warp 6      residual mode only: TMA loader of the fp32 residual tile, 128 rows x 32 columns per ring slot
 // Two accumulator buffers in TMEM (2*BN columns) let the epilogue of tile i overlap the mainloop of tile i+1.
+//
+// Epilogue data movement is shaped so that every global access is a whole 128-byte line:
+//   16-bit outputs:  registers -> smem staging tile (rows of 128 B, 16-byte chunks XOR-swizzled by row%8, conflict-free)
+//                    -> re-read with 8 threads per row -> coalesced 16-byte stores.
+//   residual:        the x tile is prefetched by TMA into a 4-slot smem ring long before the accumulator is ready
+//                    (it does not depend on the MMA), updated in place in smem (swizzled, conflict-free) and written
+//                    back by a TMA store; no thread ever waits on a global load.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -21,19 +34,24 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;
+constexpr int kSlotBytes = 128 * 128;  // one epilogue tile: 128 rows x 128 bytes
 
-template <int BN>
+template <int BN, int EPI>
 struct Cfg {
+  static constexpr bool RESID = EPI == B200_EPI_GATE_RESIDUAL;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 4 : 6);
+  static constexpr int XSLOTS = RESID ? (BN >= 256 ? 2 : 4) : 2;  // residual: x ring; else: 2 staging tiles
+  static constexpr int STAGES = RESID ? 4 : (BN >= 192 ? 4 : 6);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_STAGE_BYTES = 2 * 16384;  // two 128-row x 128-byte staging tiles for the epilogue transpose
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;  // +1024: manual 1 KiB alignment
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;            // 1 KiB aligned (TMA 128B-swizzle boxes live here)
+  static constexpr int BAR_OFF = EPI_OFF + XSLOTS * kSlotBytes;
+  static constexpr int SMEM_BYTES = BAR_OFF + BAR_BYTES + 1024;   // +1024: manual 1 KiB alignment of the base
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static_assert(2 * STAGES + 4 + 2 * XSLOTS + 1 <= BAR_BYTES / 8, "barrier area too small");
 };
 
 struct GemmDev {
@@ -41,7 +59,6 @@ struct GemmDev {
   int num_m, num_n;
   const float* bias;
   void* out16;
-  float* resid;
   const float* gate;
   long long gate_bs;
   int rows_per_batch;
@@ -56,17 +73,21 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 
 template <int BN, int EPI, bool BF16>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  using C = Cfg<BN>;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmX, const GemmDev p) {
+  using C = Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* epi_smem = smem + C::EPI_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* xfull = tempty + 2;
+  uint64_t* xempty = xfull + C::XSLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + C::XSLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,39 +95,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (C::RESID) tma_prefetch_desc(&tmX);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], 2);   // this CTA's MMAs and the peer's (its multicast half lands in our slot too)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
     }
+    for (int i = 0; i < C::XSLOTS; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // barriers of both CTAs are initialised before any multicast / remote arrival can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.num_m * p.num_n;
+  // pair-tile schedule: cluster k owns pair-tiles k, k + #clusters, ...; a pair-tile is two M-adjacent 128-row tiles of
+  // one N column; this CTA takes row-tile 2 * pair_m + rank (it may lie past M: zero-filled loads, clipped stores)
+  const uint32_t rank = cluster_ctarank();
+  const int num_pair_m = (p.num_m + 1) / 2;
+  const int num_tiles = num_pair_m * p.num_n;
+  const int first_tile = blockIdx.x >> 1;
+  const int tile_step = gridDim.x >> 1;
   const int num_kb = p.K / BK;
+  constexpr int B_HALF = C::B_BYTES / 2;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (operands)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        // n-fastest: the CTAs running concurrently share one A row-panel (the big operand, M >> N here) through L2
-        const int m_blk = tile / p.num_n, n_blk = tile % p.num_n;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m_blk = 2 * (tile / p.num_n) + static_cast<int>(rank), n_blk = tile % p.num_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);   // own A + own W half + the peer's W half
           tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+          tma_load_2d_mcast(sa + C::A_BYTES + rank * B_HALF, &tmB, &full[stage], kb * BK,
+                            n_blk * BN + static_cast<int>(rank) * (BN / 2), 0x3);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -117,7 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = umma_idesc_f16(BF16, BM, BN, false, false);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -131,99 +164,111 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BK / 16; ++k)
             umma_f16_ss(d_tmem, umma_desc_advance(da, k * 32), umma_desc_advance(db, k * 32), idesc,
                         (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          umma_commit_mcast(&empty[stage], 0x3);  // slot reusable (here AND in the peer) once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ residual-tile TMA loader
+    if constexpr (C::RESID) {
+      if (lane == 0) {
+        int slot = 0;
+        uint32_t ph = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+          const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
+          for (int c = 0; c < BN / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.N) break;
+            mbar_wait(&xempty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&xfull[slot], kSlotBytes);
+            tma_load_2d(epi_smem + slot * kSlotBytes, &tmX, &xfull[slot], col0, m0);
+            if (++slot == C::XSLOTS) { slot = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
-    // Phase A (thread = accumulator row = TMEM lane): tcgen05.ld a chunk of the row, write it to a 128-byte-per-row
-    //   staging tile in smem with the 16-byte chunks XOR-swizzled by (row % 8) -> conflict-free.
-    // Phase B (8 threads per row): re-read the staging tile so that a quarter-warp covers one full 128-byte row
-    //   segment -> every global access is a whole cache line (4 lines per warp instruction instead of 32).
+    // ------------------------------------------------------------------ epilogue warps 2..5
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
-    const int row_a = q * 32 + lane;          // phase-A row
+    const int row_a = q * 32 + lane;          // accumulator row of this thread
     const int te = threadIdx.x - 64;          // 0..127
-    const int row_b0 = te >> 3;               // phase-B row within a group of 16
-    const int ch_b = te & 7;                  // phase-B 16-byte chunk within the 128-byte row segment
-    uint8_t* stage_base = smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n, n_blk = tile % p.num_n;
-      const int m0 = m_blk * BM, n0 = n_blk * BN;
-      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
-      if constexpr (EPI == B200_EPI_GATE_RESIDUAL) {
-        constexpr int NCH = BN / 32;          // 32 fp32 columns = 128 bytes per row per chunk
-        float4 xr[8];
-        auto prefetch_x = [&](int c) {
-          const int col = n0 + c * 32 + ch_b * 4;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = m0 + it * 16 + row_b0;
-            xr[it] = (row < p.M && col < p.N) ? *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.N + col)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        };
-        prefetch_x(0);                         // independent of the accumulator: overlaps the tile's mainloop
+    if constexpr (C::RESID) {
+      int slot = 0, prev_slot = -1;
+      uint32_t ph = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
+        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        const int row = m0 + row_a;
+        const int row_c = row < p.M ? row : p.M - 1;  // rows past M are zero-filled by TMA and clipped by the store
+        const float* gate_row = p.gate + static_cast<long long>(row_c / p.rows_per_batch) * p.gate_bs;
+        const float* add_row = p.row_add ? p.row_add + static_cast<size_t>((row_c / p.row_add_div) % p.row_add_period) * p.N : nullptr;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
+        constexpr int NCH = BN / 32;
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
-          uint8_t* buf = stage_base + (chunk_ctr & 1) * 16384;
-          ++chunk_ctr;
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;                  // N-edge tile: the loader skipped these chunks too
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c * 32, v);
           tmem_ld_wait();
-          if (c == NCH - 1) {                  // all TMEM reads of this tile are done: hand the accumulator back early
+          if (c == NCH - 1 || col0 + 32 >= p.N) {  // last live chunk: all TMEM reads of this tile are done
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          uint8_t* srow = buf + row_a * 128;
+          mbar_wait(&xfull[slot], ph);
+          uint8_t* xrow = epi_smem + slot * kSlotBytes + row_a * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(srow + ((j ^ (row_a & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const int col = n0 + c * 32 + ch_b * 4;
-          if (col < p.N) {
+          for (int j = 0; j < 8; ++j) {
+            float4* xp = reinterpret_cast<float4*>(xrow + ((j ^ (row_a & 7)) << 4));
+            float4 xv = *xp;
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rl = it * 16 + row_b0;
-              const int row = m0 + rl;
-              if (row < p.M) {
-                const float4 a = *reinterpret_cast<const float4*>(buf + rl * 128 + ((ch_b ^ (rl & 7)) << 4));
-                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(row / p.rows_per_batch) * p.gate_bs + col));
-                float4 xv = xr[it];
-                xv.x = fmaf(g.x, a.x + b4.x, xv.x);
-                xv.y = fmaf(g.y, a.y + b4.y, xv.y);
-                xv.z = fmaf(g.z, a.z + b4.z, xv.z);
-                xv.w = fmaf(g.w, a.w + b4.w, xv.w);
-                if (p.row_add) {
-                  const float4 ra = __ldg(reinterpret_cast<const float4*>(
-                      p.row_add + static_cast<size_t>((row / p.row_add_div) % p.row_add_period) * p.N + col));
-                  xv.x += ra.x; xv.y += ra.y; xv.z += ra.z; xv.w += ra.w;
-                }
-                *reinterpret_cast<float4*>(p.resid + static_cast<size_t>(row) * p.N + col) = xv;
-              }
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + j);
+            xv.x = fmaf(g.x, __uint_as_float(v[4 * j + 0]) + b4.x, xv.x);
+            xv.y = fmaf(g.y, __uint_as_float(v[4 * j + 1]) + b4.y, xv.y);
+            xv.z = fmaf(g.z, __uint_as_float(v[4 * j + 2]) + b4.z, xv.z);
+            xv.w = fmaf(g.w, __uint_as_float(v[4 * j + 3]) + b4.w, xv.w);
+            if (add_row) {
+              const float4 ra = __ldg(reinterpret_cast<const float4*>(add_row + col0) + j);
+              xv.x += ra.x; xv.y += ra.y; xv.z += ra.z; xv.w += ra.w;
             }
+            *xp = xv;
           }
-          if (c + 1 < NCH) prefetch_x(c + 1);
+          fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA store
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (te == 0) {
+            tma_store_2d(&tmX, epi_smem + slot * kSlotBytes, col0, m0);
+            tma_store_commit();
+            tma_store_wait_read<1>();                   // the store issued one chunk ago has finished reading its slot
+            if (prev_slot >= 0) mbar_arrive(&xempty[prev_slot]);
+            prev_slot = slot;
+          }
+          if (++slot == C::XSLOTS) { slot = 0; ph ^= 1; }
         }
-      } else {
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (te == 0) tma_store_wait_all<0>();             // all residual writes have landed before the CTA retires
+    } else {
+      const int row_b0 = te >> 3;             // phase-B row within a group of 16
+      const int ch_b = te & 7;                // phase-B 16-byte chunk within the 128-byte row segment
+      uint32_t chunk_ctr = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
+        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         constexpr int NCH = BN / 64;           // 64 16-bit columns = 128 bytes per row per chunk
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
-          uint8_t* buf = stage_base + (chunk_ctr & 1) * 16384;
+          uint8_t* buf = epi_smem + (chunk_ctr & 1) * kSlotBytes;
           ++chunk_ctr;
           uint32_t v0[32], v1[32];
           tmem_ld_32x32b_x32(t_row + c * 64, v0);
@@ -264,6 +309,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(srow + (((hh * 4 + j) ^ (row_a & 7)) << 4)) = o;
             }
           }
+          // one barrier per chunk is enough with two staging tiles: a thread reaches the barrier of chunk k+1 only
+          // after its reads of chunk k, so nobody overwrites tile (k & 1) at chunk k+2 while it is still being read
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int col = col0 + ch_b * 8;
           if (col < p.N) {
@@ -277,13 +324,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // the peer may still multicast into our smem / arrive on our barriers until it is done too
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -292,47 +339,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN, int EPI, bool BF16>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int grid, cudaStream_t stream) {
-  using C = Cfg<BN>;
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const GemmDev& p, int grid,
+               cudaStream_t stream) {
+  using C = Cfg<BN, EPI>;
   auto kern = gemm_kernel<BN, EPI, BF16>;
   static bool attr_set = false;  // per instantiation; benign race (idempotent)
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmX, p);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
 
 template <int BN, bool BF16>
-int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int grid, cudaStream_t s) {
+int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const GemmDev& p, int grid,
+               cudaStream_t s) {
   switch (epi) {
-    case B200_EPI_BIAS: return launch_one<BN, B200_EPI_BIAS, BF16>(tmA, tmB, p, grid, s);
-    case B200_EPI_BIAS_GELU: return launch_one<BN, B200_EPI_BIAS_GELU, BF16>(tmA, tmB, p, grid, s);
-    case B200_EPI_GATE_RESIDUAL: return launch_one<BN, B200_EPI_GATE_RESIDUAL, BF16>(tmA, tmB, p, grid, s);
+    case B200_EPI_BIAS: return launch_one<BN, B200_EPI_BIAS, BF16>(tmA, tmB, tmX, p, grid, s);
+    case B200_EPI_BIAS_GELU: return launch_one<BN, B200_EPI_BIAS_GELU, BF16>(tmA, tmB, tmX, p, grid, s);
+    case B200_EPI_GATE_RESIDUAL: return launch_one<BN, B200_EPI_GATE_RESIDUAL, BF16>(tmA, tmB, tmX, p, grid, s);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return B200_ERR_UNSUPPORTED;
 }
 
 template <int BN>
-int launch_bn(int bf16, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int grid,
-              cudaStream_t s) {
-  return bf16 ? launch_epi<BN, true>(epi, tmA, tmB, p, grid, s) : launch_epi<BN, false>(epi, tmA, tmB, p, grid, s);
+int launch_bn(int bf16, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const GemmDev& p,
+              int grid, cudaStream_t s) {
+  return bf16 ? launch_epi<BN, true>(epi, tmA, tmB, tmX, p, grid, s) : launch_epi<BN, false>(epi, tmA, tmB, tmX, p, grid, s);
 }
 
 int pick_block_n(int M, int N, int sms) {
-  // minimise (waves x per-tile cost); per-tile cost ~ BN with a small penalty for narrow tiles, whose
-  // smem operand traffic per MMA cycle is higher (128 B/clk at BN=128 vs 96 B/clk at BN=256).
+  // minimise waves x per-tile time.  The kernel is bound by L2->SM operand bytes, not MMA cycles, so a tile costs
+  // ~ (A bytes + W/2 bytes per k-block) = 128 + BN/2 rather than BN (measured: r01 microbench, profiles/).
   const int cand[3] = {256, 192, 128};
-  const double pen[3] = {1.00, 1.03, 1.10};
   int best = 128;
   double best_cost = 1e300;
   for (int i = 0; i < 3; ++i) {
     const long long tiles = static_cast<long long>((M + BM - 1) / BM) * ((N + cand[i] - 1) / cand[i]);
     const long long waves = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * cand[i] * pen[i];
+    const double cost = static_cast<double>(waves) * (128 + cand[i] / 2);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = cand[i]; }
   }
   return best;
@@ -344,13 +392,17 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   B200_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, B200_ERR_SHAPE, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   B200_REQUIRE(a.K % BK == 0, B200_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", a.K, BK);
   B200_REQUIRE(a.N % 32 == 0, B200_ERR_SHAPE, "gemm: N=%d must be a multiple of 32", a.N);
+  B200_REQUIRE(a.epilogue == B200_EPI_BIAS || a.epilogue == B200_EPI_BIAS_GELU || a.epilogue == B200_EPI_GATE_RESIDUAL,
+               B200_ERR_UNSUPPORTED, "gemm: unknown epilogue %d", a.epilogue);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
                B200_ERR_ALIGN, "gemm: A and W must be 16-byte aligned");
-  if (a.epilogue == B200_EPI_GATE_RESIDUAL) {
+  const bool resid = a.epilogue == B200_EPI_GATE_RESIDUAL;
+  if (resid) {
     B200_REQUIRE(a.resid && a.gate && a.rows_per_batch > 0, B200_ERR_SHAPE, "gemm: gated-residual epilogue needs resid, gate, rows_per_batch");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(a.resid) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.gate) & 15) == 0 &&
                      (a.gate_batch_stride % 4) == 0,
                  B200_ERR_ALIGN, "gemm: resid/gate must be 16-byte aligned");
+    B200_REQUIRE(!a.row_add || (reinterpret_cast<uintptr_t>(a.row_add) & 15) == 0, B200_ERR_ALIGN, "gemm: row_add must be 16-byte aligned");
   } else {
     B200_REQUIRE(a.out16 && (reinterpret_cast<uintptr_t>(a.out16) & 15) == 0, B200_ERR_ALIGN, "gemm: out16 must be 16-byte aligned");
   }
@@ -362,7 +414,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, sms);
   B200_REQUIRE(bn == 128 || bn == 192 || bn == 256, B200_ERR_UNSUPPORTED, "gemm: block_n must be 128, 192 or 256 (got %d)", bn);
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmX;
   {
     const uint64_t dimsA[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.M)};
     const uint64_t strA[1] = {static_cast<uint64_t>(a.K) * 2};
@@ -370,8 +422,16 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     B200_TRY(make_tmap_16bit(&tmA, a.A, 2, dimsA, strA, boxA, TMAP_SW_128));
     const uint64_t dimsB[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N)};
     const uint64_t strB[1] = {static_cast<uint64_t>(a.K) * 2};
-    const uint32_t boxB[2] = {BK, static_cast<uint32_t>(bn)};
+    const uint32_t boxB[2] = {BK, static_cast<uint32_t>(bn / 2)};   // each CTA of the pair fetches half and multicasts it
     B200_TRY(make_tmap_16bit(&tmB, a.W, 2, dimsB, strB, boxB, TMAP_SW_128));
+    if (resid) {
+      const uint64_t dimsX[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M)};
+      const uint64_t strX[1] = {static_cast<uint64_t>(a.N) * 4};
+      const uint32_t boxX[2] = {32, BM};
+      B200_TRY(make_tmap(&tmX, a.resid, 4, 2, dimsX, strX, boxX, TMAP_SW_128));
+    } else {
+      tmX = tmA;  // unused
+    }
   }
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;
@@ -379,19 +439,18 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.num_n = (a.N + bn - 1) / bn;
   p.bias = a.bias;
   p.out16 = a.out16;
-  p.resid = a.resid;
   p.gate = a.gate;
   p.gate_bs = a.gate_batch_stride;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.row_add = a.row_add;
   p.row_add_div = a.row_add_div > 0 ? a.row_add_div : 1;
   p.row_add_period = a.row_add_period > 0 ? a.row_add_period : 1;
-  const int tiles = p.num_m * p.num_n;
-  const int grid = tiles < sms ? tiles : sms;
+  const int pair_tiles = ((p.num_m + 1) / 2) * p.num_n;
+  int grid = 2 * pair_tiles < sms ? 2 * pair_tiles : (sms & ~1);   // whole clusters of 2
   switch (bn) {
-    case 128: return launch_bn<128>(a.bf16, a.epilogue, tmA, tmB, p, grid, stream);
-    case 192: return launch_bn<192>(a.bf16, a.epilogue, tmA, tmB, p, grid, stream);
-    default: return launch_bn<256>(a.bf16, a.epilogue, tmA, tmB, p, grid, stream);
+    case 128: return launch_bn<128>(a.bf16, a.epilogue, tmA, tmB, tmX, p, grid, stream);
+    case 192: return launch_bn<192>(a.bf16, a.epilogue, tmA, tmB, tmX, p, grid, stream);
+    default: return launch_bn<256>(a.bf16, a.epilogue, tmA, tmB, tmX, p, grid, stream);
   }
 }
 

@@ -39,6 +39,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, TmapSwizzle sw) {
+  return make_tmap(out, base, 2, rank, dims, strides_bytes, box, sw);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle sw) {
   EncodeTiledFn fn = get_encode_fn();
   B200_REQUIRE(fn != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the CUDA driver");
   B200_REQUIRE(rank >= 2 && rank <= 5, B200_ERR_SHAPE, "tensor map rank %d unsupported", rank);
@@ -59,8 +64,10 @@ int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t
     case TMAP_SW_128: s = CU_TENSOR_MAP_SWIZZLE_128B; break;
     default: break;
   }
-  // 16-bit payload: the bit pattern is moved, never interpreted, so one element type serves fp16 and bf16.
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  // the bit pattern is moved, never interpreted, so one unsigned type per element size serves fp16/bf16 and fp32
+  B200_REQUIRE(elem_bytes == 2 || elem_bytes == 4, B200_ERR_DTYPE, "tensor map element size %d unsupported", elem_bytes);
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, s, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA,
