@@ -7,14 +7,18 @@
 //   EPI_GATE_RESIDUAL  proj / fc2 + adaLN gate + residual add, fp32 residual stream in place
 //                      (latte.py:179-180), optionally + temp_embed rows        (latte.py:357-358)
 //
-// L2 -> SM operand traffic is what bounds this kernel on B200 (a 128xBN tile needs (128+BN)*128 B per 4 MMAs), so CTAs
-// run as clusters of 2 on M-adjacent tiles that share the W tile: each CTA fetches HALF of it and TMA-multicasts that
-// half into both CTAs' shared memory (-33 % L2 reads at BN=256).  MMAs stay cta_group::1; a pipeline slot is reused
-// only after BOTH CTAs' MMAs have drained it (tcgen05.commit multicast to both "empty" barriers, arrival count 2).
+// What bounds this kernel on B200 is the operand bytes each SM must keep in flight (latency x consumption rate), so
+// CTAs run as PAIRS (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, M = 256 MMAs issued by the leader
+// CTA, each CTA staging its own 128 A rows and only HALF of the W tile (the pair's MMA reads both halves).  Per SM that
+// is 64 B per MMA cycle at BN = 256 instead of 96, and the freed shared memory buys a 6-deep TMA pipeline.
+//   * every CTA's TMA loads complete on its OWN "full" barrier; the peer forwards each completed stage to the leader with
+//     ONE remote arrive on the leader's "peer full" barrier (remote per-packet complete_tx signalling measured 3x slower);
+//   * the leader's tcgen05.commit is multicast to both CTAs' "empty" and "accumulator full" barriers;
+//   * both CTAs' epilogue warps release an accumulator on the leader's "accumulator empty" barrier (8 arrivals).
 //
 // Structure (one persistent CTA per SM, 224 threads, pair-tiles visited n-fastest so concurrent clusters share A panels in L2):
-//   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (128B-swizzled) per pipeline stage
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
+//   warp 0      TMA producer: A tile 128x64 and W half-tile (BN/2)x64 (128B-swizzled) per pipeline stage
+//   warp 1      TMEM allocator; in the leader CTA also the single-thread tcgen05.mma issuer (M=256, N=BN, K=16)
 //   warps 2..5  epilogue (thread = accumulator row = TMEM lane)
 //   warp 6      residual mode only: TMA loader of the fp32 residual tile, 128 rows x 32 columns per ring slot
 // Two accumulator buffers in TMEM (2*BN columns) let the epilogue of tile i overlap the mainloop of tile i+1.
@@ -27,6 +31,8 @@
 //                    back by a TMA store; no thread ever waits on a global load.
 #include "common.h"
 #include "ptx.cuh"
+
+#include <cstdlib>
 
 namespace b200 {
 
@@ -41,17 +47,18 @@ template <int BN, int EPI>
 struct Cfg {
   static constexpr bool RESID = EPI == B200_EPI_GATE_RESIDUAL;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;                // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int XSLOTS = RESID ? (BN >= 256 ? 2 : 4) : 2;  // residual: x ring; else: 2 staging tiles
-  static constexpr int STAGES = RESID ? 4 : (BN >= 192 ? 4 : 6);
+  static constexpr int STAGES = RESID ? (BN >= 256 ? 6 : (BN >= 192 ? 5 : 6)) : (BN >= 256 ? 6 : (BN >= 192 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;            // 1 KiB aligned (TMA 128B-swizzle boxes live here)
   static constexpr int BAR_OFF = EPI_OFF + XSLOTS * kSlotBytes;
   static constexpr int SMEM_BYTES = BAR_OFF + BAR_BYTES + 1024;   // +1024: manual 1 KiB alignment of the base
+  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1 KiB alignment");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-  static_assert(2 * STAGES + 4 + 2 * XSLOTS + 1 <= BAR_BYTES / 8, "barrier area too small");
+  static_assert(3 * STAGES + 4 + 2 * XSLOTS + 1 <= BAR_BYTES / 8, "barrier area too small");
 };
 
 struct GemmDev {
@@ -64,6 +71,7 @@ struct GemmDev {
   int rows_per_batch;
   const float* row_add;
   int row_add_div, row_add_period;
+  int dbg;  // timing experiments only (results are wrong when set): bit0 = no operand TMA, bit1 = no MMA issue
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -83,7 +91,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
-  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* pfull = bars + 2 * C::STAGES;   // leader only: "the peer's stage has landed"
+  uint64_t* tfull = bars + 3 * C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* xfull = tempty + 2;
   uint64_t* xempty = xfull + C::XSLOTS;
@@ -97,12 +106,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
     if constexpr (C::RESID) tma_prefetch_desc(&tmX);
     for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 2);   // this CTA's MMAs and the peer's (its multicast half lands in our slot too)
+      mbar_init(&full[i], 1);    // own TMA bytes
+      mbar_init(&pfull[i], 1);   // (leader's copy) one forwarded arrival from the peer per stage
+      mbar_init(&empty[i], 1);   // leader's tcgen05.commit, multicast to both CTAs
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tfull[i], 1);   // leader's tcgen05.commit, multicast to both CTAs
+      mbar_init(&tempty[i], 8);  // (leader's copy) one arrival per epilogue warp of BOTH CTAs
     }
     for (int i = 0; i < C::XSLOTS; ++i) {
       mbar_init(&xfull[i], 1);
@@ -110,7 +120,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   cluster_sync_all();   // barriers of both CTAs are initialised before any multicast / remote arrival can target them
   tc_fence_after();
@@ -124,7 +134,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int first_tile = blockIdx.x >> 1;
   const int tile_step = gridDim.x >> 1;
   const int num_kb = p.K / BK;
-  constexpr int B_HALF = C::B_BYTES / 2;
+  const bool leader = rank == 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (operands)
@@ -136,18 +146,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);   // own A + own W half + the peer's W half
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d_mcast(sa + C::A_BYTES + rank * B_HALF, &tmB, &full[stage], kb * BK,
-                            n_blk * BN + static_cast<int>(rank) * (BN / 2), 0x3);
+          if (p.dbg & 1) {
+            mbar_arrive(&full[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BF16, BM, BN, false, false);
+    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BF16, 2 * BM, BN, false, false);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -155,20 +168,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stage], phase);            // own operands landed
+          mbar_wait(&pfull[stage], phase);           // the peer's operands landed (forwarded)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t da = umma_smem_desc(sa, 0, 1024, UMMA_LAYOUT_SW128);
           const uint64_t db = umma_smem_desc(sa + C::A_BYTES, 0, 1024, UMMA_LAYOUT_SW128);
+          if (!(p.dbg & 2))
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss(d_tmem, umma_desc_advance(da, k * 32), umma_desc_advance(db, k * 32), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
-          umma_commit_mcast(&empty[stage], 0x3);  // slot reusable (here AND in the peer) once these MMAs have read it
+            umma_f16_ss_pair(d_tmem, umma_desc_advance(da, k * 32), umma_desc_advance(db, k * 32), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty[stage], 0x3);  // slot reusable in BOTH CTAs once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        umma_commit_pair(&tfull[acc], 0x3);      // accumulator complete -> both CTAs' epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else if (!leader && lane == 0) {
+      // peer CTA: forward "my stage has landed" to the leader, one remote arrive per stage
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          mbar_arrive_cluster(mapa_u32(&pfull[stage], 0));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 6) {
@@ -197,6 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int te = threadIdx.x - 64;          // 0..127
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t tempty_leader[2] = {mapa_u32(&tempty[0], 0), mapa_u32(&tempty[1], 0)};
 
     if constexpr (C::RESID) {
       int slot = 0, prev_slot = -1;
@@ -221,7 +248,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (c == NCH - 1 || col0 + 32 >= p.N) {  // last live chunk: all TMEM reads of this tile are done
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
           }
           mbar_wait(&xfull[slot], ph);
           uint8_t* xrow = epi_smem + slot * kSlotBytes + row_a * 128;
@@ -277,7 +304,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (c == NCH - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
           }
           const int col0 = n0 + c * 64;
           uint8_t* srow = buf + row_a * 128;
@@ -334,7 +361,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -373,7 +400,7 @@ int launch_bn(int bf16, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
 
 int pick_block_n(int M, int N, int sms) {
   // minimise waves x per-tile time.  The kernel is bound by L2->SM operand bytes, not MMA cycles, so a tile costs
-  // ~ (A bytes + W/2 bytes per k-block) = 128 + BN/2 rather than BN (measured: r01 microbench, profiles/).
+  // ~ (A bytes + W/2 bytes per k-block per CTA) = 128 + BN/2 rather than BN (measured: r01 microbench, profiles/).
   const int cand[3] = {256, 192, 128};
   int best = 128;
   double best_cost = 1e300;
@@ -445,6 +472,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.row_add = a.row_add;
   p.row_add_div = a.row_add_div > 0 ? a.row_add_div : 1;
   p.row_add_period = a.row_add_period > 0 ? a.row_add_period : 1;
+  {
+    const char* e = getenv("B200_GEMM_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   const int pair_tiles = ((p.num_m + 1) / 2) * p.num_n;
   int grid = 2 * pair_tiles < sms ? 2 * pair_tiles : (sms & ~1);   // whole clusters of 2
   switch (bn) {
