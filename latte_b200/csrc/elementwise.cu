@@ -86,18 +86,21 @@ void ln_dispatch(int nvmax, int blocks, cudaStream_t stream, const float* x, con
 }
 
 // ---------------------------------------------------------------------------------- patch_embed
-constexpr int PE_TOK = 8;
+constexpr int PE_TOK = 16;
 constexpr int PE_MAXK = 64;
 
+// K = C*p*p is a template parameter (16 for the 4-channel, patch-2 latents every Latte config uses) so the per-d weight
+// row lives in K registers; a block computes PE_TOK tokens x all D outputs; the write of the fp32 residual stream
+// (the only real traffic: T*D*4 bytes) is coalesced over d.
+template <int K>
 __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ x, int x_batch_mod,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ pos, float* __restrict__ out,
                                                           int total_tokens, int frames, int chans, int size, int patch,
                                                           int dim) {
-  __shared__ float in[PE_TOK][PE_MAXK];
+  __shared__ float in[PE_TOK][K];
   const int grid = size / patch;
   const int N = grid * grid;
-  const int K = chans * patch * patch;
   const int tok0 = blockIdx.x * PE_TOK;
   for (int i = threadIdx.x; i < PE_TOK * K; i += blockDim.x) {
     const int tl = i / K, k = i % K;
@@ -116,20 +119,21 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   }
   __syncthreads();
   for (int d = threadIdx.x; d < dim; d += blockDim.x) {
-    float wk[PE_MAXK];
+    float wk[K];
 #pragma unroll
-    for (int k = 0; k < PE_MAXK; ++k)
-      if (k < K) wk[k] = __ldg(w + static_cast<size_t>(d) * K + k);
+    for (int k = 0; k < K; k += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(d) * K + k));
+      wk[k] = t.x; wk[k + 1] = t.y; wk[k + 2] = t.z; wk[k + 3] = t.w;
+    }
     const float bd = __ldg(bias + d);
-#pragma unroll
+#pragma unroll 4
     for (int tl = 0; tl < PE_TOK; ++tl) {
       const int tok = tok0 + tl;
       if (tok >= total_tokens) break;
-      float acc = 0.f;
+      float acc = bd;
 #pragma unroll
-      for (int k = 0; k < PE_MAXK; ++k)
-        if (k < K) acc = fmaf(in[tl][k], wk[k], acc);
-      out[static_cast<size_t>(tok) * dim + d] = acc + bd + __ldg(pos + static_cast<size_t>(tok % N) * dim + d);
+      for (int k = 0; k < K; ++k) acc = fmaf(in[tl][k], wk[k], acc);
+      out[static_cast<size_t>(tok) * dim + d] = acc + __ldg(pos + static_cast<size_t>(tok % N) * dim + d);
     }
   }
 }
@@ -146,9 +150,12 @@ __global__ void timestep_freq_kernel(const long long* __restrict__ t, float* __r
   out[b * 256 + k] = (k < half) ? cosf(arg) : sinf(arg);
 }
 
-// ---------------------------------------------------------------------------------- gemv (warp per output row)
+// ---------------------------------------------------------------------------------- gemv (a warp owns GV_ROWS output rows)
 constexpr int GV_MAXB = 8;
+constexpr int GV_ROWS = 4;
 
+// HBM-bound on the weight matrix (adaLN: 446 MB per step for XL/2): every lane issues GV_ROWS independent 16-byte
+// loads per trip so ~4.6 KB per warp are in flight; the B input vectors live in smem (read as broadcast float4).
 template <int WBITS, bool BF16>
 __global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ W, const float* __restrict__ bias,
                                                    const float* __restrict__ in, float* __restrict__ out, int batch,
@@ -163,36 +170,55 @@ __global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ W, c
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
-  for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < J; j += gridDim.x * warps) {
-    float acc[GV_MAXB];
+  constexpr int EPC = WBITS == 32 ? 4 : 8;  // elements per 16-byte chunk
+  const int nchunk = K / EPC;
+  for (int j0 = (blockIdx.x * warps + (threadIdx.x >> 5)) * GV_ROWS; j0 < J; j0 += gridDim.x * warps * GV_ROWS) {
+    float acc[GV_ROWS][GV_MAXB];
 #pragma unroll
-    for (int b = 0; b < GV_MAXB; ++b) acc[b] = 0.f;
-    for (int k = lane * 4; k < K; k += 128) {
-      float w0, w1, w2, w3;
-      if constexpr (WBITS == 32) {
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(W) + static_cast<size_t>(j) * K + k));
-        w0 = wv.x; w1 = wv.y; w2 = wv.z; w3 = wv.w;
-      } else {
-        const uint2 wv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(W) + static_cast<size_t>(j) * K + k));
-        const float2 a = unpack2<BF16>(wv.x), c = unpack2<BF16>(wv.y);
-        w0 = a.x; w1 = a.y; w2 = c.x; w3 = c.y;
+    for (int r = 0; r < GV_ROWS; ++r)
+#pragma unroll
+      for (int b = 0; b < GV_MAXB; ++b) acc[r][b] = 0.f;
+    for (int c = lane; c < nchunk; c += 32) {
+      uint4 wv[GV_ROWS];
+#pragma unroll
+      for (int r = 0; r < GV_ROWS; ++r) {
+        const int j = j0 + r < J ? j0 + r : J - 1;
+        wv[r] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(W) + (static_cast<size_t>(j) * K + static_cast<size_t>(c) * EPC) * (WBITS / 8)));
       }
 #pragma unroll
       for (int b = 0; b < GV_MAXB; ++b) {
         if (b < batch) {
-          const float4 xv = *reinterpret_cast<const float4*>(sin_ + b * K + k);
-          acc[b] = fmaf(w0, xv.x, fmaf(w1, xv.y, fmaf(w2, xv.z, fmaf(w3, xv.w, acc[b]))));
+          const float4 x0 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC);
+          float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (WBITS == 16) x1 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC + 4);
+#pragma unroll
+          for (int r = 0; r < GV_ROWS; ++r) {
+            if constexpr (WBITS == 32) {
+              acc[r][b] = fmaf(__uint_as_float(wv[r].x), x0.x, fmaf(__uint_as_float(wv[r].y), x0.y,
+                          fmaf(__uint_as_float(wv[r].z), x0.z, fmaf(__uint_as_float(wv[r].w), x0.w, acc[r][b]))));
+            } else {
+              const float2 w0 = unpack2<BF16>(wv[r].x), w1 = unpack2<BF16>(wv[r].y), w2 = unpack2<BF16>(wv[r].z), w3 = unpack2<BF16>(wv[r].w);
+              float a = acc[r][b];
+              a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a); a = fmaf(w1.x, x0.z, a); a = fmaf(w1.y, x0.w, a);
+              a = fmaf(w2.x, x1.x, a); a = fmaf(w2.y, x1.y, a); a = fmaf(w3.x, x1.z, a); a = fmaf(w3.y, x1.w, a);
+              acc[r][b] = a;
+            }
+          }
         }
       }
     }
 #pragma unroll
-    for (int b = 0; b < GV_MAXB; ++b) {
-      if (b < batch) {
-        float r = warp_sum(acc[b]);
-        if (lane == 0) {
-          if (bias) r += __ldg(bias + j);
-          if (add_table) r += __ldg(add_table + static_cast<size_t>(add_idx[b]) * J + j);
-          out[static_cast<size_t>(b) * J + j] = silu_out ? silu(r) : r;
+    for (int r = 0; r < GV_ROWS; ++r) {
+#pragma unroll
+      for (int b = 0; b < GV_MAXB; ++b) {
+        if (b < batch) {
+          float v = warp_sum(acc[r][b]);
+          const int j = j0 + r;
+          if (lane == 0 && j < J) {
+            if (bias) v += __ldg(bias + j);
+            if (add_table) v += __ldg(add_table + static_cast<size_t>(add_idx[b]) * J + j);
+            out[static_cast<size_t>(b) * J + j] = silu_out ? silu(v) : v;
+          }
         }
       }
     }
@@ -327,11 +353,21 @@ int launch_ln_modulate(const float* x, const float* shift, const float* scale, l
 int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const float* b, const float* pos, float* out,
                        int batch, int frames, int chans, int size, int patch, int dim, cudaStream_t stream) {
   const int K = chans * patch * patch;
-  B200_REQUIRE(K <= PE_MAXK && size % patch == 0, B200_ERR_SHAPE, "patch_embed: C*p*p = %d exceeds %d", K, PE_MAXK);
+  B200_REQUIRE(size % patch == 0, B200_ERR_SHAPE, "patch_embed: size %d not divisible by patch %d", size, patch);
+  B200_REQUIRE(K == 4 || K == 8 || K == 16 || K == 32 || K == 64, B200_ERR_UNSUPPORTED,
+               "patch_embed: C*p*p = %d unsupported (4, 8, 16, 32, 64)", K);
   const int grid = size / patch;
   const int total = batch * frames * grid * grid;
-  patch_embed_kernel<<<(total + PE_TOK - 1) / PE_TOK, 256, 0, stream>>>(x, x_batch_mod, w, b, pos, out, total, frames,
-                                                                          chans, size, patch, dim);
+  const int blocks = (total + PE_TOK - 1) / PE_TOK;
+#define B200_PE(KK) patch_embed_kernel<KK><<<blocks, 256, 0, stream>>>(x, x_batch_mod, w, b, pos, out, total, frames, chans, size, patch, dim)
+  switch (K) {
+    case 4: B200_PE(4); break;
+    case 8: B200_PE(8); break;
+    case 16: B200_PE(16); break;
+    case 32: B200_PE(32); break;
+    default: B200_PE(64); break;
+  }
+#undef B200_PE
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -345,7 +381,7 @@ int launch_timestep_freq(const long long* t, float* out, int batch, cudaStream_t
 int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const float* in, float* out, int batch, int J,
                 int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx,
                 cudaStream_t stream) {
-  B200_REQUIRE(K % 4 == 0 && J > 0, B200_ERR_SHAPE, "gemv: K=%d must be a multiple of 4", K);
+  B200_REQUIRE(K % 8 == 0 && J > 0, B200_ERR_SHAPE, "gemv: K=%d must be a multiple of 8", K);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, B200_ERR_ALIGN, "gemv: W must be 16-byte aligned");
   int sms = 0;
   B200_TRY(device_sm_count(&sms));
@@ -354,8 +390,8 @@ int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const flo
     const size_t smem = static_cast<size_t>(nb) * K * sizeof(float);
     B200_REQUIRE(smem <= 48 * 1024, B200_ERR_SHAPE, "gemv: K=%d too large", K);
     const int warps = 8;
-    int blocks = (J + warps - 1) / warps;
-    const int cap = sms * 16;
+    int blocks = (J + warps * GV_ROWS - 1) / (warps * GV_ROWS);
+    const int cap = sms * 8;
     if (blocks > cap) blocks = cap;
     const float* inb = in + static_cast<size_t>(b0) * K;
     float* outb = out + static_cast<size_t>(b0) * J;

@@ -11,16 +11,18 @@
 // CTAs run as PAIRS (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, M = 256 MMAs issued by the leader
 // CTA, each CTA staging its own 128 A rows and only HALF of the W tile (the pair's MMA reads both halves).  Per SM that
 // is 64 B per MMA cycle at BN = 256 instead of 96, and the freed shared memory buys a 6-deep TMA pipeline.
-//   * every CTA's TMA loads complete on its OWN "full" barrier; the peer forwards each completed stage to the leader with
-//     ONE remote arrive on the leader's "peer full" barrier (remote per-packet complete_tx signalling measured 3x slower);
+//   * both CTAs' TMA loads complete on the LEADER's "full" barrier (cta_group::2 loads, expect_tx = 2 stages); the peer's
+//     producer adds one plain remote arrive per stage (NOT .release.cluster: that fence cost 1.5k cycles per k-block);
 //   * the leader's tcgen05.commit is multicast to both CTAs' "empty" and "accumulator full" barriers;
 //   * both CTAs' epilogue warps release an accumulator on the leader's "accumulator empty" barrier (8 arrivals).
 //
 // Structure (one persistent CTA per SM, 224 threads, pair-tiles visited n-fastest so concurrent clusters share A panels in L2):
 //   warp 0      TMA producer: A tile 128x64 and W half-tile (BN/2)x64 (128B-swizzled) per pipeline stage
 //   warp 1      TMEM allocator; in the leader CTA also the single-thread tcgen05.mma issuer (M=256, N=BN, K=16)
-//   warps 2..5  epilogue (thread = accumulator row = TMEM lane)
-//   warp 6      residual mode only: TMA loader of the fp32 residual tile, 128 rows x 32 columns per ring slot
+//   warps 2..5  epilogue warpgroup 0 (thread = accumulator row = TMEM lane)
+//   warps 6..9  epilogue warpgroup 1 (16-bit output modes: the two groups take alternate 64-column chunks; with one
+//               warp per scheduler the epilogue is instruction-latency bound, two warps per scheduler hide it)
+//   warp 10     residual mode only: TMA loader of the fp32 residual tile, 128 rows x 32 columns per ring slot
 // Two accumulator buffers in TMEM (2*BN columns) let the epilogue of tile i overlap the mainloop of tile i+1.
 //
 // Epilogue data movement is shaped so that every global access is a whole 128-byte line:
@@ -40,7 +42,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int kThreads = 224;
+constexpr int kThreads = 352;   // warps: 0 TMA, 1 MMA/forwarder, 2-5 epilogue WG0, 6-9 epilogue WG1, 10 residual loader
 constexpr int kSlotBytes = 128 * 128;  // one epilogue tile: 128 rows x 128 bytes
 
 template <int BN, int EPI>
@@ -49,8 +51,9 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;                // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int XSLOTS = RESID ? (BN >= 256 ? 2 : 4) : 2;  // residual: x ring; else: 2 staging tiles
-  static constexpr int STAGES = RESID ? (BN >= 256 ? 6 : (BN >= 192 ? 5 : 6)) : (BN >= 256 ? 6 : (BN >= 192 ? 6 : 8));
+  // residual: ring of x tiles, at least one output tile's worth so the loader runs a whole mainloop ahead; else: 2 staging tiles
+  static constexpr int XSLOTS = RESID ? (BN >= 256 ? 4 : (BN >= 192 ? 5 : 6)) : 2;
+  static constexpr int STAGES = RESID ? 5 : (BN >= 256 ? 6 : (BN >= 192 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 512;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;            // 1 KiB aligned (TMA 128B-swizzle boxes live here)
@@ -71,13 +74,18 @@ struct GemmDev {
   int rows_per_batch;
   const float* row_add;
   int row_add_div, row_add_period;
-  int dbg;  // timing experiments only (results are wrong when set): bit0 = no operand TMA, bit1 = no MMA issue
+  int dbg;  // timing experiments only (results are wrong when set): bit0 = no operand TMA, bit1 = no MMA issue, bit2 = no 16-bit epilogue
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5 x (1 + tanh(u)) == x * sigmoid(2u),  u = sqrt(2/pi) (x + 0.044715 x^3)
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+  // 0.5 x (1 + tanh(u)),  u = sqrt(2/pi) (x + 0.044715 x^3).  ONE MUFU op per element (tanh.approx, rel. error 2^-11,
+  // the same size as the 16-bit rounding of the result): with ex2 + rcp (two MUFU ops) the fc1 epilogue was bound by the
+  // 16/clk/SM MUFU pipe (r01 experiment: 4.9k cycles per 128x256 tile).
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 template <int BN, int EPI, bool BF16>
@@ -106,13 +114,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
     if constexpr (C::RESID) tma_prefetch_desc(&tmX);
     for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(&full[i], 1);    // own TMA bytes
-      mbar_init(&pfull[i], 1);   // (leader's copy) one forwarded arrival from the peer per stage
+      mbar_init(&full[i], 2);    // (leader's copy is the live one) leader's expect_tx arrival + the peer's arrival
+      mbar_init(&pfull[i], 1);   // unused
       mbar_init(&empty[i], 1);   // leader's tcgen05.commit, multicast to both CTAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);   // leader's tcgen05.commit, multicast to both CTAs
-      mbar_init(&tempty[i], 8);  // (leader's copy) one arrival per epilogue warp of BOTH CTAs
+      mbar_init(&tempty[i], 16); // (leader's copy) one arrival per epilogue warp of BOTH CTAs
     }
     for (int i = 0; i < C::XSLOTS; ++i) {
       mbar_init(&xfull[i], 1);
@@ -146,12 +154,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          const uint32_t full_leader = mapa_u32(&full[stage], 0);
           if (p.dbg & 1) {
-            mbar_arrive(&full[stage]);
+            if (leader) mbar_arrive(&full[stage]); else mbar_arrive_cluster(full_leader);
           } else {
-            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m_blk * BM);
-            tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+            // both CTAs' bytes complete on the LEADER's barrier (cta_group::2 loads may signal the pair leader)
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+            else mbar_arrive_cluster(full_leader);
+            tma_load_2d_pair(sa, &tmA, full_leader, kb * BK, m_blk * BM);
+            tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -168,8 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);            // own operands landed
-          mbar_wait(&pfull[stage], phase);           // the peer's operands landed (forwarded)
+          mbar_wait(&full[stage], phase);            // both CTAs' operands landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t da = umma_smem_desc(sa, 0, 1024, UMMA_LAYOUT_SW128);
@@ -185,19 +195,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         umma_commit_pair(&tfull[acc], 0x3);      // accumulator complete -> both CTAs' epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-    } else if (!leader && lane == 0) {
-      // peer CTA: forward "my stage has landed" to the leader, one remote arrive per stage
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          mbar_arrive_cluster(mapa_u32(&pfull[stage], 0));
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // ------------------------------------------------------------------ residual-tile TMA loader
     if constexpr (C::RESID) {
       if (lane == 0) {
@@ -207,7 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
           for (int c = 0; c < BN / 32; ++c) {
             const int col0 = n0 + c * 32;
-            if (col0 >= p.N) break;
+            if (col0 >= p.N || (p.dbg & 8)) break;
             mbar_wait(&xempty[slot], ph ^ 1);
             mbar_arrive_expect_tx(&xfull[slot], kSlotBytes);
             tma_load_2d(epi_smem + slot * kSlotBytes, &tmX, &xfull[slot], col0, m0);
@@ -217,17 +216,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------------------ epilogue warps 2..9
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     const int row_a = q * 32 + lane;          // accumulator row of this thread
-    const int te = threadIdx.x - 64;          // 0..127
+    const int wg = warp >= 6 ? 1 : 0;         // epilogue warpgroup
+    const int te = threadIdx.x - 64 - wg * 128;  // 0..127 within the warpgroup
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader[2] = {mapa_u32(&tempty[0], 0), mapa_u32(&tempty[1], 0)};
 
     if constexpr (C::RESID) {
-      int slot = 0, prev_slot = -1;
-      uint32_t ph = 0;
+      // The two warpgroups take alternate 32-column chunks (chunk counter cc, owner = cc & 1); chunk cc lives in ring
+      // slot cc % XSLOTS, filled by the loader warp in the same order.
+      uint32_t cc = 0;
+      const int bar_id = 1 + 2 * wg;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -235,21 +237,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int row_c = row < p.M ? row : p.M - 1;  // rows past M are zero-filled by TMA and clipped by the store
         const float* gate_row = p.gate + static_cast<long long>(row_c / p.rows_per_batch) * p.gate_bs;
         const float* add_row = p.row_add ? p.row_add + static_cast<size_t>((row_c / p.row_add_div) % p.row_add_period) * p.N : nullptr;
+        constexpr int NCH = BN / 32;
+        const int live = (p.N - n0) / 32 < NCH ? (p.N - n0) / 32 : NCH;   // chunks inside N (N % 32 == 0)
+        int last_mine = -1;
+        for (int c = 0; c < live; ++c)
+          if (((cc + c) & 1) == static_cast<uint32_t>(wg)) last_mine = c;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        constexpr int NCH = BN / 32;
+        if (last_mine < 0) {                   // a one-chunk edge tile owned by the other warpgroup
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
+        }
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < live; ++c) {
+          const uint32_t g = cc + c;
+          if ((g & 1) != static_cast<uint32_t>(wg)) continue;
+          const int slot = g % C::XSLOTS;
+          const uint32_t ph = (g / C::XSLOTS) & 1;
           const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;                  // N-edge tile: the loader skipped these chunks too
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c * 32, v);
           tmem_ld_wait();
-          if (c == NCH - 1 || col0 + 32 >= p.N) {  // last live chunk: all TMEM reads of this tile are done
+          if (c == last_mine) {                // all of this warp's TMEM reads of the tile are done
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
           }
+          if (p.dbg & 8) continue;     // timing experiment: accumulator read only
           mbar_wait(&xfull[slot], ph);
           uint8_t* xrow = epi_smem + slot * kSlotBytes + row_a * 128;
 #pragma unroll
@@ -258,11 +273,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float4 xv = *xp;
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + j);
-            xv.x = fmaf(g.x, __uint_as_float(v[4 * j + 0]) + b4.x, xv.x);
-            xv.y = fmaf(g.y, __uint_as_float(v[4 * j + 1]) + b4.y, xv.y);
-            xv.z = fmaf(g.z, __uint_as_float(v[4 * j + 2]) + b4.z, xv.z);
-            xv.w = fmaf(g.w, __uint_as_float(v[4 * j + 3]) + b4.w, xv.w);
+            const float4 gt = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + j);
+            xv.x = fmaf(gt.x, __uint_as_float(v[4 * j + 0]) + b4.x, xv.x);
+            xv.y = fmaf(gt.y, __uint_as_float(v[4 * j + 1]) + b4.y, xv.y);
+            xv.z = fmaf(gt.z, __uint_as_float(v[4 * j + 2]) + b4.z, xv.z);
+            xv.w = fmaf(gt.w, __uint_as_float(v[4 * j + 3]) + b4.w, xv.w);
             if (add_row) {
               const float4 ra = __ldg(reinterpret_cast<const float4*>(add_row + col0) + j);
               xv.x += ra.x; xv.y += ra.y; xv.z += ra.z; xv.w += ra.w;
@@ -270,42 +285,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             *xp = xv;
           }
           fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA store
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (te == 0) {
             tma_store_2d(&tmX, epi_smem + slot * kSlotBytes, col0, m0);
             tma_store_commit();
-            tma_store_wait_read<1>();                   // the store issued one chunk ago has finished reading its slot
-            if (prev_slot >= 0) mbar_arrive(&xempty[prev_slot]);
-            prev_slot = slot;
+            tma_store_wait_read<0>();                   // the store has read the slot: hand it back to the loader
+            mbar_arrive(&xempty[slot]);
           }
-          if (++slot == C::XSLOTS) { slot = 0; ph ^= 1; }
         }
+        cc += live;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (te == 0) tma_store_wait_all<0>();             // all residual writes have landed before the CTA retires
     } else {
       const int row_b0 = te >> 3;             // phase-B row within a group of 16
       const int ch_b = te & 7;                // phase-B 16-byte chunk within the 128-byte row segment
-      uint32_t chunk_ctr = 0;
+      uint8_t* buf = epi_smem + wg * kSlotBytes;   // one staging tile per warpgroup
+      const int bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
+      uint32_t cc = 0;                        // running chunk counter: chunk cc belongs to warpgroup (cc & 1)
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         constexpr int NCH = BN / 64;           // 64 16-bit columns = 128 bytes per row per chunk
+        // this warpgroup's last chunk of the tile (after it the accumulator is no longer read by us)
+        int last_mine = -1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          if (((cc + c) & 1) == static_cast<uint32_t>(wg)) last_mine = c;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
+        if (last_mine < 0) {                   // cannot happen for NCH >= 2, kept for safety
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
+        }
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
-          uint8_t* buf = epi_smem + (chunk_ctr & 1) * kSlotBytes;
-          ++chunk_ctr;
+          if (((cc + c) & 1) != static_cast<uint32_t>(wg)) continue;
           uint32_t v0[32], v1[32];
           tmem_ld_32x32b_x32(t_row + c * 64, v0);
           tmem_ld_32x32b_x32(t_row + c * 64 + 32, v1);
           tmem_ld_wait();
-          if (c == NCH - 1) {
+          if (c == last_mine) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
           }
+          if (p.dbg & 4) continue;   // timing experiment: accumulator read only
           const int col0 = n0 + c * 64;
           uint8_t* srow = buf + row_a * 128;
 #pragma unroll
@@ -336,9 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(srow + (((hh * 4 + j) ^ (row_a & 7)) << 4)) = o;
             }
           }
-          // one barrier per chunk is enough with two staging tiles: a thread reaches the barrier of chunk k+1 only
-          // after its reads of chunk k, so nobody overwrites tile (k & 1) at chunk k+2 while it is still being read
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");   // staging tile complete
           const int col = col0 + ch_b * 8;
           if (col < p.N) {
 #pragma unroll
@@ -350,7 +374,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     *reinterpret_cast<const uint4*>(buf + rl * 128 + ((ch_b ^ (rl & 7)) << 4));
             }
           }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");   // staging tile drained: safe to refill
         }
+        cc += NCH;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
