@@ -125,6 +125,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // qkv (written by the preceding GEMM) is visible from here
 
   if (warp == 4) {
     if (lane == 0) {
@@ -320,8 +322,7 @@ int launch_mode(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t 
     attr_set = true;
   }
   const int smem_bytes = make_plan(p.Lk, TAIL).total;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(m[0], m[1], m[2], m[3], p);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_CUDA(launch_pdl(kern, grid, dim3(kThreads), static_cast<size_t>(smem_bytes), stream, m[0], m[1], m[2], m[3], p));
   return B200_OK;
 }
 

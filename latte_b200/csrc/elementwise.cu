@@ -25,17 +25,32 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 // ---------------------------------------------------------------------------------- ln_modulate
 constexpr int LN_MAXV = 12;  // float4 per lane: dim <= 12*128 = 1536
 
-// One warp per row, the whole row in registers (NV float4 per lane, compile-time so nothing spills and the register
-// count stays low enough for full occupancy), two-pass mean/variance in fp32, one read and one write of the data.
+// One warp per row, the whole row in registers (NV float4 per lane, compile-time so nothing spills), two-pass
+// mean/variance in fp32, one read and one write of the data.  Work is split so that EVERY warp owns the same number of
+// consecutive rows and all warps are resident at once (register-limited to 32 warps/SM): a grid-stride loop left a
+// half-empty second wave.  The block's shift/scale vectors are staged in shared memory once, so the only global latency
+// on a row's critical path is the row itself.
 template <bool BF16, int NV>
 __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
                                                           const float* __restrict__ scale, long long mod_bs,
                                                           int rows_per_batch, uint16_t* __restrict__ out, int rows,
-                                                          int dim) {
+                                                          int dim, int rows_per_warp) {
+  extern __shared__ float4 s_mod[];  // [2][dim/4]: shift, scale of the batch row this block starts in
   const int lane = threadIdx.x & 31;
   const int nv = dim >> 2;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int block_row0 = blockIdx.x * (blockDim.x >> 5) * rows_per_warp;
+  pdl_launch_dependents();
+  const long long b0 = (block_row0 < rows ? block_row0 : rows - 1) / rows_per_batch;
+  pdl_wait();
+  for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) {
+    const float* src = (i < nv ? shift : scale) + b0 * mod_bs;
+    s_mod[i] = __ldg(reinterpret_cast<const float4*>(src) + (i < nv ? i : i - nv));
+  }
+  __syncthreads();
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int row = warp_global * rows_per_warp + rr;
+    if (row >= rows) break;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
     float4 v[NV];
     float s = 0.f;
@@ -58,6 +73,7 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
     }
     const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + 1e-6f);
     const long long b = row / rows_per_batch;
+    const bool staged = b == b0;
     const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_bs);
     const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
     uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * dim);
@@ -65,7 +81,8 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
     for (int i = 0; i < NV; ++i) {
       const int idx = lane + i * 32;
       if (idx < nv) {
-        const float4 h = __ldg(sh + idx), c = __ldg(sc + idx);
+        const float4 h = staged ? s_mod[idx] : __ldg(sh + idx);
+        const float4 c = staged ? s_mod[nv + idx] : __ldg(sc + idx);
         const float y0 = fmaf((v[i].x - mean) * rstd, 1.0f + c.x, h.x);
         const float y1 = fmaf((v[i].y - mean) * rstd, 1.0f + c.y, h.y);
         const float y2 = fmaf((v[i].z - mean) * rstd, 1.0f + c.z, h.z);
@@ -77,17 +94,16 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
 }
 
 template <bool BF16>
-void ln_dispatch(int nvmax, int blocks, cudaStream_t stream, const float* x, const float* shift, const float* scale,
-                 long long mod_bs, int rpb, uint16_t* out, int rows, int dim) {
-  if (nvmax <= 3) ln_modulate_kernel<BF16, 3><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
-  else if (nvmax <= 6) ln_modulate_kernel<BF16, 6><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
-  else if (nvmax <= 9) ln_modulate_kernel<BF16, 9><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
-  else ln_modulate_kernel<BF16, LN_MAXV><<<blocks, 128, 0, stream>>>(x, shift, scale, mod_bs, rpb, out, rows, dim);
+void ln_dispatch(int nvmax, int blocks, size_t smem, cudaStream_t stream, const float* x, const float* shift, const float* scale,
+                 long long mod_bs, int rpb, uint16_t* out, int rows, int dim, int rpw) {
+  if (nvmax <= 3) launch_pdl(ln_modulate_kernel<BF16, 3>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
+  else if (nvmax <= 6) launch_pdl(ln_modulate_kernel<BF16, 6>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
+  else if (nvmax <= 9) launch_pdl(ln_modulate_kernel<BF16, 9>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
+  else launch_pdl(ln_modulate_kernel<BF16, LN_MAXV>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
 }
 
 // ---------------------------------------------------------------------------------- patch_embed
 constexpr int PE_TOK = 16;
-constexpr int PE_MAXK = 64;
 
 // K = C*p*p is a template parameter (16 for the 4-channel, patch-2 latents every Latte config uses) so the per-d weight
 // row lives in K registers; a block computes PE_TOK tokens x all D outputs; the write of the fp32 residual stream
@@ -340,12 +356,14 @@ int launch_ln_modulate(const float* x, const float* shift, const float* scale, l
   const int wpb = 4;
   int sms = 0;
   B200_TRY(device_sm_count(&sms));
-  int blocks = (rows + wpb - 1) / wpb;
-  const int cap = sms * 12;  // <= 48 resident warps per SM; longer inputs loop (grid-stride) instead of relaunching waves
-  if (blocks > cap) blocks = cap;
+  // every warp gets the same number of consecutive rows and the whole grid is resident (<= 32 warps/SM by registers)
+  const int resident_warps = sms * 32;
+  const int rpw = (rows + resident_warps - 1) / resident_warps;
+  const int blocks = (rows + wpb * rpw - 1) / (wpb * rpw);
   const int nvmax = (dim / 4 + 31) / 32;
-  if (bf16) ln_dispatch<true>(nvmax, blocks, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim);
-  else ln_dispatch<false>(nvmax, blocks, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim);
+  const size_t smem = static_cast<size_t>(dim) * 2 * sizeof(float);
+  if (bf16) ln_dispatch<true>(nvmax, blocks, smem, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim, rpw);
+  else ln_dispatch<false>(nvmax, blocks, smem, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim, rpw);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

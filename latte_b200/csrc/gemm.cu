@@ -133,6 +133,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   cluster_sync_all();   // barriers of both CTAs are initialised before any multicast / remote arrival can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may begin its prologue as SMs drain
+  pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
   // pair-tile schedule: cluster k owns pair-tiles k, k + #clusters, ...; a pair-tile is two M-adjacent 128-row tiles of
   // one N column; this CTA takes row-tile 2 * pair_m + rank (it may lie past M: zero-filled loads, clipped stores)
@@ -401,8 +403,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmX, p);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, tmX, p));
   return B200_OK;
 }
 

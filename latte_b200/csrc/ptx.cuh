@@ -20,6 +20,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor is still
+// draining; everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+// predecessor's tail.  pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -127,6 +134,16 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// same, destination given as a raw shared::cluster address (may be the PEER CTA's shared memory: the pair leader
+// fetches both CTAs' operands so that no cross-SM handshake sits in the pipeline's critical loop)
+__device__ __forceinline__ void tma_load_2d_pair_raw(uint32_t dst_cluster_addr, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                     int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_cluster_addr), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -257,6 +274,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
+}
+
+// pair commit delivered to the issuing (leader) CTA's barrier only
+__device__ __forceinline__ void umma_commit_pair_local(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ----------------------------------------------------------------------------- TMEM -> registers
