@@ -82,6 +82,80 @@ typedef struct B200LatteWeights {
   const float* final_b;    /* final_layer.linear.bias     [p*p*out_channels]              */
 } B200LatteWeights;
 
+/* ---- LatteT2V (reference models/latte_t2v.py:444-944, HF maxin-cn/Latte-1 config: ada_norm_single, gelu-approximate,
+ * attention_bias, caption_channels 4096).  Parity of this entry point is UNPINNED (diffusers 0.24.0 pieces restated). */
+typedef struct B200T2VShape {
+  int32_t layers;           /* num_layers: spatial/temporal block PAIRS (28) */
+  int32_t hidden;           /* num_attention_heads * attention_head_dim */
+  int32_t heads;
+  int32_t mlp_hidden;       /* 4 * hidden */
+  int32_t patch;            /* 2 */
+  int32_t in_channels;      /* 4 */
+  int32_t out_channels;     /* 8 */
+  int32_t input_size;       /* latent H = W (sample_size, 64 for 512 px) */
+  int32_t frames;           /* video_length */
+  int32_t caption_channels; /* 4096 */
+  int32_t dtype;            /* B200_FP16 / B200_BF16 */
+} B200T2VShape;
+
+/* Packed weights; `l` runs over layers. fp32 unless the name ends in 16. State-dict names in comments. */
+typedef struct B200T2VWeights {
+  const float* patch_w;    /* pos_embed.proj.weight [D, C*p*p] */
+  const float* patch_b;
+  const float* pos_embed;  /* PatchEmbed sin-cos table [N, D] */
+  const float* temp_embed; /* temp_pos_embed [F, D] */
+  const float* t_w0;       /* adaln_single.emb.timestep_embedder.linear_1.weight [D,256] */
+  const float* t_b0;
+  const float* t_w2;       /* ...linear_2.weight [D,D] */
+  const float* t_b2;
+  const void* ada_w16;     /* adaln_single.linear.weight [6D, D] */
+  const float* ada_b;
+  const void* cap_w1_16;   /* caption_projection.linear_1.weight [D, caption_channels] */
+  const float* cap_b1;
+  const void* cap_w2_16;   /* caption_projection.linear_2.weight [D, D] */
+  const float* cap_b2;
+  const float* tables;     /* scale_shift_table of every block in execution order s0,t0,s1,t1,...: [2*layers][6][D] */
+  const float* final_table;/* scale_shift_table [2][D] */
+  const void* s_qkv_w16;   /* transformer_blocks.l.attn1.to_q|to_k|to_v.weight stacked [l][3D, D] */
+  const float* s_qkv_b;
+  const void* s_out_w16;   /* ...attn1.to_out.0.weight [l][D, D] */
+  const float* s_out_b;
+  const void* c_q_w16;     /* ...attn2.to_q.weight [l][D, D] */
+  const float* c_q_b;
+  const void* c_kv_w16;    /* ...attn2.to_k|to_v.weight stacked over ALL layers [layers*2D, D] (one GEMM per step) */
+  const float* c_kv_b;
+  const void* c_out_w16;   /* ...attn2.to_out.0.weight [l][D, D] */
+  const float* c_out_b;
+  const void* s_fc1_w16;   /* ...ff.net.0.proj.weight [l][4D, D] */
+  const float* s_fc1_b;
+  const void* s_fc2_w16;   /* ...ff.net.2.weight [l][D, 4D] */
+  const float* s_fc2_b;
+  const void* t_qkv_w16;   /* temporal_transformer_blocks.l.attn1 ... */
+  const float* t_qkv_b;
+  const void* t_out_w16;
+  const float* t_out_b;
+  const void* t_fc1_w16;
+  const float* t_fc1_b;
+  const void* t_fc2_w16;
+  const float* t_fc2_b;
+  const float* final_w;    /* proj_out.weight [p*p*out_channels, D] */
+  const float* final_b;
+} B200T2VWeights;
+
+B200_API size_t b200_t2v_workspace_bytes(const B200T2VShape* shape, int batch, int text_len);
+
+/* LatteT2V.forward (latte_t2v.py:677-941, eval, no masks):  x [batch, C, F, S, S] fp32, t [batch] int64,
+ * text [batch, text_len, caption_channels] fp32 (text_len <= 128)  ->  out [batch, out_channels, F, S, S] fp32.  */
+B200_API int b200_t2v_forward(const B200T2VShape* shape, const B200T2VWeights* w, const float* x, const int64_t* t,
+                              const float* text, int batch, int text_len, int enable_temporal, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* softmax(q k^T / sqrt(hd)) v with K/V from another sequence (diffusers Attention attn2, latte_t2v.py:862-870):
+ * q [batch*q_rows_per_batch, q_row_stride] 16-bit (first heads*head_dim columns), kv [batch*kv_len, kv_row_stride]
+ * 16-bit (columns [k heads][v heads]), kv_len <= 128 keys per sample; out [rows, heads*head_dim] 16-bit.          */
+B200_API int b200_cross_attention(const void* q, const void* kv, void* out, int batch, int q_rows_per_batch, int kv_len,
+                                  int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream);
+
 /* Thread-local description of the last failure on this thread ("" if none). */
 B200_API const char* b200_last_error(void);
 B200_API int b200_abi_version(void);

@@ -33,6 +33,24 @@ class LatteWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
 
 
+class T2VShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "layers", "hidden", "heads", "mlp_hidden", "patch", "in_channels", "out_channels", "input_size", "frames",
+        "caption_channels", "dtype")]
+
+
+T2V_WEIGHT_FIELDS = (
+    "patch_w", "patch_b", "pos_embed", "temp_embed", "t_w0", "t_b0", "t_w2", "t_b2", "ada_w16", "ada_b",
+    "cap_w1_16", "cap_b1", "cap_w2_16", "cap_b2", "tables", "final_table",
+    "s_qkv_w16", "s_qkv_b", "s_out_w16", "s_out_b", "c_q_w16", "c_q_b", "c_kv_w16", "c_kv_b", "c_out_w16", "c_out_b",
+    "s_fc1_w16", "s_fc1_b", "s_fc2_w16", "s_fc2_b",
+    "t_qkv_w16", "t_qkv_b", "t_out_w16", "t_out_b", "t_fc1_w16", "t_fc1_b", "t_fc2_w16", "t_fc2_b", "final_w", "final_b")
+
+
+class T2VWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in T2V_WEIGHT_FIELDS]
+
+
 EXPORTS = {
     "b200_last_error": (C.c_char_p, []),
     "b200_abi_version": (C.c_int, []),
@@ -46,6 +64,11 @@ EXPORTS = {
                                  C.c_int, C.c_void_p]),
     "b200_ln_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p]),
+    "b200_t2v_workspace_bytes": (C.c_size_t, [C.POINTER(T2VShape), C.c_int, C.c_int]),
+    "b200_t2v_forward": (C.c_int, [C.POINTER(T2VShape), C.POINTER(T2VWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200_cross_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200_profile_enable": (None, [C.c_int]),
     "b200_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }

@@ -124,7 +124,7 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
 
   // ---- patch embedding + pos_embed -> fp32 residual stream (latte.py:330-331)
   B200_PROF(PROF_OTHER, launch_patch_embed(x, cfg ? batch / 2 : batch, w->patch_w, w->patch_b, w->pos_embed, ws.x, batch, F,
-                              s->in_channels, s->input_size, s->patch, D, stream));
+                              s->in_channels, s->input_size, s->patch, D, 0, stream));
 
   // ---- blocks (latte.py:345-368); rows stay in (b, f, n) order for all of them
   for (int i = 0; i < depth; ++i) {
@@ -170,12 +170,179 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
   // ---- final layer + unpatchify (latte.py:374-376), then guidance (latte.py:394-398)
   const float* mf = ws.mod + static_cast<size_t>(depth) * 6 * D;  // [shift, scale]
   B200_PROF(PROF_OTHER, launch_final_layer(ws.x, mf, mf + D, mod_bs, w->final_w, w->final_b, out, batch, F, grid, s->patch,
-                              s->out_channels, D, stream));
+                              s->out_channels, D, 0, stream));
   if (cfg) {
     const long long per_sample = static_cast<long long>(F) * s->out_channels * s->input_size * s->input_size;
     B200_PROF(PROF_OTHER, launch_cfg_combine(out, batch, per_sample, F, s->out_channels, s->in_channels, s->input_size * s->input_size,
                                 cfg_scale, stream));
   }
+  return B200_OK;
+}
+
+
+// ====================================================================================================== LatteT2V
+struct T2VWorkspace {
+  float* x; uint16_t* h; uint16_t* qkv; uint16_t* g;
+  uint16_t* text16; uint16_t* cap_h; uint16_t* cap_o; uint16_t* kv_all;
+  float* ones; float* tfreq; float* th; float* emb; float* ts; float* mod;
+  size_t bytes;
+};
+
+int t2v_shape_ok(const B200T2VShape* s, int batch, int text_len) {
+  B200_REQUIRE(s != nullptr && batch > 0, B200_ERR_SHAPE, "t2v: bad shape/batch");
+  B200_REQUIRE(s->layers > 0 && s->heads > 0 && s->hidden % s->heads == 0, B200_ERR_SHAPE, "t2v: hidden %d / heads %d", s->hidden, s->heads);
+  const int hd = s->hidden / s->heads;
+  B200_REQUIRE(hd == 64 || hd == 72 || hd == 80, B200_ERR_UNSUPPORTED, "t2v: head_dim %d unsupported", hd);
+  B200_REQUIRE(s->hidden % 64 == 0 && s->mlp_hidden % 64 == 0 && s->caption_channels % 64 == 0, B200_ERR_UNSUPPORTED,
+               "t2v: hidden, mlp_hidden, caption_channels must be multiples of 64");
+  B200_REQUIRE(s->patch == 2 && s->input_size % 2 == 0, B200_ERR_UNSUPPORTED, "t2v: patch size %d not built", s->patch);
+  B200_REQUIRE(text_len >= 1 && text_len <= 128, B200_ERR_UNSUPPORTED, "t2v: text length %d (1..128 built)", text_len);
+  B200_REQUIRE(s->dtype == B200_FP16 || s->dtype == B200_BF16, B200_ERR_DTYPE, "t2v: dtype %d unknown", s->dtype);
+  B200_REQUIRE(s->out_channels * 4 <= 32, B200_ERR_UNSUPPORTED, "t2v: p*p*out_channels > 32");
+  const int grid = s->input_size / 2;
+  B200_REQUIRE((s->frames * grid * grid) % 128 == 0, B200_ERR_UNSUPPORTED, "t2v: tokens per sample must be a multiple of 128");
+  return B200_OK;
+}
+
+void t2v_carve(const B200T2VShape* s, int batch, int text_len, void* base, T2VWorkspace* ws) {
+  const size_t grid = s->input_size / s->patch;
+  const size_t T = static_cast<size_t>(batch) * s->frames * grid * grid;
+  const size_t D = s->hidden, R = static_cast<size_t>(batch) * text_len;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  ws->x = static_cast<float*>(take(T * D * 4));
+  ws->h = static_cast<uint16_t*>(take(T * D * 2));
+  ws->qkv = static_cast<uint16_t*>(take(T * 3 * D * 2));
+  ws->g = static_cast<uint16_t*>(take(T * static_cast<size_t>(s->mlp_hidden) * 2));
+  ws->text16 = static_cast<uint16_t*>(take(R * s->caption_channels * 2));
+  ws->cap_h = static_cast<uint16_t*>(take(R * D * 2));
+  ws->cap_o = static_cast<uint16_t*>(take(R * D * 2));
+  ws->kv_all = static_cast<uint16_t*>(take(R * static_cast<size_t>(s->layers) * 2 * D * 2));
+  ws->ones = static_cast<float*>(take(D * 4));
+  ws->tfreq = static_cast<float*>(take(static_cast<size_t>(batch) * 256 * 4));
+  ws->th = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
+  ws->emb = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
+  ws->ts = static_cast<float*>(take(static_cast<size_t>(batch) * 6 * D * 4));
+  ws->mod = static_cast<float*>(take(static_cast<size_t>(batch) * (static_cast<size_t>(s->layers) * 2 * 6 * D + 2 * D) * 4));
+  ws->bytes = off;
+}
+
+int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, const int64_t* t, const float* text,
+                int batch, int text_len, int enable_temporal, float* out, void* workspace, size_t workspace_bytes,
+                cudaStream_t stream) {
+  B200_TRY(t2v_shape_ok(s, batch, text_len));
+  B200_REQUIRE(w && x && t && text && out && workspace, B200_ERR_SHAPE, "t2v: NULL argument");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, B200_ERR_ALIGN, "t2v: workspace must be 1024-byte aligned");
+  B200_TRY(check_arch());
+  T2VWorkspace ws;
+  t2v_carve(s, batch, text_len, workspace, &ws);
+  B200_REQUIRE(ws.bytes <= workspace_bytes, B200_ERR_WORKSPACE, "t2v: workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+
+  const int D = s->hidden, H = s->heads, hd = D / H, F = s->frames, L = s->layers, HID = s->mlp_hidden;
+  const int grid = s->input_size / s->patch, N = grid * grid;
+  const int T = batch * F * N, R = batch * text_len;
+  const int rows_per_batch = F * N;
+  const int bf16 = s->dtype == B200_BF16;
+  const long long mod_bs = static_cast<long long>(L) * 2 * 6 * D + 2 * D;
+
+  // ---- conditioning (latte_t2v.py:782-784): emb = TimestepEmbedding(sincos(t)); ts = Linear(SiLU(emb)); tables + ts
+  B200_PROF(PROF_OTHER, launch_timestep_freq(reinterpret_cast<const long long*>(t), ws.tfreq, batch, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w2, 32, 0, w->t_b2, ws.th, ws.emb, batch, D, D, 0, 0, nullptr, nullptr, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->ada_w16, 16, bf16, w->ada_b, ws.emb, ws.ts, batch, 6 * D, D, 1, 0, nullptr, nullptr, stream));
+  B200_PROF(PROF_OTHER, launch_t2v_mod(w->tables, ws.ts, w->final_table, ws.emb, ws.mod, batch, 2 * L, D, stream));
+  B200_PROF(PROF_OTHER, launch_fill(ws.ones, 1.0f, D, stream));
+
+  // ---- text: caption projection once per sample (latte_t2v.py:789), then K/V of EVERY layer's cross-attention in one GEMM
+  B200_PROF(PROF_OTHER, launch_cast16(text, ws.text16, static_cast<long long>(R) * s->caption_channels, bf16, stream));
+  {
+    GemmArgs a{};
+    a.A = ws.text16; a.W = w->cap_w1_16; a.bias = w->cap_b1; a.M = R; a.N = D; a.K = s->caption_channels; a.bf16 = bf16;
+    a.epilogue = B200_EPI_BIAS_GELU; a.out16 = ws.cap_h;
+    B200_PROF(PROF_GEMM, launch_gemm(a, stream));
+    GemmArgs b{};
+    b.A = ws.cap_h; b.W = w->cap_w2_16; b.bias = w->cap_b2; b.M = R; b.N = D; b.K = D; b.bf16 = bf16;
+    b.epilogue = B200_EPI_BIAS; b.out16 = ws.cap_o;
+    B200_PROF(PROF_GEMM, launch_gemm(b, stream));
+    GemmArgs c{};
+    c.A = ws.cap_o; c.W = w->c_kv_w16; c.bias = w->c_kv_b; c.M = R; c.N = L * 2 * D; c.K = D; c.bf16 = bf16;
+    c.epilogue = B200_EPI_BIAS; c.out16 = ws.kv_all;
+    B200_PROF(PROF_GEMM, launch_gemm(c, stream));
+  }
+
+  // ---- patch embedding + pos_embed (latte_t2v.py:731,773); x arrives as (b c f h w)
+  B200_PROF(PROF_OTHER, launch_patch_embed(x, batch, w->patch_w, w->patch_b, w->pos_embed, ws.x, batch, F, s->in_channels,
+                                           s->input_size, s->patch, D, 1, stream));
+
+  auto linear16 = [&](const void* A, const void* W, const float* bias, int M, int Nn, int K, int epi, void* o16) {
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = bias; a.M = M; a.N = Nn; a.K = K; a.bf16 = bf16; a.epilogue = epi; a.out16 = o16;
+    return launch_gemm(a, stream);
+  };
+  auto linear_resid = [&](const void* A, const void* W, const float* bias, int K, const float* gate, long long gate_bs,
+                          const float* row_add) {
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = bias; a.M = T; a.N = D; a.K = K; a.bf16 = bf16; a.epilogue = B200_EPI_GATE_RESIDUAL;
+    a.resid = ws.x; a.gate = gate; a.gate_batch_stride = gate_bs; a.rows_per_batch = rows_per_batch;
+    if (row_add) { a.row_add = row_add; a.row_add_div = N; a.row_add_period = F; }
+    return launch_gemm(a, stream);
+  };
+  const size_t DD = static_cast<size_t>(D) * D;
+
+  for (int l = 0; l < L; ++l) {
+    // ------------------------------------------------ spatial block (diffusers BasicTransformerBlock; latte_t2v.py:862-870)
+    const float* m = ws.mod + static_cast<size_t>(2 * l) * 6 * D;
+    B200_PROF(PROF_LN, launch_ln_modulate(ws.x, m + 0 * D, m + 1 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    B200_PROF(PROF_GEMM, linear16(ws.h, static_cast<const uint16_t*>(w->s_qkv_w16) + l * 3 * DD, w->s_qkv_b + static_cast<size_t>(l) * 3 * D,
+                                  T, 3 * D, D, B200_EPI_BIAS, ws.qkv));
+    AttnArgs aa{};
+    aa.qkv = ws.qkv; aa.out = ws.h; aa.batch = batch; aa.frames = F; aa.tokens = N; aa.heads = H; aa.head_dim = hd; aa.bf16 = bf16;
+    aa.temporal = 0;
+    B200_PROF(PROF_ATTN, launch_attention(aa, stream));
+    B200_PROF(PROF_GEMM, linear_resid(ws.h, static_cast<const uint16_t*>(w->s_out_w16) + l * DD, w->s_out_b + static_cast<size_t>(l) * D, D,
+                                      m + 2 * D, mod_bs, nullptr));
+    // cross-attention on the UN-normalised stream (no norm2 before attn2 in ada_norm_single mode), residual without gate
+    B200_PROF(PROF_OTHER, launch_cast16(ws.x, ws.h, static_cast<long long>(T) * D, bf16, stream));
+    B200_PROF(PROF_GEMM, linear16(ws.h, static_cast<const uint16_t*>(w->c_q_w16) + l * DD, w->c_q_b + static_cast<size_t>(l) * D, T, D, D,
+                                  B200_EPI_BIAS, ws.qkv));
+    CrossAttnArgs ca{};
+    ca.q = ws.qkv; ca.kv = ws.kv_all + static_cast<size_t>(l) * 2 * D; ca.out = ws.h; ca.batch = batch; ca.q_rows_per_batch = rows_per_batch;
+    ca.kv_len = text_len; ca.q_row_stride = D; ca.kv_row_stride = L * 2 * D; ca.heads = H; ca.head_dim = hd; ca.bf16 = bf16;
+    B200_PROF(PROF_ATTN, launch_cross_attention(ca, stream));
+    B200_PROF(PROF_GEMM, linear_resid(ws.h, static_cast<const uint16_t*>(w->c_out_w16) + l * DD, w->c_out_b + static_cast<size_t>(l) * D, D,
+                                      ws.ones, 0, nullptr));
+    B200_PROF(PROF_LN, launch_ln_modulate(ws.x, m + 3 * D, m + 4 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    B200_PROF(PROF_GEMM, linear16(ws.h, static_cast<const uint16_t*>(w->s_fc1_w16) + static_cast<size_t>(l) * HID * D,
+                                  w->s_fc1_b + static_cast<size_t>(l) * HID, T, HID, D, B200_EPI_BIAS_GELU, ws.g));
+    // + temp_pos_embed before the first temporal block (latte_t2v.py:894-895), folded into this epilogue
+    B200_PROF(PROF_GEMM, linear_resid(ws.g, static_cast<const uint16_t*>(w->s_fc2_w16) + static_cast<size_t>(l) * D * HID,
+                                      w->s_fc2_b + static_cast<size_t>(l) * D, HID, m + 5 * D, mod_bs,
+                                      (l == 0 && enable_temporal && F > 1) ? w->temp_embed : nullptr));
+    if (!enable_temporal) continue;
+    // ------------------------------------------------ temporal block (BasicTransformerBlock_, latte_t2v.py:897-905)
+    const float* mt = ws.mod + static_cast<size_t>(2 * l + 1) * 6 * D;
+    B200_PROF(PROF_LN, launch_ln_modulate(ws.x, mt + 0 * D, mt + 1 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    B200_PROF(PROF_GEMM, linear16(ws.h, static_cast<const uint16_t*>(w->t_qkv_w16) + l * 3 * DD, w->t_qkv_b + static_cast<size_t>(l) * 3 * D,
+                                  T, 3 * D, D, B200_EPI_BIAS, ws.qkv));
+    aa.temporal = 1;
+    B200_PROF(PROF_ATTN, launch_attention(aa, stream));
+    B200_PROF(PROF_GEMM, linear_resid(ws.h, static_cast<const uint16_t*>(w->t_out_w16) + l * DD, w->t_out_b + static_cast<size_t>(l) * D, D,
+                                      mt + 2 * D, mod_bs, nullptr));
+    B200_PROF(PROF_LN, launch_ln_modulate(ws.x, mt + 3 * D, mt + 4 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
+    B200_PROF(PROF_GEMM, linear16(ws.h, static_cast<const uint16_t*>(w->t_fc1_w16) + static_cast<size_t>(l) * HID * D,
+                                  w->t_fc1_b + static_cast<size_t>(l) * HID, T, HID, D, B200_EPI_BIAS_GELU, ws.g));
+    B200_PROF(PROF_GEMM, linear_resid(ws.g, static_cast<const uint16_t*>(w->t_fc2_w16) + static_cast<size_t>(l) * D * HID,
+                                      w->t_fc2_b + static_cast<size_t>(l) * D, HID, mt + 5 * D, mod_bs, nullptr));
+  }
+
+  // ---- output head (latte_t2v.py:918-936): table + embedded_timestep -> shift, scale; LN; modulate; proj_out; unpatchify to (b c f h w)
+  const float* mf = ws.mod + static_cast<size_t>(2 * L) * 6 * D;
+  B200_PROF(PROF_OTHER, launch_final_layer(ws.x, mf, mf + D, mod_bs, w->final_w, w->final_b, out, batch, F, grid, s->patch,
+                                           s->out_channels, D, 1, stream));
   return B200_OK;
 }
 
@@ -240,6 +407,30 @@ B200_API int b200_attention(const void* qkv, void* out, int batch, int frames, i
   a.qkv = qkv; a.out = out; a.batch = batch; a.frames = frames; a.tokens = tokens; a.heads = heads;
   a.head_dim = head_dim; a.bf16 = dtype == B200_BF16; a.temporal = temporal;
   return b200::launch_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+B200_API size_t b200_t2v_workspace_bytes(const B200T2VShape* shape, int batch, int text_len) {
+  if (b200::t2v_shape_ok(shape, batch, text_len) != B200_OK) return 0;
+  b200::T2VWorkspace ws;
+  b200::t2v_carve(shape, batch, text_len, nullptr, &ws);
+  return ws.bytes;
+}
+
+B200_API int b200_t2v_forward(const B200T2VShape* shape, const B200T2VWeights* w, const float* x, const int64_t* t,
+                              const float* text, int batch, int text_len, int enable_temporal, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::t2v_forward(shape, w, x, t, text, batch, text_len, enable_temporal, out, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+B200_API int b200_cross_attention(const void* q, const void* kv, void* out, int batch, int q_rows_per_batch, int kv_len,
+                                  int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream) {
+  B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype);
+  b200::CrossAttnArgs a{};
+  a.q = q; a.kv = kv; a.out = out; a.batch = batch; a.q_rows_per_batch = q_rows_per_batch; a.kv_len = kv_len;
+  a.q_row_stride = q_row_stride; a.kv_row_stride = kv_row_stride; a.heads = heads; a.head_dim = head_dim;
+  a.bf16 = dtype == B200_BF16;
+  return b200::launch_cross_attention(a, static_cast<cudaStream_t>(stream));
 }
 
 B200_API int b200_ln_modulate(const float* x, const float* shift, const float* scale, int64_t mod_batch_stride,

@@ -27,7 +27,7 @@ namespace {
 constexpr int kThreads = 160;
 constexpr int kOCol = 0;  // O (<= 80 columns) reuses the first S columns: S is dead once every row has written its P
 
-enum { MODE_FULL = 0, MODE_PACKED = 1, MODE_TEMPORAL = 2 };
+enum { MODE_FULL = 0, MODE_PACKED = 1, MODE_TEMPORAL = 2, MODE_CROSS = 3 };
 
 struct AttnDev {
   void* out;
@@ -38,6 +38,9 @@ struct AttnDev {
   int frames;       // F
   int group;        // PACKED: N (tokens per sequence); TEMPORAL: G = 128 / F  (power of two)
   int gshift;       // log2(group)
+  int k_head0, v_head0;  // index of head 0 of K / V in the (hd, heads-like, rows) view of the K/V buffer
+  int kv_rows_per_batch; // CROSS: rows of the K/V buffer per sample (= text length L, the number of valid keys)
+  int q_rows_per_batch;  // CROSS: query rows per sample (F * N)
   int Lk;           // keys per tile: N (FULL, <= 256) or 128
   int tiles_per_seq;  // FULL: N / 128; TEMPORAL: N / G
   float scale_log2; // hd^-0.5 * log2(e)
@@ -83,6 +86,7 @@ __device__ __forceinline__ int row_key(int r, int gshift) {
 template <int MODE>
 __device__ __forceinline__ bool key_valid(int rkey, int col, int gshift) {
   if constexpr (MODE == MODE_FULL) return true;
+  if constexpr (MODE == MODE_CROSS) return col < rkey;   // rkey carries the number of valid keys (text tokens)
   return row_key<MODE>(col, gshift) == rkey;
 }
 
@@ -139,32 +143,35 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int n0 = (tile % p.tiles_per_seq) * p.group;
         const int bf0 = b * p.frames;
         tma_load_4d(smem + SQ_MAIN, &tmQ, bar_qk, 0, head, n0, bf0);
-        tma_load_4d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.heads + head, n0, bf0);
+        tma_load_4d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.k_head0 + head, n0, bf0);
         if constexpr (TAIL) {
           tma_load_4d(smem + SQ_TAIL, &tmQt, bar_qk, 64, head, n0, bf0);
-          tma_load_4d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.heads + head, n0, bf0);
+          tma_load_4d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.k_head0 + head, n0, bf0);
         }
         mbar_arrive_expect_tx(bar_v, v_bytes);
-        tma_load_4d(smem + SV_MAIN, &tmKV, bar_v, 0, 2 * p.heads + head, n0, bf0);
-        if constexpr (TAIL) tma_load_4d(smem + SV_TAIL, &tmKVt, bar_v, 64, 2 * p.heads + head, n0, bf0);
+        tma_load_4d(smem + SV_MAIN, &tmKV, bar_v, 0, p.v_head0 + head, n0, bf0);
+        if constexpr (TAIL) tma_load_4d(smem + SV_TAIL, &tmKVt, bar_v, 64, p.v_head0 + head, n0, bf0);
       } else {
         int q_row0, kv_row0;
         if constexpr (MODE == MODE_FULL) {
           const int s = tile / p.tiles_per_seq;
           kv_row0 = s * p.tokens;
           q_row0 = kv_row0 + (tile % p.tiles_per_seq) * 128;
+        } else if constexpr (MODE == MODE_CROSS) {
+          q_row0 = tile * 128;                                         // 128 consecutive query tokens of one sample
+          kv_row0 = (q_row0 / p.q_rows_per_batch) * p.kv_rows_per_batch;  // that sample's text tokens (<= 128 keys)
         } else {
           q_row0 = kv_row0 = tile * 128;
         }
         tma_load_3d(smem + SQ_MAIN, &tmQ, bar_qk, 0, head, q_row0);
-        tma_load_3d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.heads + head, kv_row0);
+        tma_load_3d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.k_head0 + head, kv_row0);
         if constexpr (TAIL) {
           tma_load_3d(smem + SQ_TAIL, &tmQt, bar_qk, 64, head, q_row0);
-          tma_load_3d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.heads + head, kv_row0);
+          tma_load_3d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.k_head0 + head, kv_row0);
         }
         mbar_arrive_expect_tx(bar_v, v_bytes);
-        tma_load_3d(smem + SV_MAIN, &tmKV, bar_v, 0, 2 * p.heads + head, kv_row0);
-        if constexpr (TAIL) tma_load_3d(smem + SV_TAIL, &tmKVt, bar_v, 64, 2 * p.heads + head, kv_row0);
+        tma_load_3d(smem + SV_MAIN, &tmKV, bar_v, 0, p.v_head0 + head, kv_row0);
+        if constexpr (TAIL) tma_load_3d(smem + SV_TAIL, &tmKVt, bar_v, 64, p.v_head0 + head, kv_row0);
       }
 
       // ---------------------------------------------------------------- S = Q K^T   (M=128, N=Lk, K=hd padded to 16)
@@ -205,7 +212,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int r = warp * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const int nchunks = Lk / 32;
-    const int rkey = row_key<MODE>(r, p.gshift);
+    const int rkey = MODE == MODE_CROSS ? p.kv_rows_per_batch : row_key<MODE>(r, p.gshift);
     mbar_wait(bar_s, 0);
     tc_fence_after();
 
@@ -326,11 +333,249 @@ int launch_mode(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t 
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Long spatial sequences (N = 512 / 1024 tokens per frame: LatteT2V at 512 px): the keys are streamed in chunks of 256
+// with the online-softmax recurrence.  S_c = Q K_c^T lands in TMEM columns [0,256); the softmax warps take the chunk
+// maximum, rescale the running output O (TMEM columns [256,336), tcgen05.ld -> * alpha -> tcgen05.st) and the running
+// sum, write P_c (16-bit, K-major SW128) to smem; O += P_c V_c accumulates in TMEM.  K_{c+1} is fetched as soon as
+// S_c has been computed, V_{c+1} as soon as O += P_c V_c has been computed.
+constexpr int L_SQ_MAIN = 0;
+constexpr int L_SK_MAIN = L_SQ_MAIN + 128 * 128;
+constexpr int L_SV_MAIN = L_SK_MAIN + 256 * 128;
+constexpr int L_SP = L_SV_MAIN + 256 * 128;
+constexpr int L_SQ_TAIL = L_SP + 128 * 256 * 2;
+constexpr int L_SK_TAIL = L_SQ_TAIL + 128 * 32;
+constexpr int L_SV_TAIL = L_SK_TAIL + 256 * 32;
+constexpr int L_SBARS = L_SV_TAIL + 256 * 32;
+constexpr int L_SMEM_BYTES = L_SBARS + 128 + 1024;
+constexpr int L_OCOL = 256;
+
+template <bool BF16, bool TAIL>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
+                 const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt, const AttnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L_SBARS);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_o = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int head = blockIdx.y;
+  const int nchunk = p.tokens / 256;
+  const int seq = tile / p.tiles_per_seq;
+  const int kv_row0 = seq * p.tokens;
+  const int q_row0 = kv_row0 + (tile % p.tiles_per_seq) * 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t k_bytes = 256 * 128 + (TAIL ? 256 * 32 : 0);
+      auto load_k = [&](int c) {
+        mbar_arrive_expect_tx(bar_k, k_bytes);
+        tma_load_3d(smem + L_SK_MAIN, &tmKV, bar_k, 0, p.k_head0 + head, kv_row0 + c * 256);
+        if constexpr (TAIL) tma_load_3d(smem + L_SK_TAIL, &tmKVt, bar_k, 64, p.k_head0 + head, kv_row0 + c * 256);
+      };
+      auto load_v = [&](int c) {
+        mbar_arrive_expect_tx(bar_v, k_bytes);
+        tma_load_3d(smem + L_SV_MAIN, &tmKV, bar_v, 0, p.v_head0 + head, kv_row0 + c * 256);
+        if constexpr (TAIL) tma_load_3d(smem + L_SV_TAIL, &tmKVt, bar_v, 64, p.v_head0 + head, kv_row0 + c * 256);
+      };
+      mbar_arrive_expect_tx(bar_q, 128 * 128 + (TAIL ? 128 * 32 : 0));
+      tma_load_3d(smem + L_SQ_MAIN, &tmQ, bar_q, 0, head, q_row0);
+      if constexpr (TAIL) tma_load_3d(smem + L_SQ_TAIL, &tmQt, bar_q, 64, head, q_row0);
+      load_k(0);
+      load_v(0);
+
+      const uint32_t idesc_s = umma_idesc_f16(BF16, 128, 256, false, false);
+      const uint32_t idesc_o = umma_idesc_f16(BF16, 128, 64, false, true);
+      const uint32_t idesc_ot = umma_idesc_f16(BF16, 128, 16, false, true);
+      const uint64_t dq = umma_smem_desc(smem_u32(smem + L_SQ_MAIN), 0, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t dk = umma_smem_desc(smem_u32(smem + L_SK_MAIN), 0, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t dqt = umma_smem_desc(smem_u32(smem + L_SQ_TAIL), 0, 256, UMMA_LAYOUT_SW32);
+      const uint64_t dkt = umma_smem_desc(smem_u32(smem + L_SK_TAIL), 0, 256, UMMA_LAYOUT_SW32);
+      const uint64_t dv = umma_smem_desc(smem_u32(smem + L_SV_MAIN), 256 * 128, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t dvt = umma_smem_desc(smem_u32(smem + L_SV_TAIL), 256 * 32, 256, UMMA_LAYOUT_SW32);
+      mbar_wait(bar_q, 0);
+      for (int c = 0; c < nchunk; ++c) {
+        const uint32_t par = c & 1;
+        mbar_wait(bar_k, par);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base, umma_desc_advance(dq, k * 32), umma_desc_advance(dk, k * 32), idesc_s, k > 0 ? 1u : 0u);
+        if constexpr (TAIL) umma_f16_ss(tmem_base, dqt, dkt, idesc_s, 1u);
+        umma_commit(bar_s);
+        mbar_wait(bar_s, par);                 // S_c computed: the K buffer is free
+        if (c + 1 < nchunk) load_k(c + 1);
+        mbar_wait(bar_v, par);
+        mbar_wait(bar_p, par);                 // P_c written, O rescaled
+        tc_fence_after();
+        for (int k = 0; k < 16; ++k) {
+          const uint64_t dp = umma_smem_desc(smem_u32(smem + L_SP + (k >> 2) * (128 * 128)) + (k & 3) * 32, 0, 1024, UMMA_LAYOUT_SW128);
+          const uint32_t accum = (c > 0 || k > 0) ? 1u : 0u;
+          umma_f16_ss(tmem_base + L_OCOL, dp, umma_desc_advance(dv, k * 16 * 128), idesc_o, accum);
+          if constexpr (TAIL) umma_f16_ss(tmem_base + L_OCOL + 64, dp, umma_desc_advance(dvt, k * 16 * 32), idesc_ot, accum);
+        }
+        umma_commit(bar_o);
+        if (c + 1 < nchunk) {
+          mbar_wait(bar_o, par);               // O += P_c V_c computed: the V buffer (and P) are free
+          load_v(c + 1);
+        }
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = smem + L_SP + r * 128;
+    const int sw = r & 7;
+    for (int c = 0; c < nchunk; ++c) {
+      const uint32_t par = c & 1;
+      mbar_wait(bar_s, par);
+      tc_fence_after();
+      float cmax = -INFINITY;
+      for (int j8 = 0; j8 < 8; ++j8) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + j8 * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+      }
+      const float m_new = fmaxf(m_run, cmax);
+      const float alpha = ex2((m_run - m_new) * p.scale_log2);   // 0 for the first chunk (m_run = -inf)
+      l_run *= alpha;
+      m_run = m_new;
+      if (c > 0) {
+        mbar_wait(bar_o, (c - 1) & 1);          // O += P_{c-1} V_{c-1} has completed: O and the P buffer are ours again
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < (TAIL ? 5 : 4); ++cc) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + L_OCOL + cc * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+          tmem_st_32x32b_x16(t_row + L_OCOL + cc * 16, v);
+        }
+        tmem_st_wait();
+      }
+      const float mscaled = m_new * p.scale_log2;
+      for (int j8 = 0; j8 < 8; ++j8) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + j8 * 32, v);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          e[j] = ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mscaled));
+          l_run += e[j];
+        }
+        uint8_t* atom = prow + (j8 >> 1) * (128 * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack2<BF16>(e[8 * i + 0], e[8 * i + 1]);
+          o.y = pack2<BF16>(e[8 * i + 2], e[8 * i + 3]);
+          o.z = pack2<BF16>(e[8 * i + 4], e[8 * i + 5]);
+          o.w = pack2<BF16>(e[8 * i + 6], e[8 * i + 7]);
+          const int chunk = ((j8 & 1) * 4 + i) ^ sw;
+          *reinterpret_cast<uint4*>(atom + chunk * 16) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    const long long out_row = q_row0 + r;
+    uint16_t* optr = reinterpret_cast<uint16_t*>(p.out) + out_row * p.D + head * p.hd;
+    const float inv = 1.0f / l_run;
+    mbar_wait(bar_o, (nchunk - 1) & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; ++c2) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + L_OCOL + c2 * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = pack2<BF16>(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+        o.y = pack2<BF16>(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+        o.z = pack2<BF16>(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+        o.w = pack2<BF16>(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+        *reinterpret_cast<uint4*>(optr + c2 * 32 + i * 8) = o;
+      }
+    }
+    if constexpr (TAIL) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_row + L_OCOL + 64, v);
+      tmem_ld_wait();
+      const int tail8 = (p.hd - 64) / 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (i >= tail8) break;
+        uint4 o;
+        o.x = pack2<BF16>(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+        o.y = pack2<BF16>(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+        o.z = pack2<BF16>(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+        o.w = pack2<BF16>(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+        *reinterpret_cast<uint4*>(optr + 64 + i * 8) = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool BF16, bool TAIL>
+int launch_long(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
+  auto kern = attn_long_kernel<BF16, TAIL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES));
+    attr_set = true;
+  }
+  B200_CHECK_CUDA(launch_pdl(kern, grid, dim3(kThreads), static_cast<size_t>(L_SMEM_BYTES), stream, m[0], m[1], m[2], m[3], p));
+  return B200_OK;
+}
+
 template <bool BF16, bool TAIL>
 int launch_tail(int mode, const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t s) {
   switch (mode) {
     case MODE_FULL: return launch_mode<BF16, TAIL, MODE_FULL>(m, p, grid, s);
     case MODE_PACKED: return launch_mode<BF16, TAIL, MODE_PACKED>(m, p, grid, s);
+    case MODE_CROSS: return launch_mode<BF16, TAIL, MODE_CROSS>(m, p, grid, s);
     default: return launch_mode<BF16, TAIL, MODE_TEMPORAL>(m, p, grid, s);
   }
 }
@@ -360,6 +605,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
 
   p.group = 1;
   p.gshift = 0;
+  p.k_head0 = H;
+  p.v_head0 = 2 * H;
+  p.kv_rows_per_batch = 0;
+  p.q_rows_per_batch = 1;
   auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
 
   CUtensorMap maps[4];
@@ -369,9 +618,28 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     const uint64_t dims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(3 * H), static_cast<uint64_t>(T)};
     const uint64_t str[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(3 * D) * 2};
     uint32_t kv_rows;
+    if (a.tokens > 256) {
+      B200_REQUIRE(a.tokens % 256 == 0, B200_ERR_UNSUPPORTED, "attention: spatial sequence length %d must be a multiple of 256", a.tokens);
+      p.Lk = 256;
+      p.tiles_per_seq = a.tokens / 128;
+      const uint32_t boxQ[3] = {64, 1, 128}, boxQt[3] = {16, 1, 128};
+      const uint32_t boxK[3] = {64, 1, 256}, boxKt[3] = {16, 1, 256};
+      B200_TRY(make_tmap_16bit(&maps[0], a.qkv, 3, dims, str, boxQ, TMAP_SW_128));
+      B200_TRY(make_tmap_16bit(&maps[2], a.qkv, 3, dims, str, boxK, TMAP_SW_128));
+      if (tail) {
+        B200_TRY(make_tmap_16bit(&maps[1], a.qkv, 3, dims, str, boxQt, TMAP_SW_32));
+        B200_TRY(make_tmap_16bit(&maps[3], a.qkv, 3, dims, str, boxKt, TMAP_SW_32));
+      } else {
+        maps[1] = maps[0];
+        maps[3] = maps[2];
+      }
+      const dim3 lgrid(a.batch * a.frames * p.tiles_per_seq, H);
+      if (a.bf16) return tail ? launch_long<true, true>(maps, p, lgrid, stream) : launch_long<true, false>(maps, p, lgrid, stream);
+      return tail ? launch_long<false, true>(maps, p, lgrid, stream) : launch_long<false, false>(maps, p, lgrid, stream);
+    }
     if (a.tokens >= 128) {
       B200_REQUIRE(a.tokens == 128 || a.tokens == 256, B200_ERR_UNSUPPORTED,
-                   "attention: spatial sequence length %d unsupported (<=64 power of two, 128, 256)", a.tokens);
+                   "attention: spatial sequence length %d unsupported (<=64 power of two, 128, 256, multiples of 256)", a.tokens);
       mode = MODE_FULL;
       p.Lk = a.tokens;
       p.tiles_per_seq = a.tokens / 128;
@@ -428,6 +696,46 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   }
   if (a.bf16) return tail ? launch_tail<true, true>(mode, maps, p, grid, stream) : launch_tail<true, false>(mode, maps, p, grid, stream);
   return tail ? launch_tail<false, true>(mode, maps, p, grid, stream) : launch_tail<false, false>(mode, maps, p, grid, stream);
+}
+
+int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream) {
+  B200_REQUIRE(a.batch > 0 && a.q_rows_per_batch > 0 && a.heads > 0, B200_ERR_SHAPE, "cross attention: bad shape");
+  B200_REQUIRE(a.head_dim == 64 || a.head_dim == 72 || a.head_dim == 80, B200_ERR_UNSUPPORTED,
+               "cross attention: head_dim %d unsupported (64, 72, 80)", a.head_dim);
+  B200_REQUIRE(a.kv_len >= 1 && a.kv_len <= 128, B200_ERR_UNSUPPORTED, "cross attention: %d keys per sample (1..128 built)", a.kv_len);
+  B200_REQUIRE(a.q_rows_per_batch % 128 == 0, B200_ERR_UNSUPPORTED, "cross attention: query rows per sample %d must be a multiple of 128",
+               a.q_rows_per_batch);
+  B200_REQUIRE(((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.kv) | reinterpret_cast<uintptr_t>(a.out)) & 15) == 0,
+               B200_ERR_ALIGN, "cross attention: q/kv/out must be 16-byte aligned");
+  B200_TRY(check_arch());
+  const int H = a.heads, hd = a.head_dim, D = H * hd;
+  const long long T = static_cast<long long>(a.batch) * a.q_rows_per_batch;
+  const long long R = static_cast<long long>(a.batch) * a.kv_len;
+  const bool tail = hd > 64;
+  AttnDev p{};
+  p.out = a.out; p.T = static_cast<int>(T); p.D = D; p.heads = H; p.hd = hd;
+  p.tokens = a.q_rows_per_batch; p.frames = 1; p.group = 1; p.gshift = 0; p.Lk = 128; p.tiles_per_seq = 1;
+  p.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
+  p.k_head0 = 0; p.v_head0 = H; p.kv_rows_per_batch = a.kv_len; p.q_rows_per_batch = a.q_rows_per_batch;
+  CUtensorMap maps[4];
+  const uint64_t qdims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(T)};
+  const uint64_t qstr[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(a.q_row_stride) * 2};
+  const uint64_t kdims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(2 * H), static_cast<uint64_t>(R)};
+  const uint64_t kstr[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(a.kv_row_stride) * 2};
+  const uint32_t box[3] = {64, 1, 128}, boxt[3] = {16, 1, 128};
+  B200_REQUIRE(a.q_row_stride >= D && a.kv_row_stride >= 2 * D && a.q_row_stride % 8 == 0 && a.kv_row_stride % 8 == 0, B200_ERR_SHAPE, "cross attention: bad row strides");
+  B200_TRY(make_tmap_16bit(&maps[0], a.q, 3, qdims, qstr, box, TMAP_SW_128));
+  B200_TRY(make_tmap_16bit(&maps[2], a.kv, 3, kdims, kstr, box, TMAP_SW_128));
+  if (tail) {
+    B200_TRY(make_tmap_16bit(&maps[1], a.q, 3, qdims, qstr, boxt, TMAP_SW_32));
+    B200_TRY(make_tmap_16bit(&maps[3], a.kv, 3, kdims, kstr, boxt, TMAP_SW_32));
+  } else {
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+  }
+  const dim3 grid(static_cast<unsigned>(T / 128), H);
+  if (a.bf16) return tail ? launch_tail<true, true>(MODE_CROSS, maps, p, grid, stream) : launch_tail<true, false>(MODE_CROSS, maps, p, grid, stream);
+  return tail ? launch_tail<false, true>(MODE_CROSS, maps, p, grid, stream) : launch_tail<false, false>(MODE_CROSS, maps, p, grid, stream);
 }
 
 }  // namespace b200

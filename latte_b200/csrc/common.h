@@ -96,10 +96,25 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 
+struct CrossAttnArgs {
+  const void* q;      // [batch * q_rows_per_batch, q_row_stride] 16-bit; queries are columns [head][head_dim] of each row
+  const void* kv;     // [batch * kv_len, kv_row_stride] 16-bit; columns [k: head][head_dim] then [v: head][head_dim]
+  void* out;          // [batch * q_rows_per_batch, heads*head_dim] 16-bit
+  int batch, q_rows_per_batch, kv_len;
+  int q_row_stride, kv_row_stride;  // elements
+  int heads, head_dim;
+  int bf16;
+};
+int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream);
+
 int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
                        int rows_per_batch, void* out16, int rows, int dim, int bf16, cudaStream_t stream);
 int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const float* b, const float* pos, float* out,
-                       int batch, int frames, int chans, int size, int patch, int dim, cudaStream_t stream);
+                       int batch, int frames, int chans, int size, int patch, int dim, int channels_first, cudaStream_t stream);
+int launch_t2v_mod(const float* tables, const float* ts, const float* final_table, const float* emb, float* mod, int batch,
+                   int nblocks, int dim, cudaStream_t stream);
+int launch_cast16(const float* in, void* out16, long long n, int bf16, cudaStream_t stream);
+int launch_fill(float* p, float v, long long n, cudaStream_t stream);
 // out[b][j] = act_out(W[j,:] . act_in(in[b,:]) + bias[j] (+ add[add_idx[b]][j]));  W fp32 (wbits=32) or 16-bit
 int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const float* in, float* out, int batch, int J,
                 int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx,
@@ -107,7 +122,7 @@ int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const flo
 int launch_timestep_freq(const long long* t, float* out, int batch, cudaStream_t stream);
 int launch_final_layer(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
                        const float* w, const float* b, float* out, int batch, int frames, int grid, int patch,
-                       int out_ch, int dim, cudaStream_t stream);
+                       int out_ch, int dim, int channels_first, cudaStream_t stream);
 int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, int out_ch, int guided_ch, int hw,
                        float scale, cudaStream_t stream);
 

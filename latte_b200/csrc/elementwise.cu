@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ pos, float* __restrict__ out,
                                                           int total_tokens, int frames, int chans, int size, int patch,
-                                                          int dim) {
+                                                          int dim, long long sb, long long sf, long long sc) {
   __shared__ float in[PE_TOK][K];
   const int grid = size / patch;
   const int N = grid * grid;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
       const int gh = n / grid, gw = n % grid;
       const int c = k / (patch * patch), ij = k % (patch * patch);
       const int ii = ij / patch, jj = ij % patch;
-      val = x[(((static_cast<size_t>(bsrc) * frames + f) * chans + c) * size + gh * patch + ii) * size + gw * patch + jj];
+      val = x[bsrc * sb + f * sf + c * sc + static_cast<long long>(gh * patch + ii) * size + gw * patch + jj];
     }
     in[tl][k] = val;
   }
@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(512) final_layer_kernel(const float* __restric
                                                           const float* __restrict__ scale, long long mod_bs,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           float* __restrict__ out, int total_tokens, int frames,
-                                                          int grid, int patch, int out_ch, int dim) {
+                                                          int grid, int patch, int out_ch, int dim, long long osb,
+                                                          long long osf, long long osc) {
   extern __shared__ float sw[];  // [n_out][dim]
   const int n_out = patch * patch * out_ch;
   for (int i = threadIdx.x; i < n_out * dim / 4; i += blockDim.x)
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(512) final_layer_kernel(const float* __restric
       const int c = lane % out_ch, pq = lane / out_ch;
       const int pi = pq / patch, qi = pq % patch;
       const int gh = n / grid, gw = n % grid;
-      out[((static_cast<size_t>(bf) * out_ch + c) * size + gh * patch + pi) * size + gw * patch + qi] = mine + __ldg(bias + lane);
+      out[(bf / frames) * osb + (bf % frames) * osf + c * osc + static_cast<long long>(gh * patch + pi) * size + gw * patch + qi] = mine + __ldg(bias + lane);
     }
   }
 }
@@ -343,7 +344,73 @@ __global__ void cfg_combine_kernel(float* __restrict__ out, int half_batch, long
   }
 }
 
+// ---------------------------------------------------------------------------------- LatteT2V helpers
+// mod[b][blk][j][:] = table[blk][j][:] + ts[b][j][:]  (scale_shift_table + adaln_single(t), latte_t2v.py:296-298), and
+// the output head's table[2][D] + embedded_timestep (latte_t2v.py:919-921) in the last slot.
+__global__ void t2v_mod_kernel(const float* __restrict__ tables, const float* __restrict__ ts, const float* __restrict__ final_table,
+                               const float* __restrict__ emb, float* __restrict__ mod, int batch, int nblocks, int dim) {
+  const long long per_b = static_cast<long long>(nblocks) * 6 * dim + 2 * dim;
+  const long long total = per_b * batch;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_b);
+    const long long w = i % per_b;
+    float v;
+    if (w < static_cast<long long>(nblocks) * 6 * dim) {
+      v = tables[w] + ts[static_cast<long long>(b) * 6 * dim + (w % (6 * dim))];
+    } else {
+      const long long u = w - static_cast<long long>(nblocks) * 6 * dim;
+      v = final_table[u] + emb[static_cast<long long>(b) * dim + (u % dim)];
+    }
+    mod[i] = v;
+  }
+}
+
+template <bool BF16>
+__global__ void cast16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack2<BF16>(v.x, v.y), pack2<BF16>(v.z, v.w));
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+
 }  // namespace
+
+int launch_t2v_mod(const float* tables, const float* ts, const float* final_table, const float* emb, float* mod, int batch,
+                   int nblocks, int dim, cudaStream_t stream) {
+  const long long total = (static_cast<long long>(nblocks) * 6 * dim + 2 * dim) * batch;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  t2v_mod_kernel<<<blocks, 256, 0, stream>>>(tables, ts, final_table, emb, mod, batch, nblocks, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_cast16(const float* in, void* out16, long long n, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(n % 4 == 0, B200_ERR_SHAPE, "cast16: element count %lld must be a multiple of 4", n);
+  const long long n4 = n / 4;
+  int blocks = static_cast<int>((n4 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (bf16) cast16_kernel<true><<<blocks, 256, 0, stream>>>(in, reinterpret_cast<uint16_t*>(out16), n4);
+  else cast16_kernel<false><<<blocks, 256, 0, stream>>>(in, reinterpret_cast<uint16_t*>(out16), n4);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_fill(float* p, float v, long long n, cudaStream_t stream) {
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  fill_kernel<<<blocks, 256, 0, stream>>>(p, v, n);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
 
 int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
                        int rows_per_batch, void* out16, int rows, int dim, int bf16, cudaStream_t stream) {
@@ -369,7 +436,7 @@ int launch_ln_modulate(const float* x, const float* shift, const float* scale, l
 }
 
 int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const float* b, const float* pos, float* out,
-                       int batch, int frames, int chans, int size, int patch, int dim, cudaStream_t stream) {
+                       int batch, int frames, int chans, int size, int patch, int dim, int channels_first, cudaStream_t stream) {
   const int K = chans * patch * patch;
   B200_REQUIRE(size % patch == 0, B200_ERR_SHAPE, "patch_embed: size %d not divisible by patch %d", size, patch);
   B200_REQUIRE(K == 4 || K == 8 || K == 16 || K == 32 || K == 64, B200_ERR_UNSUPPORTED,
@@ -377,7 +444,12 @@ int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const fl
   const int grid = size / patch;
   const int total = batch * frames * grid * grid;
   const int blocks = (total + PE_TOK - 1) / PE_TOK;
-#define B200_PE(KK) patch_embed_kernel<KK><<<blocks, 256, 0, stream>>>(x, x_batch_mod, w, b, pos, out, total, frames, chans, size, patch, dim)
+  // x is [b][f][c][h][w] (Latte, latte.py:329) or [b][c][f][h][w] (LatteT2V, latte_t2v.py:731)
+  const long long plane = static_cast<long long>(size) * size;
+  const long long sb = plane * chans * frames;
+  const long long sf = channels_first ? plane : plane * chans;
+  const long long sc = channels_first ? plane * frames : plane;
+#define B200_PE(KK) patch_embed_kernel<KK><<<blocks, 256, 0, stream>>>(x, x_batch_mod, w, b, pos, out, total, frames, chans, size, patch, dim, sb, sf, sc)
   switch (K) {
     case 4: B200_PE(4); break;
     case 8: B200_PE(8); break;
@@ -427,7 +499,7 @@ int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const flo
 
 int launch_final_layer(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
                        const float* w, const float* b, float* out, int batch, int frames, int grid, int patch,
-                       int out_ch, int dim, cudaStream_t stream) {
+                       int out_ch, int dim, int channels_first, cudaStream_t stream) {
   const int n_out = patch * patch * out_ch;
   B200_REQUIRE(n_out <= FL_MAXO && dim % 4 == 0 && dim <= FL_MAXV * 128, B200_ERR_SHAPE,
                "final_layer: p*p*Cout = %d must be <= %d, dim %d <= %d", n_out, FL_MAXO, dim, FL_MAXV * 128);
@@ -444,8 +516,12 @@ int launch_final_layer(const float* x, const float* shift, const float* scale, l
   const int warps = 16;
   int blocks = (total + warps - 1) / warps;
   if (blocks > sms) blocks = sms;
+  const long long plane = static_cast<long long>(grid * patch) * (grid * patch);
+  const long long sb = plane * out_ch * frames;
+  const long long sf = channels_first ? plane : plane * out_ch;
+  const long long sc = channels_first ? plane * frames : plane;
   final_layer_kernel<<<blocks, warps * 32, smem, stream>>>(x, shift, scale, mod_batch_stride, w, b, out, total, frames,
-                                                            grid, patch, out_ch, dim);
+                                                            grid, patch, out_ch, dim, sb, sf, sc);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -10,7 +10,9 @@ def get_models(args):
     if "LatteIMG" in name:
         raise NotImplementedError("LatteIMG (video+image joint training variant, models/latte_img.py) is not built")
     if "LatteT2V" in name:
-        raise NotImplementedError("LatteT2V (models/latte_t2v.py) is not built yet")
+        # models/__init__.py:40-41
+        from ..latte_t2v import LatteT2V
+        return LatteT2V.from_pretrained(args.pretrained_model_path, subfolder="transformer", video_length=args.video_length)
     if "Latte" in name:
         # same keyword set as the reference factory (models/__init__.py:42-49)
         return Latte_models[name](input_size=args.latent_size, num_classes=args.num_classes,

@@ -81,3 +81,16 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, rows_
                                           rows_per_batch, out.data_ptr(), x.shape[0], x.shape[1], _dt(out), _stream(x))
     _lib.check(rc, "b200_ln_modulate")
     return out
+
+
+def cross_attention(q: torch.Tensor, kv: torch.Tensor, batch: int, q_rows_per_batch: int, kv_len: int, heads: int) -> torch.Tensor:
+    """q [batch*q_rows, heads*hd] 16-bit; kv [batch*kv_len, 2*heads*hd] 16-bit ([k | v]); kv_len <= 128 -> out like q."""
+    _need_cuda(q, kv)
+    assert q.is_contiguous() and kv.is_contiguous() and q.dtype == kv.dtype
+    D = q.shape[1]
+    out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        rc = _lib.load().b200_cross_attention(q.data_ptr(), kv.data_ptr(), out.data_ptr(), batch, q_rows_per_batch, kv_len,
+                                              q.shape[1], kv.shape[1], heads, D // heads, _dt(q), _stream(q))
+    _lib.check(rc, "b200_cross_attention")
+    return out

@@ -79,6 +79,7 @@ def _attn_ref(qkv, batch, frames, tokens, heads, temporal):
     (2, 16, 256, 6, 64, False), (2, 16, 256, 6, 64, True),        # S/2
     (1, 4, 128, 2, 64, False), (2, 4, 64, 8, 72, False), (1, 2, 16, 2, 64, False),   # N = 128, packed N = 64, 16
     (2, 8, 64, 2, 64, True), (4, 4, 64, 8, 72, True), (1, 32, 32, 2, 80, True),      # F = 8, 4, 32; head_dim 80
+    (1, 2, 512, 2, 64, False), (1, 2, 1024, 4, 72, False), (2, 16, 1024, 2, 72, True),  # LatteT2V @512px: N = 1024 (online softmax)
 ])
 def test_attention(dev, dt, case):
     from latte_b200 import ops
@@ -113,7 +114,7 @@ def test_attention_properties(dev):
 def test_attention_rejects_unsupported(dev):
     from latte_b200 import ops
     with pytest.raises(RuntimeError, match="UNSUPPORTED"):
-        ops.attention(torch.zeros(1024, 3 * 2 * 64, device=dev, dtype=torch.float16), 1, 1, 1024, 2, False)   # N = 1024 not built yet
+        ops.attention(torch.zeros(384, 3 * 2 * 64, device=dev, dtype=torch.float16), 1, 1, 384, 2, False)   # N = 384: not 2^k <= 256 nor a multiple of 256
     with pytest.raises(RuntimeError, match="UNSUPPORTED"):
         ops.attention(torch.zeros(256, 3 * 2 * 48, device=dev, dtype=torch.float16), 1, 1, 256, 2, False)     # head_dim 48
 
@@ -131,3 +132,21 @@ def test_ln_modulate(dev, dt, D):
     xn = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
     bidx = torch.arange(rows, device=dev) // (rows // B)
     _close(ops.ln_modulate(x, shift, scale, rows // B, dt), xn * (1 + scale[bidx]) + shift[bidx], TOL[dt])
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", [(2, 256, 120, 4, 72), (1, 1024, 20, 2, 64), (3, 128, 128, 2, 80), (2, 512, 1, 4, 72)])
+def test_cross_attention(dev, dt, case):
+    """diffusers Attention (attn2) with text keys (latte_t2v.py:862-870): q from the video tokens, k/v from <=128 text tokens."""
+    from latte_b200 import ops
+    b, rows, L, h, hd = case
+    D = h * hd
+    g = torch.Generator().manual_seed(rows + L)
+    q = (torch.randn(b * rows, D, generator=g) * 1.5).to(dev).to(dt)
+    kv = (torch.randn(b * L, 2 * D, generator=g) * 1.5).to(dev).to(dt)
+    out = ops.cross_attention(q, kv, b, rows, L, h)
+    qf = q.float().reshape(b, rows, h, hd).transpose(1, 2)
+    kf = kv.float()[:, :D].reshape(b, L, h, hd).transpose(1, 2)
+    vf = kv.float()[:, D:].reshape(b, L, h, hd).transpose(1, 2)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * hd ** -0.5, dim=-1) @ vf).transpose(1, 2).reshape(b * rows, D)
+    _close(out, ref, TOL[dt])
