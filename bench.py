@@ -141,6 +141,40 @@ def run_reference(args):
     }), flush=True)
 
 
+def run_t2v(args):
+    """Secondary measurement (BASELINE configs[3]): one LatteT2V denoising step at 16x512x512, CFG pair (B_model = 2),
+    120 synthetic T5 tokens, seeded synthetic weights.  Prints one JSON line; not the round's bench line."""
+    from latte_b200 import LatteT2V
+    from oracle import t2v_oracle as T
+    dev = torch.device("cuda", 0)
+    cfg = T.T2VConfig()
+    net = LatteT2V()
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.05 if prm.dim() == 1 else 1.0 / prm.shape[-1] ** 0.5))
+    net = net.to(dev).half().eval()
+    x, t, text = T.make_inputs(cfg, 2, 120, 1)
+    xd, td, txd = x.to(dev), t.to(dev), text.to(dev)
+    W, K = max(args.warmup, 3), args.steps
+    with torch.no_grad():
+        for _ in range(W):
+            net(xd, td, encoder_hidden_states=txd, return_dict=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            net(xd, td, encoder_hidden_states=txd, return_dict=False)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    fl = 2 * T.algorithmic_flops_per_video(cfg, 120)
+    print(json.dumps({"metric": "denoising-steps/sec LatteT2V 16x512x512 (CFG pair per step)", "value": 1000.0 / ms, "unit": "steps/s",
+                      "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "dtype": "fp16", "data": "synthetic",
+                      "config": {"workload": "LatteT2V (Latte-1 config) 16x512x512, B_model=2, 120 text tokens",
+                                 "algorithmic_tflop_per_step": fl / 1e12, "step_tflops_achieved": fl / (ms * 1e-3) / 1e12}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,7 +184,11 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--model", default="Latte-XL/2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="latte", choices=["latte", "t2v"],
+                    help="latte = BASELINE configs[1] (the bench line); t2v = configs[3] denoiser step, a secondary measurement")
     args = ap.parse_args()
+    if args.workload == "t2v":
+        return run_t2v(args)
     if args.impl == "reference":
         return run_reference(args)
 
