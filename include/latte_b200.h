@@ -39,7 +39,7 @@ enum {
   B200_ERR_UNSUPPORTED = -7
 };
 enum { B200_FP16 = 0, B200_BF16 = 1 };
-enum { B200_EPI_BIAS = 0, B200_EPI_BIAS_GELU = 1, B200_EPI_GATE_RESIDUAL = 2 };
+enum { B200_EPI_BIAS = 0, B200_EPI_BIAS_GELU = 1, B200_EPI_GATE_RESIDUAL = 2, B200_EPI_BIAS_ADD16 = 3 };
 
 /* Model geometry: the ctor arguments of reference `Latte` (models/latte.py:208-223). */
 typedef struct B200LatteShape {
@@ -155,6 +155,43 @@ B200_API int b200_t2v_forward(const B200T2VShape* shape, const B200T2VWeights* w
  * 16-bit (columns [k heads][v heads]), kv_len <= 128 keys per sample; out [rows, heads*head_dim] 16-bit.          */
 B200_API int b200_cross_attention(const void* q, const void* kv, void* out, int batch, int q_rows_per_batch, int kv_len,
                                   int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream);
+
+/* ---- AutoencoderKL.decode (diffusers 0.24.0 SD-VAE decoder; reference call sites sample/sample.py:114,
+ * sample_ddp.py:167, pipeline_latte.py:758,771).  Parity UNPINNED (diffusers absent offline).
+ * Conv weights are 16-bit, repacked from OIHW to [Cout][ky*3+kx][Cin]; 1x1 shortcuts are [Cout][Cin]. */
+typedef struct B200VaeResnet {
+  const float* gn1_g; const float* gn1_b; const void* conv1_w16; const float* conv1_b;
+  const float* gn2_g; const float* gn2_b; const void* conv2_w16; const float* conv2_b;
+  const void* short_w16; const float* short_b;   /* NULL when cin == cout */
+  int32_t cin, cout;
+} B200VaeResnet;
+
+typedef struct B200VaeDecoder {
+  int32_t latent_channels;      /* 4 */
+  int32_t layers_per_block;     /* resnets per up block = layers_per_block + 1 (3) */
+  int32_t n_up;                 /* up blocks (4) */
+  int32_t up_channels[4];       /* output channels of the up blocks: 512, 512, 256, 128 */
+  int32_t groups;               /* 32 */
+  int32_t dtype;
+  float eps;                    /* 1e-6 */
+  const float* pq_w; const float* pq_b;             /* post_quant_conv [C,C], NULL to skip */
+  const float* conv_in_w; const float* conv_in_b;   /* [C0, C, 3, 3] fp32 */
+  B200VaeResnet mid[2];
+  const float* attn_gn_g; const float* attn_gn_b;
+  const void* attn_q_w16; const float* attn_q_b; const void* attn_k_w16; const float* attn_k_b;
+  const void* attn_v_w16;                           /* v bias is folded into attn_o_b by the packer */
+  const void* attn_o_w16; const float* attn_o_b;
+  B200VaeResnet up[12];                             /* [block][resnet] row-major, 3 per block */
+  const void* ups_w16[3]; const float* ups_b[3];    /* upsampler convs of blocks 0..n_up-2 */
+  const float* norm_out_g; const float* norm_out_b;
+  const void* conv_out_w16; const float* conv_out_b; /* rows padded to 32: [32][9][C_last], bias [32] */
+  int32_t out_channels;                             /* 3 */
+} B200VaeDecoder;
+
+B200_API size_t b200_vae_workspace_bytes(const B200VaeDecoder* d, int n_img, int h, int w);
+/* z [n_img, C, h, w] fp32 (already divided by scaling_factor, as the callers do) -> out [n_img, 3, 8h, 8w] fp32 */
+B200_API int b200_vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, float* out, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* Thread-local description of the last failure on this thread ("" if none). */
 B200_API const char* b200_last_error(void);

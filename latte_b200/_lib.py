@@ -51,6 +51,24 @@ class T2VWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in T2V_WEIGHT_FIELDS]
 
 
+class VaeResnet(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gn1_g", "gn1_b", "conv1_w16", "conv1_b", "gn2_g", "gn2_b", "conv2_w16", "conv2_b",
+                                          "short_w16", "short_b")] + [("cin", C.c_int32), ("cout", C.c_int32)]
+
+
+class VaeDecoder(C.Structure):
+    _fields_ = [("latent_channels", C.c_int32), ("layers_per_block", C.c_int32), ("n_up", C.c_int32), ("up_channels", C.c_int32 * 4),
+                ("groups", C.c_int32), ("dtype", C.c_int32), ("eps", C.c_float),
+                ("pq_w", C.c_void_p), ("pq_b", C.c_void_p), ("conv_in_w", C.c_void_p), ("conv_in_b", C.c_void_p),
+                ("mid", VaeResnet * 2),
+                ("attn_gn_g", C.c_void_p), ("attn_gn_b", C.c_void_p), ("attn_q_w16", C.c_void_p), ("attn_q_b", C.c_void_p),
+                ("attn_k_w16", C.c_void_p), ("attn_k_b", C.c_void_p), ("attn_v_w16", C.c_void_p), ("attn_o_w16", C.c_void_p),
+                ("attn_o_b", C.c_void_p),
+                ("up", VaeResnet * 12), ("ups_w16", C.c_void_p * 3), ("ups_b", C.c_void_p * 3),
+                ("norm_out_g", C.c_void_p), ("norm_out_b", C.c_void_p), ("conv_out_w16", C.c_void_p), ("conv_out_b", C.c_void_p),
+                ("out_channels", C.c_int32)]
+
+
 EXPORTS = {
     "b200_last_error": (C.c_char_p, []),
     "b200_abi_version": (C.c_int, []),
@@ -69,6 +87,9 @@ EXPORTS = {
                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200_cross_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b200_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDecoder), C.c_int, C.c_int, C.c_int]),
+    "b200_vae_decode": (C.c_int, [C.POINTER(VaeDecoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
     "b200_profile_enable": (None, [C.c_int]),
     "b200_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }

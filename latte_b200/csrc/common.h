@@ -83,6 +83,12 @@ struct GemmArgs {
   const float* row_add; // optional [period, N] fp32 added to resid rows: row_add[((row / row_add_div) % row_add_period) * N + col]
   int row_add_div, row_add_period;
   int block_n;          // 0 = auto
+  const void* add16;    // EPI_BIAS_ADD16: [M, N] 16-bit tensor added to the result (resnet shortcut)
+  // implicit-GEMM convolution (conv_taps > 0): A is an NHWC activation [conv_n, conv_h, conv_w, conv_c] (16-bit), M =
+  // conv_n*conv_h*conv_w output pixels, K = conv_taps * conv_c with W laid out [N][tap][c]; tap t reads the input pixel
+  // shifted by (conv_dx[t], conv_dy[t]) with zero padding (TMA out-of-bounds fill).
+  int conv_taps, conv_n, conv_h, conv_w, conv_c;
+  int conv_dx[9], conv_dy[9];
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 
@@ -125,5 +131,14 @@ int launch_final_layer(const float* x, const float* shift, const float* scale, l
                        int out_ch, int dim, int channels_first, cudaStream_t stream);
 int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, int out_ch, int guided_ch, int hw,
                        float scale, cudaStream_t stream);
+
+// VAE passes (vae.cu)
+int launch_gn(const void* x, float* part, const float* gamma, const float* beta, void* y, int n_img, int hw, int C, int groups,
+              float eps, int do_silu, int bf16, cudaStream_t stream);
+int launch_upsample2x(const void* x, void* y, int n_img, int h, int w, int C, cudaStream_t stream);
+int launch_conv_in(const float* z, const float* pq_w, const float* pq_b, const float* w, const float* b, void* y, int n_img, int C,
+                   int h, int wd, int Cout, int bf16, cudaStream_t stream);
+int launch_softmax_rows(const float* s, void* p, int rows, int n, float scale, int bf16, cudaStream_t stream);
+int launch_to_nchw(const void* x, float* y, int n_img, int c, int cpad, int hw, int bf16, cudaStream_t stream);
 
 }  // namespace b200

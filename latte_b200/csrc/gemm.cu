@@ -74,6 +74,10 @@ struct GemmDev {
   int rows_per_batch;
   const float* row_add;
   int row_add_div, row_add_period;
+  const uint16_t* add16;
+  // implicit-GEMM convolution: see GemmArgs
+  int conv_taps, conv_cblk, conv_h, conv_w, conv_bw, conv_bh;
+  int conv_dx[9], conv_dy[9];
   int dbg;  // timing experiments only (results are wrong when set): bit0 = no operand TMA, bit1 = no MMA issue, bit2 = no 16-bit epilogue
 };
 
@@ -163,7 +167,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // both CTAs' bytes complete on the LEADER's barrier (cta_group::2 loads may signal the pair leader)
             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
             else mbar_arrive_cluster(full_leader);
-            tma_load_2d_pair(sa, &tmA, full_leader, kb * BK, m_blk * BM);
+            if (p.conv_taps > 0) {
+              // implicit GEMM: this k-block is channels [cb*64, +64) of filter tap `tap`; the A tile is the tile's
+              // conv_bh x conv_bw pixel patch shifted by the tap offset (borders zero-filled by TMA)
+              const int tap = kb / p.conv_cblk, cb = kb % p.conv_cblk;
+              const int pix0 = m_blk * BM;
+              const int hw = p.conv_h * p.conv_w;
+              const int img = pix0 / hw, rem = pix0 % hw;
+              tma_load_4d_pair(sa, &tmA, full_leader, cb * BK, rem % p.conv_w + p.conv_dx[tap], rem / p.conv_w + p.conv_dy[tap], img);
+            } else {
+              tma_load_2d_pair(sa, &tmA, full_leader, kb * BK, m_blk * BM);
+            }
             tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -371,9 +385,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int it = 0; it < 8; ++it) {
               const int rl = it * 16 + row_b0;
               const int row = m0 + rl;
-              if (row < p.M)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(row) * p.N + col) =
-                    *reinterpret_cast<const uint4*>(buf + rl * 128 + ((ch_b ^ (rl & 7)) << 4));
+              if (row < p.M) {
+                uint4 val = *reinterpret_cast<const uint4*>(buf + rl * 128 + ((ch_b ^ (rl & 7)) << 4));
+                if constexpr (EPI == B200_EPI_BIAS_ADD16) {   // + shortcut, both already rounded to 16 bits like the reference
+                  const uint4 rs = __ldg(reinterpret_cast<const uint4*>(p.add16 + static_cast<size_t>(row) * p.N + col));
+                  const float2 a0 = unpack2<BF16>(val.x), a1 = unpack2<BF16>(val.y), a2 = unpack2<BF16>(val.z), a3 = unpack2<BF16>(val.w);
+                  const float2 r0 = unpack2<BF16>(rs.x), r1 = unpack2<BF16>(rs.y), r2 = unpack2<BF16>(rs.z), r3 = unpack2<BF16>(rs.w);
+                  val.x = pack2<BF16>(a0.x + r0.x, a0.y + r0.y);
+                  val.y = pack2<BF16>(a1.x + r1.x, a1.y + r1.y);
+                  val.z = pack2<BF16>(a2.x + r2.x, a2.y + r2.y);
+                  val.w = pack2<BF16>(a3.x + r3.x, a3.y + r3.y);
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(row) * p.N + col) = val;
+              }
             }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");   // staging tile drained: safe to refill
@@ -414,6 +438,7 @@ int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     case B200_EPI_BIAS: return launch_one<BN, B200_EPI_BIAS, BF16>(tmA, tmB, tmX, p, grid, s);
     case B200_EPI_BIAS_GELU: return launch_one<BN, B200_EPI_BIAS_GELU, BF16>(tmA, tmB, tmX, p, grid, s);
     case B200_EPI_GATE_RESIDUAL: return launch_one<BN, B200_EPI_GATE_RESIDUAL, BF16>(tmA, tmB, tmX, p, grid, s);
+    case B200_EPI_BIAS_ADD16: return launch_one<BN, B200_EPI_BIAS_ADD16, BF16>(tmA, tmB, tmX, p, grid, s);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return B200_ERR_UNSUPPORTED;
@@ -428,6 +453,7 @@ int launch_bn(int bf16, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
 int pick_block_n(int M, int N, int sms) {
   // minimise waves x per-tile time.  The kernel is bound by L2->SM operand bytes, not MMA cycles, so a tile costs
   // ~ (A bytes + W/2 bytes per k-block per CTA) = 128 + BN/2 rather than BN (measured: r01 microbench, profiles/).
+  if (N <= 128) return 128;   // narrow outputs (e.g. the VAE's 3-channel conv_out padded to 32): smallest tile that covers N
   const int cand[3] = {256, 192, 128};
   int best = 128;
   double best_cost = 1e300;
@@ -446,8 +472,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   B200_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, B200_ERR_SHAPE, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   B200_REQUIRE(a.K % BK == 0, B200_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", a.K, BK);
   B200_REQUIRE(a.N % 32 == 0, B200_ERR_SHAPE, "gemm: N=%d must be a multiple of 32", a.N);
-  B200_REQUIRE(a.epilogue == B200_EPI_BIAS || a.epilogue == B200_EPI_BIAS_GELU || a.epilogue == B200_EPI_GATE_RESIDUAL,
+  B200_REQUIRE(a.epilogue == B200_EPI_BIAS || a.epilogue == B200_EPI_BIAS_GELU || a.epilogue == B200_EPI_GATE_RESIDUAL ||
+                   a.epilogue == B200_EPI_BIAS_ADD16,
                B200_ERR_UNSUPPORTED, "gemm: unknown epilogue %d", a.epilogue);
+  B200_REQUIRE(a.epilogue != B200_EPI_BIAS_ADD16 || (a.add16 && (reinterpret_cast<uintptr_t>(a.add16) & 15) == 0), B200_ERR_ALIGN,
+               "gemm: add16 tensor missing or unaligned");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
                B200_ERR_ALIGN, "gemm: A and W must be 16-byte aligned");
   const bool resid = a.epilogue == B200_EPI_GATE_RESIDUAL;
@@ -469,11 +498,28 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   B200_REQUIRE(bn == 128 || bn == 192 || bn == 256, B200_ERR_UNSUPPORTED, "gemm: block_n must be 128, 192 or 256 (got %d)", bn);
 
   CUtensorMap tmA, tmB, tmX;
+  int conv_bw = 0, conv_bh = 0;
   {
-    const uint64_t dimsA[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.M)};
-    const uint64_t strA[1] = {static_cast<uint64_t>(a.K) * 2};
-    const uint32_t boxA[2] = {BK, BM};
-    B200_TRY(make_tmap_16bit(&tmA, a.A, 2, dimsA, strA, boxA, TMAP_SW_128));
+    if (a.conv_taps > 0) {
+      B200_REQUIRE(a.conv_taps <= 9 && a.conv_c % BK == 0 && a.K == a.conv_taps * a.conv_c &&
+                       a.M == a.conv_n * a.conv_h * a.conv_w,
+                   B200_ERR_SHAPE, "conv: inconsistent geometry (taps %d, C %d, K %d, M %d)", a.conv_taps, a.conv_c, a.K, a.M);
+      conv_bw = a.conv_w >= BM ? BM : a.conv_w;
+      conv_bh = BM / conv_bw;
+      B200_REQUIRE(BM % conv_bw == 0 && a.conv_w % conv_bw == 0 && a.conv_h % conv_bh == 0, B200_ERR_UNSUPPORTED,
+                   "conv: %dx%d feature map cannot be tiled by 128-pixel patches", a.conv_h, a.conv_w);
+      const uint64_t dimsA[4] = {static_cast<uint64_t>(a.conv_c), static_cast<uint64_t>(a.conv_w), static_cast<uint64_t>(a.conv_h),
+                                 static_cast<uint64_t>(a.conv_n)};
+      const uint64_t strA[3] = {static_cast<uint64_t>(a.conv_c) * 2, static_cast<uint64_t>(a.conv_c) * 2 * a.conv_w,
+                                static_cast<uint64_t>(a.conv_c) * 2 * a.conv_w * a.conv_h};
+      const uint32_t boxA[4] = {BK, static_cast<uint32_t>(conv_bw), static_cast<uint32_t>(conv_bh), 1};
+      B200_TRY(make_tmap_16bit(&tmA, a.A, 4, dimsA, strA, boxA, TMAP_SW_128));
+    } else {
+      const uint64_t dimsA[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.M)};
+      const uint64_t strA[1] = {static_cast<uint64_t>(a.K) * 2};
+      const uint32_t boxA[2] = {BK, BM};
+      B200_TRY(make_tmap_16bit(&tmA, a.A, 2, dimsA, strA, boxA, TMAP_SW_128));
+    }
     const uint64_t dimsB[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N)};
     const uint64_t strB[1] = {static_cast<uint64_t>(a.K) * 2};
     const uint32_t boxB[2] = {BK, static_cast<uint32_t>(bn / 2)};   // each CTA of the pair fetches half and multicasts it
@@ -499,6 +545,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.row_add = a.row_add;
   p.row_add_div = a.row_add_div > 0 ? a.row_add_div : 1;
   p.row_add_period = a.row_add_period > 0 ? a.row_add_period : 1;
+  p.add16 = static_cast<const uint16_t*>(a.add16);
+  p.conv_taps = a.conv_taps;
+  p.conv_cblk = a.conv_taps > 0 ? a.conv_c / BK : 0;
+  p.conv_h = a.conv_h; p.conv_w = a.conv_w; p.conv_bw = conv_bw; p.conv_bh = conv_bh;
+  for (int i = 0; i < 9; ++i) { p.conv_dx[i] = a.conv_dx[i]; p.conv_dy[i] = a.conv_dy[i]; }
   {
     const char* e = getenv("B200_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;

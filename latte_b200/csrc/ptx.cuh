@@ -137,6 +137,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // same, destination given as a raw shared::cluster address (may be the PEER CTA's shared memory: the pair leader
 // fetches both CTAs' operands so that no cross-SM handshake sits in the pipeline's critical loop)
 __device__ __forceinline__ void tma_load_2d_pair_raw(uint32_t dst_cluster_addr, const CUtensorMap* m, uint32_t bar_cluster_addr,

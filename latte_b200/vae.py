@@ -1,0 +1,215 @@
+"""`AutoencoderKL` — the decode half of the SD-VAE the reference samplers call once after the loop
+(`vae.decode(samples / 0.18215).sample`, sample/sample.py:114, sample_ddp.py:167, pipeline_latte.py:758,771), backed by
+TMA implicit-GEMM convolutions on the tcgen05 GEMM kernel (`b200_vae_decode`).  Parameter names follow the diffusers
+0.24.0 `AutoencoderKL` state dict (decoder.* and post_quant_conv.*; encoder keys in a checkpoint are ignored), so
+`vae/diffusion_pytorch_model.safetensors` loads unchanged.  **Parity unpinned** (diffusers absent offline).  No CPU path;
+`encode` is not built (training data path)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class _Resnet(nn.Module):
+    def __init__(self, cin, cout, groups):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-6)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-6)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.conv_shortcut = nn.Conv2d(cin, cout, 1)
+
+
+class _Attention(nn.Module):
+    def __init__(self, c, groups):
+        super().__init__()
+        self.group_norm = nn.GroupNorm(groups, c, eps=1e-6)
+        self.to_q = nn.Linear(c, c)
+        self.to_k = nn.Linear(c, c)
+        self.to_v = nn.Linear(c, c)
+        self.to_out = nn.ModuleList([nn.Linear(c, c), nn.Dropout(0.0)])
+
+
+class _Mid(nn.Module):
+    def __init__(self, c, groups):
+        super().__init__()
+        self.attentions = nn.ModuleList([_Attention(c, groups)])
+        self.resnets = nn.ModuleList([_Resnet(c, c, groups), _Resnet(c, c, groups)])
+
+
+class _Upsampler(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+
+class _UpBlock(nn.Module):
+    def __init__(self, cin, cout, n, groups, add_upsample):
+        super().__init__()
+        self.resnets = nn.ModuleList([_Resnet(cin if i == 0 else cout, cout, groups) for i in range(n)])
+        if add_upsample:
+            self.upsamplers = nn.ModuleList([_Upsampler(cout)])
+
+
+class _Decoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        up = tuple(reversed(cfg.block_out_channels))
+        g = cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.latent_channels, up[0], 3, padding=1)
+        self.mid_block = _Mid(up[0], g)
+        blocks, cin = [], up[0]
+        for i, co in enumerate(up):
+            blocks.append(_UpBlock(cin, co, cfg.layers_per_block + 1, g, i + 1 < len(up)))
+            cin = co
+        self.up_blocks = nn.ModuleList(blocks)
+        self.conv_norm_out = nn.GroupNorm(g, up[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(up[-1], cfg.out_channels, 3, padding=1)
+
+
+class DecoderOutput(SimpleNamespace):
+    pass
+
+
+class AutoencoderKL(nn.Module):
+    def __init__(self, in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 latent_channels=4, norm_num_groups=32, scaling_factor=0.18215, **unused):
+        super().__init__()
+        self.config = SimpleNamespace(in_channels=in_channels, out_channels=out_channels, block_out_channels=tuple(block_out_channels),
+                                      layers_per_block=layers_per_block, latent_channels=latent_channels,
+                                      norm_num_groups=norm_num_groups, scaling_factor=scaling_factor)
+        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        self.decoder = _Decoder(self.config)
+        self.compute_dtype = torch.float16
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+
+    @property
+    def dtype(self):
+        return self.post_quant_conv.weight.dtype
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, torch_dtype=None, **kw):
+        root = os.path.join(path, subfolder) if subfolder else path
+        with open(os.path.join(root, "config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        model = cls(**cfg)
+        st = os.path.join(root, "diffusion_pytorch_model.safetensors")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(root, "diffusion_pytorch_model.bin"), map_location="cpu")
+        own = model.state_dict()
+        model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)   # encoder / quant_conv keys are not used by decode
+        return model.to(torch_dtype) if torch_dtype is not None else model
+
+    def encode(self, *a, **k):
+        raise NotImplementedError("AutoencoderKL.encode (training data path) is not built")
+
+    # ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _pack(self):
+        ver = sum(p._version for p in self.parameters())
+        w0 = self.post_quant_conv.weight
+        key = (ver, w0.data_ptr(), w0.device, w0.dtype, self.compute_dtype)
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        dev, c = w0.device, self.config
+        od = w0.dtype if w0.dtype in (torch.float16, torch.bfloat16) else self.compute_dtype
+        keep = []
+
+        def f32(t):
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def conv16(wt):  # OIHW -> [O][ky*3+kx][I]
+            t = wt.detach().permute(0, 2, 3, 1).reshape(wt.shape[0], -1).to(device=dev, dtype=od).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def lin16(wt):
+            t = wt.detach().reshape(wt.shape[0], -1).to(device=dev, dtype=od).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def resnet(r):
+            s = _lib.VaeResnet()
+            s.gn1_g, s.gn1_b, s.conv1_w16, s.conv1_b = f32(r.norm1.weight), f32(r.norm1.bias), conv16(r.conv1.weight), f32(r.conv1.bias)
+            s.gn2_g, s.gn2_b, s.conv2_w16, s.conv2_b = f32(r.norm2.weight), f32(r.norm2.bias), conv16(r.conv2.weight), f32(r.conv2.bias)
+            s.cin, s.cout = r.conv1.weight.shape[1], r.conv1.weight.shape[0]
+            if hasattr(r, "conv_shortcut"):
+                s.short_w16, s.short_b = lin16(r.conv_shortcut.weight), f32(r.conv_shortcut.bias)
+            else:
+                s.short_w16, s.short_b = None, None
+            return s
+
+        dec = self.decoder
+        up = tuple(reversed(c.block_out_channels))
+        d = _lib.VaeDecoder()
+        d.latent_channels, d.layers_per_block, d.n_up, d.groups = c.latent_channels, c.layers_per_block, len(up), c.norm_num_groups
+        for i in range(4):
+            d.up_channels[i] = up[i] if i < len(up) else 0
+        d.dtype = _lib.BF16 if od == torch.bfloat16 else _lib.FP16
+        d.eps = 1e-6
+        d.pq_w, d.pq_b = f32(self.post_quant_conv.weight.reshape(c.latent_channels, c.latent_channels)), f32(self.post_quant_conv.bias)
+        d.conv_in_w, d.conv_in_b = f32(dec.conv_in.weight), f32(dec.conv_in.bias)
+        d.mid[0], d.mid[1] = resnet(dec.mid_block.resnets[0]), resnet(dec.mid_block.resnets[1])
+        at = dec.mid_block.attentions[0]
+        d.attn_gn_g, d.attn_gn_b = f32(at.group_norm.weight), f32(at.group_norm.bias)
+        d.attn_q_w16, d.attn_q_b = lin16(at.to_q.weight), f32(at.to_q.bias)
+        d.attn_k_w16, d.attn_k_b = lin16(at.to_k.weight), f32(at.to_k.bias)
+        d.attn_v_w16 = lin16(at.to_v.weight)
+        d.attn_o_w16 = lin16(at.to_out[0].weight)
+        # softmax rows sum to 1, so P (V + 1 b_v^T) W_o^T + b_o = P V W_o^T + (W_o b_v + b_o): fold the v bias
+        d.attn_o_b = f32(at.to_out[0].bias.detach().float() + at.to_out[0].weight.detach().float() @ at.to_v.bias.detach().float())
+        for b, blk in enumerate(dec.up_blocks):
+            for r in range(3):
+                d.up[b * 3 + r] = resnet(blk.resnets[r])
+            if hasattr(blk, "upsamplers"):
+                d.ups_w16[b], d.ups_b[b] = conv16(blk.upsamplers[0].conv.weight), f32(blk.upsamplers[0].conv.bias)
+        d.norm_out_g, d.norm_out_b = f32(dec.conv_norm_out.weight), f32(dec.conv_norm_out.bias)
+        wo = torch.zeros(32, *dec.conv_out.weight.shape[1:], dtype=torch.float32, device=dec.conv_out.weight.device)
+        wo[: c.out_channels] = dec.conv_out.weight.detach().float()
+        bo = torch.zeros(32, dtype=torch.float32, device=wo.device)
+        bo[: c.out_channels] = dec.conv_out.bias.detach().float()
+        d.conv_out_w16, d.conv_out_b = conv16(wo), f32(bo)
+        d.out_channels = c.out_channels
+        self._packed, self._packed_key = (d, keep), key
+        return self._packed
+
+    def decode(self, z, return_dict=True, **kwargs):
+        """z (n, latent_channels, h, w) -> DecoderOutput(sample=(n, 3, 8h, 8w)); extra kwargs (`num_frames`) are ignored."""
+        if not z.is_cuda:
+            raise RuntimeError("latte_b200.AutoencoderKL runs on CUDA (sm_100a) only; there is no CPU fallback")
+        lib = _lib.load()
+        dev = z.device
+        n, cz, h, w = z.shape
+        scale = 2 ** (len(self.config.block_out_channels) - 1)
+        with torch.cuda.device(dev):
+            d, _ = self._pack()
+            zf = z.detach().to(torch.float32).contiguous()
+            out = torch.empty(n, self.config.out_channels, h * scale, w * scale, dtype=torch.float32, device=dev)
+            need = lib.b200_vae_workspace_bytes(C.byref(d), n, h, w)
+            if need == 0:
+                raise RuntimeError("latte_b200: unsupported VAE configuration: " + _lib.last_error())
+            ws = self._workspace
+            if ws is None or ws.numel() < need + 1024 or ws.device != dev:
+                ws = self._workspace = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            rc = lib.b200_vae_decode(C.byref(d), zf.data_ptr(), n, h, w, out.data_ptr(), base, need,
+                                     torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "b200_vae_decode")
+        pd = self.dtype
+        out = out if pd == torch.float32 else out.to(pd)
+        return DecoderOutput(sample=out) if return_dict else (out,)

@@ -1,0 +1,118 @@
+"""CPU oracle for AutoencoderKL.decode — TEST INFRASTRUCTURE, NOT PRODUCT CODE.  **Parity unpinned.**
+
+The reference calls `vae.decode(z).sample` (sample/sample.py:114, sample/sample_ddp.py:167,
+sample/pipeline_latte.py:758,771) on diffusers' `AutoencoderKL` (diffusers==0.24.0, environment.yml:13), which is
+neither vendored in /root/reference nor installed in this image.  This file restates the published 0.24.0 decoder
+(SURVEY.md App. C.4): post_quant_conv 1x1 -> Decoder[conv_in -> UNetMidBlock2D(ResnetBlock2D, single-head Attention over
+h*w with GroupNorm, ResnetBlock2D) -> UpDecoderBlock2D x n (layers_per_block+1 ResnetBlock2D each, nearest-2x
+Upsample2D + conv on all but the last) -> GroupNorm -> SiLU -> conv_out].  State-dict key names follow diffusers.
+No reference-generated golden exists, so parity claims resting on this file are capped at "partial".
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class VaeConfig:
+    latent_channels: int = 4
+    out_channels: int = 3
+    block_out_channels: tuple = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    norm_num_groups: int = 32
+    scaling_factor: float = 0.18215
+
+    @property
+    def up_channels(self):
+        return tuple(reversed(self.block_out_channels))
+
+
+def _resnet_spec(prefix, cin, cout):
+    s = [(f"{prefix}.norm1.weight", (cin,)), (f"{prefix}.norm1.bias", (cin,)),
+         (f"{prefix}.conv1.weight", (cout, cin, 3, 3)), (f"{prefix}.conv1.bias", (cout,)),
+         (f"{prefix}.norm2.weight", (cout,)), (f"{prefix}.norm2.bias", (cout,)),
+         (f"{prefix}.conv2.weight", (cout, cout, 3, 3)), (f"{prefix}.conv2.bias", (cout,))]
+    if cin != cout:
+        s += [(f"{prefix}.conv_shortcut.weight", (cout, cin, 1, 1)), (f"{prefix}.conv_shortcut.bias", (cout,))]
+    return s
+
+
+def state_dict_spec(cfg: VaeConfig):
+    up = cfg.up_channels
+    C0 = up[0]
+    spec = [("post_quant_conv.weight", (cfg.latent_channels, cfg.latent_channels, 1, 1)), ("post_quant_conv.bias", (cfg.latent_channels,)),
+            ("decoder.conv_in.weight", (C0, cfg.latent_channels, 3, 3)), ("decoder.conv_in.bias", (C0,))]
+    spec += _resnet_spec("decoder.mid_block.resnets.0", C0, C0)
+    a = "decoder.mid_block.attentions.0"
+    spec += [(f"{a}.group_norm.weight", (C0,)), (f"{a}.group_norm.bias", (C0,))]
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        spec += [(f"{a}.{n}.weight", (C0, C0)), (f"{a}.{n}.bias", (C0,))]
+    spec += _resnet_spec("decoder.mid_block.resnets.1", C0, C0)
+    cin = C0
+    for b, co in enumerate(up):
+        for r in range(cfg.layers_per_block + 1):
+            spec += _resnet_spec(f"decoder.up_blocks.{b}.resnets.{r}", cin if r == 0 else co, co)
+        if b + 1 < len(up):
+            spec += [(f"decoder.up_blocks.{b}.upsamplers.0.conv.weight", (co, co, 3, 3)), (f"decoder.up_blocks.{b}.upsamplers.0.conv.bias", (co,))]
+        cin = co
+    spec += [("decoder.conv_norm_out.weight", (up[-1],)), ("decoder.conv_norm_out.bias", (up[-1],)),
+             ("decoder.conv_out.weight", (cfg.out_channels, up[-1], 3, 3)), ("decoder.conv_out.bias", (cfg.out_channels,))]
+    return spec
+
+
+def make_weights(cfg: VaeConfig, seed: int = 0):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in state_dict_spec(cfg):
+        if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("norm.weight") or name.endswith("norm_out.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:
+            fan_in = shape[1] * (shape[2] * shape[3] if len(shape) == 4 else 1)
+            t = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+        sd[name] = t.contiguous()
+    return sd
+
+
+def resnet(sd, p, x, groups):
+    h = F.conv2d(F.silu(F.group_norm(x, groups, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps=1e-6)), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+    h = F.conv2d(F.silu(F.group_norm(h, groups, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], eps=1e-6)), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    if p + ".conv_shortcut.weight" in sd:
+        x = F.conv2d(x, sd[p + ".conv_shortcut.weight"], sd[p + ".conv_shortcut.bias"])
+    return x + h
+
+
+def mid_attention(sd, p, x, groups):
+    n, c, h, w = x.shape
+    r = x
+    t = F.group_norm(x.reshape(n, c, h * w), groups, sd[p + ".group_norm.weight"], sd[p + ".group_norm.bias"], eps=1e-6).transpose(1, 2)
+    q = F.linear(t, sd[p + ".to_q.weight"], sd[p + ".to_q.bias"])
+    k = F.linear(t, sd[p + ".to_k.weight"], sd[p + ".to_k.bias"])
+    v = F.linear(t, sd[p + ".to_v.weight"], sd[p + ".to_v.bias"])
+    a = torch.softmax(q @ k.transpose(1, 2) * c ** -0.5, dim=-1)
+    o = F.linear(a @ v, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
+    return o.transpose(1, 2).reshape(n, c, h, w) + r
+
+
+def vae_decode(sd, cfg: VaeConfig, z):
+    """z (n, latent_channels, h, w) already divided by scaling_factor -> (n, 3, 8h, 8w) for the 4-block SD-VAE."""
+    G = cfg.norm_num_groups
+    x = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    x = F.conv2d(x, sd["decoder.conv_in.weight"], sd["decoder.conv_in.bias"], padding=1)
+    x = resnet(sd, "decoder.mid_block.resnets.0", x, G)
+    x = mid_attention(sd, "decoder.mid_block.attentions.0", x, G)
+    x = resnet(sd, "decoder.mid_block.resnets.1", x, G)
+    up = cfg.up_channels
+    for b in range(len(up)):
+        for r in range(cfg.layers_per_block + 1):
+            x = resnet(sd, f"decoder.up_blocks.{b}.resnets.{r}", x, G)
+        if b + 1 < len(up):
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            x = F.conv2d(x, sd[f"decoder.up_blocks.{b}.upsamplers.0.conv.weight"], sd[f"decoder.up_blocks.{b}.upsamplers.0.conv.bias"], padding=1)
+    x = F.silu(F.group_norm(x, G, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"], eps=1e-6))
+    return F.conv2d(x, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
