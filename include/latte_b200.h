@@ -164,6 +164,11 @@ typedef struct B200VaeResnet {
   const float* gn2_g; const float* gn2_b; const void* conv2_w16; const float* conv2_b;
   const void* short_w16; const float* short_b;   /* NULL when cin == cout */
   int32_t cin, cout;
+  /* AutoencoderKLTemporalDecoder only (NULL otherwise): the TemporalResnetBlock of a SpatioTemporalResBlock, Conv3d
+   * (3,1,1) weights repacked [C][kt][C]; conv2 weights and bias are pre-multiplied by (1 - alpha) of the AlphaBlender,
+   * so blend(x_s, x_s + conv2) == x_s + (1 - alpha) conv2 is the plain "+ shortcut" epilogue. */
+  const float* t_gn1_g; const float* t_gn1_b; const void* t_conv1_w16; const float* t_conv1_b;
+  const float* t_gn2_g; const float* t_gn2_b; const void* t_conv2_w16; const float* t_conv2_b;
 } B200VaeResnet;
 
 typedef struct B200VaeDecoder {
@@ -186,12 +191,18 @@ typedef struct B200VaeDecoder {
   const float* norm_out_g; const float* norm_out_b;
   const void* conv_out_w16; const float* conv_out_b; /* rows padded to 32: [32][9][C_last], bias [32] */
   int32_t out_channels;                             /* 3 */
+  float temporal_eps;                               /* GroupNorm eps of the temporal resnets (1e-5) */
+  const float* time_conv_w; const float* time_conv_b; /* time_conv_out Conv3d(3,3,(3,1,1)) [3][3][3] (out, in, kt), or NULL */
 } B200VaeDecoder;
 
 B200_API size_t b200_vae_workspace_bytes(const B200VaeDecoder* d, int n_img, int h, int w);
 /* z [n_img, C, h, w] fp32 (already divided by scaling_factor, as the callers do) -> out [n_img, 3, 8h, 8w] fp32 */
 B200_API int b200_vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, float* out, void* workspace,
                              size_t workspace_bytes, void* stream);
+/* AutoencoderKLTemporalDecoder.decode(z, num_frames) (pipeline_latte.py:779-798): the n_img frames are ONE clip
+ * (n_img == num_frames, as the pipeline's 14-frame chunks are); temporal convolutions zero-pad at the clip ends. */
+B200_API int b200_vae_decode_temporal(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, int num_frames, float* out,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Thread-local description of the last failure on this thread ("" if none). */
 B200_API const char* b200_last_error(void);

@@ -53,7 +53,8 @@ class T2VWeights(C.Structure):
 
 class VaeResnet(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("gn1_g", "gn1_b", "conv1_w16", "conv1_b", "gn2_g", "gn2_b", "conv2_w16", "conv2_b",
-                                          "short_w16", "short_b")] + [("cin", C.c_int32), ("cout", C.c_int32)]
+                                          "short_w16", "short_b")] + [("cin", C.c_int32), ("cout", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("t_gn1_g", "t_gn1_b", "t_conv1_w16", "t_conv1_b", "t_gn2_g", "t_gn2_b", "t_conv2_w16", "t_conv2_b")]
 
 
 class VaeDecoder(C.Structure):
@@ -66,7 +67,7 @@ class VaeDecoder(C.Structure):
                 ("attn_o_b", C.c_void_p),
                 ("up", VaeResnet * 12), ("ups_w16", C.c_void_p * 3), ("ups_b", C.c_void_p * 3),
                 ("norm_out_g", C.c_void_p), ("norm_out_b", C.c_void_p), ("conv_out_w16", C.c_void_p), ("conv_out_b", C.c_void_p),
-                ("out_channels", C.c_int32)]
+                ("out_channels", C.c_int32), ("temporal_eps", C.c_float), ("time_conv_w", C.c_void_p), ("time_conv_b", C.c_void_p)]
 
 
 EXPORTS = {
@@ -90,6 +91,8 @@ EXPORTS = {
     "b200_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDecoder), C.c_int, C.c_int, C.c_int]),
     "b200_vae_decode": (C.c_int, [C.POINTER(VaeDecoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
+    "b200_vae_decode_temporal": (C.c_int, [C.POINTER(VaeDecoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_size_t, C.c_void_p]),
     "b200_profile_enable": (None, [C.c_int]),
     "b200_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }

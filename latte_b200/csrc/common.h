@@ -88,7 +88,7 @@ struct GemmArgs {
   // conv_n*conv_h*conv_w output pixels, K = conv_taps * conv_c with W laid out [N][tap][c]; tap t reads the input pixel
   // shifted by (conv_dx[t], conv_dy[t]) with zero padding (TMA out-of-bounds fill).
   int conv_taps, conv_n, conv_h, conv_w, conv_c;
-  int conv_dx[9], conv_dy[9];
+  int conv_dx[9], conv_dy[9], conv_dz[9];   // dz shifts the image index (temporal convolution over the frames of one clip)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 
@@ -140,5 +140,6 @@ int launch_conv_in(const float* z, const float* pq_w, const float* pq_b, const f
                    int h, int wd, int Cout, int bf16, cudaStream_t stream);
 int launch_softmax_rows(const float* s, void* p, int rows, int n, float scale, int bf16, cudaStream_t stream);
 int launch_to_nchw(const void* x, float* y, int n_img, int c, int cpad, int hw, int bf16, cudaStream_t stream);
+int launch_time_conv(const float* x, const float* w, const float* b, float* y, int frames, int c, int hw, cudaStream_t stream);
 
 }  // namespace b200

@@ -77,7 +77,7 @@ struct GemmDev {
   const uint16_t* add16;
   // implicit-GEMM convolution: see GemmArgs
   int conv_taps, conv_cblk, conv_h, conv_w, conv_bw, conv_bh;
-  int conv_dx[9], conv_dy[9];
+  int conv_dx[9], conv_dy[9], conv_dz[9];
   int dbg;  // timing experiments only (results are wrong when set): bit0 = no operand TMA, bit1 = no MMA issue, bit2 = no 16-bit epilogue
 };
 
@@ -174,7 +174,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int pix0 = m_blk * BM;
               const int hw = p.conv_h * p.conv_w;
               const int img = pix0 / hw, rem = pix0 % hw;
-              tma_load_4d_pair(sa, &tmA, full_leader, cb * BK, rem % p.conv_w + p.conv_dx[tap], rem / p.conv_w + p.conv_dy[tap], img);
+              tma_load_4d_pair(sa, &tmA, full_leader, cb * BK, rem % p.conv_w + p.conv_dx[tap], rem / p.conv_w + p.conv_dy[tap], img + p.conv_dz[tap]);
             } else {
               tma_load_2d_pair(sa, &tmA, full_leader, kb * BK, m_blk * BM);
             }
@@ -549,7 +549,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.conv_taps = a.conv_taps;
   p.conv_cblk = a.conv_taps > 0 ? a.conv_c / BK : 0;
   p.conv_h = a.conv_h; p.conv_w = a.conv_w; p.conv_bw = conv_bw; p.conv_bh = conv_bh;
-  for (int i = 0; i < 9; ++i) { p.conv_dx[i] = a.conv_dx[i]; p.conv_dy[i] = a.conv_dy[i]; }
+  for (int i = 0; i < 9; ++i) { p.conv_dx[i] = a.conv_dx[i]; p.conv_dy[i] = a.conv_dy[i]; p.conv_dz[i] = a.conv_dz[i]; }
   {
     const char* e = getenv("B200_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;

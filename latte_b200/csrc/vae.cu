@@ -202,6 +202,26 @@ __global__ void __launch_bounds__(256) to_nchw_kernel(const uint16_t* __restrict
   }
 }
 
+// time_conv_out: Conv3d(C, C, (3,1,1), padding (1,0,0)) over the frames of one clip, fp32 NCHW in/out
+__global__ void __launch_bounds__(256) time_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                        float* __restrict__ y, int frames, int c, int hw) {
+  const long long total = static_cast<long long>(frames) * c * hw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(i % hw);
+    const int co = static_cast<int>((i / hw) % c);
+    const int f = static_cast<int>(i / (static_cast<long long>(hw) * c));
+    float acc = b[co];
+    for (int ci = 0; ci < c; ++ci)
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const int ff = f + kt - 1;
+        if (ff >= 0 && ff < frames) acc = fmaf(w[(co * c + ci) * 3 + kt], x[(static_cast<long long>(ff) * c + ci) * hw + pix], acc);
+      }
+    y[i] = acc;
+  }
+}
+
 inline int grid_for(long long n, int cap = 148 * 16) {
   long long b = (n + 255) / 256;
   return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
@@ -259,6 +279,13 @@ int launch_softmax_rows(const float* s, void* p, int rows, int n, float scale, i
   const int blocks = (rows * 32 + 255) / 256;
   if (bf16) softmax_rows_kernel<true><<<blocks, 256, 0, stream>>>(s, static_cast<uint16_t*>(p), rows, n, scale);
   else softmax_rows_kernel<false><<<blocks, 256, 0, stream>>>(s, static_cast<uint16_t*>(p), rows, n, scale);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_time_conv(const float* x, const float* w, const float* b, float* y, int frames, int c, int hw, cudaStream_t stream) {
+  const long long total = static_cast<long long>(frames) * c * hw;
+  time_conv_kernel<<<grid_for(total), 256, 0, stream>>>(x, w, b, y, frames, c, hw);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -337,6 +364,7 @@ struct VaeCtx {
   const B200VaeDecoder* d;
   VaeWs ws;
   int n_img, bf16;
+  int frames;     // > 0: temporal decoder, the n_img frames form n_img / frames clips
   cudaStream_t stream;
 };
 
@@ -345,7 +373,17 @@ int conv3x3(VaeCtx& c, const void* x, const void* w16, const float* bias, void* 
   a.A = x; a.W = w16; a.bias = bias; a.M = c.n_img * h * w; a.N = cout; a.K = 9 * cin; a.bf16 = c.bf16;
   a.epilogue = add16 ? B200_EPI_BIAS_ADD16 : B200_EPI_BIAS; a.out16 = y; a.add16 = add16;
   a.conv_taps = 9; a.conv_n = c.n_img; a.conv_h = h; a.conv_w = w; a.conv_c = cin;
-  for (int t = 0; t < 9; ++t) { a.conv_dx[t] = t % 3 - 1; a.conv_dy[t] = t / 3 - 1; }
+  for (int t = 0; t < 9; ++t) { a.conv_dx[t] = t % 3 - 1; a.conv_dy[t] = t / 3 - 1; a.conv_dz[t] = 0; }
+  return launch_gemm(a, c.stream);
+}
+
+// Conv3d (3,1,1), padding (1,0,0): 3 taps along the frame index of ONE clip (the image coordinate of the TMA box)
+int conv_t3(VaeCtx& c, const void* x, const void* w16, const float* bias, void* y, int h, int w, int ch, const void* add16) {
+  GemmArgs a{};
+  a.A = x; a.W = w16; a.bias = bias; a.M = c.n_img * h * w; a.N = ch; a.K = 3 * ch; a.bf16 = c.bf16;
+  a.epilogue = add16 ? B200_EPI_BIAS_ADD16 : B200_EPI_BIAS; a.out16 = y; a.add16 = add16;
+  a.conv_taps = 3; a.conv_n = c.n_img; a.conv_h = h; a.conv_w = w; a.conv_c = ch;
+  for (int t = 0; t < 9; ++t) { a.conv_dx[t] = 0; a.conv_dy[t] = 0; a.conv_dz[t] = t < 3 ? t - 1 : 0; }
   return launch_gemm(a, c.stream);
 }
 
@@ -375,16 +413,31 @@ int resnet(VaeCtx& c, const B200VaeResnet& r, int xi, int h, int w, int* out_idx
   }
   B200_TRY(conv3x3(c, t1, r.conv2_w16, r.conv2_b, t2, h, w, r.cout, r.cout, shortcut));
   *out_idx = free_[1];
+  if (r.t_conv1_w16 && c.frames > 0) {
+    // TemporalResnetBlock on x_s = t2 (GroupNorm statistics over ALL frames of the clip), blended by the AlphaBlender:
+    //   out = x_s + (1 - alpha) * conv2(silu(gn2(conv1(silu(gn1(x_s))))))   -- (1 - alpha) is folded into conv2 by the packer
+    const int clips = c.n_img / c.frames;
+    uint8_t* xs = t2;
+    uint8_t* u1 = t1;
+    uint8_t* u2 = x;     // the block input is dead by now
+    B200_TRY(launch_gn(xs, c.ws.part, r.t_gn1_g, r.t_gn1_b, u1, clips, c.frames * hw, r.cout, c.d->groups, c.d->temporal_eps, 1, c.bf16, c.stream));
+    B200_TRY(conv_t3(c, u1, r.t_conv1_w16, r.t_conv1_b, u2, h, w, r.cout, nullptr));
+    B200_TRY(launch_gn(u2, c.ws.part, r.t_gn2_g, r.t_gn2_b, u1, clips, c.frames * hw, r.cout, c.d->groups, c.d->temporal_eps, 1, c.bf16, c.stream));
+    B200_TRY(conv_t3(c, u1, r.t_conv2_w16, r.t_conv2_b, u2, h, w, r.cout, xs));
+    *out_idx = xi;
+  }
   return B200_OK;
 }
 
-int vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, float* out, void* workspace, size_t workspace_bytes,
-               cudaStream_t stream) {
+int vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, int num_frames, float* out, void* workspace,
+               size_t workspace_bytes, cudaStream_t stream) {
   B200_TRY(vae_ok(d, n_img, h, w));
+  B200_REQUIRE(num_frames == 0 || num_frames == n_img, B200_ERR_UNSUPPORTED,
+               "vae: temporal decode takes ONE clip per call (n_img %d != num_frames %d); decode clips one by one", n_img, num_frames);
   B200_REQUIRE(z && out && workspace && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, B200_ERR_ALIGN, "vae: bad pointers");
   B200_TRY(check_arch());
   VaeCtx c{};
-  c.d = d; c.n_img = n_img; c.bf16 = d->dtype == B200_BF16; c.stream = stream;
+  c.d = d; c.n_img = n_img; c.bf16 = d->dtype == B200_BF16; c.stream = stream; c.frames = num_frames;
   vae_carve(d, n_img, h, w, workspace, &c.ws);
   B200_REQUIRE(c.ws.bytes <= workspace_bytes, B200_ERR_WORKSPACE, "vae: workspace too small: need %zu bytes, got %zu", c.ws.bytes, workspace_bytes);
   const int C0 = d->up_channels[0];
@@ -445,7 +498,13 @@ int vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w,
     for (int i = 0; i < 4; ++i) if (i != xi) fr[nf++] = i;
     B200_TRY(launch_gn(c.ws.buf[xi], c.ws.part, d->norm_out_g, d->norm_out_b, c.ws.buf[fr[0]], n_img, ch * cw, cl, d->groups, d->eps, 1, c.bf16, stream));
     B200_TRY(conv3x3(c, c.ws.buf[fr[0]], d->conv_out_w16, d->conv_out_b, c.ws.buf[fr[1]], ch, cw, cl, 32, nullptr));
-    B200_TRY(launch_to_nchw(c.ws.buf[fr[1]], out, n_img, d->out_channels, 32, ch * cw, c.bf16, stream));
+    if (num_frames > 0 && d->time_conv_w) {
+      float* tmp = reinterpret_cast<float*>(c.ws.buf[fr[2]]);
+      B200_TRY(launch_to_nchw(c.ws.buf[fr[1]], tmp, n_img, d->out_channels, 32, ch * cw, c.bf16, stream));
+      B200_TRY(launch_time_conv(tmp, d->time_conv_w, d->time_conv_b, out, n_img, d->out_channels, ch * cw, stream));
+    } else {
+      B200_TRY(launch_to_nchw(c.ws.buf[fr[1]], out, n_img, d->out_channels, 32, ch * cw, c.bf16, stream));
+    }
   }
   return B200_OK;
 }
@@ -464,7 +523,13 @@ B200_API size_t b200_vae_workspace_bytes(const B200VaeDecoder* d, int n_img, int
 
 B200_API int b200_vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, float* out, void* workspace,
                              size_t workspace_bytes, void* stream) {
-  return b200::vae_decode(d, z, n_img, h, w, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  return b200::vae_decode(d, z, n_img, h, w, 0, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+B200_API int b200_vae_decode_temporal(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, int num_frames, float* out,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(num_frames > 0, B200_ERR_SHAPE, "vae: num_frames must be positive");
+  return b200::vae_decode(d, z, n_img, h, w, num_frames, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

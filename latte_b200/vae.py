@@ -79,6 +79,62 @@ class DecoderOutput(SimpleNamespace):
     pass
 
 
+# ---- AutoencoderKLTemporalDecoder containers (diffusers 0.24.0 names) --------------------------------------------
+class _TemporalResnet(nn.Module):
+    def __init__(self, c, groups):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, c, eps=1e-5)
+        self.conv1 = nn.Conv3d(c, c, (3, 1, 1), padding=(1, 0, 0))
+        self.norm2 = nn.GroupNorm(groups, c, eps=1e-5)
+        self.conv2 = nn.Conv3d(c, c, (3, 1, 1), padding=(1, 0, 0))
+
+
+class _Mixer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.mix_factor = nn.Parameter(torch.zeros(1))
+
+
+class _STBlock(nn.Module):
+    def __init__(self, cin, cout, groups):
+        super().__init__()
+        self.spatial_res_block = _Resnet(cin, cout, groups)
+        self.temporal_res_block = _TemporalResnet(cout, groups)
+        self.time_mixer = _Mixer()
+
+
+class _TMid(nn.Module):
+    def __init__(self, c, groups):
+        super().__init__()
+        self.attentions = nn.ModuleList([_Attention(c, groups)])
+        self.resnets = nn.ModuleList([_STBlock(c, c, groups), _STBlock(c, c, groups)])
+
+
+class _TUpBlock(nn.Module):
+    def __init__(self, cin, cout, n, groups, add_upsample):
+        super().__init__()
+        self.resnets = nn.ModuleList([_STBlock(cin if i == 0 else cout, cout, groups) for i in range(n)])
+        if add_upsample:
+            self.upsamplers = nn.ModuleList([_Upsampler(cout)])
+
+
+class _TemporalDecoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        up = tuple(reversed(cfg.block_out_channels))
+        g = cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.latent_channels, up[0], 3, padding=1)
+        self.mid_block = _TMid(up[0], g)
+        blocks, cin = [], up[0]
+        for i, co in enumerate(up):
+            blocks.append(_TUpBlock(cin, co, cfg.layers_per_block + 1, g, i + 1 < len(up)))
+            cin = co
+        self.up_blocks = nn.ModuleList(blocks)
+        self.conv_norm_out = nn.GroupNorm(g, up[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(up[-1], cfg.out_channels, 3, padding=1)
+        self.time_conv_out = nn.Conv3d(cfg.out_channels, cfg.out_channels, (3, 1, 1), padding=(1, 0, 0))
+
+
 class AutoencoderKL(nn.Module):
     def __init__(self, in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                  latent_channels=4, norm_num_groups=32, scaling_factor=0.18215, **unused):
@@ -86,8 +142,12 @@ class AutoencoderKL(nn.Module):
         self.config = SimpleNamespace(in_channels=in_channels, out_channels=out_channels, block_out_channels=tuple(block_out_channels),
                                       layers_per_block=layers_per_block, latent_channels=latent_channels,
                                       norm_num_groups=norm_num_groups, scaling_factor=scaling_factor)
-        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
-        self.decoder = _Decoder(self.config)
+        self._temporal = type(self).__name__ == "AutoencoderKLTemporalDecoder"
+        if self._temporal:
+            self.decoder = _TemporalDecoder(self.config)     # no post_quant_conv in the SVD decoder
+        else:
+            self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+            self.decoder = _Decoder(self.config)
         self.compute_dtype = torch.float16
         self._packed = None
         self._packed_key = None
@@ -95,7 +155,7 @@ class AutoencoderKL(nn.Module):
 
     @property
     def dtype(self):
-        return self.post_quant_conv.weight.dtype
+        return self.decoder.conv_in.weight.dtype
 
     @classmethod
     def from_pretrained(cls, path, subfolder=None, torch_dtype=None, **kw):
@@ -120,7 +180,7 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def _pack(self):
         ver = sum(p._version for p in self.parameters())
-        w0 = self.post_quant_conv.weight
+        w0 = self.decoder.conv_in.weight
         key = (ver, w0.data_ptr(), w0.device, w0.dtype, self.compute_dtype)
         if self._packed is not None and key == self._packed_key:
             return self._packed
@@ -143,7 +203,14 @@ class AutoencoderKL(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
-        def resnet(r):
+        def conv16_t(wt, scale=1.0):  # Conv3d (3,1,1): [O][I][kt][1][1] -> [O][kt][I]
+            t = (wt.detach().float() * scale).reshape(wt.shape[0], wt.shape[1], 3).permute(0, 2, 1).reshape(wt.shape[0], -1)
+            t = t.to(device=dev, dtype=od).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def resnet(blk):
+            r = blk.spatial_res_block if self._temporal else blk
             s = _lib.VaeResnet()
             s.gn1_g, s.gn1_b, s.conv1_w16, s.conv1_b = f32(r.norm1.weight), f32(r.norm1.bias), conv16(r.conv1.weight), f32(r.conv1.bias)
             s.gn2_g, s.gn2_b, s.conv2_w16, s.conv2_b = f32(r.norm2.weight), f32(r.norm2.bias), conv16(r.conv2.weight), f32(r.conv2.bias)
@@ -152,6 +219,13 @@ class AutoencoderKL(nn.Module):
                 s.short_w16, s.short_b = lin16(r.conv_shortcut.weight), f32(r.conv_shortcut.bias)
             else:
                 s.short_w16, s.short_b = None, None
+            if self._temporal:
+                t = blk.temporal_res_block
+                # AlphaBlender(learned, switch_spatial_to_temporal_mix): alpha = 1 - sigmoid(mix); out = x_s + (1 - alpha) * conv2(...)
+                one_minus_alpha = float(torch.sigmoid(blk.time_mixer.mix_factor.detach().float()))
+                s.t_gn1_g, s.t_gn1_b, s.t_conv1_w16, s.t_conv1_b = f32(t.norm1.weight), f32(t.norm1.bias), conv16_t(t.conv1.weight), f32(t.conv1.bias)
+                s.t_gn2_g, s.t_gn2_b = f32(t.norm2.weight), f32(t.norm2.bias)
+                s.t_conv2_w16, s.t_conv2_b = conv16_t(t.conv2.weight, one_minus_alpha), f32(t.conv2.bias.detach().float() * one_minus_alpha)
             return s
 
         dec = self.decoder
@@ -162,7 +236,14 @@ class AutoencoderKL(nn.Module):
             d.up_channels[i] = up[i] if i < len(up) else 0
         d.dtype = _lib.BF16 if od == torch.bfloat16 else _lib.FP16
         d.eps = 1e-6
-        d.pq_w, d.pq_b = f32(self.post_quant_conv.weight.reshape(c.latent_channels, c.latent_channels)), f32(self.post_quant_conv.bias)
+        if self._temporal:
+            d.pq_w, d.pq_b = None, None
+            d.temporal_eps = 1e-5
+            d.time_conv_w, d.time_conv_b = f32(dec.time_conv_out.weight.reshape(c.out_channels, c.out_channels, 3)), f32(dec.time_conv_out.bias)
+        else:
+            d.pq_w, d.pq_b = f32(self.post_quant_conv.weight.reshape(c.latent_channels, c.latent_channels)), f32(self.post_quant_conv.bias)
+            d.temporal_eps = 1e-5
+            d.time_conv_w, d.time_conv_b = None, None
         d.conv_in_w, d.conv_in_b = f32(dec.conv_in.weight), f32(dec.conv_in.bias)
         d.mid[0], d.mid[1] = resnet(dec.mid_block.resnets[0]), resnet(dec.mid_block.resnets[1])
         at = dec.mid_block.attentions[0]
@@ -188,8 +269,9 @@ class AutoencoderKL(nn.Module):
         self._packed, self._packed_key = (d, keep), key
         return self._packed
 
-    def decode(self, z, return_dict=True, **kwargs):
-        """z (n, latent_channels, h, w) -> DecoderOutput(sample=(n, 3, 8h, 8w)); extra kwargs (`num_frames`) are ignored."""
+    def decode(self, z, return_dict=True, num_frames=None, **kwargs):
+        """z (n, latent_channels, h, w) -> DecoderOutput(sample=(n, 3, 8h, 8w)).  `num_frames` is ignored by AutoencoderKL
+        and required by AutoencoderKLTemporalDecoder (one clip per call: n == num_frames, as pipeline_latte.py:785-792 does)."""
         if not z.is_cuda:
             raise RuntimeError("latte_b200.AutoencoderKL runs on CUDA (sm_100a) only; there is no CPU fallback")
         lib = _lib.load()
@@ -207,9 +289,21 @@ class AutoencoderKL(nn.Module):
             if ws is None or ws.numel() < need + 1024 or ws.device != dev:
                 ws = self._workspace = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
             base = (ws.data_ptr() + 1023) // 1024 * 1024
-            rc = lib.b200_vae_decode(C.byref(d), zf.data_ptr(), n, h, w, out.data_ptr(), base, need,
-                                     torch.cuda.current_stream(dev).cuda_stream)
+            if self._temporal:
+                if num_frames is None:
+                    raise ValueError("AutoencoderKLTemporalDecoder.decode needs num_frames")
+                rc = lib.b200_vae_decode_temporal(C.byref(d), zf.data_ptr(), n, h, w, int(num_frames), out.data_ptr(), base, need,
+                                                  torch.cuda.current_stream(dev).cuda_stream)
+            else:
+                rc = lib.b200_vae_decode(C.byref(d), zf.data_ptr(), n, h, w, out.data_ptr(), base, need,
+                                         torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(rc, "b200_vae_decode")
         pd = self.dtype
         out = out if pd == torch.float32 else out.to(pd)
         return DecoderOutput(sample=out) if return_dict else (out,)
+
+
+class AutoencoderKLTemporalDecoder(AutoencoderKL):
+    """The SVD temporal decoder `sample_t2x.py:31-34` loads for `enable_vae_temporal_decoder` (pipeline_latte.py:779-798):
+    every resnet is spatial ResnetBlock2D + temporal Conv3d(3,1,1) resnet blended by a learned alpha; `time_conv_out` last.
+    Same kernels as AutoencoderKL; the temporal convolutions are 3-tap implicit GEMMs shifted along the frame index."""

@@ -116,3 +116,97 @@ def vae_decode(sd, cfg: VaeConfig, z):
             x = F.conv2d(x, sd[f"decoder.up_blocks.{b}.upsamplers.0.conv.weight"], sd[f"decoder.up_blocks.{b}.upsamplers.0.conv.bias"], padding=1)
     x = F.silu(F.group_norm(x, G, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"], eps=1e-6))
     return F.conv2d(x, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+
+
+# ==================================================================================================================
+# AutoencoderKLTemporalDecoder.decode(z, num_frames) — the SVD temporal decoder the T2V pipeline uses in chunks of 14
+# frames (sample/pipeline_latte.py:779-798).  PARITY UNPINNED, restated from diffusers 0.24.0:
+# every resnet is a SpatioTemporalResBlock = ResnetBlock2D (eps 1e-6) followed by a TemporalResnetBlock
+# (GroupNorm over (c/g, f, h, w), SiLU, Conv3d (3,1,1) pad (1,0,0), twice, + input; eps 1e-5) and blended by
+# AlphaBlender(merge_strategy="learned", switch_spatial_to_temporal_mix=True):
+#     alpha = 1 - sigmoid(mix_factor);  out = alpha * x_spatial + (1 - alpha) * x_temporal
+# then GroupNorm/SiLU/conv_out and time_conv_out = Conv3d(3, 3, (3,1,1), pad (1,0,0)).  No post_quant_conv.
+def temporal_state_dict_spec(cfg: VaeConfig):
+    up = cfg.up_channels
+    C0 = up[0]
+
+    def st(prefix, cin, cout):
+        s = _resnet_spec(prefix + ".spatial_res_block", cin, cout)
+        t = prefix + ".temporal_res_block"
+        s += [(f"{t}.norm1.weight", (cout,)), (f"{t}.norm1.bias", (cout,)), (f"{t}.conv1.weight", (cout, cout, 3, 1, 1)), (f"{t}.conv1.bias", (cout,)),
+              (f"{t}.norm2.weight", (cout,)), (f"{t}.norm2.bias", (cout,)), (f"{t}.conv2.weight", (cout, cout, 3, 1, 1)), (f"{t}.conv2.bias", (cout,)),
+              (f"{prefix}.time_mixer.mix_factor", (1,))]
+        return s
+
+    spec = [("decoder.conv_in.weight", (C0, cfg.latent_channels, 3, 3)), ("decoder.conv_in.bias", (C0,))]
+    spec += st("decoder.mid_block.resnets.0", C0, C0)
+    a = "decoder.mid_block.attentions.0"
+    spec += [(f"{a}.group_norm.weight", (C0,)), (f"{a}.group_norm.bias", (C0,))]
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        spec += [(f"{a}.{n}.weight", (C0, C0)), (f"{a}.{n}.bias", (C0,))]
+    spec += st("decoder.mid_block.resnets.1", C0, C0)
+    cin = C0
+    for b, co in enumerate(up):
+        for r in range(cfg.layers_per_block + 1):
+            spec += st(f"decoder.up_blocks.{b}.resnets.{r}", cin if r == 0 else co, co)
+        if b + 1 < len(up):
+            spec += [(f"decoder.up_blocks.{b}.upsamplers.0.conv.weight", (co, co, 3, 3)), (f"decoder.up_blocks.{b}.upsamplers.0.conv.bias", (co,))]
+        cin = co
+    spec += [("decoder.conv_norm_out.weight", (up[-1],)), ("decoder.conv_norm_out.bias", (up[-1],)),
+             ("decoder.conv_out.weight", (cfg.out_channels, up[-1], 3, 3)), ("decoder.conv_out.bias", (cfg.out_channels,)),
+             ("decoder.time_conv_out.weight", (cfg.out_channels, cfg.out_channels, 3, 1, 1)), ("decoder.time_conv_out.bias", (cfg.out_channels,))]
+    return spec
+
+
+def make_temporal_weights(cfg: VaeConfig, seed: int = 0):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in temporal_state_dict_spec(cfg):
+        if name.endswith("mix_factor"):
+            t = torch.randn(shape, generator=g)
+        elif "norm" in name.split(".")[-2] and name.endswith(".weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            t = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+        sd[name] = t.contiguous()
+    return sd
+
+
+def spatio_temporal_block(sd, p, x, groups, num_frames):
+    xs = resnet(sd, p + ".spatial_res_block", x, groups)
+    n, c, h, w = xs.shape
+    b = n // num_frames
+    v = xs.reshape(b, num_frames, c, h, w).permute(0, 2, 1, 3, 4)                    # b c f h w
+    t = p + ".temporal_res_block"
+    u = F.conv3d(F.silu(F.group_norm(v, groups, sd[t + ".norm1.weight"], sd[t + ".norm1.bias"], eps=1e-5)), sd[t + ".conv1.weight"], sd[t + ".conv1.bias"], padding=(1, 0, 0))
+    u = F.conv3d(F.silu(F.group_norm(u, groups, sd[t + ".norm2.weight"], sd[t + ".norm2.bias"], eps=1e-5)), sd[t + ".conv2.weight"], sd[t + ".conv2.bias"], padding=(1, 0, 0))
+    xt = v + u
+    alpha = 1.0 - torch.sigmoid(sd[p + ".time_mixer.mix_factor"])
+    out = alpha * v + (1.0 - alpha) * xt
+    return out.permute(0, 2, 1, 3, 4).reshape(n, c, h, w)
+
+
+def vae_temporal_decode(sd, cfg: VaeConfig, z, num_frames):
+    G = cfg.norm_num_groups
+    x = F.conv2d(z, sd["decoder.conv_in.weight"], sd["decoder.conv_in.bias"], padding=1)
+    x = spatio_temporal_block(sd, "decoder.mid_block.resnets.0", x, G, num_frames)
+    x = mid_attention(sd, "decoder.mid_block.attentions.0", x, G)
+    x = spatio_temporal_block(sd, "decoder.mid_block.resnets.1", x, G, num_frames)
+    up = cfg.up_channels
+    for b in range(len(up)):
+        for r in range(cfg.layers_per_block + 1):
+            x = spatio_temporal_block(sd, f"decoder.up_blocks.{b}.resnets.{r}", x, G, num_frames)
+        if b + 1 < len(up):
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            x = F.conv2d(x, sd[f"decoder.up_blocks.{b}.upsamplers.0.conv.weight"], sd[f"decoder.up_blocks.{b}.upsamplers.0.conv.bias"], padding=1)
+    x = F.silu(F.group_norm(x, G, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"], eps=1e-6))
+    x = F.conv2d(x, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+    n, c, h, w = x.shape
+    v = x.reshape(n // num_frames, num_frames, c, h, w).permute(0, 2, 1, 3, 4)
+    v = F.conv3d(v, sd["decoder.time_conv_out.weight"], sd["decoder.time_conv_out.bias"], padding=(1, 0, 0))
+    return v.permute(0, 2, 1, 3, 4).reshape(n, c, h, w)

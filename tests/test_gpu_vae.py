@@ -47,3 +47,26 @@ def test_surface():
     vae = vae.cuda().half()
     out = vae.decode(torch.randn(2, 4, 16, 16, device="cuda").half(), num_frames=2).sample   # kwargs like the temporal decoder call
     assert out.dtype == torch.float16 and out.shape == (2, 3, 64, 64)
+
+
+@pytest.mark.parametrize("case", [((64, 128, 128), 16, 4, 16, 16), ((64, 64, 128, 128), 16, 14, 16, 16)])
+def test_temporal_decoder_matches_oracle(case):
+    """AutoencoderKLTemporalDecoder.decode(z, num_frames) (pipeline_latte.py:779-798; 14-frame chunk): spatial resnets +
+    Conv3d(3,1,1) temporal resnets (GroupNorm over the clip) blended by the learned alpha, then time_conv_out."""
+    from latte_b200 import AutoencoderKLTemporalDecoder
+    from oracle import vae_oracle as V
+    block_out, groups, n, h, w = case
+    cfg = V.VaeConfig(block_out_channels=block_out, norm_num_groups=groups)
+    sd = V.make_temporal_weights(cfg, 5)
+    z = torch.randn(n, 4, h, w, generator=torch.Generator().manual_seed(6))
+    vae = AutoencoderKLTemporalDecoder(block_out_channels=block_out, norm_num_groups=groups)
+    vae.load_state_dict(sd, strict=True)
+    vae = vae.cuda().eval()
+    with torch.no_grad():
+        out = vae.decode(z.cuda(), num_frames=n).sample.cpu()
+        ref = V.vae_temporal_decode(sd, cfg, z, n)
+    err = (out - ref).abs()
+    assert out.shape == ref.shape
+    assert err.max().item() < 3e-2 and err.mean().item() < 3e-3, f"max {err.max().item():.3e} mean {err.mean().item():.3e}"
+    with pytest.raises(RuntimeError, match="ONE clip"):
+        vae.decode(z.cuda(), num_frames=n // 2)
