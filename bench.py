@@ -301,6 +301,31 @@ def main():
         "clocks": clk,
     }
     if world == 1:
+        # End-to-end frames/s of BASELINE configs[1] (second half of BASELINE.json's metric): one 16-frame video =
+        # 250 DDIM steps (the measured step) + ONE AutoencoderKL decode of the 16 latents (measured here with the SD-VAE
+        # topology, synthetic weights) — sampler elementwise math and mp4 encoding excluded (reference code, out of scope).
+        try:
+            from latte_b200 import AutoencoderKL
+            vae = AutoencoderKL().to(dev).half().eval()
+            zl = torch.randn(cfg.num_frames, 4, cfg.input_size, cfg.input_size, device=dev)
+            with torch.no_grad():
+                for _ in range(2):
+                    vae.decode(zl / 0.18215)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    vae.decode(zl / 0.18215)
+                e1.record()
+                torch.cuda.synchronize()
+            ms_dec = e0.elapsed_time(e1) / 3
+            n_steps = 250
+            res["frames_per_sec_e2e"] = {"value": cfg.num_frames / ((n_steps * ms_total / K + ms_dec) * 1e-3), "unit": "frames/s",
+                                         "ddim_steps": n_steps, "ms_per_step": ms_total / K, "vae_decode_ms_16_frames": ms_dec,
+                                         "vae_tflops_achieved": 16 * 0.622 / (ms_dec * 1e-3)}
+            del vae
+        except Exception as e:  # noqa: BLE001
+            res["frames_per_sec_e2e"] = {"error": repr(e)[:200]}
         # The reference's own 1-GPU path (north_star's ">= 5x" denominator): the oracle restatement run as PyTorch eager
         # on this GPU exactly as sample.py does (model.half(), tf32 allowed, 'math' attention) — a baseline leg, never
         # part of the product path.
