@@ -178,7 +178,7 @@ def make_inputs(cfg: LatteConfig, batch: int, seed: int = 123):
 def timestep_embedding(t: torch.Tensor, dim: int = 256, max_period: int = 10000) -> torch.Tensor:
     """latte.py:98-116 — [cos(t w_k), sin(t w_k)], w_k = exp(-ln(1e4) k / half); fp32 like the reference."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(device=t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
