@@ -22,15 +22,14 @@
 //   warps 2..5  epilogue warpgroup 0 (thread = accumulator row = TMEM lane)
 //   warps 6..9  epilogue warpgroup 1 (16-bit output modes: the two groups take alternate 64-column chunks; with one
 //               warp per scheduler the epilogue is instruction-latency bound, two warps per scheduler hide it)
-//   warp 10     residual mode only: TMA loader of the fp32 residual tile, 128 rows x 32 columns per ring slot
+//   warp 10     spare
 // Two accumulator buffers in TMEM (2*BN columns) let the epilogue of tile i overlap the mainloop of tile i+1.
 //
 // Epilogue data movement is shaped so that every global access is a whole 128-byte line:
 //   16-bit outputs:  registers -> smem staging tile (rows of 128 B, 16-byte chunks XOR-swizzled by row%8, conflict-free)
 //                    -> re-read with 8 threads per row -> coalesced 16-byte stores.
-//   residual:        the x tile is prefetched by TMA into a 4-slot smem ring long before the accumulator is ready
-//                    (it does not depend on the MMA), updated in place in smem (swizzled, conflict-free) and written
-//                    back by a TMA store; no thread ever waits on a global load.
+//   residual:        x is never loaded: the delta gate*(acc+bias) goes to a swizzled smem tile and a TMA reduce-add
+//                    (cp.reduce.async.bulk.tensor ... .add, fp32) folds it into the residual stream in L2.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -51,9 +50,9 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;                // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // residual: ring of x tiles, at least one output tile's worth so the loader runs a whole mainloop ahead; else: 2 staging tiles
-  static constexpr int XSLOTS = RESID ? (BN >= 256 ? 4 : (BN >= 192 ? 5 : 6)) : 2;
-  static constexpr int STAGES = RESID ? 5 : (BN >= 256 ? 6 : (BN >= 192 ? 6 : 8));
+  // residual: 2 staging tiles per epilogue warpgroup (TMA reduce-add sources); else: 1 per warpgroup
+  static constexpr int XSLOTS = RESID ? 4 : 2;
+  static constexpr int STAGES = RESID ? (BN >= 256 ? 5 : (BN >= 192 ? 5 : 6)) : (BN >= 256 ? 6 : (BN >= 192 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 512;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;            // 1 KiB aligned (TMA 128B-swizzle boxes live here)
@@ -213,24 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 10) {
-    // ------------------------------------------------------------------ residual-tile TMA loader
-    if constexpr (C::RESID) {
-      if (lane == 0) {
-        int slot = 0;
-        uint32_t ph = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-          const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
-          for (int c = 0; c < BN / 32; ++c) {
-            const int col0 = n0 + c * 32;
-            if (col0 >= p.N || (p.dbg & 8)) break;
-            mbar_wait(&xempty[slot], ph ^ 1);
-            mbar_arrive_expect_tx(&xfull[slot], kSlotBytes);
-            tma_load_2d(epi_smem + slot * kSlotBytes, &tmX, &xfull[slot], col0, m0);
-            if (++slot == C::XSLOTS) { slot = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
+    // spare warp (kept so the warp-role layout is the same for every epilogue mode)
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..9
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
@@ -242,15 +224,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t tempty_leader[2] = {mapa_u32(&tempty[0], 0), mapa_u32(&tempty[1], 0)};
 
     if constexpr (C::RESID) {
-      // The two warpgroups take alternate 32-column chunks (chunk counter cc, owner = cc & 1); chunk cc lives in ring
-      // slot cc % XSLOTS, filled by the loader warp in the same order.
-      uint32_t cc = 0;
-      const int bar_id = 1 + 2 * wg;
+      // x += gate * (acc + bias) (+ row_add) WITHOUT loading x: the delta tile goes registers -> smem (128-byte rows,
+      // 16-byte chunks XOR-swizzled to match the tensor map) -> TMA reduce-add into the fp32 residual stream.  Each
+      // element receives exactly one add per GEMM, so results are deterministic.  The two warpgroups take alternate
+      // 32-column chunks (owner = running chunk counter & 1) and double-buffer their own two staging tiles.
+      uint32_t cc = 0, mine = 0;
+      const int bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         const int row = m0 + row_a;
-        const int row_c = row < p.M ? row : p.M - 1;  // rows past M are zero-filled by TMA and clipped by the store
+        const int row_c = row < p.M ? row : p.M - 1;  // rows past M produce deltas that the TMA store clips
         const float* gate_row = p.gate + static_cast<long long>(row_c / p.rows_per_batch) * p.gate_bs;
         const float* add_row = p.row_add ? p.row_add + static_cast<size_t>((row_c / p.row_add_div) % p.row_add_period) * p.N : nullptr;
         constexpr int NCH = BN / 32;
@@ -267,10 +251,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
 #pragma unroll 1
         for (int c = 0; c < live; ++c) {
-          const uint32_t g = cc + c;
-          if ((g & 1) != static_cast<uint32_t>(wg)) continue;
-          const int slot = g % C::XSLOTS;
-          const uint32_t ph = (g / C::XSLOTS) & 1;
+          if (((cc + c) & 1) != static_cast<uint32_t>(wg)) continue;
           const int col0 = n0 + c * 32;
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c * 32, v);
@@ -281,38 +262,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
           }
           if (p.dbg & 8) continue;     // timing experiment: accumulator read only
-          mbar_wait(&xfull[slot], ph);
-          uint8_t* xrow = epi_smem + slot * kSlotBytes + row_a * 128;
+          uint8_t* slot = epi_smem + (wg * 2 + (mine & 1)) * kSlotBytes;
+          ++mine;
+          uint8_t* drow = slot + row_a * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4* xp = reinterpret_cast<float4*>(xrow + ((j ^ (row_a & 7)) << 4));
-            float4 xv = *xp;
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
             const float4 gt = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + j);
-            xv.x = fmaf(gt.x, __uint_as_float(v[4 * j + 0]) + b4.x, xv.x);
-            xv.y = fmaf(gt.y, __uint_as_float(v[4 * j + 1]) + b4.y, xv.y);
-            xv.z = fmaf(gt.z, __uint_as_float(v[4 * j + 2]) + b4.z, xv.z);
-            xv.w = fmaf(gt.w, __uint_as_float(v[4 * j + 3]) + b4.w, xv.w);
+            float4 dv;
+            dv.x = gt.x * (__uint_as_float(v[4 * j + 0]) + b4.x);
+            dv.y = gt.y * (__uint_as_float(v[4 * j + 1]) + b4.y);
+            dv.z = gt.z * (__uint_as_float(v[4 * j + 2]) + b4.z);
+            dv.w = gt.w * (__uint_as_float(v[4 * j + 3]) + b4.w);
             if (add_row) {
               const float4 ra = __ldg(reinterpret_cast<const float4*>(add_row + col0) + j);
-              xv.x += ra.x; xv.y += ra.y; xv.z += ra.z; xv.w += ra.w;
+              dv.x += ra.x; dv.y += ra.y; dv.z += ra.z; dv.w += ra.w;
             }
-            *xp = xv;
+            *reinterpret_cast<float4*>(drow + ((j ^ (row_a & 7)) << 4)) = dv;
           }
-          fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA store
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA engine
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");
           if (te == 0) {
-            tma_store_2d(&tmX, epi_smem + slot * kSlotBytes, col0, m0);
+            tma_reduce_add_2d(&tmX, slot, col0, m0);
             tma_store_commit();
-            tma_store_wait_read<0>();                   // the store has read the slot: hand it back to the loader
-            mbar_arrive(&xempty[slot]);
+            tma_store_wait_read<1>();                   // the reduce issued one chunk ago (other tile) has read its smem
           }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");   // ... so the other staging tile may be rewritten
         }
         cc += live;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (te == 0) tma_store_wait_all<0>();             // all residual writes have landed before the CTA retires
+      if (te == 0) tma_store_wait_all<0>();             // all residual updates have landed before the CTA retires
     } else {
       const int row_b0 = te >> 3;             // phase-B row within a group of 16
       const int ch_b = te & 7;                // phase-B 16-byte chunk within the 128-byte row segment
