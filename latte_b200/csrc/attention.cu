@@ -17,6 +17,7 @@
 // CTA = 160 threads: warps 0-3 softmax/epilogue (thread = tile row = TMEM lane), warp 4 = TMA + MMA issuer.
 //   S = Q K^T -> TMEM cols [0,Lk)  ->  registers: mask, max, exp2, sum -> P (16-bit) to smem (K-major SW128)
 //   O = P V   -> TMEM cols [256,336) -> registers: * 1/sum -> global.
+#include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -44,6 +45,7 @@ struct AttnDev {
   int Lk;           // keys per tile: N (FULL, <= 256) or 128
   int tiles_per_seq;  // FULL: N / 128; TEMPORAL: N / G
   float scale_log2; // hd^-0.5 * log2(e)
+  int dbg;          // B200_ATTN_DBG bits (pipelined kernel only): 1 no TMA, 2 no softmax math, 4 no output stores, 8 no MMA
 };
 
 // Shared-memory plan (bytes, every piece 1 KiB aligned), sized by the key count Lk so that several CTAs fit per SM:
@@ -320,8 +322,328 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent, software-pipelined variant (the one the launchers use): one CTA per SM walks a list of (tile, head) work
+// items with everything double-buffered, so the tensor pipe, the TMA engine and the two softmax warpgroups overlap
+// across consecutive tiles instead of running back to back inside one short-lived CTA:
+//   smem : 2 x {Q, K, V (+ head_dim tails)}             TMEM : 2 x 256 columns
+//   per buffer: S = Q K^T -> cols [0,Lk) fp32;  P (16-bit, packed two per column) overwrites cols [0,Lk/2) in place
+//               (tcgen05.st from the thread that owns the row);  O = P V (A operand from TMEM) -> cols [Lk/2, Lk/2+80).
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 / 6-9 = softmax+epilogue for even / odd tiles.
+//   MMA issue order  S_0, S_1, PV_0, S_2, PV_1, ...: S_{i+1} runs on the tensor pipe while tile i is in its softmax.
+// P never touches shared memory, which is what makes room for the second Q/K/V buffer.
+constexpr int kPipeThreads = 320;
+
+struct PipePlan {
+  int q_main, k_main, v_main, q_tail, k_tail, v_tail, buf_bytes, bars, total;
+};
+__host__ __device__ inline PipePlan make_pipe_plan(int Lk, bool tail) {
+  PipePlan s;
+  s.q_main = 0;
+  s.k_main = 128 * 128;
+  s.v_main = s.k_main + Lk * 128;
+  s.q_tail = s.v_main + Lk * 128;
+  s.k_tail = s.q_tail + (tail ? 128 * 32 : 0);
+  s.v_tail = s.k_tail + (tail ? Lk * 32 : 0);
+  s.buf_bytes = s.v_tail + (tail ? Lk * 32 : 0);
+  s.bars = 2 * s.buf_bytes;
+  s.total = s.bars + 256 + 1024;
+  return s;
+}
+
+template <bool BF16, bool TAIL, int MODE>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
+                 const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt, const AttnDev p,
+                 const int total_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const PipePlan sp = make_pipe_plan(p.Lk, TAIL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* qk_full = bars + 0;   // [2] TMA: Q and K of the buffer have landed
+  uint64_t* v_full = bars + 2;    // [2] TMA: V has landed
+  uint64_t* s_full = bars + 4;    // [2] MMA: S is complete in TMEM          (also: the Q/K smem of the buffer is free)
+  uint64_t* p_full = bars + 6;    // [2] softmax (128 arrivals): P is in TMEM
+  uint64_t* o_full = bars + 8;    // [2] MMA: O is complete in TMEM          (also: the V smem of the buffer is free)
+  uint64_t* o_free = bars + 10;   // [2] epilogue (128 arrivals): O has been read, the TMEM buffer may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Lk = p.Lk;
+  const int H = p.heads;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(qk_full + b, 1);
+      mbar_init(v_full + b, 1);
+      mbar_init(s_full + b, 1);
+      mbar_init(p_full + b, 128);
+      mbar_init(o_full + b, 1);
+      mbar_init(o_free + b, 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // qkv (written by the preceding GEMM) is visible from here
+
+  const int first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      const uint32_t qk_bytes = 128 * 128 + Lk * 128 + (TAIL ? (128 * 32 + Lk * 32) : 0);
+      const uint32_t v_bytes = Lk * 128 + (TAIL ? Lk * 32 : 0);
+      int i = 0;
+      for (int item = first; item < total_items; item += step, ++i) {
+        const int b = i & 1;
+        const uint32_t par = (i >> 1) & 1;
+        uint8_t* buf = smem + b * sp.buf_bytes;
+        const int head = item % H;
+        const int tile = item / H;
+        if (i >= 2) mbar_wait(s_full + b, par ^ 1);    // S of the tile that used this buffer is done: Q/K smem is free
+        if (p.dbg & 1) {
+          mbar_arrive(qk_full + b);
+          if (i >= 2) mbar_wait(o_full + b, par ^ 1);
+          mbar_arrive(v_full + b);
+          continue;
+        }
+        mbar_arrive_expect_tx(qk_full + b, qk_bytes);
+        if constexpr (MODE == MODE_TEMPORAL) {
+          const int bb = tile / p.tiles_per_seq;
+          const int n0 = (tile % p.tiles_per_seq) * p.group;
+          const int bf0 = bb * p.frames;
+          tma_load_4d(buf + sp.q_main, &tmQ, qk_full + b, 0, head, n0, bf0);
+          tma_load_4d(buf + sp.k_main, &tmKV, qk_full + b, 0, p.k_head0 + head, n0, bf0);
+          if constexpr (TAIL) {
+            tma_load_4d(buf + sp.q_tail, &tmQt, qk_full + b, 64, head, n0, bf0);
+            tma_load_4d(buf + sp.k_tail, &tmKVt, qk_full + b, 64, p.k_head0 + head, n0, bf0);
+          }
+          if (i >= 2) mbar_wait(o_full + b, par ^ 1);  // PV of the tile that used this buffer is done: V smem is free
+          mbar_arrive_expect_tx(v_full + b, v_bytes);
+          tma_load_4d(buf + sp.v_main, &tmKV, v_full + b, 0, p.v_head0 + head, n0, bf0);
+          if constexpr (TAIL) tma_load_4d(buf + sp.v_tail, &tmKVt, v_full + b, 64, p.v_head0 + head, n0, bf0);
+        } else {
+          int q_row0, kv_row0;
+          if constexpr (MODE == MODE_FULL) {
+            const int s = tile / p.tiles_per_seq;
+            kv_row0 = s * p.tokens;
+            q_row0 = kv_row0 + (tile % p.tiles_per_seq) * 128;
+          } else if constexpr (MODE == MODE_CROSS) {
+            q_row0 = tile * 128;
+            kv_row0 = (q_row0 / p.q_rows_per_batch) * p.kv_rows_per_batch;
+          } else {
+            q_row0 = kv_row0 = tile * 128;
+          }
+          tma_load_3d(buf + sp.q_main, &tmQ, qk_full + b, 0, head, q_row0);
+          tma_load_3d(buf + sp.k_main, &tmKV, qk_full + b, 0, p.k_head0 + head, kv_row0);
+          if constexpr (TAIL) {
+            tma_load_3d(buf + sp.q_tail, &tmQt, qk_full + b, 64, head, q_row0);
+            tma_load_3d(buf + sp.k_tail, &tmKVt, qk_full + b, 64, p.k_head0 + head, kv_row0);
+          }
+          if (i >= 2) mbar_wait(o_full + b, par ^ 1);
+          mbar_arrive_expect_tx(v_full + b, v_bytes);
+          tma_load_3d(buf + sp.v_main, &tmKV, v_full + b, 0, p.v_head0 + head, kv_row0);
+          if constexpr (TAIL) tma_load_3d(buf + sp.v_tail, &tmKVt, v_full + b, 64, p.v_head0 + head, kv_row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      const int n_items = first < total_items ? (total_items - first + step - 1) / step : 0;
+      const uint32_t idesc_s = umma_idesc_f16(BF16, 128, static_cast<uint32_t>(Lk), false, false);
+      const uint32_t idesc_o = umma_idesc_f16(BF16, 128, 64, false, true);   // B = V is MN-major ([key][hd] in smem)
+      const uint32_t idesc_ot = umma_idesc_f16(BF16, 128, 16, false, true);
+      const int ksteps = Lk / 16;
+      auto issue_s = [&](int i) {
+        const int b = i & 1;
+        const uint32_t par = (i >> 1) & 1;
+        uint8_t* buf = smem + b * sp.buf_bytes;
+        mbar_wait(qk_full + b, par);
+        if (i >= 2) mbar_wait(o_free + b, par ^ 1);     // the epilogue of the previous user has drained the TMEM buffer
+        tc_fence_after();
+        const uint32_t tS = tmem_base + b * 256;
+        const uint64_t dq = umma_smem_desc(smem_u32(buf + sp.q_main), 0, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t dk = umma_smem_desc(smem_u32(buf + sp.k_main), 0, 1024, UMMA_LAYOUT_SW128);
+        if (!(p.dbg & 8)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tS, umma_desc_advance(dq, k * 32), umma_desc_advance(dk, k * 32), idesc_s, k > 0 ? 1u : 0u);
+          if constexpr (TAIL) {
+            const uint64_t dqt = umma_smem_desc(smem_u32(buf + sp.q_tail), 0, 256, UMMA_LAYOUT_SW32);
+            const uint64_t dkt = umma_smem_desc(smem_u32(buf + sp.k_tail), 0, 256, UMMA_LAYOUT_SW32);
+            umma_f16_ss(tS, dqt, dkt, idesc_s, 1u);
+          }
+        }
+        umma_commit(s_full + b);
+      };
+      if (n_items > 0) issue_s(0);
+      for (int i = 0; i < n_items; ++i) {
+        if (i + 1 < n_items) issue_s(i + 1);
+        const int b = i & 1;
+        const uint32_t par = (i >> 1) & 1;
+        uint8_t* buf = smem + b * sp.buf_bytes;
+        mbar_wait(v_full + b, par);
+        mbar_wait(p_full + b, par);
+        tc_fence_after();
+        const uint32_t tP = tmem_base + b * 256;
+        const uint32_t tO = tP + (Lk >> 1);
+        const uint64_t dv = umma_smem_desc(smem_u32(buf + sp.v_main), static_cast<uint32_t>(Lk) * 128, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t dvt = umma_smem_desc(smem_u32(buf + sp.v_tail), static_cast<uint32_t>(Lk) * 32, 256, UMMA_LAYOUT_SW32);
+        for (int k = 0; k < ksteps && !(p.dbg & 8); ++k) {
+          umma_f16_ts(tO, tP + k * 8, umma_desc_advance(dv, k * 16 * 128), idesc_o, k > 0 ? 1u : 0u);
+          if constexpr (TAIL) umma_f16_ts(tO + 64, tP + k * 8, umma_desc_advance(dvt, k * 16 * 32), idesc_ot, k > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full + b);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax + epilogue: thread = tile row
+    const int wg = (warp - 2) >> 2;            // warpgroup 0 takes the even work items of this CTA, 1 the odd ones
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int nchunks = Lk / 32;
+    const int rkey = MODE == MODE_CROSS ? p.kv_rows_per_batch : row_key<MODE>(r, p.gshift);
+    const uint32_t t_row = tmem_base + wg * 256 + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_o = t_row + (Lk >> 1);
+    int i = wg;
+    for (int item = first + wg * step; item < total_items; item += 2 * step, i += 2) {
+      const uint32_t par = (i >> 1) & 1;
+      const int head = item % H;
+      const int tile = item / H;
+      mbar_wait(s_full + wg, par);
+      tc_fence_after();
+
+      const int nch = (p.dbg & 2) ? 0 : nchunks;
+      float mx = -INFINITY;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      const float mscaled = mx * p.scale_log2;
+      float sum = 0.f;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float e0 = ex2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -mscaled));
+          float e1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -mscaled));
+          if (!key_valid<MODE>(rkey, c * 32 + 2 * j, p.gshift)) e0 = 0.f;
+          if (!key_valid<MODE>(rkey, c * 32 + 2 * j + 1, p.gshift)) e1 = 0.f;
+          sum += e0 + e1;
+          pk[j] = pack2<BF16>(e0, e1);
+        }
+        tmem_st_32x32b_x16(t_row + c * 16, pk);   // P chunk c lands on S columns that have already been consumed
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full + wg);
+
+      long long out_row;
+      bool row_ok = true;
+      if constexpr (MODE == MODE_TEMPORAL) {
+        const int bb = tile / p.tiles_per_seq;
+        const int n0 = (tile % p.tiles_per_seq) * p.group;
+        out_row = (static_cast<long long>(bb) * p.frames + r / p.group) * p.tokens + n0 + r % p.group;
+      } else if constexpr (MODE == MODE_FULL) {
+        out_row = static_cast<long long>(tile / p.tiles_per_seq) * p.tokens + (tile % p.tiles_per_seq) * 128 + r;
+      } else {
+        out_row = static_cast<long long>(tile) * 128 + r;
+        row_ok = out_row < p.T;
+      }
+      uint16_t* optr = reinterpret_cast<uint16_t*>(p.out) + out_row * p.D + head * p.hd;
+      const float inv = 1.0f / sum;
+
+      mbar_wait(o_full + wg, par);
+      tc_fence_after();
+      uint32_t o0[32], o1[32], o2[16];
+      tmem_ld_32x32b_x32(t_o, o0);
+      tmem_ld_32x32b_x32(t_o + 32, o1);
+      if constexpr (TAIL) tmem_ld_32x32b_x16(t_o + 64, o2);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free + wg);                   // O is in registers: the MMA warp may start S of the tile after next
+      if (row_ok && !(p.dbg & 4)) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          uint4 o;
+          o.x = pack2<BF16>(__uint_as_float(o0[8 * i4 + 0]) * inv, __uint_as_float(o0[8 * i4 + 1]) * inv);
+          o.y = pack2<BF16>(__uint_as_float(o0[8 * i4 + 2]) * inv, __uint_as_float(o0[8 * i4 + 3]) * inv);
+          o.z = pack2<BF16>(__uint_as_float(o0[8 * i4 + 4]) * inv, __uint_as_float(o0[8 * i4 + 5]) * inv);
+          o.w = pack2<BF16>(__uint_as_float(o0[8 * i4 + 6]) * inv, __uint_as_float(o0[8 * i4 + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + i4 * 8) = o;
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          uint4 o;
+          o.x = pack2<BF16>(__uint_as_float(o1[8 * i4 + 0]) * inv, __uint_as_float(o1[8 * i4 + 1]) * inv);
+          o.y = pack2<BF16>(__uint_as_float(o1[8 * i4 + 2]) * inv, __uint_as_float(o1[8 * i4 + 3]) * inv);
+          o.z = pack2<BF16>(__uint_as_float(o1[8 * i4 + 4]) * inv, __uint_as_float(o1[8 * i4 + 5]) * inv);
+          o.w = pack2<BF16>(__uint_as_float(o1[8 * i4 + 6]) * inv, __uint_as_float(o1[8 * i4 + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + 32 + i4 * 8) = o;
+        }
+        if constexpr (TAIL) {
+          const int tail8 = (p.hd - 64) / 8;  // 1 (hd 72) or 2 (hd 80)
+#pragma unroll
+          for (int i4 = 0; i4 < 2; ++i4) {
+            if (i4 >= tail8) break;
+            uint4 o;
+            o.x = pack2<BF16>(__uint_as_float(o2[8 * i4 + 0]) * inv, __uint_as_float(o2[8 * i4 + 1]) * inv);
+            o.y = pack2<BF16>(__uint_as_float(o2[8 * i4 + 2]) * inv, __uint_as_float(o2[8 * i4 + 3]) * inv);
+            o.z = pack2<BF16>(__uint_as_float(o2[8 * i4 + 4]) * inv, __uint_as_float(o2[8 * i4 + 5]) * inv);
+            o.w = pack2<BF16>(__uint_as_float(o2[8 * i4 + 6]) * inv, __uint_as_float(o2[8 * i4 + 7]) * inv);
+            *reinterpret_cast<uint4*>(optr + 64 + i4 * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool BF16, bool TAIL, int MODE>
+int launch_pipe(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
+  auto kern = attn_pipe_kernel<BF16, TAIL, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, make_pipe_plan(256, true).total));
+    attr_set = true;
+  }
+  const int smem_bytes = make_pipe_plan(p.Lk, TAIL).total;
+  const int total = static_cast<int>(grid.x * grid.y);
+  int sms = 148;
+  B200_TRY(device_sm_count(&sms));
+  const int ctas = total < sms ? total : sms;
+  B200_CHECK_CUDA(launch_pdl(kern, dim3(ctas), dim3(kPipeThreads), static_cast<size_t>(smem_bytes), stream, m[0], m[1], m[2], m[3], p, total));
+  return B200_OK;
+}
+
 template <bool BF16, bool TAIL, int MODE>
 int launch_mode(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
+  static const bool use_old = getenv("B200_ATTN_OLD") != nullptr;   // A/B switch: the one-tile-per-CTA kernel
+  if (!use_old) return launch_pipe<BF16, TAIL, MODE>(m, p, grid, stream);
   auto kern = attn_kernel<BF16, TAIL, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -602,6 +924,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.tokens = a.tokens;
   p.frames = a.frames;
   p.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
+  { const char* e = getenv("B200_ATTN_DBG"); p.dbg = e ? atoi(e) : 0; }
 
   p.group = 1;
   p.gshift = 0;

@@ -30,6 +30,8 @@
 //                    -> re-read with 8 threads per row -> coalesced 16-byte stores.
 //   residual:        x is never loaded: the delta gate*(acc+bias) goes to a swizzled smem tile and a TMA reduce-add
 //                    (cp.reduce.async.bulk.tensor ... .add, fp32) folds it into the residual stream in L2.
+#include <mutex>
+#include <cstdio>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -77,7 +79,73 @@ struct GemmDev {
   // implicit-GEMM convolution: see GemmArgs
   int conv_taps, conv_cblk, conv_h, conv_w, conv_bw, conv_bh;
   int conv_dx[9], conv_dy[9], conv_dz[9];
+  int streamk;  // residual epilogue only: split the last partial wave of tiles along K across all pairs (see TileSched)
+  unsigned long long* sk_flags;   // stream-K ordering flags, one per (streamed tile, CTA rank, epilogue warpgroup)
+  unsigned long long sk_tag;      // launch id << 16: a flag holds tag | (k-blocks of the tile already added into x)
   int dbg;  // timing experiments only (results are wrong when set): bit0 = no operand TMA, bit1 = no MMA issue, bit2 = no 16-bit epilogue
+};
+
+__device__ __forceinline__ void flag_release(unsigned long long* f, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+}
+__device__ __forceinline__ void flag_wait(const unsigned long long* f, unsigned long long want) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v == want) return;
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must not hang the GPU
+      printf("gemm: stream-K flag wait timed out (block %d)\n", blockIdx.x);
+      __trap();
+    }
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Work schedule of one CTA pair.  Data-parallel part: pair k owns tiles k, k + P, ... for the `full_waves` complete waves.
+// Stream-K part (residual epilogue only, where partial sums can be reduce-added into x): the tiles of the last, partial
+// wave (and of the full wave before it) are flattened into (tile, k-block) units and every pair takes an equal contiguous share, so no SM idles while a
+// few pairs finish a whole extra tile.  A segment is (tile, [kb0, kb1)); bias / row_add go with the segment that has kb0 = 0.
+// The partial sums of a tile are added into x in k order (a global flag per tile carries "k-blocks added so far"; the
+// epilogue of a kb0 > 0 segment waits for flag == kb0), so the result is bit-reproducible although several pairs add to it.
+struct TileSched {
+  int pair, P, num_tiles, num_kb, full_waves, wave;
+  long long u, u_end;
+  __device__ TileSched(int pair_, int P_, int num_tiles_, int num_kb_, bool streamk)
+      : pair(pair_), P(P_), num_tiles(num_tiles_), num_kb(num_kb_), wave(0) {
+    if (streamk) {
+      // stream the partial wave TOGETHER WITH the last full wave: every pair's share is then at least one tile long, so
+      // a tile is cut at most once (two segments) and the ordered adds never form a chain of waiting pairs
+      full_waves = num_tiles / P;
+      if (full_waves > 0) --full_waves;
+      const long long units = static_cast<long long>(num_tiles - full_waves * P) * num_kb;
+      u = units * pair / P;
+      u_end = units * (pair + 1) / P;
+    } else {
+      full_waves = (num_tiles + P - 1) / P;
+      u = u_end = 0;
+    }
+  }
+  __device__ bool next(int& tile, int& kb0, int& kb1) {
+    if (wave < full_waves) {
+      tile = wave * P + pair;
+      ++wave;
+      kb0 = 0;
+      kb1 = num_kb;
+      return tile < num_tiles;     // only the last data-parallel wave can run past the end
+    }
+    if (u >= u_end) return false;
+    // streamed share, walked from its END: the segment that starts a tile (kb0 = 0) is done first and the one that
+    // continues a tile begun by the previous pair (kb0 > 0) last, by which time that pair's part has long been added
+    const int t = static_cast<int>((u_end - 1) / num_kb);
+    const long long t0 = static_cast<long long>(t) * num_kb;
+    kb1 = static_cast<int>(u_end - t0);
+    kb0 = u > t0 ? static_cast<int>(u - t0) : 0;
+    tile = full_waves * P + t;
+    u_end = t0 + kb0;
+    return true;
+  }
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -144,9 +212,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t rank = cluster_ctarank();
   const int num_pair_m = (p.num_m + 1) / 2;
   const int num_tiles = num_pair_m * p.num_n;
-  const int first_tile = blockIdx.x >> 1;
-  const int tile_step = gridDim.x >> 1;
+  const int my_pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
   const int num_kb = p.K / BK;
+  const bool streamk = C::RESID && p.streamk != 0;
   const bool leader = rank == 0;
 
   if (warp == 0) {
@@ -154,9 +223,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      TileSched sched(my_pair, num_pairs, num_tiles, num_kb, streamk);
+      int tile, kb0, kb1;
+      while (sched.next(tile, kb0, kb1)) {
         const int m_blk = 2 * (tile / p.num_n) + static_cast<int>(rank), n_blk = tile % p.num_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           const uint32_t full_leader = mapa_u32(&full[stage], 0);
@@ -189,11 +260,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = umma_idesc_f16(BF16, 2 * BM, BN, false, false);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      TileSched sched(my_pair, num_pairs, num_tiles, num_kb, streamk);
+      int tile, kb0, kb1;
+      while (sched.next(tile, kb0, kb1)) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);            // both CTAs' operands landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -203,7 +276,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_f16_ss_pair(d_tmem, umma_desc_advance(da, k * 32), umma_desc_advance(db, k * 32), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
+                             (kb != kb0 || k != 0) ? 1u : 0u);
           umma_commit_pair(&empty[stage], 0x3);  // slot reusable in BOTH CTAs once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -226,22 +299,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if constexpr (C::RESID) {
       // x += gate * (acc + bias) (+ row_add) WITHOUT loading x: the delta tile goes registers -> smem (128-byte rows,
       // 16-byte chunks XOR-swizzled to match the tensor map) -> TMA reduce-add into the fp32 residual stream.  Each
-      // element receives exactly one add per GEMM, so results are deterministic.  The two warpgroups take alternate
-      // 32-column chunks (owner = running chunk counter & 1) and double-buffer their own two staging tiles.
+      // element receives one add per GEMM -- or, for stream-K tiles, one per segment in a fixed (k) order -- so results
+      // are deterministic.  The two warpgroups take alternate 32-column chunks (owner = running chunk counter & 1, or
+      // the chunk's own parity for stream-K so that a column always belongs to the same warpgroup) and double-buffer
+      // their own two staging tiles.
       uint32_t cc = 0, mine = 0;
       const int bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      TileSched sched(my_pair, num_pairs, num_tiles, num_kb, streamk);
+      int tile, kb0, kb1;
+      while (sched.next(tile, kb0, kb1)) {
+        const bool first_seg = kb0 == 0;       // bias and row_add are added once per output element
         const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         const int row = m0 + row_a;
         const int row_c = row < p.M ? row : p.M - 1;  // rows past M produce deltas that the TMA store clips
         const float* gate_row = p.gate + static_cast<long long>(row_c / p.rows_per_batch) * p.gate_bs;
-        const float* add_row = p.row_add ? p.row_add + static_cast<size_t>((row_c / p.row_add_div) % p.row_add_period) * p.N : nullptr;
+        const float* add_row = (p.row_add && first_seg) ? p.row_add + static_cast<size_t>((row_c / p.row_add_div) % p.row_add_period) * p.N : nullptr;
         constexpr int NCH = BN / 32;
         const int live = (p.N - n0) / 32 < NCH ? (p.N - n0) / 32 : NCH;   // chunks inside N (N % 32 == 0)
+        const uint32_t cbase = streamk ? 0u : cc;
         int last_mine = -1;
         for (int c = 0; c < live; ++c)
-          if (((cc + c) & 1) == static_cast<uint32_t>(wg)) last_mine = c;
+          if (((cbase + c) & 1) == static_cast<uint32_t>(wg)) last_mine = c;
+        // stream-K ordering: this warpgroup's adds for the tile follow those of the segment that ends at kb0
+        const bool partial = kb0 > 0 || kb1 < num_kb;
+        unsigned long long* flag = nullptr;
+        if (partial) flag = p.sk_flags + (static_cast<size_t>(tile - sched.full_waves * num_pairs) * 2 + rank) * 2 + wg;
+        bool must_wait = kb0 > 0;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         if (last_mine < 0) {                   // a one-chunk edge tile owned by the other warpgroup
@@ -251,7 +335,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
 #pragma unroll 1
         for (int c = 0; c < live; ++c) {
-          if (((cc + c) & 1) != static_cast<uint32_t>(wg)) continue;
+          if (((cbase + c) & 1) != static_cast<uint32_t>(wg)) continue;
           const int col0 = n0 + c * 32;
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c * 32, v);
@@ -268,7 +352,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+            if (p.bias && first_seg) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
             const float4 gt = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + j);
             float4 dv;
             dv.x = gt.x * (__uint_as_float(v[4 * j + 0]) + b4.x);
@@ -284,11 +368,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           fence_proxy_async_smem();                     // generic-proxy smem writes -> visible to the TMA engine
           asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");
           if (te == 0) {
+            if (must_wait) {
+              flag_wait(flag, p.sk_tag | static_cast<unsigned long long>(kb0));
+              fence_proxy_async_all();
+            }
             tma_reduce_add_2d(&tmX, slot, col0, m0);
             tma_store_commit();
             tma_store_wait_read<1>();                   // the reduce issued one chunk ago (other tile) has read its smem
           }
+          must_wait = false;
           asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");   // ... so the other staging tile may be rewritten
+        }
+        if (partial && kb1 < num_kb && last_mine >= 0 && te == 0 && !(p.dbg & 8)) {
+          tma_store_wait_all<0>();                      // this segment's adds have been performed ...
+          __threadfence();
+          flag_release(flag, p.sk_tag | static_cast<unsigned long long>(kb1));   // ... the next segment may add
         }
         cc += live;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -300,7 +394,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint8_t* buf = epi_smem + wg * kSlotBytes;   // one staging tile per warpgroup
       const int bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
       uint32_t cc = 0;                        // running chunk counter: chunk cc belongs to warpgroup (cc & 1)
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      TileSched sched(my_pair, num_pairs, num_tiles, num_kb, false);
+      int tile, kb0, kb1;
+      while (sched.next(tile, kb0, kb1)) {
         const int m0 = (2 * (tile / p.num_n) + static_cast<int>(rank)) * BM, n0 = (tile % p.num_n) * BN;
         const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         constexpr int NCH = BN / 64;           // 64 16-bit columns = 128 bytes per row per chunk
@@ -431,17 +527,45 @@ int launch_bn(int bf16, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
   return bf16 ? launch_epi<BN, true>(epi, tmA, tmB, tmX, p, grid, s) : launch_epi<BN, false>(epi, tmA, tmB, tmX, p, grid, s);
 }
 
-int pick_block_n(int M, int N, int sms) {
+constexpr int kStreamKMinKb = 32;          // K / 64 below which the split costs more than the idle tail it removes
+constexpr int kSkFlagsPerLaunch = 1024;    // flags (u64) per launch: 4 per streamed tile
+constexpr int kSkSlices = 256;             // ring of flag slices: a slice is reused 256 stream-K launches later
+
+// A fresh slice of the per-device flag ring and a launch id.  Flags are never reset: a flag is meaningful only when its
+// upper 48 bits equal the id of the launch that reads it.
+int streamk_flags(unsigned long long** slice, unsigned long long* id) {
+  static std::mutex mu;
+  static unsigned long long* ring[64] = {};
+  static unsigned long long next_id = 1;
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  B200_REQUIRE(dev >= 0 && dev < 64, B200_ERR_UNSUPPORTED, "gemm: device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ring[dev]) {
+    const size_t bytes = static_cast<size_t>(kSkSlices) * kSkFlagsPerLaunch * sizeof(unsigned long long);
+    B200_CHECK_CUDA(cudaMalloc(&ring[dev], bytes));
+    B200_CHECK_CUDA(cudaMemset(ring[dev], 0, bytes));
+    B200_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  *id = next_id++;
+  *slice = ring[dev] + (*id % kSkSlices) * kSkFlagsPerLaunch;
+  return B200_OK;
+}
+
+int pick_block_n(int M, int N, int K, bool resid, int sms) {
   // minimise waves x per-tile time.  The kernel is bound by L2->SM operand bytes, not MMA cycles, so a tile costs
   // ~ (A bytes + W/2 bytes per k-block per CTA) = 128 + BN/2 rather than BN (measured: r01 microbench, profiles/).
+  // Where the last wave is streamed along K (residual epilogue, long K) there is no wave rounding.
   if (N <= 128) return 128;   // narrow outputs (e.g. the VAE's 3-channel conv_out padded to 32): smallest tile that covers N
+  static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
+  const bool sk = resid && !no_sk && K / BK >= kStreamKMinKb;
   const int cand[3] = {256, 192, 128};
   int best = 128;
   double best_cost = 1e300;
   for (int i = 0; i < 3; ++i) {
     const long long tiles = static_cast<long long>((M + BM - 1) / BM) * ((N + cand[i] - 1) / cand[i]);
-    const long long waves = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * (128 + cand[i] / 2);
+    const double waves = (sk && tiles > sms) ? static_cast<double>(tiles) / sms : static_cast<double>((tiles + sms - 1) / sms);
+    const double cost = waves * (128 + cand[i] / 2);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = cand[i]; }
   }
   return best;
@@ -475,7 +599,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   int sms = 0;
   B200_TRY(device_sm_count(&sms));
 
-  int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, sms);
+  int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL, sms);
   B200_REQUIRE(bn == 128 || bn == 192 || bn == 256, B200_ERR_UNSUPPORTED, "gemm: block_n must be 128, 192 or 256 (got %d)", bn);
 
   CUtensorMap tmA, tmB, tmX;
@@ -537,6 +661,22 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   const int pair_tiles = ((p.num_m + 1) / 2) * p.num_n;
   int grid = 2 * pair_tiles < sms ? 2 * pair_tiles : (sms & ~1);   // whole clusters of 2
+  {
+    // stream-K over the last partial wave: only where partial sums can be reduce-added (residual epilogue) and K is
+    // long enough to be worth splitting; B200_GEMM_NO_STREAMK=1 restores the one-add-per-element schedule.
+    static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
+    const int pairs = grid / 2;
+    p.streamk = (resid && !no_sk && pair_tiles > pairs && pair_tiles % pairs != 0 && p.K / BK >= kStreamKMinKb) ? 1 : 0;
+    p.sk_flags = nullptr;
+    p.sk_tag = 0;
+    if (p.streamk) {
+      const int streamed = pair_tiles % pairs + pairs;  // tiles of the partial wave and of the full wave before it
+      B200_REQUIRE(streamed * 4 <= kSkFlagsPerLaunch, B200_ERR_UNSUPPORTED, "gemm: stream-K flag slice too small");
+      unsigned long long id = 0;
+      B200_TRY(streamk_flags(&p.sk_flags, &id));
+      p.sk_tag = id << 16;
+    }
+  }
   switch (bn) {
     case 128: return launch_bn<128>(a.bf16, a.epilogue, tmA, tmB, tmX, p, grid, stream);
     case 192: return launch_bn<192>(a.bf16, a.epilogue, tmA, tmB, tmX, p, grid, stream);

@@ -85,7 +85,10 @@ def test_properties_at_baseline_shape(golden_dir):
         full = net(xd, td, y=yd)
         assert torch.equal(full, net(xd, td, y=yd))
         solo = net(xd[1:], td[1:], y=yd[1:])
-        assert (solo - full[1:]).abs().max().item() < 1e-5          # no cross-sample coupling (attention is per sample)
+        # no cross-sample coupling (attention is per sample).  Not bit-equal: the residual GEMMs split K differently for
+        # M = 4096 and M = 8192 rows (stream-K), and a 1-ulp change of the fp32 stream can flip 16-bit operand roundings
+        # downstream, so the two runs differ by 16-bit rounding noise (same size as the error against the fp32 golden)
+        assert (solo - full[1:]).abs().max().item() < 5e-3
         c1 = net.forward_with_cfg(xd, td, y=yd, cfg_scale=1.0)
         twice = net(torch.cat([xd[:1], xd[:1]]), td, y=yd)
         assert (c1[:1, :, :4] - twice[:1, :, :4]).abs().max().item() < 1e-4

@@ -46,6 +46,31 @@ def test_linear_epilogues(dev, dt, shape):
     _close(resid, want, 2e-4 if dt == torch.float16 else 2e-4)  # fp32 residual stream: only accumulation-order noise
 
 
+@pytest.mark.parametrize("shape", [(8192, 1152, 4608), (8192 + 128, 1152, 2048), (4096 * 5, 384, 4096)])
+def test_residual_linear_streamk(dev, shape):
+    """The last partial wave of the gated-residual GEMM is split along K across all CTA pairs and the partial sums are
+    reduce-added into x in k order (gemm.cu TileSched): same numbers as the unsplit restatement, bit-identical reruns."""
+    from latte_b200 import ops
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn(M, K, generator=g).to(dev).half()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).half()
+    bias = torch.randn(N, generator=g).to(dev)
+    B = 2
+    rpb = (M + B - 1) // B
+    gate = torch.randn(B, N, generator=g).to(dev)
+    x0 = torch.randn(M, N, generator=g).to(dev)
+    want = x0 + gate[torch.arange(M, device=dev) // rpb] * (A.float() @ W.float().t() + bias)
+    for bn in (0, 128, 192, 256):
+        outs = []
+        for _ in range(3):
+            x = x0.clone()
+            ops.linear_gate_residual_(x, A, W, bias, gate, rpb, block_n=bn)
+            outs.append(x)
+        _close(outs[0], want, 3e-4)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_linear_is_linear_and_deterministic(dev):
     """Size-independent properties at the full XL/2 fc1 shape: f(a) + f(b) == f(a + b) (no bias) up to rounding; reruns are bit-identical."""
     from latte_b200 import ops
