@@ -8,6 +8,7 @@
 //                 repeated rows (latte.py:172-178)
 //   final_layer   LN + modulate + Linear(D, p*p*Cout) + unpatchify scatter                   (latte.py:197-201,297-310,374-376)
 //   cfg_combine   classifier-free guidance on eps channels                                   (latte.py:394-398)
+#include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -30,7 +31,7 @@ constexpr int LN_MAXV = 12;  // float4 per lane: dim <= 12*128 = 1536
 // consecutive rows and all warps are resident at once (register-limited to 32 warps/SM): a grid-stride loop left a
 // half-empty second wave.  The block's shift/scale vectors are staged in shared memory once, so the only global latency
 // on a row's critical path is the row itself.
-template <bool BF16, int NV>
+template <bool BF16, int NV, bool PREFETCH>
 __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
                                                           const float* __restrict__ scale, long long mod_bs,
                                                           int rows_per_batch, uint16_t* __restrict__ out, int rows,
@@ -42,23 +43,33 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
   const int block_row0 = blockIdx.x * (blockDim.x >> 5) * rows_per_warp;
   pdl_launch_dependents();
   const long long b0 = (block_row0 < rows ? block_row0 : rows - 1) / rows_per_batch;
-  pdl_wait();
+  // shift / scale come from the conditioning path at the start of the step (a plainly launched kernel that completed
+  // before any programmatically-launched one began), not from the kernel just before this one: stage them while that
+  // kernel is still draining.  x (the residual stream it updates) is only touched after pdl_wait().
   for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) {
     const float* src = (i < nv ? shift : scale) + b0 * mod_bs;
     s_mod[i] = __ldg(reinterpret_cast<const float4*>(src) + (i < nv ? i : i - nv));
   }
   __syncthreads();
-  for (int rr = 0; rr < rows_per_warp; ++rr) {
-    const int row = warp_global * rows_per_warp + rr;
-    if (row >= rows) break;
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
-    float4 v[NV];
-    float s = 0.f;
+  pdl_wait();
+  const int row0 = warp_global * rows_per_warp;
+  float4 v[NV], vn[NV];
+  if (row0 < rows) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row0) * dim);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int idx = lane + i * 32;
-      if (idx < nv) v[i] = xr[idx];
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nv) v[i] = xr[lane + i * 32];
+  }
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int row = row0 + rr;
+    if (row >= rows) break;
+    if (PREFETCH && rr + 1 < rows_per_warp && row + 1 < rows) {   // next row's loads are in flight while this row is reduced
+      const float4* xn = reinterpret_cast<const float4*>(x + static_cast<size_t>(row + 1) * dim);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (lane + i * 32 < nv) vn[i] = xn[lane + i * 32];
     }
+    float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (lane + i * 32 < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -90,16 +101,45 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
         orow[idx] = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
       }
     }
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = vn[i];
+    } else if (rr + 1 < rows_per_warp && row + 1 < rows) {
+      const float4* xn = reinterpret_cast<const float4*>(x + static_cast<size_t>(row + 1) * dim);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (lane + i * 32 < nv) v[i] = xn[lane + i * 32];
+    }
   }
 }
 
-template <bool BF16>
-void ln_dispatch(int nvmax, int blocks, size_t smem, cudaStream_t stream, const float* x, const float* shift, const float* scale,
-                 long long mod_bs, int rpb, uint16_t* out, int rows, int dim, int rpw) {
-  if (nvmax <= 3) launch_pdl(ln_modulate_kernel<BF16, 3>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
-  else if (nvmax <= 6) launch_pdl(ln_modulate_kernel<BF16, 6>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
-  else if (nvmax <= 9) launch_pdl(ln_modulate_kernel<BF16, 9>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
-  else launch_pdl(ln_modulate_kernel<BF16, LN_MAXV>, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw);
+template <bool BF16, int NV, bool PREFETCH>
+int ln_launch(cudaStream_t stream, const float* x, const float* shift, const float* scale, long long mod_bs, int rpb,
+              uint16_t* out, int rows, int dim, int sms) {
+  auto kern = ln_modulate_kernel<BF16, NV, PREFETCH>;
+  const size_t smem = static_cast<size_t>(dim) * 2 * sizeof(float);
+  static int blocks_per_sm = 0;   // per instantiation: what the register/smem footprint really allows
+  if (blocks_per_sm == 0) {
+    int n = 0;
+    B200_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, smem));
+    blocks_per_sm = n > 0 ? n : 1;
+  }
+  // every warp gets the same number of consecutive rows and the whole grid is resident in one wave
+  const int wpb = 4;
+  const int resident_warps = sms * blocks_per_sm * wpb;
+  const int rpw = (rows + resident_warps - 1) / resident_warps;
+  const int blocks = (rows + wpb * rpw - 1) / (wpb * rpw);
+  B200_CHECK_CUDA(launch_pdl(kern, dim3(blocks), dim3(128), smem, stream, x, shift, scale, mod_bs, rpb, out, rows, dim, rpw));
+  return B200_OK;
+}
+
+template <bool BF16, bool PREFETCH>
+int ln_dispatch(int nvmax, cudaStream_t stream, const float* x, const float* shift, const float* scale, long long mod_bs,
+                int rpb, uint16_t* out, int rows, int dim, int sms) {
+  if (nvmax <= 3) return ln_launch<BF16, 3, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
+  if (nvmax <= 6) return ln_launch<BF16, 6, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
+  if (nvmax <= 9) return ln_launch<BF16, 9, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
+  return ln_launch<BF16, LN_MAXV, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
 }
 
 // ---------------------------------------------------------------------------------- patch_embed
@@ -194,30 +234,43 @@ __global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ W, c
     for (int r = 0; r < GV_ROWS; ++r)
 #pragma unroll
       for (int b = 0; b < GV_MAXB; ++b) acc[r][b] = 0.f;
-    for (int c = lane; c < nchunk; c += 32) {
-      uint4 wv[GV_ROWS];
+    // two 16-byte chunks per row per trip: 2 * GV_ROWS independent loads in flight per lane (the op is a pure weight stream)
+    for (int c0 = lane; c0 < nchunk; c0 += 64) {
+      uint4 wv[2][GV_ROWS];
+      const bool has2 = c0 + 32 < nchunk;
 #pragma unroll
-      for (int r = 0; r < GV_ROWS; ++r) {
-        const int j = j0 + r < J ? j0 + r : J - 1;
-        wv[r] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(W) + (static_cast<size_t>(j) * K + static_cast<size_t>(c) * EPC) * (WBITS / 8)));
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int r = 0; r < GV_ROWS; ++r) {
+          const int j = j0 + r < J ? j0 + r : J - 1;
+          const int c = c0 + h * 32;
+          if (h == 0 || has2)
+            wv[h][r] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(W) + (static_cast<size_t>(j) * K + static_cast<size_t>(c) * EPC) * (WBITS / 8)));
+          else
+            wv[h][r] = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
 #pragma unroll
-      for (int b = 0; b < GV_MAXB; ++b) {
-        if (b < batch) {
-          const float4 x0 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC);
-          float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (WBITS == 16) x1 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC + 4);
+      for (int h = 0; h < 2; ++h) {
+        const int c = (h == 0 || has2) ? c0 + h * 32 : c0;   // (zero weights: any valid x address)
 #pragma unroll
-          for (int r = 0; r < GV_ROWS; ++r) {
-            if constexpr (WBITS == 32) {
-              acc[r][b] = fmaf(__uint_as_float(wv[r].x), x0.x, fmaf(__uint_as_float(wv[r].y), x0.y,
-                          fmaf(__uint_as_float(wv[r].z), x0.z, fmaf(__uint_as_float(wv[r].w), x0.w, acc[r][b]))));
-            } else {
-              const float2 w0 = unpack2<BF16>(wv[r].x), w1 = unpack2<BF16>(wv[r].y), w2 = unpack2<BF16>(wv[r].z), w3 = unpack2<BF16>(wv[r].w);
-              float a = acc[r][b];
-              a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a); a = fmaf(w1.x, x0.z, a); a = fmaf(w1.y, x0.w, a);
-              a = fmaf(w2.x, x1.x, a); a = fmaf(w2.y, x1.y, a); a = fmaf(w3.x, x1.z, a); a = fmaf(w3.y, x1.w, a);
-              acc[r][b] = a;
+        for (int b = 0; b < GV_MAXB; ++b) {
+          if (b < batch) {
+            const float4 x0 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC);
+            float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (WBITS == 16) x1 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC + 4);
+#pragma unroll
+            for (int r = 0; r < GV_ROWS; ++r) {
+              if constexpr (WBITS == 32) {
+                acc[r][b] = fmaf(__uint_as_float(wv[h][r].x), x0.x, fmaf(__uint_as_float(wv[h][r].y), x0.y,
+                            fmaf(__uint_as_float(wv[h][r].z), x0.z, fmaf(__uint_as_float(wv[h][r].w), x0.w, acc[r][b]))));
+              } else {
+                const float2 w0 = unpack2<BF16>(wv[h][r].x), w1 = unpack2<BF16>(wv[h][r].y), w2 = unpack2<BF16>(wv[h][r].z), w3 = unpack2<BF16>(wv[h][r].w);
+                float a = acc[r][b];
+                a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a); a = fmaf(w1.x, x0.z, a); a = fmaf(w1.y, x0.w, a);
+                a = fmaf(w2.x, x1.x, a); a = fmaf(w2.y, x1.y, a); a = fmaf(w3.x, x1.z, a); a = fmaf(w3.y, x1.w, a);
+                acc[r][b] = a;
+              }
             }
           }
         }
@@ -420,19 +473,17 @@ int launch_ln_modulate(const float* x, const float* shift, const float* scale, l
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(out16) & 7) == 0,
                B200_ERR_ALIGN, "ln_modulate: pointers must be 16-byte aligned");
-  const int wpb = 4;
   int sms = 0;
   B200_TRY(device_sm_count(&sms));
-  // every warp gets the same number of consecutive rows and the whole grid is resident (<= 32 warps/SM by registers)
-  const int resident_warps = sms * 32;
-  const int rpw = (rows + resident_warps - 1) / resident_warps;
-  const int blocks = (rows + wpb * rpw - 1) / (wpb * rpw);
   const int nvmax = (dim / 4 + 31) / 32;
-  const size_t smem = static_cast<size_t>(dim) * 2 * sizeof(float);
-  if (bf16) ln_dispatch<true>(nvmax, blocks, smem, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim, rpw);
-  else ln_dispatch<false>(nvmax, blocks, smem, stream, x, shift, scale, mod_batch_stride, rows_per_batch, reinterpret_cast<uint16_t*>(out16), rows, dim, rpw);
-  B200_CHECK_CUDA(cudaGetLastError());
-  return B200_OK;
+  static const bool prefetch = getenv("B200_LN_PREFETCH") ? atoi(getenv("B200_LN_PREFETCH")) != 0 : false;   // measured r01: no gain, 2x the registers
+  uint16_t* o = reinterpret_cast<uint16_t*>(out16);
+  if (prefetch) {
+    if (bf16) return ln_dispatch<true, true>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
+    return ln_dispatch<false, true>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
+  }
+  if (bf16) return ln_dispatch<true, false>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
+  return ln_dispatch<false, false>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
 }
 
 int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const float* b, const float* pos, float* out,

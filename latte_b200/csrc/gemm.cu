@@ -531,6 +531,11 @@ constexpr int kStreamKMinKb = 32;          // K / 64 below which the split costs
 constexpr int kSkFlagsPerLaunch = 1024;    // flags (u64) per launch: 4 per streamed tile
 constexpr int kSkSlices = 256;             // ring of flag slices: a slice is reused 256 stream-K launches later
 
+int streamk_min_kb() {
+  static const int v = getenv("B200_GEMM_SK_MINKB") ? atoi(getenv("B200_GEMM_SK_MINKB")) : kStreamKMinKb;
+  return v;
+}
+
 // A fresh slice of the per-device flag ring and a launch id.  Flags are never reset: a flag is meaningful only when its
 // upper 48 bits equal the id of the launch that reads it.
 int streamk_flags(unsigned long long** slice, unsigned long long* id) {
@@ -558,7 +563,7 @@ int pick_block_n(int M, int N, int K, bool resid, int sms) {
   // Where the last wave is streamed along K (residual epilogue, long K) there is no wave rounding.
   if (N <= 128) return 128;   // narrow outputs (e.g. the VAE's 3-channel conv_out padded to 32): smallest tile that covers N
   static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
-  const bool sk = resid && !no_sk && K / BK >= kStreamKMinKb;
+  const bool sk = resid && !no_sk && K / BK >= streamk_min_kb();
   const int cand[3] = {256, 192, 128};
   int best = 128;
   double best_cost = 1e300;
@@ -666,7 +671,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     // long enough to be worth splitting; B200_GEMM_NO_STREAMK=1 restores the one-add-per-element schedule.
     static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
     const int pairs = grid / 2;
-    p.streamk = (resid && !no_sk && pair_tiles > pairs && pair_tiles % pairs != 0 && p.K / BK >= kStreamKMinKb) ? 1 : 0;
+    p.streamk = (resid && !no_sk && pair_tiles > pairs && pair_tiles % pairs != 0 && p.K / BK >= streamk_min_kb()) ? 1 : 0;
     p.sk_flags = nullptr;
     p.sk_tag = 0;
     if (p.streamk) {
