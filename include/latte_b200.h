@@ -245,6 +245,36 @@ B200_API int b200_attention(const void* qkv, void* out, int batch, int frames, i
 B200_API int b200_ln_modulate(const float* x, const float* shift, const float* scale, int64_t mod_batch_stride,
                      int rows_per_batch, void* out16, int rows, int dim, int dtype, void* stream);
 
+/* ---- sampler step: the fp32 arithmetic the reference's GaussianDiffusion does around every model
+ * call, as ONE kernel with device-resident schedule tables.  Replaces p_mean_variance (diffusion/gaussian_diffusion.py:
+ * 254-336, EPSILON mean + LEARNED_RANGE variance), p_sample (:380-419), ddim_sample (:517-564) and the per-call
+ * _extract_into_tensor H2D copies (:869-881).                                                                            */
+enum { B200_SAMPLER_DDPM = 0, B200_SAMPLER_DDIM = 1 };
+typedef struct {
+  int num_timesteps;                             /* length of every table (the respaced chain)                           */
+  const float* sqrt_recip_alphas_cumprod;        /* device, fp32 = the reference's float64 table cast with .float()      */
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* posterior_log_variance_clipped;
+  const float* log_betas;                        /* np.log(betas)                                                        */
+  /* DDIM only (may be NULL for DDPM): the per-timestep scalars of ddim_sample (:544-556) evaluated ONCE by the caller in
+   * fp32 with the reference's expressions on the fp32 alphas_cumprod / alphas_cumprod_prev values:
+   *   ddim_sqrt_alpha_prev = sqrt(abar_prev);  ddim_sigma = eta * sqrt((1-abar_prev)/(1-abar)) * sqrt(1 - abar/abar_prev);
+   *   ddim_dir = sqrt(1 - abar_prev - ddim_sigma^2)                                                                     */
+  const float* ddim_sqrt_alpha_prev;
+  const float* ddim_sigma;
+  const float* ddim_dir;
+} B200SamplerTables;
+
+/* x_t (B,F,C,H,W) fp32, t (B,) int64 chain indices (device), model_out (B,F,2C,H,W) in model_out_dtype (0 fp32, 1 fp16,
+ * 2 bf16), noise (B,F,C,H,W) fp32 or NULL (= zeros; DDIM with sigma == 0 only).  Outputs, each fp32 (B,F,C,H,W) or NULL:
+ * x_prev ('sample'), pred_xstart, mean, log_variance (p_mean_variance's dict).  hw = H*W must be a multiple of 4.       */
+B200_API int b200_sampler_step(const B200SamplerTables* tables, int method, int clip_denoised, const int64_t* t,
+                               const float* x, const void* model_out, int model_out_dtype, const float* noise, int batch,
+                               int frames, int channels, int hw, float* x_prev, float* pred_xstart, float* mean,
+                               float* log_variance, void* stream);
+
 /* Measurement hook (bench.py roofline): while enabled, b200_latte_forward brackets every kernel launch with
  * CUDA events on the launching stream.  b200_profile_collect waits for them and returns, per class
  * {0 tensor-core GEMM, 1 attention, 2 LN+modulate, 3 other}, the summed device time in ms and the launch count,

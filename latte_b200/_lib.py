@@ -70,6 +70,12 @@ class VaeDecoder(C.Structure):
                 ("out_channels", C.c_int32), ("temporal_eps", C.c_float), ("time_conv_w", C.c_void_p), ("time_conv_b", C.c_void_p)]
 
 
+class SamplerTables(C.Structure):
+    _fields_ = [("num_timesteps", C.c_int)] + [(n, C.c_void_p) for n in (
+        "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+        "posterior_log_variance_clipped", "log_betas", "ddim_sqrt_alpha_prev", "ddim_sigma", "ddim_dir")]
+
+
 EXPORTS = {
     "b200_last_error": (C.c_char_p, []),
     "b200_abi_version": (C.c_int, []),
@@ -93,6 +99,9 @@ EXPORTS = {
                                   C.c_void_p]),
     "b200_vae_decode_temporal": (C.c_int, [C.POINTER(VaeDecoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_size_t, C.c_void_p]),
+    "b200_sampler_step": (C.c_int, [C.POINTER(SamplerTables), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_profile_enable": (None, [C.c_int]),
     "b200_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }

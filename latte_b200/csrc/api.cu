@@ -351,6 +351,15 @@ int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, 
 
 extern "C" {
 
+B200_API int b200_sampler_step(const B200SamplerTables* tables, int method, int clip_denoised, const int64_t* t,
+                               const float* x, const void* model_out, int model_out_dtype, const float* noise, int batch,
+                               int frames, int channels, int hw, float* x_prev, float* pred_xstart, float* mean,
+                               float* log_variance, void* stream) {
+  return b200::launch_sampler_step(tables, method, clip_denoised, reinterpret_cast<const long long*>(t), x, model_out,
+                                   model_out_dtype, noise, batch, frames, channels, hw, x_prev, pred_xstart, mean,
+                                   log_variance, static_cast<cudaStream_t>(stream));
+}
+
 B200_API void b200_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(b200::g_prof.mu);
   b200::g_prof.on = on != 0;

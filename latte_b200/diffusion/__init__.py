@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's `diffusion` package for the SAMPLING path:
+`create_diffusion(str(steps))` returns an object with the reference's `ddim_sample_loop`, `p_sample_loop`, their
+`*_progressive` generators, `ddim_sample`, `p_sample` and `p_mean_variance` (same names, arguments and return dicts:
+diffusion/__init__.py:10-47, diffusion/gaussian_diffusion.py:254-336, 380-516, 517-689, diffusion/respace.py:65-130), so
+`sample/sample.py:67,100-107` and `sample/sample_ddp.py:87,149-156` run on it unchanged.
+
+What differs from the reference is only HOW a step is computed: the schedule tables are built once in float64 numpy (the
+reference's formulas), cast to fp32 exactly as `_extract_into_tensor` does, and kept on the device; the ~40 elementwise
+launches and ~12 pageable H2D copies the reference issues around every model call become ONE kernel
+(`b200_sampler_step`, latte_b200/csrc/sampler.cu) and the timestep tensors are slices of device-resident tables, so a
+sampling loop never synchronises the host with the GPU.  The per-step `randn_like` is still drawn in BOTH methods (the
+reference consumes RNG at eta = 0 too, gaussian_diffusion.py:555).
+
+CUDA tensors only -- there is no CPU path (the CPU truth is oracle/sampler_oracle.py, test infrastructure).
+Not built (raise NotImplementedError): cond_fn / denoised_fn hooks, predict_xstart, fixed-variance models, training_losses.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+DDPM, DDIM = 0, 1
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _space_timesteps(num_timesteps: int, section_counts) -> set:
+    """respace.py:12-62 ("ddimN" integer stride, or per-section fractional strides with python `round`)."""
+    if isinstance(section_counts, str):
+        if section_counts.startswith("ddim"):
+            want = int(section_counts[len("ddim"):])
+            for stride in range(1, num_timesteps):
+                if len(range(0, num_timesteps, stride)) == want:
+                    return set(range(0, num_timesteps, stride))
+            raise ValueError(f"cannot create exactly {num_timesteps} steps with an integer stride")
+        section_counts = [int(v) for v in section_counts.split(",")]
+    size_per, extra = divmod(num_timesteps, len(section_counts))
+    start, steps = 0, []
+    for i, count in enumerate(section_counts):
+        size = size_per + (1 if i < extra else 0)
+        if size < count:
+            raise ValueError(f"cannot divide section of {size} steps into {count}")
+        frac = 1 if count <= 1 else (size - 1) / (count - 1)
+        cur = 0.0
+        for _ in range(count):
+            steps.append(start + round(cur))
+            cur += frac
+        start += size
+    return set(steps)
+
+
+class SpacedDiffusion:
+    """The sampling half of respace.SpacedDiffusion(GaussianDiffusion): eps-prediction, learned-range variance."""
+
+    def __init__(self, use_timesteps, betas):
+        base = np.array(betas, dtype=np.float64)
+        self.original_num_steps = len(base)
+        self.use_timesteps = set(use_timesteps)
+        base_ac = np.cumprod(1.0 - base, axis=0)
+        last, new_betas, self.timestep_map = 1.0, [], []
+        for i, ac in enumerate(base_ac):                       # respace.py:77-86
+            if i in self.use_timesteps:
+                new_betas.append(1 - ac / last)
+                last = ac
+                self.timestep_map.append(i)
+        b = self.betas = np.array(new_betas, dtype=np.float64)  # gaussian_diffusion.py:171-208
+        assert b.ndim == 1 and (b > 0).all() and (b <= 1).all()
+        self.num_timesteps = int(b.shape[0])
+        alphas = 1.0 - b
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.alphas_cumprod_next = np.append(self.alphas_cumprod[1:], 0.0)
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = b * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = (np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+                                               if len(b) > 1 else np.array([]))
+        self.posterior_mean_coef1 = b * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        self._dev = {}   # (device, batch, eta) -> (SamplerTables, keep-alive tensor, t table, mapped-t table)
+
+    # ------------------------------------------------------------------ device-resident state
+    _BASE = ["sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+             "posterior_log_variance_clipped"]
+
+    def _state(self, device: torch.device, batch: int, eta: float = 0.0):
+        """(tables, keep-alive tensor, t table, mapped-t table) for this device / batch size / DDIM eta, built once."""
+        key = (device, batch, float(eta))
+        st = self._dev.get(key)
+        if st is None:
+            f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64)).float()   # noqa: E731  float64 table -> .float()
+            base = [f32(getattr(self, n)) for n in self._BASE] + [f32(np.log(self.betas))]
+            # DDIM scalars in fp32 with the reference's expressions (gaussian_diffusion.py:544-556), evaluated on the host
+            ab, abp = f32(self.alphas_cumprod), f32(self.alphas_cumprod_prev)
+            sigma = float(eta) * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
+            ddim = [torch.sqrt(abp), sigma, torch.sqrt(1 - abp - sigma ** 2)]
+            flat = torch.stack(base + ddim).to(device)
+            tab = _lib.SamplerTables()
+            tab.num_timesteps = self.num_timesteps
+            for i, n in enumerate(self._BASE + ["log_betas", "ddim_sqrt_alpha_prev", "ddim_sigma", "ddim_dir"]):
+                setattr(tab, n, flat[i].data_ptr())
+            t_table = torch.arange(self.num_timesteps, device=device, dtype=torch.int64).unsqueeze(1).repeat(1, batch).contiguous()
+            mapped = torch.tensor(self.timestep_map, device=device, dtype=torch.int64)[t_table].contiguous()
+            st = self._dev[key] = (tab, flat, t_table, mapped)
+        return st
+
+    # ------------------------------------------------------------------ one step
+    def _step(self, method, model_output, x, t, noise, clip_denoised, eta, want):
+        if not x.is_cuda:
+            raise RuntimeError("latte_b200.diffusion runs on CUDA tensors only (no CPU path)")
+        if isinstance(model_output, tuple):
+            model_output = model_output[0]
+        B, F, C_ = x.shape[:3]
+        hw = int(np.prod(x.shape[3:]))
+        if tuple(model_output.shape) != (B, F, 2 * C_, *x.shape[3:]):
+            raise ValueError(f"model output {tuple(model_output.shape)} != {(B, F, 2 * C_, *x.shape[3:])} (learn_sigma layout)")
+        if model_output.dtype not in _DT:
+            raise TypeError(f"model output dtype {model_output.dtype} unsupported")
+        x = x.float().contiguous()
+        model_output = model_output.contiguous()
+        t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        if noise is not None:
+            noise = noise.float().contiguous()
+        tab = self._state(x.device, B, eta)[0]
+        outs = {k: torch.empty_like(x) for k in want}
+        ptr = lambda k: outs[k].data_ptr() if k in outs else None   # noqa: E731
+        lib = _lib.load()
+        rc = lib.b200_sampler_step(C.byref(tab), method, int(bool(clip_denoised)), t.data_ptr(), x.data_ptr(),
+                                   model_output.data_ptr(), _DT[model_output.dtype], noise.data_ptr() if noise is not None else None,
+                                   B, F, C_, hw, ptr("sample"), ptr("pred_xstart"), ptr("mean"), ptr("log_variance"),
+                                   torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc, "b200_sampler_step")
+        return outs
+
+    def _call_model(self, model, x, t, model_kwargs, mapped=None):
+        """_WrappedModel.__call__ (respace.py:125-130): the model sees ORIGINAL timesteps.  The loops pass `mapped`, a row of
+        the device-resident table; a free-standing call gathers from the cached device copy of timestep_map."""
+        if mapped is None:
+            key = ("map", x.device)
+            mt = self._dev.get(key)
+            if mt is None:
+                mt = self._dev[key] = torch.tensor(self.timestep_map, device=x.device, dtype=torch.int64)
+            mapped = mt[t.to(device=x.device, dtype=torch.int64)]
+        return model(x, mapped, **(model_kwargs or {}))
+
+    @staticmethod
+    def _no_hooks(denoised_fn, cond_fn):
+        if denoised_fn is not None or cond_fn is not None:
+            raise NotImplementedError("denoised_fn / cond_fn hooks are not built in latte_b200.diffusion")
+
+    def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None):
+        self._no_hooks(denoised_fn, None)
+        mo = self._call_model(model, x, t, model_kwargs)
+        o = self._step(DDPM, mo, x, t, None, clip_denoised, 0.0, ("mean", "log_variance", "pred_xstart"))
+        return {"mean": o["mean"], "variance": torch.exp(o["log_variance"]), "log_variance": o["log_variance"],
+                "pred_xstart": o["pred_xstart"], "extra": None}
+
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, noise=None, _mapped=None):
+        self._no_hooks(denoised_fn, cond_fn)
+        mo = self._call_model(model, x, t, model_kwargs, _mapped)
+        if noise is None:
+            noise = torch.randn_like(x, dtype=torch.float32)
+        return self._step(DDPM, mo, x, t, noise, clip_denoised, 0.0, ("sample", "pred_xstart"))
+
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0, noise=None,
+                    _mapped=None):
+        self._no_hooks(denoised_fn, cond_fn)
+        mo = self._call_model(model, x, t, model_kwargs, _mapped)
+        if noise is None:
+            noise = torch.randn_like(x, dtype=torch.float32)   # drawn even at eta = 0, as the reference does
+        return self._step(DDIM, mo, x, t, noise, clip_denoised, eta, ("sample", "pred_xstart"))
+
+    # ------------------------------------------------------------------ loops
+    def _loop(self, step_fn, model, shape, noise, device, progress, **kw):
+        if device is None:
+            device = next(model.parameters()).device
+        device = torch.device(device)
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else torch.randn(*shape, device=device)
+        _, _, t_table, mapped_table = self._state(device, shape[0])
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        for i in indices:
+            with torch.no_grad():
+                out = step_fn(model, img, t_table[i], _mapped=mapped_table[i], **kw)
+            yield out
+            img = out["sample"]
+
+    def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                  model_kwargs=None, device=None, progress=False):
+        yield from self._loop(self.p_sample, model, shape, noise, device, progress, clip_denoised=clip_denoised,
+                              denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs)
+
+    def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                      device=None, progress=False):
+        final = None
+        for final in self.p_sample_loop_progressive(model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress):
+            pass
+        return final["sample"]
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, eta=0.0):
+        yield from self._loop(self.ddim_sample, model, shape, noise, device, progress, clip_denoised=clip_denoised,
+                              denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                         device=None, progress=False, eta=0.0):
+        final = None
+        for final in self.ddim_sample_loop_progressive(model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                                                       device, progress, eta):
+            pass
+        return final["sample"]
+
+    def training_losses(self, *a, **k):
+        raise NotImplementedError("training_losses is not built in latte_b200.diffusion (sampling path only)")
+
+
+def create_diffusion(timestep_respacing, noise_schedule="linear", use_kl=False, sigma_small=False, predict_xstart=False,
+                     learn_sigma=True, rescale_learned_sigmas=False, diffusion_steps=1000):
+    """diffusion/__init__.py:10-47 for the configuration every Latte script uses."""
+    if noise_schedule != "linear" or predict_xstart or not learn_sigma:
+        raise NotImplementedError("only the linear schedule with eps-prediction and learned-range variance is built")
+    scale = 1000 / diffusion_steps
+    betas = np.linspace(scale * 0.0001, scale * 0.02, diffusion_steps, dtype=np.float64)   # gaussian_diffusion.py:110-118
+    if timestep_respacing is None or timestep_respacing == "":
+        timestep_respacing = [diffusion_steps]
+    return SpacedDiffusion(_space_timesteps(diffusion_steps, timestep_respacing), betas)
