@@ -222,6 +222,20 @@ B200_API int b200_latte_forward(const B200LatteShape* shape, const B200LatteWeig
                        const int64_t* y, int batch, int use_cfg, float cfg_scale, float* out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Whole-trajectory conditioning.  The per-sample conditioning -- t_embedder(t) + y_embedder(y)
+ * (latte.py:332-339), every block's adaLN_modulation (:160-163,177) and the final layer's (:192-195) -- depends only on
+ * (t, y), so a sampler that knows its timesteps can evaluate all of it before the loop: n = steps x batch rows here, then
+ * b200_latte_forward_conditioned per step with that step's `batch` rows.  Same kernels and arithmetic as inside
+ * b200_latte_forward (bit-identical output); what it saves per step is the 446 MB adaLN weight stream and 4 launches.
+ *   mod_out: [n, depth*6*hidden + 2*hidden] fp32 (b200_latte_conditioning_bytes), 1024-byte aligned.            */
+B200_API size_t b200_latte_conditioning_bytes(const B200LatteShape* shape, int n);
+B200_API size_t b200_latte_conditioning_workspace_bytes(const B200LatteShape* shape, int n);
+B200_API int b200_latte_conditioning(const B200LatteShape* shape, const B200LatteWeights* w, const int64_t* t, const int64_t* y,
+                                     int n, float* mod_out, void* workspace, size_t workspace_bytes, void* stream);
+B200_API int b200_latte_forward_conditioned(const B200LatteShape* shape, const B200LatteWeights* w, const float* x,
+                                            const float* mod, int batch, int use_cfg, float cfg_scale, float* out,
+                                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* out = epilogue(A @ W^T + bias) on tcgen05 tensor cores — replaces the nn.Linear calls of the block
  * (latte.py:50 qkv, :75 proj, timm Mlp fc1/fc2 via :171).  A [M,K], W [N,K] 16-bit; bias [N] fp32 or NULL.
  *   B200_EPI_BIAS           out16[M,N] = acc + bias

@@ -83,6 +83,13 @@ EXPORTS = {
     "b200_latte_forward": (C.c_int, [C.POINTER(LatteShape), C.POINTER(LatteWeights), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),
+    "b200_latte_conditioning_bytes": (C.c_size_t, [C.POINTER(LatteShape), C.c_int]),
+    "b200_latte_conditioning_workspace_bytes": (C.c_size_t, [C.POINTER(LatteShape), C.c_int]),
+    "b200_latte_conditioning": (C.c_int, [C.POINTER(LatteShape), C.POINTER(LatteWeights), C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200_latte_forward_conditioned": (C.c_int, [C.POINTER(LatteShape), C.POINTER(LatteWeights), C.c_void_p, C.c_void_p,
+                                                 C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                 C.c_void_p]),
     "b200_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "b200_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -90,13 +90,36 @@ void carve(const B200LatteShape* s, int batch, void* base, Workspace* ws) {
   ws->bytes = off;
 }
 
+// ---- conditioning, once per SAMPLE (latte.py:332-339): c = t_embedder(t) (+ y_embedder(y)); mod = adaLN(SiLU(c)) for all
+// blocks and the final layer.  `n` rows; scratch tfreq [n,256], th [n,D], c [n,D]; mod [n, depth*6D + 2D].
+int conditioning(const B200LatteShape* s, const B200LatteWeights* w, const int64_t* t, const int64_t* y, int n, float* tfreq,
+                 float* th, float* c, float* mod, cudaStream_t stream) {
+  const int D = s->hidden;
+  const int bf16 = s->dtype == B200_BF16;
+  const long long mod_bs = static_cast<long long>(s->depth) * 6 * D + 2 * D;
+  B200_PROF(PROF_OTHER, launch_timestep_freq(reinterpret_cast<const long long*>(t), tfreq, n, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, tfreq, th, n, D, 256, 0, 1, nullptr, nullptr, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w2, 32, 0, w->t_b2, th, c, n, D, D, 0, 0, s->num_embed > 0 ? w->y_table : nullptr,
+                       reinterpret_cast<const long long*>(y), stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->ada_w16, 16, bf16, w->ada_b, c, mod, n, static_cast<int>(mod_bs), D, 1, 0, nullptr,
+                       nullptr, stream));
+  return B200_OK;
+}
+
+size_t conditioning_scratch_bytes(const B200LatteShape* s, int n) {
+  return align_up(static_cast<size_t>(n) * 256 * 4, 1024) + 2 * align_up(static_cast<size_t>(n) * s->hidden * 4, 1024);
+}
+
+// premod != NULL: the caller already holds this batch's conditioning rows (b200_latte_conditioning, e.g. for a whole
+// sampling trajectory at once -- SURVEY.md 8f rank 2); t is then unused and the adaLN weights are not read.
 int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, const int64_t* t, const int64_t* y,
-            int batch, int use_cfg, float cfg_scale, float* out, void* workspace, size_t workspace_bytes,
-            cudaStream_t stream) {
+            const float* premod, int batch, int use_cfg, float cfg_scale, float* out, void* workspace,
+            size_t workspace_bytes, cudaStream_t stream) {
   B200_TRY(shape_ok(s, batch));
-  B200_REQUIRE(w && x && t && out && workspace, B200_ERR_SHAPE, "NULL argument");
-  B200_REQUIRE((s->num_embed > 0) == (y != nullptr && w->y_table != nullptr), B200_ERR_SHAPE,
+  B200_REQUIRE(w && x && (t || premod) && out && workspace, B200_ERR_SHAPE, "NULL argument");
+  B200_REQUIRE(premod || (s->num_embed > 0) == (y != nullptr && w->y_table != nullptr), B200_ERR_SHAPE,
                "labels y and y_table must be given iff num_embed > 0 (extras == 2)");
+  B200_REQUIRE(!premod || (reinterpret_cast<uintptr_t>(premod) & 15) == 0, B200_ERR_ALIGN, "conditioning rows must be 16-byte aligned");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, B200_ERR_ALIGN, "workspace must be 1024-byte aligned");
   const bool cfg = use_cfg != 0;
   B200_REQUIRE(!cfg || batch % 2 == 0, B200_ERR_SHAPE, "classifier-free guidance needs an even batch (got %d)", batch);
@@ -114,13 +137,8 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
   const long long mod_bs = static_cast<long long>(depth) * 6 * D + 2 * D;
   const int HID = s->mlp_hidden;
 
-  // ---- conditioning, once per SAMPLE (latte.py:332-339): c = t_embedder(t) (+ y_embedder(y)); mod = adaLN(SiLU(c)) for all blocks
-  B200_PROF(PROF_OTHER, launch_timestep_freq(reinterpret_cast<const long long*>(t), ws.tfreq, batch, stream));
-  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, stream));
-  B200_PROF(PROF_OTHER, launch_gemv(w->t_w2, 32, 0, w->t_b2, ws.th, ws.c, batch, D, D, 0, 0, s->num_embed > 0 ? w->y_table : nullptr,
-                       reinterpret_cast<const long long*>(y), stream));
-  B200_PROF(PROF_OTHER, launch_gemv(w->ada_w16, 16, bf16, w->ada_b, ws.c, ws.mod, batch, static_cast<int>(mod_bs), D, 1, 0, nullptr,
-                       nullptr, stream));
+  if (premod) ws.mod = const_cast<float*>(premod);
+  else B200_TRY(conditioning(s, w, t, y, batch, ws.tfreq, ws.th, ws.c, ws.mod, stream));
 
   // ---- patch embedding + pos_embed -> fp32 residual stream (latte.py:330-331)
   B200_PROF(PROF_OTHER, launch_patch_embed(x, cfg ? batch / 2 : batch, w->patch_w, w->patch_b, w->pos_embed, ws.x, batch, F,
@@ -394,7 +412,42 @@ B200_API size_t b200_latte_workspace_bytes(const B200LatteShape* shape, int batc
 B200_API int b200_latte_forward(const B200LatteShape* shape, const B200LatteWeights* w, const float* x, const int64_t* t,
                        const int64_t* y, int batch, int use_cfg, float cfg_scale, float* out, void* workspace,
                        size_t workspace_bytes, void* stream) {
-  return b200::forward(shape, w, x, t, y, batch, use_cfg, cfg_scale, out, workspace, workspace_bytes,
+  return b200::forward(shape, w, x, t, y, nullptr, batch, use_cfg, cfg_scale, out, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+B200_API size_t b200_latte_conditioning_bytes(const B200LatteShape* shape, int n) {
+  if (b200::shape_ok(shape, n) != B200_OK) return 0;
+  return static_cast<size_t>(n) * (static_cast<size_t>(shape->depth) * 6 * shape->hidden + 2 * shape->hidden) * sizeof(float);
+}
+
+B200_API size_t b200_latte_conditioning_workspace_bytes(const B200LatteShape* shape, int n) {
+  if (b200::shape_ok(shape, n) != B200_OK) return 0;
+  return b200::conditioning_scratch_bytes(shape, n);
+}
+
+B200_API int b200_latte_conditioning(const B200LatteShape* shape, const B200LatteWeights* w, const int64_t* t, const int64_t* y,
+                                     int n, float* mod_out, void* workspace, size_t workspace_bytes, void* stream) {
+  B200_TRY(b200::shape_ok(shape, n));
+  B200_REQUIRE(w && t && mod_out && workspace, B200_ERR_SHAPE, "NULL argument");
+  B200_REQUIRE((shape->num_embed > 0) == (y != nullptr && w->y_table != nullptr), B200_ERR_SHAPE,
+               "labels y and y_table must be given iff num_embed > 0 (extras == 2)");
+  B200_REQUIRE(((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(mod_out)) & 1023) == 0, B200_ERR_ALIGN,
+               "workspace and mod_out must be 1024-byte aligned");
+  B200_REQUIRE(workspace_bytes >= b200::conditioning_scratch_bytes(shape, n), B200_ERR_WORKSPACE, "conditioning workspace too small");
+  B200_TRY(b200::check_arch());
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  float* tfreq = reinterpret_cast<float*>(base);
+  float* th = reinterpret_cast<float*>(base + b200::align_up(static_cast<size_t>(n) * 256 * 4, 1024));
+  float* c = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(th) + b200::align_up(static_cast<size_t>(n) * shape->hidden * 4, 1024));
+  return b200::conditioning(shape, w, t, y, n, tfreq, th, c, mod_out, static_cast<cudaStream_t>(stream));
+}
+
+B200_API int b200_latte_forward_conditioned(const B200LatteShape* shape, const B200LatteWeights* w, const float* x,
+                                            const float* mod, int batch, int use_cfg, float cfg_scale, float* out,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(mod != nullptr, B200_ERR_SHAPE, "conditioning rows are NULL");
+  return b200::forward(shape, w, x, nullptr, nullptr, mod, batch, use_cfg, cfg_scale, out, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
 }
 

@@ -17,6 +17,7 @@ Not built (raise NotImplementedError): cond_fn / denoised_fn hooks, predict_xsta
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -137,7 +138,7 @@ class SpacedDiffusion:
         _lib.check(rc, "b200_sampler_step")
         return outs
 
-    def _call_model(self, model, x, t, model_kwargs, mapped=None):
+    def _call_model(self, model, x, t, model_kwargs, mapped=None, traj=None):
         """_WrappedModel.__call__ (respace.py:125-130): the model sees ORIGINAL timesteps.  The loops pass `mapped`, a row of
         the device-resident table; a free-standing call gathers from the cached device copy of timestep_map."""
         if mapped is None:
@@ -146,7 +147,10 @@ class SpacedDiffusion:
             if mt is None:
                 mt = self._dev[key] = torch.tensor(self.timestep_map, device=x.device, dtype=torch.int64)
             mapped = mt[t.to(device=x.device, dtype=torch.int64)]
-        return model(x, mapped, **(model_kwargs or {}))
+        kw = dict(model_kwargs or {})
+        if traj is not None:
+            kw["trajectory_step"] = traj      # latte_b200.Latte: conditioning rows precomputed for the whole loop
+        return model(x, mapped, **kw)
 
     @staticmethod
     def _no_hooks(denoised_fn, cond_fn):
@@ -160,17 +164,18 @@ class SpacedDiffusion:
         return {"mean": o["mean"], "variance": torch.exp(o["log_variance"]), "log_variance": o["log_variance"],
                 "pred_xstart": o["pred_xstart"], "extra": None}
 
-    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, noise=None, _mapped=None):
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, noise=None, _mapped=None,
+                 _traj=None):
         self._no_hooks(denoised_fn, cond_fn)
-        mo = self._call_model(model, x, t, model_kwargs, _mapped)
+        mo = self._call_model(model, x, t, model_kwargs, _mapped, _traj)
         if noise is None:
             noise = torch.randn_like(x, dtype=torch.float32)
         return self._step(DDPM, mo, x, t, noise, clip_denoised, 0.0, ("sample", "pred_xstart"))
 
     def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0, noise=None,
-                    _mapped=None):
+                    _mapped=None, _traj=None):
         self._no_hooks(denoised_fn, cond_fn)
-        mo = self._call_model(model, x, t, model_kwargs, _mapped)
+        mo = self._call_model(model, x, t, model_kwargs, _mapped, _traj)
         if noise is None:
             noise = torch.randn_like(x, dtype=torch.float32)   # drawn even at eta = 0, as the reference does
         return self._step(DDIM, mo, x, t, noise, clip_denoised, eta, ("sample", "pred_xstart"))
@@ -187,11 +192,22 @@ class SpacedDiffusion:
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
-        for i in indices:
-            with torch.no_grad():
-                out = step_fn(model, img, t_table[i], _mapped=mapped_table[i], **kw)
-            yield out
-            img = out["sample"]
+        # this repo's module can evaluate the (t, y)-only conditioning of ALL steps before the loop
+        owner = getattr(model, "__self__", None)
+        armed = False
+        if (owner is not None and hasattr(owner, "precompute_conditioning") and not getattr(owner, "training", False)
+                and not os.environ.get("B200_NO_TRAJECTORY_CONDITIONING")):
+            owner.precompute_conditioning(mapped_table, (kw.get("model_kwargs") or {}).get("y"))
+            armed = True
+        try:
+            for i in indices:
+                with torch.no_grad():
+                    out = step_fn(model, img, t_table[i], _mapped=mapped_table[i], _traj=i if armed else None, **kw)
+                yield out
+                img = out["sample"]
+        finally:
+            if armed:
+                owner.clear_conditioning()
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                                   model_kwargs=None, device=None, progress=False):

@@ -144,6 +144,7 @@ class Latte(nn.Module):
         self.initialize_weights()
         self._packed = None
         self._packed_key = None
+        self._trajectory = None
         self._workspace = None
 
     # -------------------------------------------------------------------------------------------
@@ -260,7 +261,7 @@ class Latte(nn.Module):
             self._workspace = ws
         return ws, need
 
-    def _run(self, x, t, y, use_cfg, cfg_scale):
+    def _run(self, x, t, y, use_cfg, cfg_scale, trajectory_step=None):
         if not x.is_cuda:
             raise RuntimeError("latte_b200.Latte runs on CUDA (sm_100a) only; there is no CPU fallback "
                                "(the CPU truth lives in oracle/, which is test infrastructure)")
@@ -293,26 +294,76 @@ class Latte(nn.Module):
             ws, need = self._get_workspace(shape, B, dev)
             base = (ws.data_ptr() + 1023) // 1024 * 1024
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.b200_latte_forward(C.byref(shape), C.byref(w), xf.data_ptr(), tt.data_ptr(),
-                                        yy.data_ptr() if yy is not None else None, B, int(use_cfg), float(cfg_scale),
-                                        out.data_ptr(), base, need, stream)
-            _lib.check(rc, "b200_latte_forward")
+            traj = self._trajectory
+            if trajectory_step is not None and traj is not None:
+                mod = traj[int(trajectory_step)]                    # [B, depth*6D + 2D] rows precomputed for this step
+                if mod.shape[0] != B or mod.device != dev:
+                    raise ValueError("precomputed conditioning does not match this batch")
+                rc = lib.b200_latte_forward_conditioned(C.byref(shape), C.byref(w), xf.data_ptr(), mod.data_ptr(), B, int(use_cfg),
+                                                        float(cfg_scale), out.data_ptr(), base, need, stream)
+                _lib.check(rc, "b200_latte_forward_conditioned")
+            else:
+                rc = lib.b200_latte_forward(C.byref(shape), C.byref(w), xf.data_ptr(), tt.data_ptr(),
+                                            yy.data_ptr() if yy is not None else None, B, int(use_cfg), float(cfg_scale),
+                                            out.data_ptr(), base, need, stream)
+                _lib.check(rc, "b200_latte_forward")
         pd = self.blocks[0].attn.qkv.weight.dtype
         return out if pd == torch.float32 else out.to(pd)
 
-    def forward(self, x, t, y=None, text_embedding=None, use_fp16=False):
+    def forward(self, x, t, y=None, text_embedding=None, use_fp16=False, trajectory_step=None):
         """x (N,F,C,H,W), t (N,), y (N,) -> (N,F,out_channels,H,W) (latte.py:314-377).  `use_fp16` is accepted for
-        call compatibility; the operand precision follows the parameter dtype (`.half()` as in sample.py:72-75)."""
+        call compatibility; the operand precision follows the parameter dtype (`.half()` as in sample.py:72-75).
+        `trajectory_step` (not in the reference): use row `trajectory_step` of `precompute_conditioning` instead of (t, y)."""
         if text_embedding is not None:
             raise NotImplementedError("text_embedding (extras=78) is outside the built hot path")
-        return self._run(x, t, y, False, 0.0)
+        return self._run(x, t, y, False, 0.0, trajectory_step)
 
-    def forward_with_cfg(self, x, t, y=None, cfg_scale=7.0, use_fp16=False, text_embedding=None):
+    def forward_with_cfg(self, x, t, y=None, cfg_scale=7.0, use_fp16=False, text_embedding=None, trajectory_step=None):
         """Classifier-free guidance variant (latte.py:379-398): the first half of `x` is run with (t, y) of both
         halves; eps channels [:in_channels] of both halves become uncond + s * (cond - uncond)."""
         if text_embedding is not None:
             raise NotImplementedError("text_embedding (extras=78) is outside the built hot path")
-        return self._run(x, t, y, True, float(cfg_scale))
+        return self._run(x, t, y, True, float(cfg_scale), trajectory_step)
+
+    # ------------------------------------------------------------------ whole-trajectory conditioning (SURVEY.md 8f rank 2)
+    def precompute_conditioning(self, timesteps, y=None):
+        """The conditioning path (t_embedder + y_embedder, latte.py:332-339; every adaLN_modulation, :160-163,192-195) depends
+        only on (t, y).  `timesteps` (steps, B) int64 = the ORIGINAL timesteps the sampler will feed, step by step; `y` (B,).
+        Evaluates all steps * B rows once (same kernels and arithmetic as inside forward -> bit-identical outputs) and keeps
+        them on the device; `forward*(…, trajectory_step=i)` then skips the 446 MB/step adaLN weight stream.  Used by
+        latte_b200.diffusion's loops; `clear_conditioning()` drops the cache."""
+        lib = _lib.load()
+        dev = self.pos_embed.device
+        if dev.type != "cuda":
+            raise RuntimeError("latte_b200.Latte runs on CUDA (sm_100a) only; there is no CPU fallback")
+        steps, B = timesteps.shape
+        with torch.cuda.device(dev):
+            shape, w, _, _ = self._pack()
+            tt = timesteps.detach().to(device=dev, dtype=torch.int64).contiguous().view(-1)
+            yy = None
+            if self.extras == 2:
+                if y is None:
+                    raise ValueError("class-conditional model (extras=2) needs labels y")
+                yy = y.detach().to(device=dev, dtype=torch.int64).view(1, B).expand(steps, B).contiguous().view(-1)
+            n = steps * B
+            row = lib.b200_latte_conditioning_bytes(C.byref(shape), 1) // 4
+            if row == 0:
+                raise RuntimeError("latte_b200: unsupported configuration: " + _lib.last_error())
+            mod = torch.empty(n * row + 256, dtype=torch.float32, device=dev)
+            off = (-(mod.data_ptr() // 4)) % 256                      # 1024-byte aligned start
+            mod = mod[off:off + n * row]
+            need = lib.b200_latte_conditioning_workspace_bytes(C.byref(shape), n)
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            rc = lib.b200_latte_conditioning(C.byref(shape), C.byref(w), tt.data_ptr(), yy.data_ptr() if yy is not None else None,
+                                             n, mod.data_ptr(), base, need, torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "b200_latte_conditioning")
+            ws.record_stream(torch.cuda.current_stream(dev))
+        self._trajectory = mod.view(steps, B, row)
+        return self._trajectory
+
+    def clear_conditioning(self):
+        self._trajectory = None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -129,3 +129,36 @@ def test_sampler_drives_latte_module(dev, golden_dir):
     # 8 model calls with fp16 operands (per-call error ~2e-3 of the output scale); with random weights and no clipping the
     # trajectory grows to |x| ~ 4e2, so compare relative to the sample's scale
     assert (out.cpu() - ref).abs().max().item() < 5e-3 * ref.abs().max().item()
+
+
+def test_trajectory_conditioning_is_bit_identical(dev, monkeypatch):
+    """conditioning rows for all steps evaluated before the loop (b200_latte_conditioning +
+    b200_latte_forward_conditioned) give bit-identical model outputs and bit-identical trajectories."""
+    from latte_b200 import Latte
+    from latte_b200.diffusion import create_diffusion
+    from oracle import latte_oracle as O
+    cfg = O.make_config("Latte-tiny72/2", input_size=16, num_frames=16)
+    net = Latte(input_size=16, hidden_size=cfg.hidden_size, depth=cfg.depth, num_heads=cfg.num_heads, num_frames=16,
+                num_classes=cfg.num_classes, extras=2)
+    net.load_state_dict(O.make_weights(cfg, 9))
+    net = net.to(dev).eval()
+    x, t, y = (v.to(dev) for v in O.make_inputs(cfg, 2, 10))
+    steps = torch.tensor([[999, 999], [500, 500], [int(t[0]), int(t[1])]], device=dev)
+    with torch.no_grad():
+        plain = net(x, t, y=y)
+        plain_cfg = net.forward_with_cfg(x, t, y=y, cfg_scale=3.0)
+        traj = net.precompute_conditioning(steps, y)
+        assert traj.shape[:2] == (3, 2)
+        assert torch.equal(net(x, t, y=y, trajectory_step=2), plain)
+        assert torch.equal(net.forward_with_cfg(x, t, y=y, cfg_scale=3.0, trajectory_step=2), plain_cfg)
+        assert not torch.equal(net(x, t, y=y, trajectory_step=0), plain)      # a different timestep's rows
+        net.clear_conditioning()
+        assert torch.equal(net(x, t, y=y, trajectory_step=2), plain)          # cache dropped -> (t, y) path
+        d = create_diffusion("8")
+        zz = torch.cat([x[:1], x[:1]], 0)
+        kw = dict(y=y, cfg_scale=4.0)
+        a = d.ddim_sample_loop(net.forward_with_cfg, zz.shape, zz, clip_denoised=False, model_kwargs=kw, device=dev)
+        assert net._trajectory is None                                          # dropped when the loop ends
+        monkeypatch.setenv("B200_NO_TRAJECTORY_CONDITIONING", "1")
+        b = d.ddim_sample_loop(net.forward_with_cfg, zz.shape, zz, clip_denoised=False, model_kwargs=kw, device=dev)
+    assert torch.equal(a, b)
