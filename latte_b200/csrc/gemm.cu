@@ -227,6 +227,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int tile, kb0, kb1;
       while (sched.next(tile, kb0, kb1)) {
         const int m_blk = 2 * (tile / p.num_n) + static_cast<int>(rank), n_blk = tile % p.num_n;
+        // narrow edge tile (N not a multiple of BN): the pair's MMA shrinks to the live columns (see the MMA warp), so the two
+        // halves of the W tile are the two halves of the LIVE columns
+        const int n_live = ((p.N - n_blk * BN) < BN && !(p.dbg & 64)) ? (p.N - n_blk * BN) : BN;
+        const int w_row0 = n_blk * BN + static_cast<int>(rank) * (n_live / 2);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -248,7 +252,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             } else {
               tma_load_2d_pair(sa, &tmA, full_leader, kb * BK, m_blk * BM);
             }
-            tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+            tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, w_row0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -257,7 +261,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BF16, 2 * BM, BN, false, false);
+      constexpr uint32_t idesc_full = umma_idesc_f16(BF16, 2 * BM, BN, false, false);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       TileSched sched(my_pair, num_pairs, num_tiles, num_kb, streamk);
@@ -266,6 +270,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        // edge tile: only the live columns (a multiple of 32) are multiplied -- no tensor work / energy on zero padding
+        const int n0 = (tile % p.num_n) * BN;
+        const int n_live = ((p.N - n0) < BN && !(p.dbg & 64)) ? (p.N - n0) : BN;   // dbg bit 6: A/B switch (full-width edge tiles)
+        const uint32_t idesc = n_live == BN ? idesc_full : umma_idesc_f16(BF16, 2 * BM, static_cast<uint32_t>(n_live), false, false);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);            // both CTAs' operands landed
           tc_fence_after();
