@@ -522,22 +522,25 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(s_full + wg, par);
       tc_fence_after();
 
-      const int nch = (p.dbg & 2) ? 0 : nchunks;
+      const int nch = (p.dbg & 2) ? 0 : nchunks;   // Lk / 32: 4 or 8
+      // pass 1: row maximum.  Two 32-column TMEM loads are in flight per wait (the loads, not the math, set the pace).
       float mx = -INFINITY;
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
+      for (int c = 0; c < nch; c += 2) {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, va);
+        tmem_ld_32x32b_x32(t_row + (c + 1) * 32, vb);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) {
+          if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(va[j]));
+          if (key_valid<MODE>(rkey, (c + 1) * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(vb[j]));
+        }
       }
       const float mscaled = mx * p.scale_log2;
       float sum = 0.f;
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
-        tmem_ld_wait();
+      // pass 2: P = exp2(s * scale - max), written over the S columns already consumed.  The load of chunk c+1 is in flight
+      // while chunk c is exponentiated (P chunk c lands in S chunk c/2 <= c, never in a chunk still being loaded).
+      auto emit = [&](const uint32_t (&v)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -548,7 +551,20 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           sum += e0 + e1;
           pk[j] = pack2<BF16>(e0, e1);
         }
-        tmem_st_32x32b_x16(t_row + c * 16, pk);   // P chunk c lands on S columns that have already been consumed
+        tmem_st_32x32b_x16(t_row + c * 16, pk);
+      };
+      if (nch > 0) {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(t_row, va);
+        tmem_ld_wait();
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_32x32b_x32(t_row + (c + 1) * 32, vb);
+          emit(va, c);
+          tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld_32x32b_x32(t_row + (c + 2) * 32, va);
+          emit(vb, c + 1);
+          tmem_ld_wait();
+        }
       }
       tmem_st_wait();
       tc_fence_before();
