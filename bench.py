@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--model", default="Latte-XL/2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-video", action="store_true", help="skip the measured 250-step video + VAE decode (profiler runs)")
     ap.add_argument("--workload", default="latte", choices=["latte", "t2v"],
                     help="latte = BASELINE configs[1] (the bench line); t2v = configs[3] denoiser step, a secondary measurement")
     args = ap.parse_args()
@@ -279,6 +280,14 @@ def main():
     gemm_ms_step = ms[0] / K
     achieved = gemm_flops_step / (gemm_ms_step * 1e-3) / 1e12
     launches = sum(nl) // K
+    # DRAM bytes per GEMM launch from the committed ncu --set full capture (tools/ncu_traffic.py), same units as `achieved`'s
+    # numerator is per launch; null until a capture of the current kernels has been committed
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     res = {
         "metric": METRIC, "value": world * K / (ms_total * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -294,13 +303,13 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05, 4 launches/block)",
                      "achieved": achieved, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tensor_sustained"], "traffic": None,
+                     "frac": achieved / peaks["tensor_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                      "gemm_ms_per_step": gemm_ms_step, "attn_ms_per_step": ms[1] / K, "ln_ms_per_step": ms[2] / K,
                      "other_ms_per_step": ms[3] / K, "instrumented_pass_ms_per_step": sum(ms) / K},
         "clocks": clk,
     }
-    if world == 1:
+    if world == 1 and not args.no_video:
         # End-to-end frames/s of BASELINE configs[1] (second half of BASELINE.json's metric): one 16-frame video =
         # 250 DDIM steps (the measured step) + ONE AutoencoderKL decode of the 16 latents (measured here with the SD-VAE
         # topology, synthetic weights) — sampler elementwise math and mp4 encoding excluded (reference code, out of scope).

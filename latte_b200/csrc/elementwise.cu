@@ -234,43 +234,30 @@ __global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ W, c
     for (int r = 0; r < GV_ROWS; ++r)
 #pragma unroll
       for (int b = 0; b < GV_MAXB; ++b) acc[r][b] = 0.f;
-    // two 16-byte chunks per row per trip: 2 * GV_ROWS independent loads in flight per lane (the op is a pure weight stream)
-    for (int c0 = lane; c0 < nchunk; c0 += 64) {
-      uint4 wv[2][GV_ROWS];
-      const bool has2 = c0 + 32 < nchunk;
+    for (int c = lane; c < nchunk; c += 32) {
+      uint4 wv[GV_ROWS];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int r = 0; r < GV_ROWS; ++r) {
-          const int j = j0 + r < J ? j0 + r : J - 1;
-          const int c = c0 + h * 32;
-          if (h == 0 || has2)
-            wv[h][r] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(W) + (static_cast<size_t>(j) * K + static_cast<size_t>(c) * EPC) * (WBITS / 8)));
-          else
-            wv[h][r] = make_uint4(0u, 0u, 0u, 0u);
-        }
+      for (int r = 0; r < GV_ROWS; ++r) {
+        const int j = j0 + r < J ? j0 + r : J - 1;
+        wv[r] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(W) + (static_cast<size_t>(j) * K + static_cast<size_t>(c) * EPC) * (WBITS / 8)));
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = (h == 0 || has2) ? c0 + h * 32 : c0;   // (zero weights: any valid x address)
+      for (int b = 0; b < GV_MAXB; ++b) {
+        if (b < batch) {
+          const float4 x0 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC);
+          float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (WBITS == 16) x1 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC + 4);
 #pragma unroll
-        for (int b = 0; b < GV_MAXB; ++b) {
-          if (b < batch) {
-            const float4 x0 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC);
-            float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (WBITS == 16) x1 = *reinterpret_cast<const float4*>(sin_ + b * K + c * EPC + 4);
-#pragma unroll
-            for (int r = 0; r < GV_ROWS; ++r) {
-              if constexpr (WBITS == 32) {
-                acc[r][b] = fmaf(__uint_as_float(wv[h][r].x), x0.x, fmaf(__uint_as_float(wv[h][r].y), x0.y,
-                            fmaf(__uint_as_float(wv[h][r].z), x0.z, fmaf(__uint_as_float(wv[h][r].w), x0.w, acc[r][b]))));
-              } else {
-                const float2 w0 = unpack2<BF16>(wv[h][r].x), w1 = unpack2<BF16>(wv[h][r].y), w2 = unpack2<BF16>(wv[h][r].z), w3 = unpack2<BF16>(wv[h][r].w);
-                float a = acc[r][b];
-                a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a); a = fmaf(w1.x, x0.z, a); a = fmaf(w1.y, x0.w, a);
-                a = fmaf(w2.x, x1.x, a); a = fmaf(w2.y, x1.y, a); a = fmaf(w3.x, x1.z, a); a = fmaf(w3.y, x1.w, a);
-                acc[r][b] = a;
-              }
+          for (int r = 0; r < GV_ROWS; ++r) {
+            if constexpr (WBITS == 32) {
+              acc[r][b] = fmaf(__uint_as_float(wv[r].x), x0.x, fmaf(__uint_as_float(wv[r].y), x0.y,
+                          fmaf(__uint_as_float(wv[r].z), x0.z, fmaf(__uint_as_float(wv[r].w), x0.w, acc[r][b]))));
+            } else {
+              const float2 w0 = unpack2<BF16>(wv[r].x), w1 = unpack2<BF16>(wv[r].y), w2 = unpack2<BF16>(wv[r].z), w3 = unpack2<BF16>(wv[r].w);
+              float a = acc[r][b];
+              a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a); a = fmaf(w1.x, x0.z, a); a = fmaf(w1.y, x0.w, a);
+              a = fmaf(w2.x, x1.x, a); a = fmaf(w2.y, x1.y, a); a = fmaf(w3.x, x1.z, a); a = fmaf(w3.y, x1.w, a);
+              acc[r][b] = a;
             }
           }
         }
