@@ -289,6 +289,13 @@ B200_API int b200_sampler_step(const B200SamplerTables* tables, int method, int 
                                int frames, int channels, int hw, float* x_prev, float* pred_xstart, float* mean,
                                float* log_variance, void* stream);
 
+/* Host-only introspection (no GPU touched): the work schedule b200_linear would use on a device with `num_sms` SMs --
+ * chosen tile width, number of CTA pairs, whether the last waves are split along K (stream-K, residual epilogue), and
+ * the (pair, tile, kb0, kb1) segments in each pair's execution order (up to max_segments quadruples; the return value
+ * is the total count, negative on error).  The CPU tests check coverage and the ordering invariant on it.            */
+B200_API int b200_gemm_schedule(int M, int N, int K, int epilogue, int block_n, int num_sms, int* block_n_out, int* pairs_out,
+                                int* streamk_out, int32_t* segments, int max_segments);
+
 /* Measurement hook (bench.py roofline): while enabled, b200_latte_forward brackets every kernel launch with
  * CUDA events on the launching stream.  b200_profile_collect waits for them and returns, per class
  * {0 tensor-core GEMM, 1 attention, 2 LN+modulate, 3 other}, the summed device time in ms and the launch count,

@@ -378,6 +378,11 @@ B200_API int b200_sampler_step(const B200SamplerTables* tables, int method, int 
                                    log_variance, static_cast<cudaStream_t>(stream));
 }
 
+B200_API int b200_gemm_schedule(int M, int N, int K, int epilogue, int block_n, int num_sms, int* block_n_out, int* pairs_out,
+                                int* streamk_out, int32_t* segments, int max_segments) {
+  return b200::gemm_schedule(M, N, K, epilogue, block_n, num_sms, block_n_out, pairs_out, streamk_out, segments, max_segments);
+}
+
 B200_API void b200_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(b200::g_prof.mu);
   b200::g_prof.on = on != 0;

@@ -112,7 +112,7 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 struct TileSched {
   int pair, P, num_tiles, num_kb, full_waves, wave;
   long long u, u_end;
-  __device__ TileSched(int pair_, int P_, int num_tiles_, int num_kb_, bool streamk)
+  __host__ __device__ TileSched(int pair_, int P_, int num_tiles_, int num_kb_, bool streamk)
       : pair(pair_), P(P_), num_tiles(num_tiles_), num_kb(num_kb_), wave(0) {
     if (streamk) {
       // stream the partial wave TOGETHER WITH the last full wave: every pair's share is then at least one tile long, so
@@ -127,7 +127,7 @@ struct TileSched {
       u = u_end = 0;
     }
   }
-  __device__ bool next(int& tile, int& kb0, int& kb1) {
+  __host__ __device__ bool next(int& tile, int& kb0, int& kb1) {
     if (wave < full_waves) {
       tile = wave * P + pair;
       ++wave;
@@ -584,7 +584,44 @@ int pick_block_n(int M, int N, int K, bool resid, int sms) {
   return best;
 }
 
+// The scheduling decisions of one launch (shared by launch_gemm and the schedule dump the CPU tests read).
+struct GemmPlan { int bn, pairs, pair_tiles, num_kb, streamk; };
+GemmPlan plan_gemm(int M, int N, int K, bool resid, int block_n, int sms) {
+  static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
+  GemmPlan g;
+  g.bn = block_n ? block_n : pick_block_n(M, N, K, resid, sms);
+  const int num_m = (M + BM - 1) / BM, num_n = (N + g.bn - 1) / g.bn;
+  g.pair_tiles = ((num_m + 1) / 2) * num_n;
+  const int grid = 2 * g.pair_tiles < sms ? 2 * g.pair_tiles : (sms & ~1);   // whole clusters of 2
+  g.pairs = grid / 2;
+  g.num_kb = K / BK;
+  g.streamk = (resid && !no_sk && g.pair_tiles > g.pairs && g.pair_tiles % g.pairs != 0 && g.num_kb >= streamk_min_kb()) ? 1 : 0;
+  return g;
+}
+
 }  // namespace
+
+int gemm_schedule(int M, int N, int K, int epilogue, int block_n, int sms, int* bn_out, int* pairs_out, int* streamk_out,
+                  int* segments, int max_segments) {
+  B200_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0 && sms >= 2, B200_ERR_SHAPE, "gemm_schedule: bad arguments");
+  B200_REQUIRE(block_n == 0 || block_n == 128 || block_n == 192 || block_n == 256, B200_ERR_UNSUPPORTED, "gemm_schedule: block_n %d", block_n);
+  const GemmPlan g = plan_gemm(M, N, K, epilogue == B200_EPI_GATE_RESIDUAL, block_n, sms);
+  if (bn_out) *bn_out = g.bn;
+  if (pairs_out) *pairs_out = g.pairs;
+  if (streamk_out) *streamk_out = g.streamk;
+  int n = 0;
+  for (int pair = 0; pair < g.pairs; ++pair) {
+    TileSched sched(pair, g.pairs, g.pair_tiles, g.num_kb, g.streamk != 0);
+    int tile, kb0, kb1;
+    while (sched.next(tile, kb0, kb1)) {       // in the order the pair executes them
+      if (segments && n < max_segments) {
+        segments[4 * n + 0] = pair; segments[4 * n + 1] = tile; segments[4 * n + 2] = kb0; segments[4 * n + 3] = kb1;
+      }
+      ++n;
+    }
+  }
+  return n;
+}
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   B200_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, B200_ERR_SHAPE, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
@@ -612,8 +649,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   int sms = 0;
   B200_TRY(device_sm_count(&sms));
 
-  int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL, sms);
-  B200_REQUIRE(bn == 128 || bn == 192 || bn == 256, B200_ERR_UNSUPPORTED, "gemm: block_n must be 128, 192 or 256 (got %d)", bn);
+  B200_REQUIRE(a.block_n == 0 || a.block_n == 128 || a.block_n == 192 || a.block_n == 256, B200_ERR_UNSUPPORTED,
+               "gemm: block_n must be 128, 192 or 256 (got %d)", a.block_n);
+  const GemmPlan plan = plan_gemm(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL, a.block_n, sms);
+  const int bn = plan.bn;
 
   CUtensorMap tmA, tmB, tmX;
   int conv_bw = 0, conv_bh = 0;
@@ -672,14 +711,13 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const char* e = getenv("B200_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
-  const int pair_tiles = ((p.num_m + 1) / 2) * p.num_n;
-  int grid = 2 * pair_tiles < sms ? 2 * pair_tiles : (sms & ~1);   // whole clusters of 2
+  const int pair_tiles = plan.pair_tiles;
+  const int grid = 2 * plan.pairs;
   {
-    // stream-K over the last partial wave: only where partial sums can be reduce-added (residual epilogue) and K is
-    // long enough to be worth splitting; B200_GEMM_NO_STREAMK=1 restores the one-add-per-element schedule.
-    static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
-    const int pairs = grid / 2;
-    p.streamk = (resid && !no_sk && pair_tiles > pairs && pair_tiles % pairs != 0 && p.K / BK >= streamk_min_kb()) ? 1 : 0;
+    // stream-K over the last waves: only where partial sums can be reduce-added (residual epilogue) and K is long enough
+    // to be worth splitting (plan_gemm); B200_GEMM_NO_STREAMK=1 restores the one-add-per-element schedule.
+    const int pairs = plan.pairs;
+    p.streamk = plan.streamk;
     p.sk_flags = nullptr;
     p.sk_tag = 0;
     if (p.streamk) {
