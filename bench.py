@@ -24,6 +24,7 @@ import os
 import subprocess
 import sys
 import threading
+import datetime
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -45,24 +46,33 @@ def load_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def start(self):
+        """Launch the poller EARLY (before warm-up: nvidia-smi can take a second to come up); only samples whose own
+        timestamp falls between mark_begin() and mark_end() are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)            # let the sample that covers the end of the window arrive
         self.proc.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
@@ -71,6 +81,9 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or datetime.datetime.now())):
+                    continue
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
@@ -79,7 +92,8 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "device-timed region of `value` + of `e2e` (same workload, back to back)"}
 
 
 def build_case(model_name: str, seed: int):
@@ -243,16 +257,18 @@ def main():
         return sharding.max_over_ranks(e0.elapsed_time(e1), dev)
 
     with torch.no_grad():
-        for _ in range(W):
-            step_resident()
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
-        ms_total = timed(step_resident, K)
-        clk = clocks.stop() if rank == 0 else None
+        for _ in range(W):
+            step_resident()
         for _ in range(2):
             step_e2e()
+        clocks.mark_begin()
+        ms_total = timed(step_resident, K)
         ms_e2e = timed(step_e2e, K)
+        clocks.mark_end()
+        clk = clocks.stop() if rank == 0 else None
 
         # instrumented pass: per-kernel-class device time from events on the launching stream
         import ctypes as C
