@@ -31,7 +31,7 @@ constexpr int LN_MAXV = 12;  // float4 per lane: dim <= 12*128 = 1536
 // consecutive rows and all warps are resident at once (register-limited to 32 warps/SM): a grid-stride loop left a
 // half-empty second wave.  The block's shift/scale vectors are staged in shared memory once, so the only global latency
 // on a row's critical path is the row itself.
-template <bool BF16, int NV, bool PREFETCH>
+template <bool BF16, int NV>
 __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
                                                           const float* __restrict__ scale, long long mod_bs,
                                                           int rows_per_batch, uint16_t* __restrict__ out, int rows,
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
   __syncthreads();
   pdl_wait();
   const int row0 = warp_global * rows_per_warp;
-  float4 v[NV], vn[NV];
+  float4 v[NV];
   if (row0 < rows) {
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row0) * dim);
 #pragma unroll
@@ -63,12 +63,6 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
   for (int rr = 0; rr < rows_per_warp; ++rr) {
     const int row = row0 + rr;
     if (row >= rows) break;
-    if (PREFETCH && rr + 1 < rows_per_warp && row + 1 < rows) {   // next row's loads are in flight while this row is reduced
-      const float4* xn = reinterpret_cast<const float4*>(x + static_cast<size_t>(row + 1) * dim);
-#pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (lane + i * 32 < nv) vn[i] = xn[lane + i * 32];
-    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
@@ -101,10 +95,7 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
         orow[idx] = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
       }
     }
-    if constexpr (PREFETCH) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = vn[i];
-    } else if (rr + 1 < rows_per_warp && row + 1 < rows) {
+    if (rr + 1 < rows_per_warp && row + 1 < rows) {
       const float4* xn = reinterpret_cast<const float4*>(x + static_cast<size_t>(row + 1) * dim);
 #pragma unroll
       for (int i = 0; i < NV; ++i)
@@ -113,10 +104,10 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const float* __restric
   }
 }
 
-template <bool BF16, int NV, bool PREFETCH>
+template <bool BF16, int NV>
 int ln_launch(cudaStream_t stream, const float* x, const float* shift, const float* scale, long long mod_bs, int rpb,
               uint16_t* out, int rows, int dim, int sms) {
-  auto kern = ln_modulate_kernel<BF16, NV, PREFETCH>;
+  auto kern = ln_modulate_kernel<BF16, NV>;
   const size_t smem = static_cast<size_t>(dim) * 2 * sizeof(float);
   static int blocks_per_sm = 0;   // per instantiation: what the register/smem footprint really allows
   if (blocks_per_sm == 0) {
@@ -133,13 +124,13 @@ int ln_launch(cudaStream_t stream, const float* x, const float* shift, const flo
   return B200_OK;
 }
 
-template <bool BF16, bool PREFETCH>
+template <bool BF16>
 int ln_dispatch(int nvmax, cudaStream_t stream, const float* x, const float* shift, const float* scale, long long mod_bs,
                 int rpb, uint16_t* out, int rows, int dim, int sms) {
-  if (nvmax <= 3) return ln_launch<BF16, 3, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
-  if (nvmax <= 6) return ln_launch<BF16, 6, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
-  if (nvmax <= 9) return ln_launch<BF16, 9, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
-  return ln_launch<BF16, LN_MAXV, PREFETCH>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
+  if (nvmax <= 3) return ln_launch<BF16, 3>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
+  if (nvmax <= 6) return ln_launch<BF16, 6>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
+  if (nvmax <= 9) return ln_launch<BF16, 9>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
+  return ln_launch<BF16, LN_MAXV>(stream, x, shift, scale, mod_bs, rpb, out, rows, dim, sms);
 }
 
 // ---------------------------------------------------------------------------------- patch_embed
@@ -463,14 +454,9 @@ int launch_ln_modulate(const float* x, const float* shift, const float* scale, l
   int sms = 0;
   B200_TRY(device_sm_count(&sms));
   const int nvmax = (dim / 4 + 31) / 32;
-  static const bool prefetch = getenv("B200_LN_PREFETCH") ? atoi(getenv("B200_LN_PREFETCH")) != 0 : false;   // measured r01: no gain, 2x the registers
   uint16_t* o = reinterpret_cast<uint16_t*>(out16);
-  if (prefetch) {
-    if (bf16) return ln_dispatch<true, true>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
-    return ln_dispatch<false, true>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
-  }
-  if (bf16) return ln_dispatch<true, false>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
-  return ln_dispatch<false, false>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
+  if (bf16) return ln_dispatch<true>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
+  return ln_dispatch<false>(nvmax, stream, x, shift, scale, mod_batch_stride, rows_per_batch, o, rows, dim, sms);
 }
 
 int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const float* b, const float* pos, float* out,
