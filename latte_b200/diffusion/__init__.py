@@ -182,8 +182,8 @@ class SpacedDiffusion:
 
     # ------------------------------------------------------------------ loops
     def _loop(self, step_fn, model, shape, noise, device, progress, **kw):
-        if device is None:
-            device = next(model.parameters()).device
+        if device is None:   # the reference needs `device=` when handed a bound method (sample.py:102); accept both here
+            device = next(getattr(model, "__self__", model).parameters()).device
         device = torch.device(device)
         assert isinstance(shape, (tuple, list))
         img = noise if noise is not None else torch.randn(*shape, device=device)
