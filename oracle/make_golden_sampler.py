@@ -48,6 +48,16 @@ def main():
                                             ("ddpm", "ddpm", 0.0, False), ("ddpm_clip", "ddpm", 0.0, True)]:
                 z, xs, x0s = trajectory(d, method, shape, 1234, eta, clip)
                 blob[f"{name}_z"], blob[f"{name}_x"], blob[f"{name}_x0"] = z, xs, x0s
+        if spacing == "250":
+            # training_losses on the UNSPACED chain (train.py:131 create_diffusion(timestep_respacing="")), t = 0 included
+            dt = ref.create_diffusion("")
+            torch.manual_seed(77)
+            x0 = torch.randn(4, 3, 4, 8, 8).clamp(-1, 1)
+            noise = torch.randn_like(x0)
+            t = torch.tensor([0, 1, 500, 999])
+            terms = dt.training_losses(toy_model, x0, t, model_kwargs={}, noise=noise)
+            blob.update(train_x0=x0.numpy(), train_noise=noise.numpy(), train_t=t.numpy(),
+                        **{f"train_{k}": v.detach().numpy() for k, v in terms.items()})
         path = os.path.join(out_dir, f"sampler_{spacing}.npz")
         np.savez_compressed(path, **blob)
         print("wrote", path, {k: v.shape for k, v in blob.items() if k.endswith("_x")})

@@ -11,6 +11,8 @@ what the reference's `diffusion/` package does on the sampling path:
   p_sample / p_sample_loop            diffusion/gaussian_diffusion.py:380-516
   ddim_sample / ddim_sample_loop      diffusion/gaussian_diffusion.py:517-564, 604-689
   _WrappedModel timestep mapping      diffusion/respace.py:118-130
+  q_sample, training_losses (MSE+VB)  diffusion/gaussian_diffusion.py:223-236, 686-795     (train.py:220-222; groundwork for the
+  normal_kl, discretized log-lik.     diffusion/diffusion_utils.py:10-88                    training row, BASELINE config 5)
   _extract_into_tensor                diffusion/gaussian_diffusion.py:869-881   (float64 table -> fp32 value)
 
 Pinned: tests/test_oracle_sampler.py checks every table and whole short trajectories against tests/golden/sampler_*.npz,
@@ -166,6 +168,64 @@ def sample_loop(s: Schedule, model, shape, noise, method="ddim", clip_denoised=T
         if record is not None:
             record.append((img.clone(), out["pred_xstart"].clone()))
     return img
+
+
+# ------------------------------------------------------------------------------------------------ training losses
+def q_sample(s: Schedule, x_start, t, noise):
+    """gaussian_diffusion.py:223-236: x_t = sqrt(abar_t) x_0 + sqrt(1 - abar_t) noise."""
+    return (_extract(np.sqrt(s.alphas_cumprod), t, x_start.shape) * x_start
+            + _extract(np.sqrt(1.0 - s.alphas_cumprod), t, x_start.shape) * noise)
+
+
+def normal_kl(mean1, logvar1, mean2, logvar2):
+    """diffusion_utils.py:10-37."""
+    return 0.5 * (-1.0 + logvar2 - logvar1 + torch.exp(logvar1 - logvar2) + ((mean1 - mean2) ** 2) * torch.exp(-logvar2))
+
+
+def _approx_std_normal_cdf(x):
+    """diffusion_utils.py:40-45 (tanh approximation)."""
+    return 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * torch.pow(x, 3))))
+
+
+def discretized_gaussian_log_likelihood(x, means, log_scales):
+    """diffusion_utils.py:63-88: log-probability of the 1/255-wide bin around x in [-1, 1]."""
+    centered = x - means
+    inv_stdv = torch.exp(-log_scales)
+    cdf_plus = _approx_std_normal_cdf(inv_stdv * (centered + 1.0 / 255.0))
+    cdf_min = _approx_std_normal_cdf(inv_stdv * (centered - 1.0 / 255.0))
+    log_cdf_plus = torch.log(cdf_plus.clamp(min=1e-12))
+    log_one_minus_cdf_min = torch.log((1.0 - cdf_min).clamp(min=1e-12))
+    cdf_delta = cdf_plus - cdf_min
+    return torch.where(x < -0.999, log_cdf_plus,
+                       torch.where(x > 0.999, log_one_minus_cdf_min, torch.log(cdf_delta.clamp(min=1e-12))))
+
+
+def _mean_flat(t):
+    return t.mean(dim=list(range(1, t.dim())))
+
+
+def vb_terms_bpd(s: Schedule, model_output, x_start, x_t, t):
+    """gaussian_diffusion.py:686-716 (clip_denoised=False, as training_losses calls it): KL to the true posterior in bits,
+    decoder NLL at t == 0."""
+    true_mean = _extract(s.posterior_mean_coef1, t, x_t.shape) * x_start + _extract(s.posterior_mean_coef2, t, x_t.shape) * x_t
+    true_logvar = _extract(s.posterior_log_variance_clipped, t, x_t.shape)
+    out = p_mean_variance(s, model_output, x_t, t, clip_denoised=False)
+    kl = _mean_flat(normal_kl(true_mean, true_logvar, out["mean"], out["log_variance"])) / np.log(2.0)
+    nll = _mean_flat(-discretized_gaussian_log_likelihood(x_start, out["mean"], 0.5 * out["log_variance"])) / np.log(2.0)
+    return torch.where(t == 0, nll, kl)
+
+
+def training_losses(s: Schedule, model, x_start, t, noise, model_kwargs=None):
+    """gaussian_diffusion.py:719-795 for LossType.MSE + LEARNED_RANGE (what create_diffusion builds, train.py:131):
+    loss = mean((noise - eps)^2) + vb(eps.detach(), var_values); the model sees the ORIGINAL timestep (respace.py:125-130)."""
+    x_t = q_sample(s, x_start, t, noise)
+    mo = model(x_t, torch.from_numpy(s.timestep_map)[t], **(model_kwargs or {}))
+    C = x_t.shape[2]
+    eps, var_values = torch.split(mo, C, dim=2)
+    frozen = torch.cat([eps.detach(), var_values], dim=2)
+    vb = vb_terms_bpd(s, frozen, x_start, x_t, t)
+    mse = _mean_flat((noise - eps) ** 2)
+    return {"loss": mse + vb, "mse": mse, "vb": vb}
 
 
 def toy_model(x: torch.Tensor, t: torch.Tensor, gain: float = 1.0) -> torch.Tensor:

@@ -67,3 +67,15 @@ def test_mirror_rejects_what_is_not_built():
         d.training_losses(None, None, None)
     with pytest.raises(RuntimeError):   # no CPU path
         d.ddim_sample(lambda x, t: torch.cat([x, x], 2), torch.zeros(1, 2, 4, 4, 4), torch.zeros(1, dtype=torch.long))
+
+
+def test_training_losses_equal_reference(golden_dir):
+    """Groundwork for the training row (BASELINE config 5): training_losses (MSE + learned-range VB, gaussian_diffusion.py:
+    719-795) on the unspaced chain of train.py:131, t = 0 (decoder NLL branch) included — bit-identical loss / mse / vb."""
+    g = _golden(golden_dir, "250")
+    s = S.make_schedule("")
+    assert s.num_timesteps == 1000 and s.timestep_map.tolist() == list(range(1000))
+    out = S.training_losses(s, S.toy_model, torch.from_numpy(g["train_x0"]), torch.from_numpy(g["train_t"]),
+                            torch.from_numpy(g["train_noise"]))
+    for k in ("loss", "mse", "vb"):
+        assert np.array_equal(out[k].numpy(), g["train_" + k]), k
