@@ -148,7 +148,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": done,
         "warmup": min(args.warmup, 1), "ms_per_step": 1000 * el / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} class-conditional 16x256x256, one forward_with_cfg (B_model=2) per step, CPU"},
+        "config": {"workload": f"{args.model} class-conditional 16x256x256 sampling step: forward_with_cfg on B_model=2 "
+                               f"(1 video x CFG pair) per GPU; seeded synthetic weights/latents",
+                   "arm": "reference CPU path (oracle port of the pure-Python reference, torch CPU fp32 eager) on the host cores"},
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                          "sample": f"{done} full forward_with_cfg step(s) of the oracle port (torch CPU fp32, {cores} threads = best of a sweep on {os.cpu_count()} cores), bounded to {budget_s:.0f}s"},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
