@@ -1,15 +1,18 @@
-"""CPU oracle for LatteT2V.forward — TEST INFRASTRUCTURE, NOT PRODUCT CODE.  **Parity unpinned.**
+"""CPU oracle for LatteT2V.forward — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 Restates `/root/reference/models/latte_t2v.py` (Vchitect/Latte @ b27c24a) for the configuration the reference ships
 (HF `maxin-cn/Latte-1` transformer config, SURVEY.md App. C.2: `norm_type="ada_norm_single"`, no affine LayerNorms,
 `activation_fn="gelu-approximate"`, `attention_bias=True`, `caption_channels=4096`).  Control flow follows
 `latte_t2v.py:729-941`; the temporal block follows `BasicTransformerBlock_` (`:294-299,314-325,364-367,385,389-392`).
 
-The spatial block, attention, feed-forward, patch embedding, timestep embedding and caption projection live in
-**diffusers==0.24.0** (pinned in `environment.yml:13`), which is neither vendored in the reference nor installed in this
-image, and there is no network: they are restated from the published 0.24.0 behaviour summarised in SURVEY.md App. C.3.
-No reference-generated golden exists for this file (the reference module cannot be imported here), so every parity claim
-that rests on it is capped at "partial" until it is checked against a diffusers install.
+Pin (round 2): `oracle/make_golden_t2v.py` runs the UNMODIFIED reference module (through `oracle/ref_shim/diffusers`,
+which supplies only the library leaves it imports) and commits whole-forward outputs -- with and without temporal blocks,
+with padded-prompt masks, at N = 64 / 256 / 1024 tokens per frame, and the 28-layer 16x512x512 Latte-1 shape -- plus
+direct outputs of `BasicTransformerBlock_`, `AdaLayerNormSingle` and `FeedForward`; `tests/test_oracle_t2v.py` holds
+this restatement to them.  So the forward control flow, the temporal block, adaLN-single, the feed-forward and the
+mask -> bias conversion are **pinned to reference code**.  Still only shim-restated (diffusers==0.24.0, pinned in
+`environment.yml:13`, is neither vendored nor installed and there is no network): the spatial `BasicTransformerBlock`,
+`Attention`/`AttnProcessor2_0`, `PatchEmbed`, `CaptionProjection`, `CombinedTimestepSizeEmbeddings`.
 """
 from __future__ import annotations
 
@@ -122,14 +125,18 @@ def _lin(sd, name, x):
     return F.linear(x, sd[name + ".weight"].to(x.dtype), sd[name + ".bias"].to(x.dtype))
 
 
-def attention(sd, prefix, x, ctx, heads):
-    """diffusers Attention + AttnProcessor2_0: to_q(x), to_k/to_v(ctx), per-head softmax(q k^T / sqrt(hd)) v, to_out[0]."""
+def attention(sd, prefix, x, ctx, heads, key_bias=None):
+    """diffusers Attention + AttnProcessor2_0: to_q(x), to_k/to_v(ctx), per-head softmax(q k^T / sqrt(hd) + bias) v,
+    to_out[0].  key_bias (B, L): additive, broadcast over heads and queries (latte_t2v.py:766-771)."""
     B, S, D = x.shape
     hd = D // heads
     q = _lin(sd, prefix + ".to_q", x).reshape(B, S, heads, hd).transpose(1, 2)
     k = _lin(sd, prefix + ".to_k", ctx).reshape(B, -1, heads, hd).transpose(1, 2)
     v = _lin(sd, prefix + ".to_v", ctx).reshape(B, -1, heads, hd).transpose(1, 2)
-    a = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1)
+    scores = q @ k.transpose(-1, -2) * hd ** -0.5
+    if key_bias is not None:
+        scores = scores + key_bias.to(scores.dtype)[:, None, None, :]
+    a = torch.softmax(scores, dim=-1)
     o = (a @ v).transpose(1, 2).reshape(B, S, D)
     return _lin(sd, prefix + ".to_out.0", o)
 
@@ -140,15 +147,15 @@ def feed_forward(sd, prefix, x):
     return _lin(sd, prefix + ".net.2", h)
 
 
-def spatial_block(sd, i, x, text, ts, heads):
+def spatial_block(sd, i, x, text, ts, heads, text_bias=None):
     """diffusers BasicTransformerBlock, ada_norm_single (call at latte_t2v.py:862-870).
-    x (B*F, N, D), text (B*F, L, D), ts (B*F, 6D)."""
+    x (B*F, N, D), text (B*F, L, D), ts (B*F, 6D), text_bias (B*F, L) additive or None."""
     p = f"transformer_blocks.{i}"
     n = x.shape[0]
     sh1, sc1, g1, sh2, sc2, g2 = (sd[p + ".scale_shift_table"].to(x.dtype)[None] + ts.reshape(n, 6, -1)).chunk(6, dim=1)
     h = LO.layer_norm(x) * (1 + sc1) + sh1
     x = x + g1 * attention(sd, p + ".attn1", h, h, heads)
-    x = x + attention(sd, p + ".attn2", x, text, heads)          # no norm before attn2 in this mode
+    x = x + attention(sd, p + ".attn2", x, text, heads, text_bias)   # no norm before attn2 in this mode
     h = LO.layer_norm(x) * (1 + sc2) + sh2
     return x + g2 * feed_forward(sd, p + ".ff", h)
 
@@ -164,9 +171,18 @@ def temporal_block(sd, i, x, ts, heads):
     return x + g2 * feed_forward(sd, p + ".ff", h)
 
 
-def t2v_forward(sd, cfg: T2VConfig, x, t, text, dtype=torch.float32, enable_temporal=True):
-    """LatteT2V.forward (latte_t2v.py:729-941), eval mode, no masks, use_image_num = 0.
-    x (B, C, F, H, W); t (B,); text (B, L, caption_channels) -> (B, out_channels, F, H, W)."""
+def adaln_single(sd, t, dtype=torch.float32):
+    """AdaLayerNormSingle (latte_t2v.py:398-428): emb = TimestepEmbedding(Timesteps(t)); returns (Linear(SiLU(emb)), emb)."""
+    tf = LO.timestep_embedding(t).to(dtype)
+    emb = _lin(sd, "adaln_single.emb.timestep_embedder.linear_2", F.silu(_lin(sd, "adaln_single.emb.timestep_embedder.linear_1", tf)))
+    return _lin(sd, "adaln_single.linear", F.silu(emb)), emb
+
+
+def t2v_forward(sd, cfg: T2VConfig, x, t, text, dtype=torch.float32, enable_temporal=True, text_mask=None):
+    """LatteT2V.forward (latte_t2v.py:729-941), eval mode, use_image_num = 0.
+    x (B, C, F, H, W); t (B,); text (B, L, caption_channels); text_mask (B, L) 1 = keep / 0 = discard or None
+    (encoder_attention_mask, converted to the bias (1 - mask) * -10000 and repeated per frame, :766-771)
+    -> (B, out_channels, F, H, W)."""
     B, C, Fr, Hh, Ww = x.shape
     D, p, heads = cfg.inner_dim, cfg.patch_size, cfg.num_attention_heads
     N = (Hh // p) * (Ww // p)
@@ -176,16 +192,17 @@ def t2v_forward(sd, cfg: T2VConfig, x, t, text, dtype=torch.float32, enable_temp
     h = patches @ sd["pos_embed.proj.weight"].to(dtype).reshape(D, -1).t() + sd["pos_embed.proj.bias"].to(dtype)
     h = h + pos_embed_table(cfg).to(dtype)
     # :782-784 adaln_single: emb = TimestepEmbedding(Timesteps(t)); ts = Linear(SiLU(emb))
-    tf = LO.timestep_embedding(t).to(dtype)
-    emb = _lin(sd, "adaln_single.emb.timestep_embedder.linear_2", F.silu(_lin(sd, "adaln_single.emb.timestep_embedder.linear_1", tf)))
-    ts = _lin(sd, "adaln_single.linear", F.silu(emb))
+    ts, emb = adaln_single(sd, t, dtype)
     # :789 caption projection, :798 repeat per frame
     txt = _lin(sd, "caption_projection.linear_2", F.gelu(_lin(sd, "caption_projection.linear_1", text.to(dtype)), approximate="tanh"))
     txt_sp = txt.repeat_interleave(Fr, dim=0)
+    bias_sp = None
+    if text_mask is not None:
+        bias_sp = ((1 - text_mask.to(dtype)) * -10000.0).repeat_interleave(Fr, dim=0)
     ts_sp = ts.repeat_interleave(Fr, dim=0)            # :801
     ts_tm = ts.repeat_interleave(N, dim=0)             # :802
     for i in range(cfg.num_layers):
-        h = spatial_block(sd, i, h, txt_sp, ts_sp, heads)                                   # :862-870
+        h = spatial_block(sd, i, h, txt_sp, ts_sp, heads, bias_sp)                          # :862-870
         if enable_temporal:
             h = h.reshape(B, Fr, N, D).permute(0, 2, 1, 3).reshape(B * N, Fr, D)            # :874
             if i == 0 and Fr > 1:
