@@ -6,7 +6,9 @@
  * caller's CUDA stream.  Rules:
  *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
  *   - every function enqueues work on `stream` and returns; it never synchronises, never allocates
- *     device memory and keeps no pointer past the call;
+ *     device memory and keeps no pointer past the call; the only host state is a per-thread cache of encoded
+ *     TMA descriptors (pure functions of pointer + shape) and per-device kernel attributes, so a call may be
+ *     captured into a CUDA graph and replayed (tests/test_gpu_graph.py);
  *   - return value 0 = ok, negative B200_ERR_* otherwise; text via b200_last_error() (thread-local);
  *   - sm_100 only: any other device returns B200_ERR_ARCH. There is no CPU fallback.
  * All matrices are row-major.  "16-bit" means IEEE fp16 (dtype = B200_FP16) or bfloat16 (B200_BF16).
@@ -21,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define B200_API __attribute__((visibility("default")))
 #else
@@ -83,7 +85,9 @@ typedef struct B200LatteWeights {
 } B200LatteWeights;
 
 /* ---- LatteT2V (reference models/latte_t2v.py:444-944, HF maxin-cn/Latte-1 config: ada_norm_single, gelu-approximate,
- * attention_bias, caption_channels 4096).  Parity of this entry point is UNPINNED (diffusers 0.24.0 pieces restated). */
+ * attention_bias, caption_channels 4096).  Parity: the forward control flow, the temporal block, adaLN-single and the
+ * mask -> bias conversion are pinned to goldens generated by the unmodified reference module (oracle/make_golden_t2v.py);
+ * the diffusers 0.24.0 leaves it calls (spatial block, Attention, PatchEmbed, CaptionProjection) are shim-restated. */
 typedef struct B200T2VShape {
   int32_t layers;           /* num_layers: spatial/temporal block PAIRS (28) */
   int32_t hidden;           /* num_attention_heads * attention_head_dim */
@@ -144,17 +148,20 @@ typedef struct B200T2VWeights {
 
 B200_API size_t b200_t2v_workspace_bytes(const B200T2VShape* shape, int batch, int text_len);
 
-/* LatteT2V.forward (latte_t2v.py:677-941, eval, no masks):  x [batch, C, F, S, S] fp32, t [batch] int64,
- * text [batch, text_len, caption_channels] fp32 (text_len <= 128)  ->  out [batch, out_channels, F, S, S] fp32.  */
+/* LatteT2V.forward (latte_t2v.py:677-941, eval):  x [batch, C, F, S, S] fp32, t [batch] int64,
+ * text [batch, text_len, caption_channels] fp32 (text_len <= 128)  ->  out [batch, out_channels, F, S, S] fp32.
+ * text_bias: NULL, or [batch, 128] fp32 = the additive cross-attention bias of encoder_attention_mask,
+ * (1 - mask) * -10000 per text token (latte_t2v.py:766-771; columns >= text_len are ignored), 16-byte aligned.  */
 B200_API int b200_t2v_forward(const B200T2VShape* shape, const B200T2VWeights* w, const float* x, const int64_t* t,
-                              const float* text, int batch, int text_len, int enable_temporal, float* out,
-                              void* workspace, size_t workspace_bytes, void* stream);
+                              const float* text, const float* text_bias, int batch, int text_len, int enable_temporal,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream);
 
-/* softmax(q k^T / sqrt(hd)) v with K/V from another sequence (diffusers Attention attn2, latte_t2v.py:862-870):
+/* softmax(q k^T / sqrt(hd) + key_bias) v with K/V from another sequence (diffusers Attention attn2, latte_t2v.py:862-870):
  * q [batch*q_rows_per_batch, q_row_stride] 16-bit (first heads*head_dim columns), kv [batch*kv_len, kv_row_stride]
- * 16-bit (columns [k heads][v heads]), kv_len <= 128 keys per sample; out [rows, heads*head_dim] 16-bit.          */
-B200_API int b200_cross_attention(const void* q, const void* kv, void* out, int batch, int q_rows_per_batch, int kv_len,
-                                  int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream);
+ * 16-bit (columns [k heads][v heads]), kv_len <= 128 keys per sample; key_bias NULL or [batch, 128] fp32 additive bias
+ * per key (broadcast over heads and queries); out [rows, heads*head_dim] 16-bit.                                  */
+B200_API int b200_cross_attention(const void* q, const void* kv, const float* key_bias, void* out, int batch, int q_rows_per_batch,
+                                  int kv_len, int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream);
 
 /* ---- AutoencoderKL.decode (diffusers 0.24.0 SD-VAE decoder; reference call sites sample/sample.py:114,
  * sample_ddp.py:167, pipeline_latte.py:758,771).  Parity UNPINNED (diffusers absent offline).
@@ -242,10 +249,14 @@ B200_API int b200_latte_forward_conditioned(const B200LatteShape* shape, const B
  *   B200_EPI_BIAS_GELU      out16[M,N] = gelu_tanh(acc + bias)                     (latte.py:169)
  *   B200_EPI_GATE_RESIDUAL  resid[M,N] (fp32, in place) += gate[row / rows_per_batch][col] * (acc + bias)
  *                           (latte.py:179-180); gate row stride = gate_batch_stride floats.
- * K % 64 == 0, N % 32 == 0 required; M arbitrary.                                                  */
+ * K % 64 == 0, N % 32 == 0 required; M arbitrary.
+ * sk_flags: NULL, or B200_GEMM_SK_FLAGS 64-bit words of device memory that the caller zeroed ONCE.  With it the
+ * residual epilogue may split the last waves of tiles along K across all SMs ("ordered stream-K": partial sums are
+ * added into resid in k order, so results stay bit-reproducible); every launch leaves the words zero again.    */
+#define B200_GEMM_SK_FLAGS 1024
 B200_API int b200_linear(const void* A, const void* W, const float* bias, int M, int N, int K, int dtype, int epilogue,
                 void* out16, float* resid, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
-                int block_n, void* stream);
+                int block_n, void* sk_flags, void* stream);
 
 /* softmax(q k^T / sqrt(hd)) v per head — replaces Attention.forward 'math' mode between the qkv and
  * proj Linears (latte.py:50-70).  qkv [T, 3*heads*head_dim] 16-bit with T = batch*frames*tokens rows in
@@ -253,6 +264,11 @@ B200_API int b200_linear(const void* A, const void* W, const float* bias, int M,
  * (latte.py:353); temporal = 1: one sequence per (b, n) over f (latte.py:355-367) — no transpose pass. */
 B200_API int b200_attention(const void* qkv, void* out, int batch, int frames, int tokens, int heads, int head_dim,
                    int dtype, int temporal, void* stream);
+
+/* A/B switch for the <= 256-key attention kernels (process-wide): 0 = library default (or B200_ATTN_IMPL from the
+ * environment), 2 = the two-tile pipeline of round 1, 3 = the role-warp kernel (two warpgroups per 256-key tile,
+ * three 128-key tiles in flight, TMA-stored output).  Both are exact implementations of the same contract.      */
+B200_API int b200_set_attention_impl(int impl);
 
 /* out16[r, :] = LayerNorm(x[r, :]; no affine, eps 1e-6) * (1 + scale[b]) + shift[b], b = r / rows_per_batch
  * — replaces norm1/norm2 + modulate (latte.py:28-29, 166-168, 179-180). x fp32 [rows, dim].          */

@@ -37,15 +37,15 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile what is stale and link in place.  Safe under concurrent callers (every torchrun rank imports the package):
+    a library newer than all sources is returned untouched; otherwise ONE process builds under a file lock, links to a
+    temporary name and renames it into place, so nobody ever dlopens a half-written file."""
+    import fcntl
+    sources = [os.path.join(CSRC, s) for s in SOURCES]
+    if not force and os.path.exists(LIB) and not _stale(LIB, sources + HEADERS):
+        return LIB
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
-    objs, jobs = [], []
-    for src in SOURCES:
-        sp = os.path.join(CSRC, src)
-        op = os.path.join(BUILD, src.replace(".cu", ".o"))
-        objs.append(op)
-        if force or _stale(op, [sp] + HEADERS):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", sp, "-o", op])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,14 +54,27 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if verbose and r.stderr:
             sys.stderr.write(r.stderr)
 
-    if jobs:
-        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-            list(ex.map(run, jobs))
-    if jobs or not os.path.exists(LIB):
-        # cudart is linked statically (nvcc default); the driver API is resolved at run time, so the
-        # library loads on machines without libcuda (the CPU-only container)
-        run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-             "-Xcompiler", "-fPIC"])
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(LIB) and not _stale(LIB, sources + HEADERS):
+                return LIB              # another process built it while we waited
+            objs, jobs = [], []
+            for sp in sources:
+                op = os.path.join(BUILD, os.path.basename(sp).replace(".cu", ".o"))
+                objs.append(op)
+                if force or _stale(op, [sp] + HEADERS):
+                    jobs.append([nvcc, *NVCC_FLAGS, "-c", sp, "-o", op])
+            if jobs:
+                with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+                    list(ex.map(run, jobs))
+            # cudart is linked statically (nvcc default); the driver API is resolved at run time, so the
+            # library loads on machines without libcuda (the CPU-only container)
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            run([nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"])
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

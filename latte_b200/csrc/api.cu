@@ -50,6 +50,7 @@ struct Workspace {
   float* th;         // [B, D]   SiLU(Linear(256, D))
   float* c;          // [B, D]   t_emb (+ y_emb)
   float* mod;        // [B, depth*6D + 2D]
+  unsigned long long* sk_flags;   // [B200_GEMM_SK_FLAGS] stream-K ordering flags (zeroed at the start of every forward)
   size_t bytes;
 };
 
@@ -87,6 +88,7 @@ void carve(const B200LatteShape* s, int batch, void* base, Workspace* ws) {
   ws->th = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
   ws->c = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
   ws->mod = static_cast<float*>(take(static_cast<size_t>(batch) * (static_cast<size_t>(s->depth) * 6 * D + 2 * D) * 4));
+  ws->sk_flags = static_cast<unsigned long long*>(take(static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8));
   ws->bytes = off;
 }
 
@@ -137,6 +139,9 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
   const long long mod_bs = static_cast<long long>(depth) * 6 * D + 2 * D;
   const int HID = s->mlp_hidden;
 
+  // stream-K ordering flags: zero at the start of the step (every stream-K GEMM leaves them zero again; this memset only
+  // makes the step independent of whatever the workspace held before -- a fresh allocation, an aborted run)
+  B200_CHECK_CUDA(cudaMemsetAsync(ws.sk_flags, 0, static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8, stream));
   if (premod) ws.mod = const_cast<float*>(premod);
   else B200_TRY(conditioning(s, w, t, y, batch, ws.tfreq, ws.th, ws.c, ws.mod, stream));
 
@@ -166,7 +171,7 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
     GemmArgs gp{};
     gp.A = ws.h; gp.W = proj_w; gp.bias = w->proj_b + static_cast<size_t>(i) * D;
     gp.M = T; gp.N = D; gp.K = D; gp.bf16 = bf16; gp.epilogue = B200_EPI_GATE_RESIDUAL; gp.resid = ws.x;
-    gp.gate = m + 2 * D; gp.gate_batch_stride = mod_bs; gp.rows_per_batch = rows_per_batch;
+    gp.gate = m + 2 * D; gp.gate_batch_stride = mod_bs; gp.rows_per_batch = rows_per_batch; gp.sk_flags = ws.sk_flags;
     B200_PROF(PROF_GEMM, launch_gemm(gp, stream));
 
     B200_PROF(PROF_LN, launch_ln_modulate(ws.x, m + 3 * D, m + 4 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
@@ -178,7 +183,7 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
     GemmArgs g2{};
     g2.A = ws.g; g2.W = fc2_w; g2.bias = w->fc2_b + static_cast<size_t>(i) * D;
     g2.M = T; g2.N = D; g2.K = HID; g2.bf16 = bf16; g2.epilogue = B200_EPI_GATE_RESIDUAL; g2.resid = ws.x;
-    g2.gate = m + 5 * D; g2.gate_batch_stride = mod_bs; g2.rows_per_batch = rows_per_batch;
+    g2.gate = m + 5 * D; g2.gate_batch_stride = mod_bs; g2.rows_per_batch = rows_per_batch; g2.sk_flags = ws.sk_flags;
     if (i == 0) {  // x = x + temp_embed before the first temporal block (latte.py:357-358), folded into block 0's last epilogue
       g2.row_add = w->temp_embed; g2.row_add_div = N; g2.row_add_period = F;
     }
@@ -203,6 +208,7 @@ struct T2VWorkspace {
   float* x; uint16_t* h; uint16_t* qkv; uint16_t* g;
   uint16_t* text16; uint16_t* cap_h; uint16_t* cap_o; uint16_t* kv_all;
   float* ones; float* tfreq; float* th; float* emb; float* ts; float* mod;
+  unsigned long long* sk_flags;
   size_t bytes;
 };
 
@@ -246,12 +252,13 @@ void t2v_carve(const B200T2VShape* s, int batch, int text_len, void* base, T2VWo
   ws->emb = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
   ws->ts = static_cast<float*>(take(static_cast<size_t>(batch) * 6 * D * 4));
   ws->mod = static_cast<float*>(take(static_cast<size_t>(batch) * (static_cast<size_t>(s->layers) * 2 * 6 * D + 2 * D) * 4));
+  ws->sk_flags = static_cast<unsigned long long*>(take(static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8));
   ws->bytes = off;
 }
 
 int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, const int64_t* t, const float* text,
-                int batch, int text_len, int enable_temporal, float* out, void* workspace, size_t workspace_bytes,
-                cudaStream_t stream) {
+                const float* text_bias, int batch, int text_len, int enable_temporal, float* out, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream) {
   B200_TRY(t2v_shape_ok(s, batch, text_len));
   B200_REQUIRE(w && x && t && text && out && workspace, B200_ERR_SHAPE, "t2v: NULL argument");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, B200_ERR_ALIGN, "t2v: workspace must be 1024-byte aligned");
@@ -267,6 +274,7 @@ int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, 
   const int bf16 = s->dtype == B200_BF16;
   const long long mod_bs = static_cast<long long>(L) * 2 * 6 * D + 2 * D;
 
+  B200_CHECK_CUDA(cudaMemsetAsync(ws.sk_flags, 0, static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8, stream));
   // ---- conditioning (latte_t2v.py:782-784): emb = TimestepEmbedding(sincos(t)); ts = Linear(SiLU(emb)); tables + ts
   B200_PROF(PROF_OTHER, launch_timestep_freq(reinterpret_cast<const long long*>(t), ws.tfreq, batch, stream));
   B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, stream));
@@ -305,7 +313,7 @@ int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, 
                           const float* row_add) {
     GemmArgs a{};
     a.A = A; a.W = W; a.bias = bias; a.M = T; a.N = D; a.K = K; a.bf16 = bf16; a.epilogue = B200_EPI_GATE_RESIDUAL;
-    a.resid = ws.x; a.gate = gate; a.gate_batch_stride = gate_bs; a.rows_per_batch = rows_per_batch;
+    a.resid = ws.x; a.gate = gate; a.gate_batch_stride = gate_bs; a.rows_per_batch = rows_per_batch; a.sk_flags = ws.sk_flags;
     if (row_add) { a.row_add = row_add; a.row_add_div = N; a.row_add_period = F; }
     return launch_gemm(a, stream);
   };
@@ -330,6 +338,7 @@ int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, 
     CrossAttnArgs ca{};
     ca.q = ws.qkv; ca.kv = ws.kv_all + static_cast<size_t>(l) * 2 * D; ca.out = ws.h; ca.batch = batch; ca.q_rows_per_batch = rows_per_batch;
     ca.kv_len = text_len; ca.q_row_stride = D; ca.kv_row_stride = L * 2 * D; ca.heads = H; ca.head_dim = hd; ca.bf16 = bf16;
+    ca.key_bias = text_bias;     // padded prompts: (1 - mask) * -10000 per text token (latte_t2v.py:766-771), or NULL
     B200_PROF(PROF_ATTN, launch_cross_attention(ca, stream));
     B200_PROF(PROF_GEMM, linear_resid(ws.h, static_cast<const uint16_t*>(w->c_out_w16) + l * DD, w->c_out_b + static_cast<size_t>(l) * D, D,
                                       ws.ones, 0, nullptr));
@@ -404,6 +413,8 @@ B200_API int b200_profile_collect(double* ms_per_class, int* launches_per_class,
   return B200_OK;
 }
 
+B200_API int b200_set_attention_impl(int impl) { return b200::set_attention_impl(impl); }
+
 B200_API const char* b200_last_error(void) { return b200::get_error(); }
 B200_API int b200_abi_version(void) { return B200_ABI_VERSION; }
 
@@ -458,9 +469,11 @@ B200_API int b200_latte_forward_conditioned(const B200LatteShape* shape, const B
 
 B200_API int b200_linear(const void* A, const void* W, const float* bias, int M, int N, int K, int dtype, int epilogue,
                 void* out16, float* resid, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
-                int block_n, void* stream) {
+                int block_n, void* sk_flags, void* stream) {
   B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(sk_flags) & 7) == 0, B200_ERR_ALIGN, "sk_flags must be 8-byte aligned");
   b200::GemmArgs a{};
+  a.sk_flags = static_cast<unsigned long long*>(sk_flags);
   a.A = A; a.W = W; a.bias = bias; a.M = M; a.N = N; a.K = K; a.bf16 = dtype == B200_BF16; a.epilogue = epilogue;
   a.out16 = out16; a.resid = resid; a.gate = gate; a.gate_batch_stride = gate_batch_stride;
   a.rows_per_batch = rows_per_batch; a.block_n = block_n;
@@ -484,17 +497,19 @@ B200_API size_t b200_t2v_workspace_bytes(const B200T2VShape* shape, int batch, i
 }
 
 B200_API int b200_t2v_forward(const B200T2VShape* shape, const B200T2VWeights* w, const float* x, const int64_t* t,
-                              const float* text, int batch, int text_len, int enable_temporal, float* out,
-                              void* workspace, size_t workspace_bytes, void* stream) {
-  return b200::t2v_forward(shape, w, x, t, text, batch, text_len, enable_temporal, out, workspace, workspace_bytes,
+                              const float* text, const float* text_bias, int batch, int text_len, int enable_temporal,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(!text_bias || (reinterpret_cast<uintptr_t>(text_bias) & 15) == 0, B200_ERR_ALIGN, "t2v: text_bias must be 16-byte aligned");
+  return b200::t2v_forward(shape, w, x, t, text, text_bias, batch, text_len, enable_temporal, out, workspace, workspace_bytes,
                            static_cast<cudaStream_t>(stream));
 }
 
-B200_API int b200_cross_attention(const void* q, const void* kv, void* out, int batch, int q_rows_per_batch, int kv_len,
-                                  int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream) {
+B200_API int b200_cross_attention(const void* q, const void* kv, const float* key_bias, void* out, int batch, int q_rows_per_batch,
+                                  int kv_len, int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream) {
   B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype);
   b200::CrossAttnArgs a{};
   a.q = q; a.kv = kv; a.out = out; a.batch = batch; a.q_rows_per_batch = q_rows_per_batch; a.kv_len = kv_len;
+  a.key_bias = key_bias;
   a.q_row_stride = q_row_stride; a.kv_row_stride = kv_row_stride; a.heads = heads; a.head_dim = head_dim;
   a.bf16 = dtype == B200_BF16;
   return b200::launch_cross_attention(a, static_cast<cudaStream_t>(stream));

@@ -25,10 +25,11 @@ namespace b200 {
 
 namespace {
 
-constexpr int kThreads = 160;
-constexpr int kOCol = 0;  // O (<= 80 columns) reuses the first S columns: S is dead once every row has written its P
+constexpr int kThreads = 160;          // attn_long_kernel: warps 0-3 softmax/epilogue, warp 4 TMA + MMA issuer
+constexpr int kAttnDefaultImpl = 2;    // launch_mode: which kernel serves the <= 256-key modes (see B200_ATTN_IMPL)
 
 enum { MODE_FULL = 0, MODE_PACKED = 1, MODE_TEMPORAL = 2, MODE_CROSS = 3 };
+volatile int g_attn_impl = 0;   // b200_set_attention_impl: 0 = default / environment, 2 or 3 = forced (A/B tests)
 
 struct AttnDev {
   void* out;
@@ -45,32 +46,9 @@ struct AttnDev {
   int Lk;           // keys per tile: N (FULL, <= 256) or 128
   int tiles_per_seq;  // FULL: N / 128; TEMPORAL: N / G
   float scale_log2; // hd^-0.5 * log2(e)
-  int dbg;          // B200_ATTN_DBG bits (pipelined kernel only): 1 no TMA, 2 no softmax math, 4 no output stores, 8 no MMA
+  int dbg;          // B200_ATTN_DBG bits: 1 no TMA*, 2 no softmax math*, 4 no output stores*, 8 no MMA* (* v2 only, wrong results), 16 v3: all exponentials on the MUFU pipe
+  const float* key_bias;  // CROSS: additive bias on the scores, fp32 [batch][128] (natural-log units, e.g. 0 / -10000), or nullptr
 };
-
-// Shared-memory plan (bytes, every piece 1 KiB aligned), sized by the key count Lk so that several CTAs fit per SM:
-//   region A: [Q main 128x128B][K main Lk x128B][Q tail 128x32B][K tail Lk x32B]   -- later overwritten by P (128 x Lk 16-bit)
-//   region V: [V main Lk x128B][V tail Lk x32B]
-// Lk=256: 64 KiB + 40 KiB -> 2 CTAs/SM (TMEM 256 cols each); Lk=128: 40 KiB + 20 KiB -> 3 CTAs/SM (TMEM 128 cols each).
-struct SmemPlan {
-  int q_main, k_main, q_tail, k_tail, p, v_main, v_tail, bars, total;
-};
-__host__ __device__ inline SmemPlan make_plan(int Lk, bool tail) {
-  SmemPlan s;
-  s.q_main = 0;
-  s.k_main = 128 * 128;
-  s.q_tail = s.k_main + Lk * 128;
-  s.k_tail = s.q_tail + (tail ? 128 * 32 : 0);
-  const int qk_end = s.k_tail + (tail ? Lk * 32 : 0);
-  const int p_bytes = 128 * Lk * 2;
-  s.p = 0;
-  const int region_a = qk_end > p_bytes ? qk_end : p_bytes;
-  s.v_main = region_a;
-  s.v_tail = s.v_main + Lk * 128;
-  s.bars = s.v_tail + (tail ? Lk * 32 : 0);
-  s.total = s.bars + 128 + 1024;
-  return s;
-}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -90,236 +68,6 @@ __device__ __forceinline__ bool key_valid(int rkey, int col, int gshift) {
   if constexpr (MODE == MODE_FULL) return true;
   if constexpr (MODE == MODE_CROSS) return col < rkey;   // rkey carries the number of valid keys (text tokens)
   return row_key<MODE>(col, gshift) == rkey;
-}
-
-template <bool BF16, bool TAIL, int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
-attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
-            const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt, const AttnDev p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const SmemPlan sp = make_plan(p.Lk, TAIL);
-  const int SQ_MAIN = sp.q_main, SK_MAIN = sp.k_main, SQ_TAIL = sp.q_tail, SK_TAIL = sp.k_tail, SP = sp.p,
-            SV_MAIN = sp.v_main, SV_TAIL = sp.v_tail;
-  const uint32_t kTmemCols = static_cast<uint32_t>(p.Lk);  // 128 or 256 (power of two >= 32)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
-  uint64_t* bar_qk = bars + 0;
-  uint64_t* bar_v = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int head = blockIdx.y;
-  const int Lk = p.Lk;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKV);
-    mbar_init(bar_qk, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
-    mbar_init(bar_o, 1);
-    fence_mbar_init();
-  }
-  if (warp == 4) tmem_alloc(tmem_slot, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();
-  pdl_wait();   // qkv (written by the preceding GEMM) is visible from here
-
-  if (warp == 4) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA loads
-      const uint32_t qk_bytes = 128 * 128 + Lk * 128 + (TAIL ? (128 * 32 + Lk * 32) : 0);
-      const uint32_t v_bytes = Lk * 128 + (TAIL ? Lk * 32 : 0);
-      mbar_arrive_expect_tx(bar_qk, qk_bytes);
-      if constexpr (MODE == MODE_TEMPORAL) {
-        const int b = tile / p.tiles_per_seq;
-        const int n0 = (tile % p.tiles_per_seq) * p.group;
-        const int bf0 = b * p.frames;
-        tma_load_4d(smem + SQ_MAIN, &tmQ, bar_qk, 0, head, n0, bf0);
-        tma_load_4d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.k_head0 + head, n0, bf0);
-        if constexpr (TAIL) {
-          tma_load_4d(smem + SQ_TAIL, &tmQt, bar_qk, 64, head, n0, bf0);
-          tma_load_4d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.k_head0 + head, n0, bf0);
-        }
-        mbar_arrive_expect_tx(bar_v, v_bytes);
-        tma_load_4d(smem + SV_MAIN, &tmKV, bar_v, 0, p.v_head0 + head, n0, bf0);
-        if constexpr (TAIL) tma_load_4d(smem + SV_TAIL, &tmKVt, bar_v, 64, p.v_head0 + head, n0, bf0);
-      } else {
-        int q_row0, kv_row0;
-        if constexpr (MODE == MODE_FULL) {
-          const int s = tile / p.tiles_per_seq;
-          kv_row0 = s * p.tokens;
-          q_row0 = kv_row0 + (tile % p.tiles_per_seq) * 128;
-        } else if constexpr (MODE == MODE_CROSS) {
-          q_row0 = tile * 128;                                         // 128 consecutive query tokens of one sample
-          kv_row0 = (q_row0 / p.q_rows_per_batch) * p.kv_rows_per_batch;  // that sample's text tokens (<= 128 keys)
-        } else {
-          q_row0 = kv_row0 = tile * 128;
-        }
-        tma_load_3d(smem + SQ_MAIN, &tmQ, bar_qk, 0, head, q_row0);
-        tma_load_3d(smem + SK_MAIN, &tmKV, bar_qk, 0, p.k_head0 + head, kv_row0);
-        if constexpr (TAIL) {
-          tma_load_3d(smem + SQ_TAIL, &tmQt, bar_qk, 64, head, q_row0);
-          tma_load_3d(smem + SK_TAIL, &tmKVt, bar_qk, 64, p.k_head0 + head, kv_row0);
-        }
-        mbar_arrive_expect_tx(bar_v, v_bytes);
-        tma_load_3d(smem + SV_MAIN, &tmKV, bar_v, 0, p.v_head0 + head, kv_row0);
-        if constexpr (TAIL) tma_load_3d(smem + SV_TAIL, &tmKVt, bar_v, 64, p.v_head0 + head, kv_row0);
-      }
-
-      // ---------------------------------------------------------------- S = Q K^T   (M=128, N=Lk, K=hd padded to 16)
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      const uint32_t idesc_s = umma_idesc_f16(BF16, 128, static_cast<uint32_t>(Lk), false, false);
-      const uint64_t dq = umma_smem_desc(smem_u32(smem + SQ_MAIN), 0, 1024, UMMA_LAYOUT_SW128);
-      const uint64_t dk = umma_smem_desc(smem_u32(smem + SK_MAIN), 0, 1024, UMMA_LAYOUT_SW128);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16_ss(tmem_base, umma_desc_advance(dq, k * 32), umma_desc_advance(dk, k * 32), idesc_s, k > 0 ? 1u : 0u);
-      if constexpr (TAIL) {
-        const uint64_t dqt = umma_smem_desc(smem_u32(smem + SQ_TAIL), 0, 256, UMMA_LAYOUT_SW32);
-        const uint64_t dkt = umma_smem_desc(smem_u32(smem + SK_TAIL), 0, 256, UMMA_LAYOUT_SW32);
-        umma_f16_ss(tmem_base, dqt, dkt, idesc_s, 1u);
-      }
-      umma_commit(bar_s);
-
-      // ---------------------------------------------------------------- O = P V   (M=128, N=64 (+16), K=Lk)
-      mbar_wait(bar_v, 0);
-      mbar_wait(bar_p, 0);
-      tc_fence_after();
-      const uint32_t idesc_o = umma_idesc_f16(BF16, 128, 64, false, true);   // B = V is MN-major ([key][hd] in smem)
-      const uint32_t idesc_ot = umma_idesc_f16(BF16, 128, 16, false, true);
-      const uint64_t dv = umma_smem_desc(smem_u32(smem + SV_MAIN), static_cast<uint32_t>(Lk) * 128, 1024, UMMA_LAYOUT_SW128);
-      const uint64_t dvt = umma_smem_desc(smem_u32(smem + SV_TAIL), static_cast<uint32_t>(Lk) * 32, 256, UMMA_LAYOUT_SW32);
-      const int ksteps = Lk / 16;
-      for (int k = 0; k < ksteps; ++k) {
-        const uint64_t dp = umma_smem_desc(smem_u32(smem + SP + (k >> 2) * (128 * 128)) + (k & 3) * 32, 0, 1024, UMMA_LAYOUT_SW128);
-        umma_f16_ss(tmem_base + kOCol, dp, umma_desc_advance(dv, k * 16 * 128), idesc_o, k > 0 ? 1u : 0u);
-        if constexpr (TAIL)
-          umma_f16_ss(tmem_base + kOCol + 64, dp, umma_desc_advance(dvt, k * 16 * 32), idesc_ot, k > 0 ? 1u : 0u);
-      }
-      umma_commit(bar_o);
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax + epilogue: thread = tile row
-    const int r = warp * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const int nchunks = Lk / 32;
-    const int rkey = MODE == MODE_CROSS ? p.kv_rows_per_batch : row_key<MODE>(r, p.gshift);
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    const float mscaled = mx * p.scale_log2;
-    float sum = 0.f;
-    uint8_t* prow = smem + SP + r * 128;
-    const int sw = r & 7;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + c * 32, v);
-      tmem_ld_wait();
-      float e[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mscaled));
-        e[j] = key_valid<MODE>(rkey, c * 32 + j, p.gshift) ? x : 0.f;
-        sum += e[j];
-      }
-      uint8_t* atom = prow + (c >> 1) * (128 * 128);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 o;
-        o.x = pack2<BF16>(e[8 * i + 0], e[8 * i + 1]);
-        o.y = pack2<BF16>(e[8 * i + 2], e[8 * i + 3]);
-        o.z = pack2<BF16>(e[8 * i + 4], e[8 * i + 5]);
-        o.w = pack2<BF16>(e[8 * i + 6], e[8 * i + 7]);
-        const int chunk = ((c & 1) * 4 + i) ^ sw;  // 128B swizzle: 16-byte chunk index XOR (row % 8)
-        *reinterpret_cast<uint4*>(atom + chunk * 16) = o;
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(bar_p);
-
-    // output row of this thread
-    long long out_row;
-    bool row_ok = true;
-    if constexpr (MODE == MODE_TEMPORAL) {
-      const int b = tile / p.tiles_per_seq;
-      const int n0 = (tile % p.tiles_per_seq) * p.group;
-      out_row = (static_cast<long long>(b) * p.frames + r / p.group) * p.tokens + n0 + r % p.group;
-    } else if constexpr (MODE == MODE_FULL) {
-      out_row = static_cast<long long>(tile / p.tiles_per_seq) * p.tokens + (tile % p.tiles_per_seq) * 128 + r;
-    } else {
-      out_row = static_cast<long long>(tile) * 128 + r;
-      row_ok = out_row < p.T;
-    }
-    uint16_t* optr = reinterpret_cast<uint16_t*>(p.out) + out_row * p.D + head * p.hd;
-    const float inv = 1.0f / sum;
-
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + kOCol + c * 32, v);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 o;
-          o.x = pack2<BF16>(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
-          o.y = pack2<BF16>(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
-          o.z = pack2<BF16>(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
-          o.w = pack2<BF16>(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(optr + c * 32 + i * 8) = o;
-        }
-      }
-    }
-    if constexpr (TAIL) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(t_row + kOCol + 64, v);
-      tmem_ld_wait();
-      if (row_ok) {
-        const int tail8 = (p.hd - 64) / 8;  // 1 (hd 72) or 2 (hd 80)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (i >= tail8) break;
-          uint4 o;
-          o.x = pack2<BF16>(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
-          o.y = pack2<BF16>(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
-          o.z = pack2<BF16>(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
-          o.w = pack2<BF16>(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(optr + 64 + i * 8) = o;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -523,6 +271,12 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
 
       const int nch = (p.dbg & 2) ? 0 : nchunks;   // Lk / 32: 4 or 8
+      // CROSS with a key bias (padded prompts): scores are s * scale + bias[sample][key]; the sample's 128 bias values are
+      // read through the read-only path (same addresses for every thread of the tile)
+      const float* brow = nullptr;
+      if constexpr (MODE == MODE_CROSS) {
+        if (p.key_bias) brow = p.key_bias + static_cast<size_t>((static_cast<long long>(tile) * 128) / p.q_rows_per_batch) * 128;
+      }
       // pass 1: row maximum.  Two 32-column TMEM loads are in flight per wait (the loads, not the math, set the pace).
       float mx = -INFINITY;
       for (int c = 0; c < nch; c += 2) {
@@ -532,11 +286,16 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(va[j]));
-          if (key_valid<MODE>(rkey, (c + 1) * 32 + j, p.gshift)) mx = fmaxf(mx, __uint_as_float(vb[j]));
+          float a = __uint_as_float(va[j]), b = __uint_as_float(vb[j]);
+          if (MODE == MODE_CROSS && brow) {
+            a = fmaf(a, p.scale_log2, __ldg(brow + c * 32 + j) * 1.4426950408889634f);
+            b = fmaf(b, p.scale_log2, __ldg(brow + (c + 1) * 32 + j) * 1.4426950408889634f);
+          }
+          if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, a);
+          if (key_valid<MODE>(rkey, (c + 1) * 32 + j, p.gshift)) mx = fmaxf(mx, b);
         }
       }
-      const float mscaled = mx * p.scale_log2;
+      const float mscaled = (MODE == MODE_CROSS && brow) ? mx : mx * p.scale_log2;
       float sum = 0.f;
       // pass 2: P = exp2(s * scale - max), written over the S columns already consumed.  The load of chunk c+1 is in flight
       // while chunk c is exponentiated (P chunk c lands in S chunk c/2 <= c, never in a chunk still being loaded).
@@ -544,8 +303,13 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float e0 = ex2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -mscaled));
-          float e1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -mscaled));
+          float b0 = -mscaled, b1 = -mscaled;
+          if (MODE == MODE_CROSS && brow) {
+            b0 = fmaf(__ldg(brow + c * 32 + 2 * j), 1.4426950408889634f, -mscaled);
+            b1 = fmaf(__ldg(brow + c * 32 + 2 * j + 1), 1.4426950408889634f, -mscaled);
+          }
+          float e0 = ex2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, b0));
+          float e1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, b1));
           if (!key_valid<MODE>(rkey, c * 32 + 2 * j, p.gshift)) e0 = 0.f;
           if (!key_valid<MODE>(rkey, c * 32 + 2 * j + 1, p.gshift)) e1 = 0.f;
           sum += e0 + e1;
@@ -639,14 +403,503 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v3 (round 2): the same TMEM-resident design, re-cut so that more of every engine's work overlaps.
+//   * work is split by ROLE WARP, each an in-order stream with its own barriers: warp 0 = TMA producer for Q and K,
+//     warp 3 = TMA producer for V, warp 1 = MMA issuer (+ TMEM allocator), warp 2 = output store (TMA bulk store),
+//     warps 4.. = softmax/epilogue warpgroups.  No role ever waits on behalf of another.
+//   * a "slot" = one tile in flight = one smem stage {Q, K, V} + one TMEM region.
+//       LK = 256 (spatial, 256 keys):  2 slots x 256 TMEM columns; TWO warpgroups per tile, each owning 128 key columns
+//                                      (row max and row sum exchanged through smem + a 256-thread named barrier), so the
+//                                      S -> softmax -> PV chain of a tile is half as long;
+//       LK = 128 (temporal / cross / packed / N = 128):  3 slots x 160 TMEM columns, one warpgroup per tile.
+//     TMEM per slot: S fp32 [0,LK); P (16-bit, packed two per column) is written over the start of each warpgroup's own
+//     S columns -- keys [0,128) -> cols [0,64), keys [128,256) -> cols [128,192); O main (64 cols) at [64,128), O tail
+//     (16 cols, head_dim 72/80) at [192,208) resp. [128,144): columns that are dead by the time P V is issued.
+//   * the output never leaves through per-thread stores: O * 1/sum goes registers -> the slot's V tile in shared memory
+//     (dense [128][head_dim] rows; V is dead once P V has completed) -> ONE TMA bulk store per tile whose box does the
+//     (b, f, n) regrouping for temporal tiles, exactly like the loads.  The V producer refills the stage when the store
+//     has read it (v_free).
+//   * temporal tiles with G = 8 tokens x 16 frames: a row has 16 live keys out of 128 (col % 8 == row % 8).  They are
+//     picked out of the TMEM row with a select tree in ONE pass, so a row costs 16 exponentials instead of 128.
+//   * spatial tiles: 5 of every 16 exponentials are evaluated on the FMA pipe (Cody-Waite split + degree-4 polynomial,
+//     2.8e-6 relative error, far below the 16-bit rounding of P) because the 16-op/clk MUFU pipe is what bounds a
+//     128 x 256 tile (2048 clk) once the chain overlaps.
+template <int LK>
+struct V3 {
+  static constexpr int NSLOT = LK == 256 ? 2 : 3;
+  static constexpr int WG_PER_TILE = LK == 256 ? 2 : 1;
+  static constexpr int NWG = NSLOT * WG_PER_TILE;
+  static constexpr int THREADS = 128 + NWG * 128;
+  static constexpr int SLOT_COLS = LK == 256 ? 256 : 160;
+  static constexpr int O_COL = 64;
+  static constexpr int OT_COL = LK == 256 ? 192 : 128;
+  static constexpr int TILE_THREADS = WG_PER_TILE * 128;
+};
+
+struct V3Plan {
+  int q_main, q_tail, k_main, k_tail, v_main, v_tail, stage_bytes, xch, bias, bars, total;
+};
+__host__ __device__ inline V3Plan make_v3_plan(int LK, bool tail) {
+  const int nslot = LK == 256 ? 2 : 3;
+  V3Plan s;
+  s.q_main = 0;
+  s.q_tail = 128 * 128;
+  s.k_main = s.q_tail + (tail ? 128 * 32 : 0);
+  s.k_tail = s.k_main + LK * 128;
+  s.v_main = s.k_tail + (tail ? LK * 32 : 0);
+  s.v_tail = s.v_main + LK * 128;     // contiguous with v_main: the output staging tile [128][hd] spans both
+  s.stage_bytes = s.v_tail + (tail ? LK * 32 : 0);
+  s.xch = nslot * s.stage_bytes;                       // float [nslot][2 kinds][2 halves][128]
+  s.bias = s.xch + nslot * 2 * 2 * 128 * 4;            // float [nslot][128]
+  s.bars = s.bias + nslot * 128 * 4;
+  s.total = s.bars + 256 + 1024;
+  return s;
+}
+
+// 2^x for x <= 0 on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-4 minimax polynomial
+// (max relative error 2.8e-6), 2^n by adding n to the exponent field.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;              // 1.5 * 2^23: the integer n sits in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float pl = fmaf(0.009582852944731712f, f, 0.055906426161527634f);
+  pl = fmaf(pl, f, 0.24024099111557007f);
+  pl = fmaf(pl, f, 0.6931241750717163f);
+  pl = fmaf(pl, f, 1.0f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
+__device__ __forceinline__ float sel8(const uint32_t* v, int g) {   // v[g], g in [0,8), without dynamic register indexing
+  const uint32_t a0 = (g & 1) ? v[1] : v[0], a1 = (g & 1) ? v[3] : v[2], a2 = (g & 1) ? v[5] : v[4], a3 = (g & 1) ? v[7] : v[6];
+  const uint32_t b0 = (g & 2) ? a1 : a0, b1 = (g & 2) ? a3 : a2;
+  return __uint_as_float((g & 4) ? b1 : b0);
+}
+
+template <bool BF16, bool TAIL, int MODE, int LK>
+__global__ void __launch_bounds__(V3<LK>::THREADS, 1)
+attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
+               const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt,
+               const __grid_constant__ CUtensorMap tmO, const AttnDev p, const int total_items) {
+  using C = V3<LK>;
+  constexpr int NSLOT = C::NSLOT;
+  static_assert(MODE == MODE_FULL || LK == 128, "only the unmasked spatial mode has 256-key tiles");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const V3Plan sp = make_v3_plan(LK, TAIL);
+  float* xch = reinterpret_cast<float*>(smem + sp.xch);
+  float* sbias = reinterpret_cast<float*>(smem + sp.bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* qk_full = bars + 0 * NSLOT;    // TMA: Q and K of the stage have landed
+  uint64_t* v_full = bars + 1 * NSLOT;     // TMA: V has landed
+  uint64_t* s_full = bars + 2 * NSLOT;     // MMA: S complete in TMEM (also: the stage's Q/K smem is free)
+  uint64_t* p_full = bars + 3 * NSLOT;     // softmax (all threads of the tile): P is in TMEM
+  uint64_t* o_full = bars + 4 * NSLOT;     // MMA: O complete in TMEM (also: V smem no longer read by the tensor pipe)
+  uint64_t* o_free = bars + 5 * NSLOT;     // epilogue (all threads of the tile): O is in registers, the TMEM slot is free
+  uint64_t* o_staged = bars + 6 * NSLOT;   // epilogue (all threads of the tile): the output tile is staged in the V smem
+  uint64_t* v_free = bars + 7 * NSLOT;     // store warp: the bulk store has read the staging tile, V may be refilled
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 * NSLOT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int H = p.heads;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+    for (int b = 0; b < NSLOT; ++b) {
+      mbar_init(qk_full + b, 1);
+      mbar_init(v_full + b, 1);
+      mbar_init(s_full + b, 1);
+      mbar_init(p_full + b, C::TILE_THREADS);
+      mbar_init(o_full + b, 1);
+      mbar_init(o_free + b, C::TILE_THREADS);
+      mbar_init(o_staged + b, C::TILE_THREADS);
+      mbar_init(v_free + b, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // qkv (written by the preceding GEMM) is visible from here
+
+  const int first = blockIdx.x, step = gridDim.x;
+  const int n_items = first < total_items ? (total_items - first + step - 1) / step : 0;
+
+  // tile coordinates of local work item i: the TMA coordinates of its Q rows / K,V rows / output rows
+  struct Coord { int head, c2, c3, kv2; };
+  auto coord = [&](int i) {
+    const int item = first + i * step;
+    Coord c;
+    c.head = item % H;
+    const int tile = item / H;
+    if constexpr (MODE == MODE_TEMPORAL) {
+      c.c2 = (tile % p.tiles_per_seq) * p.group;      // first token of the group
+      c.c3 = (tile / p.tiles_per_seq) * p.frames;     // first (b, f) image
+      c.kv2 = c.c2;
+    } else if constexpr (MODE == MODE_FULL) {
+      const int s = tile / p.tiles_per_seq;
+      c.kv2 = s * p.tokens;
+      c.c2 = c.kv2 + (tile % p.tiles_per_seq) * 128;
+      c.c3 = 0;
+    } else if constexpr (MODE == MODE_CROSS) {
+      c.c2 = tile * 128;
+      c.kv2 = (c.c2 / p.q_rows_per_batch) * p.kv_rows_per_batch;
+      c.c3 = c.c2 / p.q_rows_per_batch;               // sample index (key-bias row)
+    } else {
+      c.c2 = c.kv2 = tile * 128;
+      c.c3 = 0;
+    }
+    return c;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer: Q and K
+      const uint32_t qk_bytes = 128 * 128 + LK * 128 + (TAIL ? (128 * 32 + LK * 32) : 0);
+      for (int i = 0; i < n_items; ++i) {
+        const int sl = i % NSLOT, u = i / NSLOT;
+        uint8_t* buf = smem + sl * sp.stage_bytes;
+        const Coord c = coord(i);
+        if (u > 0) mbar_wait(s_full + sl, (u - 1) & 1);     // S of the tile that used this stage is done
+        mbar_arrive_expect_tx(qk_full + sl, qk_bytes);
+        if constexpr (MODE == MODE_TEMPORAL) {
+          tma_load_4d(buf + sp.q_main, &tmQ, qk_full + sl, 0, c.head, c.c2, c.c3);
+          tma_load_4d(buf + sp.k_main, &tmKV, qk_full + sl, 0, p.k_head0 + c.head, c.c2, c.c3);
+          if constexpr (TAIL) {
+            tma_load_4d(buf + sp.q_tail, &tmQt, qk_full + sl, 64, c.head, c.c2, c.c3);
+            tma_load_4d(buf + sp.k_tail, &tmKVt, qk_full + sl, 64, p.k_head0 + c.head, c.c2, c.c3);
+          }
+        } else {
+          tma_load_3d(buf + sp.q_main, &tmQ, qk_full + sl, 0, c.head, c.c2);
+          tma_load_3d(buf + sp.k_main, &tmKV, qk_full + sl, 0, p.k_head0 + c.head, c.kv2);
+          if constexpr (TAIL) {
+            tma_load_3d(buf + sp.q_tail, &tmQt, qk_full + sl, 64, c.head, c.c2);
+            tma_load_3d(buf + sp.k_tail, &tmKVt, qk_full + sl, 64, p.k_head0 + c.head, c.kv2);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer: V
+      const uint32_t v_bytes = LK * 128 + (TAIL ? LK * 32 : 0);
+      for (int i = 0; i < n_items; ++i) {
+        const int sl = i % NSLOT, u = i / NSLOT;
+        uint8_t* buf = smem + sl * sp.stage_bytes;
+        const Coord c = coord(i);
+        if (u > 0) mbar_wait(v_free + sl, (u - 1) & 1);     // the previous tile's output has left the staging tile
+        mbar_arrive_expect_tx(v_full + sl, v_bytes);
+        if constexpr (MODE == MODE_TEMPORAL) {
+          tma_load_4d(buf + sp.v_main, &tmKV, v_full + sl, 0, p.v_head0 + c.head, c.c2, c.c3);
+          if constexpr (TAIL) tma_load_4d(buf + sp.v_tail, &tmKVt, v_full + sl, 64, p.v_head0 + c.head, c.c2, c.c3);
+        } else {
+          tma_load_3d(buf + sp.v_main, &tmKV, v_full + sl, 0, p.v_head0 + c.head, c.kv2);
+          if constexpr (TAIL) tma_load_3d(buf + sp.v_tail, &tmKVt, v_full + sl, 64, p.v_head0 + c.head, c.kv2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_s = umma_idesc_f16(BF16, 128, LK, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_f16(BF16, 128, 64, false, true);   // B = V is MN-major ([key][hd] in smem)
+      constexpr uint32_t idesc_ot = umma_idesc_f16(BF16, 128, 16, false, true);
+      auto issue_s = [&](int i) {
+        const int sl = i % NSLOT, u = i / NSLOT;
+        uint8_t* buf = smem + sl * sp.stage_bytes;
+        mbar_wait(qk_full + sl, u & 1);
+        if (u > 0) mbar_wait(o_free + sl, (u - 1) & 1);      // the previous tile's O has been read out of this slot
+        tc_fence_after();
+        const uint32_t tS = tmem_base + sl * C::SLOT_COLS;
+        const uint64_t dq = umma_smem_desc(smem_u32(buf + sp.q_main), 0, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t dk = umma_smem_desc(smem_u32(buf + sp.k_main), 0, 1024, UMMA_LAYOUT_SW128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tS, umma_desc_advance(dq, k * 32), umma_desc_advance(dk, k * 32), idesc_s, k > 0 ? 1u : 0u);
+        if constexpr (TAIL) {
+          const uint64_t dqt = umma_smem_desc(smem_u32(buf + sp.q_tail), 0, 256, UMMA_LAYOUT_SW32);
+          const uint64_t dkt = umma_smem_desc(smem_u32(buf + sp.k_tail), 0, 256, UMMA_LAYOUT_SW32);
+          umma_f16_ss(tS, dqt, dkt, idesc_s, 1u);
+        }
+        umma_commit(s_full + sl);
+      };
+      auto issue_pv = [&](int i) {
+        const int sl = i % NSLOT, u = i / NSLOT;
+        uint8_t* buf = smem + sl * sp.stage_bytes;
+        mbar_wait(v_full + sl, u & 1);
+        mbar_wait(p_full + sl, u & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + sl * C::SLOT_COLS;
+        const uint64_t dv = umma_smem_desc(smem_u32(buf + sp.v_main), static_cast<uint32_t>(LK) * 128, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t dvt = umma_smem_desc(smem_u32(buf + sp.v_tail), static_cast<uint32_t>(LK) * 32, 256, UMMA_LAYOUT_SW32);
+#pragma unroll
+        for (int k = 0; k < LK / 16; ++k) {
+          const uint32_t tP = tS + (k < 8 ? k * 8 : 128 + (k - 8) * 8);   // keys [128,256): P sits at columns [128,192)
+          umma_f16_ts(tS + C::O_COL, tP, umma_desc_advance(dv, k * 16 * 128), idesc_o, k > 0 ? 1u : 0u);
+          if constexpr (TAIL) umma_f16_ts(tS + C::OT_COL, tP, umma_desc_advance(dvt, k * 16 * 32), idesc_ot, k > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full + sl);
+      };
+      for (int j = 0; j < NSLOT - 1 && j < n_items; ++j) issue_s(j);
+      for (int i = 0; i < n_items; ++i) {
+        if (i + NSLOT - 1 < n_items) issue_s(i + NSLOT - 1);
+        issue_pv(i);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ output store: staging tile -> global (TMA)
+      for (int i = 0; i < n_items; ++i) {
+        const int sl = i % NSLOT, u = i / NSLOT;
+        const Coord c = coord(i);
+        mbar_wait(o_staged + sl, u & 1);
+        if (!(p.dbg & 4)) {
+          const uint8_t* src = smem + sl * sp.stage_bytes + sp.v_main;
+          if constexpr (MODE == MODE_TEMPORAL) tma_store_4d(&tmO, src, 0, c.head, c.c2, c.c3);
+          else tma_store_3d(&tmO, src, 0, c.head, c.c2);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        mbar_arrive(v_free + sl);
+      }
+      tma_store_wait_all<0>();
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax + epilogue warpgroups
+    const int wg = (warp - 4) >> 2;
+    const int sl = wg / C::WG_PER_TILE;            // the slot this warpgroup serves
+    const int h = wg % C::WG_PER_TILE;             // LK = 256: which 128 key columns
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                   // tile row = TMEM lane
+    const uint32_t t_slot = tmem_base + sl * C::SLOT_COLS + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_s = t_slot + h * 128;         // my S columns; my P is written over their first 64 columns
+    float* xmax = xch + (sl * 4 + 0) * 128;        // [2 halves][128]
+    float* xsum = xch + (sl * 4 + 2) * 128;
+    float* bias_s = sbias + sl * 128;
+    const int bar_id = 1 + sl;
+    uint8_t* stage_out = smem + sl * sp.stage_bytes + sp.v_main;
+    const int row_bytes = p.hd * 2;
+    const bool use_poly = !(p.dbg & 16);
+
+    for (int i = sl; i < n_items; i += NSLOT) {
+      const int u = i / NSLOT;
+      float sum = 0.f;
+      bool have_bias = false;
+      if constexpr (MODE == MODE_CROSS) {
+        have_bias = p.key_bias != nullptr;
+        if (have_bias) {        // this sample's additive key bias (natural-log units) -> smem, once per tile
+          const Coord c = coord(i);
+          bias_s[r] = __ldg(p.key_bias + static_cast<size_t>(c.c3) * 128 + r) * 1.4426950408889634f;
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
+      }
+      mbar_wait(s_full + sl, u & 1);
+      tc_fence_after();
+
+      bool done = false;
+      if constexpr (MODE == MODE_TEMPORAL) done = p.group == 8;
+      if (done) {
+        // ---- one pass: the row's 16 live keys are columns g, g + 8, ..., g = r % 8
+        const int g = r & 7;
+        float xs[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_s + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xs[c * 4 + k] = sel8(v + 8 * k, g);
+        }
+        float mx = xs[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) mx = fmaxf(mx, xs[k]);
+        const float ms = mx * p.scale_log2;
+        uint32_t pk16[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float e = ex2(fmaf(xs[k], p.scale_log2, -ms));
+          sum += e;
+          pk16[k] = (g & 1) ? pack2<BF16>(0.f, e) : pack2<BF16>(e, 0.f);
+        }
+        const int w = g >> 1;   // which of the group's 4 packed words holds the live key
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {     // 32 key columns = 16 packed words = 4 groups of 4 words
+          uint32_t o16[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o16[4 * k + j] = (j == w) ? pk16[c * 4 + k] : 0u;
+          }
+          tmem_st_32x32b_x16(t_s + c * 16, o16);
+        }
+      } else {
+        // ---- two passes over my 128 key columns: row maximum, then P = exp2(s * scale (+ bias) - max)
+        const int rkey = MODE == MODE_CROSS ? p.kv_rows_per_batch : row_key<MODE>(r, p.gshift);
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(t_s + c * 32, va);
+          tmem_ld_32x32b_x32(t_s + (c + 1) * 32, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(va[j]), b = __uint_as_float(vb[j]);
+            if constexpr (MODE == MODE_CROSS) {
+              if (have_bias) {
+                a = fmaf(a, p.scale_log2, bias_s[c * 32 + j]);
+                b = fmaf(b, p.scale_log2, bias_s[(c + 1) * 32 + j]);
+              }
+            }
+            if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, a);
+            if (key_valid<MODE>(rkey, (c + 1) * 32 + j, p.gshift)) mx = fmaxf(mx, b);
+          }
+        }
+        if constexpr (LK == 256) {      // the other warpgroup holds the other half of the row
+          xmax[h * 128 + r] = mx;
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+          mx = fmaxf(mx, xmax[(h ^ 1) * 128 + r]);
+        }
+        const float ms = have_bias ? mx : mx * p.scale_log2;
+        auto emit = [&](const uint32_t (&v)[16], int c) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float e[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int jj = 2 * j + t;
+              float x;
+              if (MODE == MODE_CROSS && have_bias) x = fmaf(__uint_as_float(v[jj]), p.scale_log2, bias_s[c * 16 + jj]) - ms;
+              else x = fmaf(__uint_as_float(v[jj]), p.scale_log2, -ms);
+              // 5 of 16 exponentials on the FMA pipe (spatial tiles only: their rows are 256 keys long)
+              if (MODE == MODE_FULL && use_poly && (jj % 3 == 2)) e[t] = ex2_poly(x);
+              else e[t] = ex2(x);
+              if (!key_valid<MODE>(rkey, c * 16 + jj, p.gshift)) e[t] = 0.f;
+              sum += e[t];
+            }
+            pk[j] = pack2<BF16>(e[0], e[1]);
+          }
+          tmem_st_32x32b_x8(t_s + c * 8, pk);
+        };
+        uint32_t va[16], vb[16];
+        tmem_ld_32x32b_x16(t_s, va);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_32x32b_x16(t_s + (c + 1) * 16, vb);
+          emit(va, c);
+          tmem_ld_wait();
+          if (c + 2 < 8) tmem_ld_32x32b_x16(t_s + (c + 2) * 16, va);
+          emit(vb, c + 1);
+          tmem_ld_wait();
+        }
+      }
+      if constexpr (LK == 256) xsum[h * 128 + r] = sum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full + sl);
+      if constexpr (LK == 256) {
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        sum += xsum[(h ^ 1) * 128 + r];
+      }
+      const float inv = 1.0f / sum;
+
+      // ---- epilogue: O * 1/sum -> 16-bit -> dense [128][hd] staging tile in the (dead) V smem of this stage
+      mbar_wait(o_full + sl, u & 1);
+      tc_fence_after();
+      uint8_t* drow = stage_out + r * row_bytes;
+      auto put32 = [&](const uint32_t (&o)[32], int col0) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          uint4 w;
+          w.x = pack2<BF16>(__uint_as_float(o[8 * i4 + 0]) * inv, __uint_as_float(o[8 * i4 + 1]) * inv);
+          w.y = pack2<BF16>(__uint_as_float(o[8 * i4 + 2]) * inv, __uint_as_float(o[8 * i4 + 3]) * inv);
+          w.z = pack2<BF16>(__uint_as_float(o[8 * i4 + 4]) * inv, __uint_as_float(o[8 * i4 + 5]) * inv);
+          w.w = pack2<BF16>(__uint_as_float(o[8 * i4 + 6]) * inv, __uint_as_float(o[8 * i4 + 7]) * inv);
+          *reinterpret_cast<uint4*>(drow + (col0 + i4 * 8) * 2) = w;
+        }
+      };
+      auto put_tail = [&](const uint32_t (&o)[16]) {
+        const int tail8 = (p.hd - 64) / 8;   // 1 (hd 72) or 2 (hd 80)
+#pragma unroll
+        for (int i4 = 0; i4 < 2; ++i4) {
+          if (i4 < tail8) {
+            uint4 w;
+            w.x = pack2<BF16>(__uint_as_float(o[8 * i4 + 0]) * inv, __uint_as_float(o[8 * i4 + 1]) * inv);
+            w.y = pack2<BF16>(__uint_as_float(o[8 * i4 + 2]) * inv, __uint_as_float(o[8 * i4 + 3]) * inv);
+            w.z = pack2<BF16>(__uint_as_float(o[8 * i4 + 4]) * inv, __uint_as_float(o[8 * i4 + 5]) * inv);
+            w.w = pack2<BF16>(__uint_as_float(o[8 * i4 + 6]) * inv, __uint_as_float(o[8 * i4 + 7]) * inv);
+            *reinterpret_cast<uint4*>(drow + (64 + i4 * 8) * 2) = w;
+          }
+        }
+      };
+      if constexpr (LK == 256) {
+        uint32_t o0[32], ot[16];
+        tmem_ld_32x32b_x32(t_slot + C::O_COL + h * 32, o0);
+        if (TAIL && h == 0) tmem_ld_32x32b_x16(t_slot + C::OT_COL, ot);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(o_free + sl);
+        put32(o0, h * 32);
+        if (TAIL && h == 0) put_tail(ot);
+      } else {
+        uint32_t o0[32], o1[32], ot[16];
+        tmem_ld_32x32b_x32(t_slot + C::O_COL, o0);
+        tmem_ld_32x32b_x32(t_slot + C::O_COL + 32, o1);
+        if constexpr (TAIL) tmem_ld_32x32b_x16(t_slot + C::OT_COL, ot);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(o_free + sl);
+        put32(o0, 0);
+        put32(o1, 32);
+        if constexpr (TAIL) put_tail(ot);
+      }
+      fence_proxy_async_smem();       // the staging tile is read by the TMA engine
+      mbar_arrive(o_staged + sl);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool BF16, bool TAIL, int MODE, int LK>
+int launch_v3_lk(const CUtensorMap* m, const AttnDev& p, int total, cudaStream_t stream) {
+  auto kern = attn_v3_kernel<BF16, TAIL, MODE, LK>;
+  const int smem_bytes = make_v3_plan(LK, TAIL).total;
+  B200_SET_SMEM_ONCE(kern, smem_bytes);
+  int sms = 148;
+  B200_TRY(device_sm_count(&sms));
+  const int ctas = total < sms ? total : sms;
+  B200_CHECK_CUDA(launch_pdl(kern, dim3(ctas), dim3(V3<LK>::THREADS), static_cast<size_t>(smem_bytes), stream, m[0], m[1], m[2], m[3], m[4], p, total));
+  return B200_OK;
+}
+
+template <bool BF16, bool TAIL, int MODE>
+int launch_v3(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
+  const int total = static_cast<int>(grid.x * grid.y);
+  if constexpr (MODE == MODE_FULL) {
+    if (p.Lk == 256) return launch_v3_lk<BF16, TAIL, MODE, 256>(m, p, total, stream);
+  }
+  return launch_v3_lk<BF16, TAIL, MODE, 128>(m, p, total, stream);
+}
+
 template <bool BF16, bool TAIL, int MODE>
 int launch_pipe(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
   auto kern = attn_pipe_kernel<BF16, TAIL, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, make_pipe_plan(256, true).total));
-    attr_set = true;
-  }
+  B200_SET_SMEM_ONCE(kern, make_pipe_plan(256, true).total);
   const int smem_bytes = make_pipe_plan(p.Lk, TAIL).total;
   const int total = static_cast<int>(grid.x * grid.y);
   int sms = 148;
@@ -658,17 +911,13 @@ int launch_pipe(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t 
 
 template <bool BF16, bool TAIL, int MODE>
 int launch_mode(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
-  static const bool use_old = getenv("B200_ATTN_OLD") != nullptr;   // A/B switch: the one-tile-per-CTA kernel
-  if (!use_old) return launch_pipe<BF16, TAIL, MODE>(m, p, grid, stream);
-  auto kern = attn_kernel<BF16, TAIL, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, make_plan(256, true).total));
-    attr_set = true;
-  }
-  const int smem_bytes = make_plan(p.Lk, TAIL).total;
-  B200_CHECK_CUDA(launch_pdl(kern, grid, dim3(kThreads), static_cast<size_t>(smem_bytes), stream, m[0], m[1], m[2], m[3], p));
-  return B200_OK;
+  // B200_ATTN_IMPL: 3 = v3 (role warps, 2 warpgroups per 256-key tile / 3 tiles in flight, TMA-stored output),
+  //                 2 = the round-1 two-tile pipeline (A/B switch)
+  static const int env_impl = env_int("B200_ATTN_IMPL", kAttnDefaultImpl);
+  const int forced = g_attn_impl;
+  const int impl = forced ? forced : env_impl;
+  if (impl == 2) return launch_pipe<BF16, TAIL, MODE>(m, p, grid, stream);
+  return launch_v3<BF16, TAIL, MODE>(m, p, grid, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -899,11 +1148,7 @@ attn_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 template <bool BF16, bool TAIL>
 int launch_long(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
   auto kern = attn_long_kernel<BF16, TAIL>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES));
-    attr_set = true;
-  }
+  B200_SET_SMEM_ONCE(kern, L_SMEM_BYTES);
   B200_CHECK_CUDA(launch_pdl(kern, grid, dim3(kThreads), static_cast<size_t>(L_SMEM_BYTES), stream, m[0], m[1], m[2], m[3], p));
   return B200_OK;
 }
@@ -919,6 +1164,12 @@ int launch_tail(int mode, const CUtensorMap* m, const AttnDev& p, dim3 grid, cud
 }
 
 }  // namespace
+
+int set_attention_impl(int impl) {
+  B200_REQUIRE(impl == 0 || impl == 2 || impl == 3, B200_ERR_UNSUPPORTED, "attention implementation %d unknown (0 default, 2, 3)", impl);
+  g_attn_impl = impl;
+  return B200_OK;
+}
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   B200_REQUIRE(a.batch > 0 && a.frames > 0 && a.tokens > 0 && a.heads > 0, B200_ERR_SHAPE, "attention: bad shape");
@@ -940,7 +1191,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.tokens = a.tokens;
   p.frames = a.frames;
   p.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
-  { const char* e = getenv("B200_ATTN_DBG"); p.dbg = e ? atoi(e) : 0; }
+  static const int dbg = env_int("B200_ATTN_DBG", 0);
+  p.dbg = dbg;
+  p.key_bias = nullptr;
 
   p.group = 1;
   p.gshift = 0;
@@ -950,7 +1203,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.q_rows_per_batch = 1;
   auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
 
-  CUtensorMap maps[4];
+  CUtensorMap maps[5];
   int mode;
   dim3 grid;
   if (!a.temporal) {
@@ -1005,6 +1258,12 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
       maps[1] = maps[0];
       maps[3] = maps[2];
     }
+    {   // output tile store: dense [128][hd] rows of the staging tile -> rows (b, f, n) of out, columns of this head
+      const uint64_t odims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(T)};
+      const uint64_t ostr[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(D) * 2};
+      const uint32_t obox[3] = {static_cast<uint32_t>(hd), 1, 128};
+      B200_TRY(make_tmap_16bit(&maps[4], a.out, 3, odims, ostr, obox, TMAP_SW_NONE));
+    }
   } else {
     const int F = a.frames;
     B200_REQUIRE(F >= 4 && F <= 128 && 128 % F == 0, B200_ERR_UNSUPPORTED,
@@ -1032,6 +1291,13 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
       maps[1] = maps[0];
       maps[3] = maps[0];
     }
+    {   // output store with the same (token group) x (frames) box as the loads: tile row f*G + g -> out row (b*F + f)*N + n0 + g
+      const uint64_t odims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(a.tokens),
+                                 static_cast<uint64_t>(a.batch) * F};
+      const uint64_t ostr[3] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(D) * 2 * a.tokens};
+      const uint32_t obox[4] = {static_cast<uint32_t>(hd), 1, static_cast<uint32_t>(G), static_cast<uint32_t>(F)};
+      B200_TRY(make_tmap_16bit(&maps[4], a.out, 4, odims, ostr, obox, TMAP_SW_NONE));
+    }
   }
   if (a.bf16) return tail ? launch_tail<true, true>(mode, maps, p, grid, stream) : launch_tail<true, false>(mode, maps, p, grid, stream);
   return tail ? launch_tail<false, true>(mode, maps, p, grid, stream) : launch_tail<false, false>(mode, maps, p, grid, stream);
@@ -1056,7 +1322,11 @@ int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream) {
   p.tokens = a.q_rows_per_batch; p.frames = 1; p.group = 1; p.gshift = 0; p.Lk = 128; p.tiles_per_seq = 1;
   p.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
   p.k_head0 = 0; p.v_head0 = H; p.kv_rows_per_batch = a.kv_len; p.q_rows_per_batch = a.q_rows_per_batch;
-  CUtensorMap maps[4];
+  static const int dbg = env_int("B200_ATTN_DBG", 0);
+  p.dbg = dbg;
+  B200_REQUIRE(!a.key_bias || (reinterpret_cast<uintptr_t>(a.key_bias) & 15) == 0, B200_ERR_ALIGN, "cross attention: key_bias must be 16-byte aligned");
+  p.key_bias = a.key_bias;
+  CUtensorMap maps[5];
   const uint64_t qdims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(T)};
   const uint64_t qstr[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(a.q_row_stride) * 2};
   const uint64_t kdims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(2 * H), static_cast<uint64_t>(R)};
@@ -1071,6 +1341,12 @@ int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream) {
   } else {
     maps[1] = maps[0];
     maps[3] = maps[2];
+  }
+  {
+    const uint64_t odims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(T)};
+    const uint64_t ostr[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(D) * 2};
+    const uint32_t obox[3] = {static_cast<uint32_t>(hd), 1, 128};
+    B200_TRY(make_tmap_16bit(&maps[4], a.out, 3, odims, ostr, obox, TMAP_SW_NONE));
   }
   const dim3 grid(static_cast<unsigned>(T / 128), H);
   if (a.bf16) return tail ? launch_tail<true, true>(MODE_CROSS, maps, p, grid, stream) : launch_tail<true, false>(MODE_CROSS, maps, p, grid, stream);

@@ -64,6 +64,22 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 // ---- device-property cache ----------------------------------------------------------------------
+int current_device(int* out);   // ordinal in [0, 64)
+int env_int(const char* name, int dflt);   // call through a function-local `static const` so the environment is read once
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember it per (kernel instantiation, device ordinal)
+struct PerDeviceOnce {
+  bool done[64] = {};
+};
+#define B200_SET_SMEM_ONCE(kern, bytes)                                                                        \
+  do {                                                                                                         \
+    static b200::PerDeviceOnce _once;                                                                          \
+    int _dev = 0;                                                                                              \
+    B200_TRY(b200::current_device(&_dev));                                                                     \
+    if (!_once.done[_dev]) {                                                                                   \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));       \
+      _once.done[_dev] = true;                                                                                 \
+    }                                                                                                          \
+  } while (0)
 int device_sm_count(int* out);
 int check_arch();  // B200_ERR_ARCH unless the current device is sm_100
 
@@ -83,6 +99,7 @@ struct GemmArgs {
   const float* row_add; // optional [period, N] fp32 added to resid rows: row_add[((row / row_add_div) % row_add_period) * N + col]
   int row_add_div, row_add_period;
   int block_n;          // 0 = auto
+  unsigned long long* sk_flags;  // B200_GEMM_SK_FLAGS zeroed u64 (caller's workspace) or nullptr: enables ordered stream-K
   const void* add16;    // EPI_BIAS_ADD16: [M, N] 16-bit tensor added to the result (resnet shortcut)
   // implicit-GEMM convolution (conv_taps > 0): A is an NHWC activation [conv_n, conv_h, conv_w, conv_c] (16-bit), M =
   // conv_n*conv_h*conv_w output pixels, K = conv_taps * conv_c with W laid out [N][tap][c]; tap t reads the input pixel
@@ -110,8 +127,11 @@ struct CrossAttnArgs {
   int q_row_stride, kv_row_stride;  // elements
   int heads, head_dim;
   int bf16;
+  const float* key_bias;  // optional [batch][128] fp32 additive score bias per key (encoder_attention_mask -> (1-m)*-10000,
+                          // latte_t2v.py:766-771); entries >= kv_len are ignored
 };
 int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream);
+int set_attention_impl(int impl);
 
 int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
                        int rows_per_batch, void* out16, int rows, int dim, int bf16, cudaStream_t stream);

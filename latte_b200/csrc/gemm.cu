@@ -30,7 +30,6 @@
 //                    -> re-read with 8 threads per row -> coalesced 16-byte stores.
 //   residual:        x is never loaded: the delta gate*(acc+bias) goes to a swizzled smem tile and a TMA reduce-add
 //                    (cp.reduce.async.bulk.tensor ... .add, fp32) folds it into the residual stream in L2.
-#include <mutex>
 #include <cstdio>
 #include "common.h"
 #include "ptx.cuh"
@@ -80,8 +79,10 @@ struct GemmDev {
   int conv_taps, conv_cblk, conv_h, conv_w, conv_bw, conv_bh;
   int conv_dx[9], conv_dy[9], conv_dz[9];
   int streamk;  // residual epilogue only: split the last partial wave of tiles along K across all pairs (see TileSched)
-  unsigned long long* sk_flags;   // stream-K ordering flags, one per (streamed tile, CTA rank, epilogue warpgroup)
-  unsigned long long sk_tag;      // launch id << 16: a flag holds tag | (k-blocks of the tile already added into x)
+  // stream-K ordering flags (caller's workspace), one per (streamed tile, CTA rank, epilogue warpgroup): "k-blocks of the
+  // tile already added into x".  All zero between launches: the segment that completes a tile resets its flag, so the
+  // protocol holds no host-side state and a captured CUDA graph replays it unchanged.
+  unsigned long long* sk_flags;
   int dbg;  // timing experiments only (results are wrong when set): bit0 = no operand TMA, bit1 = no MMA issue, bit2 = no 16-bit epilogue
 };
 
@@ -377,7 +378,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");
           if (te == 0) {
             if (must_wait) {
-              flag_wait(flag, p.sk_tag | static_cast<unsigned long long>(kb0));
+              flag_wait(flag, static_cast<unsigned long long>(kb0));
+              // nobody else waits on this flag; the segment that completes the tile leaves it zero for the next launch
+              if (kb1 == num_kb) flag_release(flag, 0ull);
               fence_proxy_async_all();
             }
             tma_reduce_add_2d(&tmX, slot, col0, m0);
@@ -390,7 +393,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (partial && kb1 < num_kb && last_mine >= 0 && te == 0 && !(p.dbg & 8)) {
           tma_store_wait_all<0>();                      // this segment's adds have been performed ...
           __threadfence();
-          flag_release(flag, p.sk_tag | static_cast<unsigned long long>(kb1));   // ... the next segment may add
+          flag_release(flag, static_cast<unsigned long long>(kb1));   // ... the next segment may add
         }
         cc += live;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -507,11 +510,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
                cudaStream_t stream) {
   using C = Cfg<BN, EPI>;
   auto kern = gemm_kernel<BN, EPI, BF16>;
-  static bool attr_set = false;  // per instantiation; benign race (idempotent)
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  B200_SET_SMEM_ONCE(kern, C::SMEM_BYTES);
   B200_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, tmX, p));
   return B200_OK;
 }
@@ -536,41 +535,20 @@ int launch_bn(int bf16, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
 }
 
 constexpr int kStreamKMinKb = 32;          // K / 64 below which the split costs more than the idle tail it removes
-constexpr int kSkFlagsPerLaunch = 1024;    // flags (u64) per launch: 4 per streamed tile
-constexpr int kSkSlices = 256;             // ring of flag slices: a slice is reused 256 stream-K launches later
+constexpr int kSkFlags = B200_GEMM_SK_FLAGS;   // flags (u64) in the caller's buffer: 4 per streamed tile
 
 int streamk_min_kb() {
-  static const int v = getenv("B200_GEMM_SK_MINKB") ? atoi(getenv("B200_GEMM_SK_MINKB")) : kStreamKMinKb;
+  static const int v = env_int("B200_GEMM_SK_MINKB", kStreamKMinKb);
   return v;
 }
 
-// A fresh slice of the per-device flag ring and a launch id.  Flags are never reset: a flag is meaningful only when its
-// upper 48 bits equal the id of the launch that reads it.
-int streamk_flags(unsigned long long** slice, unsigned long long* id) {
-  static std::mutex mu;
-  static unsigned long long* ring[64] = {};
-  static unsigned long long next_id = 1;
-  int dev = 0;
-  B200_CHECK_CUDA(cudaGetDevice(&dev));
-  B200_REQUIRE(dev >= 0 && dev < 64, B200_ERR_UNSUPPORTED, "gemm: device index %d out of range", dev);
-  std::lock_guard<std::mutex> lock(mu);
-  if (!ring[dev]) {
-    const size_t bytes = static_cast<size_t>(kSkSlices) * kSkFlagsPerLaunch * sizeof(unsigned long long);
-    B200_CHECK_CUDA(cudaMalloc(&ring[dev], bytes));
-    B200_CHECK_CUDA(cudaMemset(ring[dev], 0, bytes));
-    B200_CHECK_CUDA(cudaDeviceSynchronize());
-  }
-  *id = next_id++;
-  *slice = ring[dev] + (*id % kSkSlices) * kSkFlagsPerLaunch;
-  return B200_OK;
-}
 
 int pick_block_n(int M, int N, int K, bool resid, int sms) {
   // minimise waves x per-tile time.  The kernel is bound by L2->SM operand bytes, not MMA cycles, so a tile costs
   // ~ (A bytes + W/2 bytes per k-block per CTA) = 128 + BN/2 rather than BN (measured: r01 microbench, profiles/).
   // Where the last wave is streamed along K (residual epilogue, long K) there is no wave rounding.
   if (N <= 128) return 128;   // narrow outputs (e.g. the VAE's 3-channel conv_out padded to 32): smallest tile that covers N
-  static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
+  static const bool no_sk = env_int("B200_GEMM_NO_STREAMK", 0) != 0;
   const bool sk = resid && !no_sk && K / BK >= streamk_min_kb();
   const int cand[3] = {256, 192, 128};
   int best = 128;
@@ -587,7 +565,7 @@ int pick_block_n(int M, int N, int K, bool resid, int sms) {
 // The scheduling decisions of one launch (shared by launch_gemm and the schedule dump the CPU tests read).
 struct GemmPlan { int bn, pairs, pair_tiles, num_kb, streamk; };
 GemmPlan plan_gemm(int M, int N, int K, bool resid, int block_n, int sms) {
-  static const bool no_sk = getenv("B200_GEMM_NO_STREAMK") != nullptr;
+  static const bool no_sk = env_int("B200_GEMM_NO_STREAMK", 0) != 0;
   GemmPlan g;
   g.bn = block_n ? block_n : pick_block_n(M, N, K, resid, sms);
   const int num_m = (M + BM - 1) / BM, num_n = (N + g.bn - 1) / g.bn;
@@ -707,26 +685,19 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.conv_cblk = a.conv_taps > 0 ? a.conv_c / BK : 0;
   p.conv_h = a.conv_h; p.conv_w = a.conv_w; p.conv_bw = conv_bw; p.conv_bh = conv_bh;
   for (int i = 0; i < 9; ++i) { p.conv_dx[i] = a.conv_dx[i]; p.conv_dy[i] = a.conv_dy[i]; p.conv_dz[i] = a.conv_dz[i]; }
-  {
-    const char* e = getenv("B200_GEMM_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  static const int dbg = env_int("B200_GEMM_DBG", 0);
+  p.dbg = dbg;
   const int pair_tiles = plan.pair_tiles;
   const int grid = 2 * plan.pairs;
   {
     // stream-K over the last waves: only where partial sums can be reduce-added (residual epilogue) and K is long enough
     // to be worth splitting (plan_gemm); B200_GEMM_NO_STREAMK=1 restores the one-add-per-element schedule.
     const int pairs = plan.pairs;
-    p.streamk = plan.streamk;
-    p.sk_flags = nullptr;
-    p.sk_tag = 0;
-    if (p.streamk) {
-      const int streamed = pair_tiles % pairs + pairs;  // tiles of the partial wave and of the full wave before it
-      B200_REQUIRE(streamed * 4 <= kSkFlagsPerLaunch, B200_ERR_UNSUPPORTED, "gemm: stream-K flag slice too small");
-      unsigned long long id = 0;
-      B200_TRY(streamk_flags(&p.sk_flags, &id));
-      p.sk_tag = id << 16;
-    }
+    // the ordering flags live in the CALLER's buffer (zeroed once; every launch leaves it zeroed): without one the
+    // schedule stays data-parallel
+    const int streamed = pair_tiles % pairs + pairs;  // tiles of the partial wave and of the full wave before it
+    p.streamk = (plan.streamk && a.sk_flags != nullptr && streamed * 4 <= kSkFlags) ? 1 : 0;
+    p.sk_flags = p.streamk ? a.sk_flags : nullptr;
   }
   switch (bn) {
     case 128: return launch_bn<128>(a.bf16, a.epilogue, tmA, tmB, tmX, p, grid, stream);

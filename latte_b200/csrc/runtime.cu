@@ -1,8 +1,10 @@
 // Host-side runtime pieces: thread-local error text, TMA tensor-map encoding, device queries.
 #include "common.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 namespace b200 {
 
@@ -42,8 +44,56 @@ int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t
   return make_tmap(out, base, 2, rank, dims, strides_bytes, box, sw);
 }
 
+// ---- descriptor cache.  A denoising step re-issues the same ~20 distinct (pointer, shape, box) combinations hundreds of
+// times (203 launches, 2-4 maps each); a map is a pure function of its arguments, so encoded maps are kept per thread
+// keyed by those arguments.  Bounded: the table is dropped when it grows past kTmapCacheMax entries.
+namespace {
+struct TmapKey {
+  uint64_t base;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  uint32_t rank_elem_sw;
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); }
+    return static_cast<size_t>(h);
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+constexpr size_t kTmapCacheMax = 4096;
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle sw);
+}  // namespace
+
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle sw) {
+  B200_REQUIRE(rank >= 2 && rank <= 5, B200_ERR_SHAPE, "tensor map rank %d unsupported", rank);
+  thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey k;
+  std::memset(&k, 0, sizeof(k));
+  k.base = reinterpret_cast<uint64_t>(base);
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) k.strides[i] = strides_bytes[i];
+  k.rank_elem_sw = static_cast<uint32_t>(rank) | (static_cast<uint32_t>(elem_bytes) << 8) | (static_cast<uint32_t>(sw) << 16);
+  auto it = cache.find(k);
+  if (it != cache.end()) {
+    *out = it->second;
+    return B200_OK;
+  }
+  B200_TRY(encode_tmap(out, base, elem_bytes, rank, dims, strides_bytes, box, sw));
+  if (cache.size() >= kTmapCacheMax) cache.clear();
+  cache.emplace(k, *out);
+  return B200_OK;
+}
+
+namespace {
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle sw) {
   EncodeTiledFn fn = get_encode_fn();
   B200_REQUIRE(fn != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the CUDA driver");
   B200_REQUIRE(rank >= 2 && rank <= 5, B200_ERR_SHAPE, "tensor map rank %d unsupported", rank);
@@ -77,6 +127,13 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
                base);
   return B200_OK;
 }
+}  // namespace
+
+// ---- experiment switches: read from the environment ONCE per process (they select code paths for A/B timing only)
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 namespace {
 struct DevInfo {
@@ -100,6 +157,14 @@ int dev_info(DevInfo* out) {
   return B200_OK;
 }
 }  // namespace
+
+int current_device(int* out) {
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  B200_REQUIRE(dev >= 0 && dev < 64, B200_ERR_CUDA, "device ordinal %d out of range", dev);
+  *out = dev;
+  return B200_OK;
+}
 
 int device_sm_count(int* out) {
   DevInfo d;

@@ -22,7 +22,7 @@ import os
 import numpy as np
 import torch
 
-from .. import _lib
+from latte_b200 import _lib   # absolute: this package is also importable as top-level `diffusion` through a symlink
 
 DDPM, DDIM = 0, 1
 _DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
@@ -84,6 +84,12 @@ class SpacedDiffusion:
         self.posterior_mean_coef1 = b * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
         self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
         self._dev = {}   # (device, batch, eta) -> (SamplerTables, keep-alive tensor, t table, mapped-t table)
+
+    def __getstate__(self):
+        """The device tables (ctypes structs with raw pointers) are a cache, not state: copies / pickles start empty."""
+        state = dict(self.__dict__)
+        state["_dev"] = {}
+        return state
 
     # ------------------------------------------------------------------ device-resident state
     _BASE = ["sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
@@ -197,8 +203,15 @@ class SpacedDiffusion:
         armed = False
         if (owner is not None and hasattr(owner, "precompute_conditioning") and not getattr(owner, "training", False)
                 and not os.environ.get("B200_NO_TRAJECTORY_CONDITIONING")):
-            owner.precompute_conditioning(mapped_table, (kw.get("model_kwargs") or {}).get("y"))
-            armed = True
+            # steps x B rows of (depth*6D + 2D) fp32: 0.8 MB per row for XL/2.  Bounded: past the budget (long chains at a
+            # large batch) the loop falls back to the per-step conditioning path instead of risking an OOM the reference
+            # would not have hit.
+            row_bytes = getattr(owner, "conditioning_row_bytes", lambda: 0)()
+            need = row_bytes * self.num_timesteps * shape[0]
+            free = torch.cuda.mem_get_info(device)[0] if device.type == "cuda" else 0
+            if 0 < need <= min(int(os.environ.get("B200_TRAJECTORY_BUDGET_MB", "4096")) << 20, free // 4):
+                owner.precompute_conditioning(mapped_table, (kw.get("model_kwargs") or {}).get("y"))
+                armed = True
         try:
             for i in indices:
                 with torch.no_grad():

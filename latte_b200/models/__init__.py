@@ -2,7 +2,7 @@
 
 `sample/sample.py:56`, `sample/sample_ddp.py:88` and `train.py:90` call `get_models(args)`; putting this
 package ahead of the reference's on sys.path swaps the denoiser and nothing else."""
-from ..latte import Latte, Latte_models  # noqa: F401
+from latte_b200.latte import Latte, Latte_models  # noqa: F401  (absolute: also importable as top-level `models` via a symlink)
 
 
 def get_models(args):
@@ -11,7 +11,7 @@ def get_models(args):
         raise NotImplementedError("LatteIMG (video+image joint training variant, models/latte_img.py) is not built")
     if "LatteT2V" in name:
         # models/__init__.py:40-41
-        from ..latte_t2v import LatteT2V
+        from latte_b200.latte_t2v import LatteT2V
         return LatteT2V.from_pretrained(args.pretrained_model_path, subfolder="transformer", video_length=args.video_length)
     if "Latte" in name:
         # same keyword set as the reference factory (models/__init__.py:42-49)

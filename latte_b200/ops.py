@@ -19,6 +19,17 @@ def _stream(t: torch.Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+_SK_FLAGS = {}
+
+
+def _sk_flags(device):
+    """Per-device stream-K ordering flags for `b200_linear` (zeroed once; every launch leaves them zero, include/latte_b200.h)."""
+    buf = _SK_FLAGS.get(device)
+    if buf is None:
+        buf = _SK_FLAGS[device] = torch.zeros(_lib.GEMM_SK_FLAGS, dtype=torch.int64, device=device)
+    return buf
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -36,14 +47,15 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, g
     with torch.cuda.device(a.device):
         rc = _lib.load().b200_linear(a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, M, N, K,
                                      _dt(a), _lib.EPI_BIAS_GELU if gelu else _lib.EPI_BIAS, out.data_ptr(), None, None,
-                                     0, 1, block_n, _stream(a))
+                                     0, 1, block_n, None, _stream(a))
     _lib.check(rc, "b200_linear")
     return out
 
 
 def linear_gate_residual_(resid: torch.Tensor, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
-                          gate: torch.Tensor, rows_per_batch: int, block_n: int = 0) -> torch.Tensor:
-    """resid (fp32 [M,N], in place) += gate[row // rows_per_batch] * (a @ w.T + bias); gate fp32 [B, N]."""
+                          gate: torch.Tensor, rows_per_batch: int, block_n: int = 0, stream_k: bool = True) -> torch.Tensor:
+    """resid (fp32 [M,N], in place) += gate[row // rows_per_batch] * (a @ w.T + bias); gate fp32 [B, N].
+    stream_k=False withholds the flag buffer, which keeps the data-parallel schedule (one add per element)."""
     _need_cuda(resid, a, w, bias, gate)
     assert resid.dtype == torch.float32 and gate.dtype == torch.float32 and resid.is_contiguous()
     assert gate.stride(-1) == 1
@@ -52,7 +64,8 @@ def linear_gate_residual_(resid: torch.Tensor, a: torch.Tensor, w: torch.Tensor,
     with torch.cuda.device(a.device):
         rc = _lib.load().b200_linear(a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, M, N, K,
                                      _dt(a), _lib.EPI_GATE_RESIDUAL, None, resid.data_ptr(), gate.data_ptr(),
-                                     gate.stride(0), rows_per_batch, block_n, _stream(a))
+                                     gate.stride(0), rows_per_batch, block_n,
+                                     _sk_flags(a.device).data_ptr() if stream_k else None, _stream(a))
     _lib.check(rc, "b200_linear")
     return resid
 
@@ -83,14 +96,19 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, rows_
     return out
 
 
-def cross_attention(q: torch.Tensor, kv: torch.Tensor, batch: int, q_rows_per_batch: int, kv_len: int, heads: int) -> torch.Tensor:
-    """q [batch*q_rows, heads*hd] 16-bit; kv [batch*kv_len, 2*heads*hd] 16-bit ([k | v]); kv_len <= 128 -> out like q."""
-    _need_cuda(q, kv)
+def cross_attention(q: torch.Tensor, kv: torch.Tensor, batch: int, q_rows_per_batch: int, kv_len: int, heads: int,
+                    key_bias: torch.Tensor | None = None) -> torch.Tensor:
+    """q [batch*q_rows, heads*hd] 16-bit; kv [batch*kv_len, 2*heads*hd] 16-bit ([k | v]); kv_len <= 128 -> out like q.
+    key_bias: optional fp32 [batch, 128] additive score bias per key (columns >= kv_len ignored)."""
+    _need_cuda(q, kv, key_bias)
     assert q.is_contiguous() and kv.is_contiguous() and q.dtype == kv.dtype
+    if key_bias is not None:
+        assert key_bias.dtype == torch.float32 and key_bias.is_contiguous() and tuple(key_bias.shape) == (batch, 128)
     D = q.shape[1]
     out = torch.empty_like(q)
     with torch.cuda.device(q.device):
-        rc = _lib.load().b200_cross_attention(q.data_ptr(), kv.data_ptr(), out.data_ptr(), batch, q_rows_per_batch, kv_len,
+        rc = _lib.load().b200_cross_attention(q.data_ptr(), kv.data_ptr(), key_bias.data_ptr() if key_bias is not None else None,
+                                              out.data_ptr(), batch, q_rows_per_batch, kv_len,
                                               q.shape[1], kv.shape[1], heads, D // heads, _dt(q), _stream(q))
     _lib.check(rc, "b200_cross_attention")
     return out

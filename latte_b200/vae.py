@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._cache import DeviceCacheMixin
 
 
 class _Resnet(nn.Module):
@@ -135,7 +136,7 @@ class _TemporalDecoder(nn.Module):
         self.time_conv_out = nn.Conv3d(cfg.out_channels, cfg.out_channels, (3, 1, 1), padding=(1, 0, 0))
 
 
-class AutoencoderKL(nn.Module):
+class AutoencoderKL(DeviceCacheMixin, nn.Module):
     def __init__(self, in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                  latent_channels=4, norm_num_groups=32, scaling_factor=0.18215, **unused):
         super().__init__()

@@ -55,9 +55,9 @@ def test_abi_version_and_error_text(lib):
     from latte_b200 import _lib
     assert lib.b200_abi_version() == _lib.ABI_VERSION
     # host-side validation runs before any CUDA call: a bad shape must come back as an error code + message
-    rc = lib.b200_linear(None, None, None, 128, 128, 65, 0, 0, None, None, None, 0, 1, 0, None)
+    rc = lib.b200_linear(None, None, None, 128, 128, 65, 0, 0, None, None, None, 0, 1, 0, None, None)
     assert rc == -1 and "multiple of 64" in _lib.last_error()
-    rc = lib.b200_linear(None, None, None, 128, 128, 64, 7, 0, None, None, None, 0, 1, 0, None)
+    rc = lib.b200_linear(None, None, None, 128, 128, 64, 7, 0, None, None, None, 0, 1, 0, None, None)
     assert rc == -2
     rc = lib.b200_attention(None, None, 1, 16, 256, 4, 48, 0, 0, None)
     assert rc == -7 and "head_dim" in _lib.last_error()

@@ -69,6 +69,13 @@ def test_residual_linear_streamk(dev, shape):
             outs.append(x)
         _close(outs[0], want, 3e-4)
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+        # the ordering flags live in the caller's buffer and every launch leaves them zero (no host-side launch counter:
+        # that is what makes the step CUDA-graph replayable)
+        torch.cuda.synchronize()
+        assert int(ops._sk_flags(A.device).abs().sum()) == 0
+        x = x0.clone()
+        ops.linear_gate_residual_(x, A, W, bias, gate, rpb, block_n=bn, stream_k=False)   # data-parallel schedule
+        _close(x, want, 3e-4)
 
 
 def test_linear_is_linear_and_deterministic(dev):
@@ -98,6 +105,17 @@ def _attn_ref(qkv, batch, frames, tokens, heads, temporal):
     return o.reshape(T, D)
 
 
+@pytest.fixture(params=[2, 3], ids=["attn_v2", "attn_v3"])
+def attn_impl(request):
+    """Both attention kernels serve the same contract (include/latte_b200.h: b200_set_attention_impl); every attention
+    test runs against each, whichever is the library default."""
+    from latte_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.b200_set_attention_impl(request.param), "b200_set_attention_impl")
+    yield request.param
+    lib.b200_set_attention_impl(0)
+
+
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("case", [
     (2, 16, 256, 16, 72, False), (2, 16, 256, 16, 72, True),      # XL/2 spatial / temporal
@@ -106,7 +124,7 @@ def _attn_ref(qkv, batch, frames, tokens, heads, temporal):
     (2, 8, 64, 2, 64, True), (4, 4, 64, 8, 72, True), (1, 32, 32, 2, 80, True),      # F = 8, 4, 32; head_dim 80
     (1, 2, 512, 2, 64, False), (1, 2, 1024, 4, 72, False), (2, 16, 1024, 2, 72, True),  # LatteT2V @512px: N = 1024 (online softmax)
 ])
-def test_attention(dev, dt, case):
+def test_attention(dev, dt, case, attn_impl):
     from latte_b200 import ops
     b, f, n, h, hd, temporal = case
     g = torch.Generator().manual_seed(b * 1000 + f * 10 + n + hd)
@@ -114,7 +132,7 @@ def test_attention(dev, dt, case):
     _close(ops.attention(qkv, b, f, n, h, temporal), _attn_ref(qkv, b, f, n, h, temporal), TOL[dt])
 
 
-def test_attention_properties(dev):
+def test_attention_properties(dev, attn_impl):
     """V = 1 -> out = 1; Q = 0 -> out = mean of V over the sequence; permuting the keys of a sequence leaves the output unchanged."""
     from latte_b200 import ops
     b, f, n, h, hd = 1, 16, 256, 16, 72
@@ -161,7 +179,7 @@ def test_ln_modulate(dev, dt, D):
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("case", [(2, 256, 120, 4, 72), (1, 1024, 20, 2, 64), (3, 128, 128, 2, 80), (2, 512, 1, 4, 72)])
-def test_cross_attention(dev, dt, case):
+def test_cross_attention(dev, dt, case, attn_impl):
     """diffusers Attention (attn2) with text keys (latte_t2v.py:862-870): q from the video tokens, k/v from <=128 text tokens."""
     from latte_b200 import ops
     b, rows, L, h, hd = case
@@ -175,3 +193,31 @@ def test_cross_attention(dev, dt, case):
     vf = kv.float()[:, D:].reshape(b, L, h, hd).transpose(1, 2)
     ref = (torch.softmax(qf @ kf.transpose(-1, -2) * hd ** -0.5, dim=-1) @ vf).transpose(1, 2).reshape(b * rows, D)
     _close(out, ref, TOL[dt])
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", [(2, 256, 120, 4, 72, (12, 120)), (3, 128, 20, 2, 64, (1, 20, 7)), (2, 1024, 128, 2, 80, (128, 3))])
+def test_cross_attention_key_bias(dev, dt, case, attn_impl):
+    """Padded prompts (latte_t2v.py:766-771): the keep-mask becomes the additive bias (1 - m) * -10000 on the scores."""
+    from latte_b200 import ops
+    b, rows, L, h, hd, valid = case
+    D = h * hd
+    g = torch.Generator().manual_seed(rows + L + 1)
+    q = (torch.randn(b * rows, D, generator=g) * 1.5).to(dev).to(dt)
+    kv = (torch.randn(b * L, 2 * D, generator=g) * 1.5).to(dev).to(dt)
+    mask = torch.zeros(b, L)
+    for i in range(b):
+        mask[i, : valid[i]] = 1
+    bias = torch.zeros(b, 128)
+    bias[:, :L] = (1 - mask) * -10000.0
+    bias[:, L:] = 123.0                 # columns >= kv_len must be ignored
+    out = ops.cross_attention(q, kv, b, rows, L, h, key_bias=bias.to(dev))
+    qf = q.float().reshape(b, rows, h, hd).transpose(1, 2)
+    kf = kv.float()[:, :D].reshape(b, L, h, hd).transpose(1, 2)
+    vf = kv.float()[:, D:].reshape(b, L, h, hd).transpose(1, 2)
+    sc = qf @ kf.transpose(-1, -2) * hd ** -0.5 + bias[:, :L].to(dev)[:, None, None, :]
+    ref = (torch.softmax(sc, dim=-1) @ vf).transpose(1, 2).reshape(b * rows, D)
+    _close(out, ref, TOL[dt])
+    # an all-ones mask is the unmasked result (the bias path rounds s * scale once more: not bit-identical)
+    zero = torch.zeros(b, 128, device=dev)
+    _close(ops.cross_attention(q, kv, b, rows, L, h, key_bias=zero), ops.cross_attention(q, kv, b, rows, L, h), 2e-3 if dt == torch.float16 else 2e-2)

@@ -97,3 +97,38 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dp, f)).read()
                 assert not pat.search(text), f
+
+
+def test_dropin_packages_import_through_symlinks(tmp_path):
+    """`models` and `diffusion` put ahead of the reference's on sys.path as symlinks to
+    latte_b200/models and latte_b200/diffusion must import as TOP-LEVEL packages (relative imports broke it)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.symlink(os.path.join(root, "latte_b200", "models"), tmp_path / "models")
+    os.symlink(os.path.join(root, "latte_b200", "diffusion"), tmp_path / "diffusion")
+    code = ("import models, diffusion; from types import SimpleNamespace as N; "
+            "m = models.get_models(N(model='Latte-S/2', latent_size=32, num_classes=101, num_frames=16, learn_sigma=True, extras=2)); "
+            "d = diffusion.create_diffusion('250'); print(type(m).__name__, d.num_timesteps)")
+    env = dict(os.environ, PYTHONPATH=f"{tmp_path}{os.pathsep}{root}", LATTE_B200_NO_BUILD="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split() == ["Latte", "250"]
+
+
+def test_device_caches_are_not_pickled():
+    """copy.deepcopy (EMA, train.py:95-97) and pickle must work after the packing cache holds ctypes pointer structs."""
+    import copy
+    import pickle
+    from latte_b200 import Latte, _lib
+    from latte_b200.diffusion import create_diffusion
+    net = Latte(input_size=16, hidden_size=128, depth=2, num_heads=2, num_frames=4, num_classes=5, extras=2)
+    net._packed = (_lib.LatteShape(), _lib.LatteWeights(), {}, None)      # what a forward leaves behind
+    net._graphs = {"k": object()}
+    twin = copy.deepcopy(net)
+    assert twin._packed is None and twin._graphs is None
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), twin.state_dict().values()))
+    pickle.loads(pickle.dumps(net))
+    d = create_diffusion("8")
+    d._dev["x"] = _lib.SamplerTables()
+    assert copy.deepcopy(d)._dev == {}
