@@ -104,20 +104,35 @@ def build_case(model_name: str, seed: int):
     return O, cfg, sd, x, t, y
 
 
-def tune_cpu_threads(O) -> int:
-    """torch CPU eager is far from monotone in thread count on many-core hosts (128 threads were 4x slower than 8 on
-    the r01 box): time a Latte-S/2 forward at a few counts and keep the best, so the CPU arm is the reference's best."""
+def cpu_step_factory(O, model_name, cfg, sd, x, t, y):
+    """One `forward_with_cfg` step on the host cores: the UNMODIFIED reference module when oracle/_ref was materialised
+    (oracle/make_ref.py), else the oracle port.  Returns (callable, kind, description)."""
+    from oracle import ref_loader
+    m = ref_loader.build_latte(model_name, cfg, sd)
+    if m is not None:
+        return (lambda: m.forward_with_cfg(x, t, y=y, cfg_scale=7.0)), "reference", \
+            "unmodified reference models/latte.py (oracle/_ref + timm shim), torch CPU fp32 eager, 'math' attention"
+    return (lambda: O.latte_forward_with_cfg(sd, cfg, x, t, y, 7.0)), "port", \
+        "oracle port of the pure-Python reference (oracle/_ref absent), torch CPU fp32 eager"
+
+
+def tune_cpu_threads(O, model_name) -> int:
+    """torch CPU eager is far from monotone in thread count on many-core hosts (128 threads were 4x slower than 8 on the
+    r01 box).  Sweep on the WORKLOAD'S OWN op shapes -- a 2-block model of the same width / heads / token count as
+    `model_name` (every Linear, attention and LayerNorm call has the shape it has in the full model; only the block count
+    differs) -- and keep the best, so the CPU arm is the reference's best."""
+    import dataclasses
     cores = os.cpu_count() or 1
-    cfg = O.make_config("Latte-S/2")
+    cfg = dataclasses.replace(O.make_config(model_name), depth=2)
     sd = O.make_weights(cfg, 0)
     x, t, y = O.make_inputs(cfg, 2, 1)
     best, best_t = 1, float("inf")
     for n in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
         torch.set_num_threads(n)
         with torch.no_grad():
-            O.latte_forward(sd, cfg, x, t, y)          # warm the pool
+            O.latte_forward_with_cfg(sd, cfg, x, t, y, 7.0)          # warm the pool
             t0 = time.perf_counter()
-            O.latte_forward(sd, cfg, x, t, y)
+            O.latte_forward_with_cfg(sd, cfg, x, t, y, 7.0)
             el = time.perf_counter() - t0
         if el < best_t:
             best, best_t = n, el
@@ -125,44 +140,57 @@ def tune_cpu_threads(O) -> int:
     return best
 
 
+WORKLOAD = ("{model} class-conditional 16x256x256 sampling step: forward_with_cfg on B_model=2 (1 video x CFG pair) per GPU; "
+            "seeded synthetic weights/latents")
+
+
 def run_reference(args):
-    """CPU arm: the oracle restatement of Latte.forward_with_cfg on this box's host cores (rank 0 only)."""
+    """Reference arm: the reference's own CPU implementation of the step on this box's host cores (rank 0 only): W warm-up
+    and K timed `forward_with_cfg` calls, as the main arm, bounded by a wall-clock budget (said in `sample` if it bites)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     O, cfg, sd, x, t, y = build_case(args.model, 0)
-    cores = tune_cpu_threads(O)
-    budget_s = 150.0
-    t0 = time.perf_counter()
+    cores = tune_cpu_threads(O, args.model)
+    step, kind, what = cpu_step_factory(O, args.model, cfg, sd, x, t, y)
+    budget_s = 420.0
+    W, K = max(args.warmup, 0), args.steps
+    t_start = time.perf_counter()
     with torch.no_grad():
-        for _ in range(min(args.warmup, 1)):
-            O.latte_forward_with_cfg(sd, cfg, x, t, y, 7.0)
-        warm = time.perf_counter() - t0
+        warm_done = 0
+        for _ in range(W):
+            if warm_done >= 1 and (time.perf_counter() - t_start) > 0.2 * budget_s:
+                break
+            step()
+            warm_done += 1
         done, t1 = 0, time.perf_counter()
-        while done < args.steps and (time.perf_counter() - t1) + warm < budget_s:
-            O.latte_forward_with_cfg(sd, cfg, x, t, y, 7.0)
+        while done < K and (done == 0 or (time.perf_counter() - t_start) * (1 + 1.0 / max(done, 1)) < budget_s):
+            step()
             done += 1
         el = time.perf_counter() - t1
     v = done / el
+    note = "" if (done == K and warm_done == W) else f" (bounded to {budget_s:.0f}s of wall clock: {warm_done}/{W} warm-up, {done}/{K} timed)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": done,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1000 * el / done, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm_done, "ms_per_step": 1000 * el / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} class-conditional 16x256x256 sampling step: forward_with_cfg on B_model=2 "
-                               f"(1 video x CFG pair) per GPU; seeded synthetic weights/latents",
-                   "arm": "reference CPU path (oracle port of the pure-Python reference, torch CPU fp32 eager) on the host cores"},
-        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{done} full forward_with_cfg step(s) of the oracle port (torch CPU fp32, {cores} threads = best of a sweep on {os.cpu_count()} cores), bounded to {budget_s:.0f}s"},
+        "config": {"workload": WORKLOAD.format(model=args.model)},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": kind,
+                         "sample": f"{done} full forward_with_cfg step(s): {what}; {cores} threads = best of a sweep on "
+                                   f"{os.cpu_count()} host threads over the model's own op shapes{note}"},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 def run_t2v(args):
-    """Secondary measurement (BASELINE configs[3]): one LatteT2V denoising step at 16x512x512, CFG pair (B_model = 2),
-    120 synthetic T5 tokens, seeded synthetic weights.  Prints one JSON line; not the round's bench line."""
-    from latte_b200 import LatteT2V
+    """Secondary workload (BASELINE configs[3]): one LatteT2V denoising step at 16x512x512, CFG pair (B_model = 2), 120
+    synthetic T5 tokens, seeded synthetic weights; then the AutoencoderKLTemporalDecoder decode of the 16 latents in the
+    pipeline's chunks of 14 + 2 frames (pipeline_latte.py:785-792).  Prints one JSON line; not the round's bench line."""
+    import ctypes as C
+    from latte_b200 import LatteT2V, _lib
     from oracle import t2v_oracle as T
     dev = torch.device("cuda", 0)
+    lib = _lib.load()
     cfg = T.T2VConfig()
     net = LatteT2V()
     g = torch.Generator().manual_seed(0)
@@ -183,12 +211,118 @@ def run_t2v(args):
             net(xd, td, encoder_hidden_states=txd, return_dict=False)
         e1.record()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / K
+        ms = e0.elapsed_time(e1) / K
+        _lib.profile_enable(True)
+        for _ in range(K):
+            net(xd, td, encoder_hidden_states=txd, return_dict=False)
+        torch.cuda.synchronize()
+        pm, pn = (C.c_double * 4)(), (C.c_int * 4)()
+        _lib.check(lib.b200_profile_collect(pm, pn, 4), "b200_profile_collect")
+        _lib.profile_enable(False)
+    peaks = load_peaks()
     fl = 2 * T.algorithmic_flops_per_video(cfg, 120)
-    print(json.dumps({"metric": "denoising-steps/sec LatteT2V 16x512x512 (CFG pair per step)", "value": 1000.0 / ms, "unit": "steps/s",
-                      "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "dtype": "fp16", "data": "synthetic",
-                      "config": {"workload": "LatteT2V (Latte-1 config) 16x512x512, B_model=2, 120 text tokens",
-                                 "algorithmic_tflop_per_step": fl / 1e12, "step_tflops_achieved": fl / (ms * 1e-3) / 1e12}}), flush=True)
+    gfl = 2 * T.gemm_flops_per_video(cfg, 120)
+    achieved = gfl / (pm[0] / K * 1e-3) / 1e12
+    res = {"metric": "denoising-steps/sec LatteT2V 16x512x512 (CFG pair per step)", "value": 1000.0 / ms, "unit": "steps/s",
+           "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "dtype": "fp16", "data": "synthetic",
+           "config": {"workload": "LatteT2V (Latte-1 config) 16x512x512, B_model=2, 120 text tokens",
+                      "algorithmic_tflop_per_step": fl / 1e12, "step_tflops_achieved": fl / (ms * 1e-3) / 1e12},
+           "gpu_launches": int(sum(pn) // K),
+           "roofline": {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05)", "achieved": achieved, "peak": peaks["tensor_sustained"],
+                        "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": None,
+                        "peak_source": peaks["source"] + ", sustained figure", "gemm_ms_per_step": pm[0] / K,
+                        "attn_ms_per_step": pm[1] / K, "ln_ms_per_step": pm[2] / K, "other_ms_per_step": pm[3] / K}}
+    try:
+        from latte_b200 import AutoencoderKLTemporalDecoder
+        vae = AutoencoderKLTemporalDecoder().to(dev).half().eval()
+        z = torch.randn(16, 4, 64, 64, device=dev)
+
+        def decode():
+            with torch.no_grad():
+                return torch.cat([vae.decode(z[:14], num_frames=14).sample, vae.decode(z[14:], num_frames=2).sample])
+        decode()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            img = decode()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_dec = e0.elapsed_time(e1) / 3
+        res["temporal_decoder"] = {"ms_16_frames_512px": ms_dec, "chunks": "14 + 2 frames (pipeline_latte.py:785-792)",
+                                   "tflops_achieved": 16 * 3.043 / (ms_dec * 1e-3), "frac_of_sustained_peak": 16 * 3.043 / (ms_dec * 1e-3) / peaks["tensor_sustained"],
+                                   "decoded_shape": list(img.shape)}
+    except Exception as e:  # noqa: BLE001
+        res["temporal_decoder"] = {"error": repr(e)[:300]}
+    print(json.dumps(res), flush=True)
+
+
+def run_video_leg(net, cfg, xd, yd, dev, world, barrier, sharding):
+    """frames/s END TO END (second half of BASELINE.json's metric), measured on every rank: one 16-frame video per rank =
+    create_diffusion("250").ddim_sample_loop(model.forward_with_cfg, ...) (sample.py:100-107 on this repo's module and
+    fused sampler step) + AutoencoderKL.decode (SD-VAE topology, synthetic weights) + uint8 conversion, then the decoded
+    frames of all ranks are gathered with NCCL (sharding.gather_frames: the ONE collective of the sampling path).
+    Wall clock incl. host code, max over ranks; value = world * frames / that."""
+    from latte_b200 import AutoencoderKL
+    from latte_b200.diffusion import create_diffusion
+    vae = AutoencoderKL().to(dev).half().eval()
+    n_steps = 250
+    diffusion = create_diffusion(str(n_steps))
+    zz = torch.cat([xd[:1], xd[:1]], 0)
+    kw = dict(y=yd, cfg_scale=7.0)
+
+    def one_video():
+        with torch.no_grad():
+            smp = diffusion.ddim_sample_loop(net.forward_with_cfg, zz.shape, zz, clip_denoised=False, model_kwargs=kw, device=dev)
+            smp, _ = smp.chunk(2, dim=0)
+            img = vae.decode(smp[0] / 0.18215).sample                                   # (16, 3, 256, 256)
+            u8 = ((img.float() * 0.5 + 0.5).clamp(0, 1) * 255).add_(0.5).to(torch.uint8)  # sample.py:116-117
+            return sharding.gather_frames(u8.permute(0, 2, 3, 1).contiguous()[None])    # [world, 16, 256, 256, 3]
+
+    one_video()                     # warm-up: graph capture, VAE packing, NCCL channel setup
+    with torch.no_grad():
+        zl = smp_latents = torch.randn(cfg.num_frames, 4, cfg.input_size, cfg.input_size, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            vae.decode(zl / 0.18215)
+        e1.record()
+        torch.cuda.synchronize()
+    ms_dec = e0.elapsed_time(e1) / 3
+    barrier()
+    t0 = time.perf_counter()
+    frames = one_video()
+    torch.cuda.synchronize()
+    sec = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    del smp_latents
+    return {"value": world * cfg.num_frames / sec, "unit": "frames/s", "n_gpus": world, "ddim_steps": n_steps,
+            "measured": "wall clock (max over ranks) of ddim_sample_loop(250 steps, fused sampler step, trajectory conditioning, graph replay) "
+                        "+ AutoencoderKL.decode + uint8 conversion + NCCL all_gather of the decoded frames; one 16-frame video per GPU",
+            "sec_per_video": sec, "ms_per_step_incl_sampler": (sec * 1e3 - ms_dec) / n_steps, "vae_decode_ms_16_frames": ms_dec,
+            "vae_tflops_achieved": 16 * 0.622 / (ms_dec * 1e-3), "gathered_shape": list(frames.shape),
+            "gather_bytes_per_rank": int(frames.numel() // world)}
+
+
+def run_ddp_batch_leg(net, cfg, args, dev, world, rank, barrier, sharding, steps):
+    """BASELINE configs[2]: the sample_ddp.py batch -- per_proc_batch_size 2 videos per rank (ucf101_sample.yaml), i.e.
+    B_model = 4 rows per forward_with_cfg -- as device-timed steps/s (one step advances 2 videos per GPU)."""
+    from oracle import latte_oracle as O
+    x4, t4, y4 = O.make_inputs(cfg, 4, 777 + sharding.rank_seed(0, rank, world))
+    x4, t4, y4 = x4.to(dev), t4.to(dev), y4.to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            net.forward_with_cfg(x4, t4, y=y4, cfg_scale=7.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            net.forward_with_cfg(x4, t4, y=y4, cfg_scale=7.0)
+        e1.record()
+        barrier()
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    return {"value": world * 1000.0 / ms, "unit": "steps/s (B_model = 4: 2 videos x CFG pair per GPU per step)", "ms_per_step": ms,
+            "steps": steps, "videos_per_step": 2 * world}
 
 
 def main():
@@ -232,7 +366,9 @@ def main():
     lib = _lib.load()
     xd, td, yd = x.to(dev), t.to(dev), y.to(dev)
     x_host = x.clone().pin_memory()
-    out_host = torch.empty(2, cfg.num_frames, cfg.out_channels, cfg.input_size, cfg.input_size).pin_memory()
+    out_host = [torch.empty(2, cfg.num_frames, cfg.out_channels, cfg.input_size, cfg.input_size).pin_memory() for _ in range(2)]
+    out_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_count = [0]
 
     def barrier():
         if world > 1:
@@ -243,10 +379,17 @@ def main():
         return net.forward_with_cfg(xd, td, y=yd, cfg_scale=7.0)
 
     def step_e2e():
+        """One step as a serving loop issues it: H2D of this step's latents from pinned memory, the public module call, D2H of
+        the result into one of two pinned buffers.  The host waits for a buffer only when it is about to be reused (two steps
+        later), so enqueueing step i+1 overlaps the GPU work of step i; every result still lands in host memory inside the
+        timed region (the closing barrier + synchronize waits for the last two)."""
+        k = e2e_count[0] & 1
+        e2e_count[0] += 1
+        out_ready[k].synchronize()           # the result this buffer held two steps ago is on the host: safe to overwrite
         xg = x_host.to(dev, non_blocking=True)
         o = net.forward_with_cfg(xg, td, y=yd, cfg_scale=7.0)
-        out_host.copy_(o, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller needs the result on the host
+        out_host[k].copy_(o, non_blocking=True)
+        out_ready[k].record()
 
     def timed(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,10 +414,12 @@ def main():
         ms_e2e = timed(step_e2e, K)
         clocks.mark_end()
         clk = clocks.stop() if rank == 0 else None
+        # the same step over 250 back-to-back calls (one DDIM-250 video's worth): the power-capped, sustained-clock figure
+        ms_sustained = timed(step_resident, 250) / 250
 
         # instrumented pass: per-kernel-class device time from events on the launching stream
         import ctypes as C
-        lib.b200_profile_enable(1)
+        _lib.profile_enable(True)       # the modules launch eagerly (no graph replay) while events bracket every kernel
         barrier()
         for _ in range(K):
             step_resident()
@@ -282,8 +427,19 @@ def main():
         ms = (C.c_double * 4)()
         nl = (C.c_int * 4)()
         _lib.check(lib.b200_profile_collect(ms, nl, 4), "b200_profile_collect")
-        lib.b200_profile_enable(0)
+        _lib.profile_enable(False)
 
+    # ---- legs every rank takes part in (they end in a collective): frames/s end to end and the sample_ddp batch
+    video_leg, ddp_leg = None, None
+    if not args.no_video:
+        try:
+            video_leg = run_video_leg(net, cfg, xd, yd, dev, world, barrier, sharding)
+        except Exception as e:  # noqa: BLE001
+            video_leg = {"error": repr(e)[:300]}
+        try:
+            ddp_leg = run_ddp_batch_leg(net, cfg, args, dev, world, rank, barrier, sharding, max(K // 2, 5))
+        except Exception as e:  # noqa: BLE001
+            ddp_leg = {"error": repr(e)[:300]}
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -310,14 +466,17 @@ def main():
         "metric": METRIC, "value": world * K / (ms_total * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{args.model} class-conditional 16x256x256 sampling step: forward_with_cfg on B_model=2 "
-                               f"(1 video x CFG pair) per GPU; seeded synthetic weights/latents",
+        "config": {"workload": WORKLOAD.format(model=args.model),
                    "l2": "no explicit flush: 1.35 GB of 16-bit weights stream through the 126 MB L2 every step",
                    "parallelism": f"replicas x{world} (sample_ddp partitioning), no data-path collective",
                    "algorithmic_tflop_per_step": step_flops / 1e12,
                    "step_tflops_achieved": step_flops / (ms_total / K * 1e-3) / 1e12},
         "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                "d2h_bytes_per_step": out_host.numel() * 4},
+                "d2h_bytes_per_step": out_host[0].numel() * 4,
+                "pattern": "pinned H2D -> Latte.forward_with_cfg (CUDA-graph replay) -> pinned D2H, double-buffered: the host waits on a "
+                           "result buffer only before reusing it"},
+        "sustained": {"ms_per_step": ms_sustained, "value": world * 1000.0 / ms_sustained, "steps": 250,
+                      "note": "same step, 250 back-to-back calls (sustained clocks under the power cap); `value` above is the K-step burst"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05, 4 launches/block)",
                      "achieved": achieved, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
@@ -327,95 +486,56 @@ def main():
                      "other_ms_per_step": ms[3] / K, "instrumented_pass_ms_per_step": sum(ms) / K},
         "clocks": clk,
     }
+    if video_leg is not None:
+        res["frames_per_sec_e2e"] = video_leg
+    if ddp_leg is not None:
+        res["sample_ddp_batch"] = ddp_leg
     if world == 1 and not args.no_video:
-        # End-to-end frames/s of BASELINE configs[1] (second half of BASELINE.json's metric): one 16-frame video =
-        # 250 DDIM steps (the measured step) + ONE AutoencoderKL decode of the 16 latents (measured here with the SD-VAE
-        # topology, synthetic weights) — sampler elementwise math and mp4 encoding excluded (reference code, out of scope).
+        # The reference's own 1-GPU path (north_star's ">= 5x" denominator): the UNMODIFIED reference module run as PyTorch
+        # eager on this GPU exactly as sample.py does (model.half(), use_fp16=True, tf32 allowed, 'math' attention) when
+        # oracle/_ref is present, else the oracle port -- a baseline leg, never part of the product path.
         try:
-            from latte_b200 import AutoencoderKL
-            vae = AutoencoderKL().to(dev).half().eval()
-            zl = torch.randn(cfg.num_frames, 4, cfg.input_size, cfg.input_size, device=dev)
-            with torch.no_grad():
-                for _ in range(2):
-                    vae.decode(zl / 0.18215)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(3):
-                    vae.decode(zl / 0.18215)
-                e1.record()
-                torch.cuda.synchronize()
-            ms_dec = e0.elapsed_time(e1) / 3
-            # the WHOLE video, measured: sample.py:100-114 on this repo's module + sampler + VAE --
-            # create_diffusion("250").ddim_sample_loop(model.forward_with_cfg, ...) then vae.decode, wall clock incl. host code
-            from latte_b200.diffusion import create_diffusion
-            n_steps = 250
-            diffusion = create_diffusion(str(n_steps))
-            zz = torch.cat([xd[:1], xd[:1]], 0)
-            kw = dict(y=yd, cfg_scale=7.0)
-
-            def one_video():
-                with torch.no_grad():
-                    smp = diffusion.ddim_sample_loop(net.forward_with_cfg, zz.shape, zz, clip_denoised=False, model_kwargs=kw, device=dev)
-                    smp, _ = smp.chunk(2, dim=0)
-                    return vae.decode(smp[0] / 0.18215).sample
-            one_video()
-            torch.cuda.synchronize()
-            # the model alone over the same 250 back-to-back steps (sustained clocks, unlike the short timed region above)
-            es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            es0.record()
-            for _ in range(n_steps):
-                step_resident()
-            es1.record()
-            torch.cuda.synchronize()
-            ms_sustained = es0.elapsed_time(es1) / n_steps
-            t0 = time.perf_counter()
-            frames = one_video()
-            torch.cuda.synchronize()
-            sec_video = time.perf_counter() - t0
-            res["frames_per_sec_e2e"] = {"value": cfg.num_frames / sec_video, "unit": "frames/s", "ddim_steps": n_steps,
-                                         "measured": "wall clock of ddim_sample_loop(250 steps, fused sampler step) + AutoencoderKL.decode, one 16-frame video",
-                                         "sec_per_video": sec_video, "ms_per_step_incl_sampler": (sec_video * 1e3 - ms_dec) / n_steps,
-                                         "ms_per_step_model_only": ms_total / K, "ms_per_step_model_only_250_steps": ms_sustained, "vae_decode_ms_16_frames": ms_dec,
-                                         "vae_tflops_achieved": 16 * 0.622 / (ms_dec * 1e-3),
-                                         "decoded_shape": list(frames.shape)}
-            del vae
-        except Exception as e:  # noqa: BLE001
-            res["frames_per_sec_e2e"] = {"error": repr(e)[:200]}
-        # The reference's own 1-GPU path (north_star's ">= 5x" denominator): the oracle restatement run as PyTorch eager
-        # on this GPU exactly as sample.py does (model.half(), tf32 allowed, 'math' attention) — a baseline leg, never
-        # part of the product path.
-        try:
+            from oracle import ref_loader
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
-            sdg = {k: v.to(dev).half() for k, v in sd.items()}
-            xg = xd.half()
+            ref_model = ref_loader.build_latte(args.model, cfg, sd)
+            if ref_model is not None:
+                ref_model = ref_model.to(dev).half()
+                xg = xd.half()
+                eager_step = lambda: ref_model.forward_with_cfg(xg, td, y=yd, cfg_scale=7.0, use_fp16=True)   # noqa: E731
+                kind = "reference (unmodified models/latte.py from oracle/_ref, PyTorch eager fp16 on this GPU, cuBLAS/ATen kernels)"
+            else:
+                sdg = {k: v.to(dev).half() for k, v in sd.items()}
+                xg = xd.half()
+                eager_step = lambda: O.latte_forward_with_cfg(sdg, cfg, xg, td, yd, 7.0, dtype=torch.float16)   # noqa: E731
+                kind = "port (oracle restatement, PyTorch eager fp16 on this GPU, cuBLAS/ATen kernels)"
             with torch.no_grad():
-                for _ in range(3):
-                    O.latte_forward_with_cfg(sdg, cfg, xg, td, yd, 7.0, dtype=torch.float16)
+                for _ in range(max(W, 3)):
+                    eager_step()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                n_e = 10
                 e0.record()
-                for _ in range(n_e):
-                    O.latte_forward_with_cfg(sdg, cfg, xg, td, yd, 7.0, dtype=torch.float16)
+                for _ in range(K):
+                    eager_step()
                 e1.record()
                 torch.cuda.synchronize()
-            ms_eager = e0.elapsed_time(e1) / n_e
-            res["gpu_eager_baseline"] = {"value": 1000.0 / ms_eager, "unit": "steps/s", "ms_per_step": ms_eager,
-                                         "kind": "port (oracle restatement, PyTorch eager fp16 on this GPU, cuBLAS/ATen kernels)",
-                                         "speedup_of_value": (K / (ms_total * 1e-3)) / (1000.0 / ms_eager)}
-            del sdg
+            ms_eager = e0.elapsed_time(e1) / K
+            res["gpu_eager_baseline"] = {"value": 1000.0 / ms_eager, "unit": "steps/s", "ms_per_step": ms_eager, "steps": K,
+                                         "kind": kind, "speedup_of_value": (K / (ms_total * 1e-3)) / (1000.0 / ms_eager),
+                                         "speedup_of_e2e": (K / (ms_e2e * 1e-3)) / (1000.0 / ms_eager)}
+            del ref_model
         except Exception as e:  # noqa: BLE001
             res["gpu_eager_baseline"] = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline and world == 1:
-        cores = tune_cpu_threads(O)
+        cores = tune_cpu_threads(O, args.model)
+        step, kind, what = cpu_step_factory(O, args.model, cfg, sd, x, t, y)
         with torch.no_grad():
             t0 = time.perf_counter()
-            O.latte_forward_with_cfg(sd, cfg, x, t, y, 7.0)
+            step()
             el = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": 1.0 / el, "unit": "steps/s", "cores": cores, "kind": "port",
-                               "sample": f"1 full forward_with_cfg step of the oracle port (torch CPU fp32 eager, {cores} threads = best of a sweep on {os.cpu_count()} cores)"}
+        res["cpu_baseline"] = {"value": 1.0 / el, "unit": "steps/s", "cores": cores, "kind": kind,
+                               "sample": f"1 full forward_with_cfg step: {what}; {cores} threads = best of a sweep on "
+                                         f"{os.cpu_count()} host threads over the model's own op shapes"}
     else:
         res["cpu_baseline"] = None
     print(json.dumps(res), flush=True)

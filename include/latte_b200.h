@@ -82,6 +82,8 @@ typedef struct B200LatteWeights {
   const float* fc2_b;      /*                             [depth][D]                      */
   const float* final_w;    /* final_layer.linear.weight   [p*p*out_channels, D]           */
   const float* final_b;    /* final_layer.linear.bias     [p*p*out_channels]              */
+  const void* final_w16;   /* 16-bit copy of final_w: the head then runs LN+modulate -> tcgen05 GEMM (N = p*p*out_channels,
+                              fp32 result) -> unpatchify; NULL keeps the fp32 CUDA-core head                 */
 } B200LatteWeights;
 
 /* ---- LatteT2V (reference models/latte_t2v.py:444-944, HF maxin-cn/Latte-1 config: ada_norm_single, gelu-approximate,
@@ -144,6 +146,7 @@ typedef struct B200T2VWeights {
   const float* t_fc2_b;
   const float* final_w;    /* proj_out.weight [p*p*out_channels, D] */
   const float* final_b;
+  const void* final_w16;   /* 16-bit copy of final_w (tensor-core head) or NULL */
 } B200T2VWeights;
 
 B200_API size_t b200_t2v_workspace_bytes(const B200T2VShape* shape, int batch, int text_len);

@@ -27,7 +27,7 @@ class LatteShape(C.Structure):
 WEIGHT_FIELDS = (
     "patch_w", "patch_b", "pos_embed", "temp_embed", "t_w0", "t_b0", "t_w2", "t_b2", "y_table",
     "ada_w16", "ada_b", "qkv_w16", "qkv_b", "proj_w16", "proj_b", "fc1_w16", "fc1_b", "fc2_w16", "fc2_b",
-    "final_w", "final_b")
+    "final_w", "final_b", "final_w16")
 
 
 class LatteWeights(C.Structure):
@@ -45,7 +45,8 @@ T2V_WEIGHT_FIELDS = (
     "cap_w1_16", "cap_b1", "cap_w2_16", "cap_b2", "tables", "final_table",
     "s_qkv_w16", "s_qkv_b", "s_out_w16", "s_out_b", "c_q_w16", "c_q_b", "c_kv_w16", "c_kv_b", "c_out_w16", "c_out_b",
     "s_fc1_w16", "s_fc1_b", "s_fc2_w16", "s_fc2_b",
-    "t_qkv_w16", "t_qkv_b", "t_out_w16", "t_out_b", "t_fc1_w16", "t_fc1_b", "t_fc2_w16", "t_fc2_b", "final_w", "final_b")
+    "t_qkv_w16", "t_qkv_b", "t_out_w16", "t_out_b", "t_fc1_w16", "t_fc1_b", "t_fc2_w16", "t_fc2_b", "final_w", "final_b",
+    "final_w16")
 
 
 class T2VWeights(C.Structure):

@@ -51,8 +51,16 @@ struct Workspace {
   float* c;          // [B, D]   t_emb (+ y_emb)
   float* mod;        // [B, depth*6D + 2D]
   unsigned long long* sk_flags;   // [B200_GEMM_SK_FLAGS] stream-K ordering flags (zeroed at the start of every forward)
+  float* head;       // [T, 32]  fp32 output of the head GEMM (zeroed, then reduce-added into), followed by 32 ones (its "gate")
   size_t bytes;
 };
+
+// ---- output head (latte.py:197-201,297-310,374-376): LayerNorm + modulate -> Linear(D, p*p*C_out) -> unpatchify.
+// With a 16-bit weight copy and p*p*C_out a multiple of 32 the Linear runs on the tensor cores: the GEMM's gated-residual
+// epilogue on a zeroed fp32 buffer with gate = 1 IS "fp32 out = acc + bias".  Otherwise the fp32 CUDA-core kernel.
+int output_head(const float* x, uint16_t* h, float* head, const float* shift, const float* scale, long long mod_bs,
+                const float* w32, const void* w16, const float* bias, float* out, int batch, int F, int grid, int patch,
+                int out_ch, int D, int bf16, int channels_first, unsigned long long* sk_flags, cudaStream_t stream);
 
 int shape_ok(const B200LatteShape* s, int batch) {
   B200_REQUIRE(s != nullptr, B200_ERR_SHAPE, "shape is NULL");
@@ -89,6 +97,7 @@ void carve(const B200LatteShape* s, int batch, void* base, Workspace* ws) {
   ws->c = static_cast<float*>(take(static_cast<size_t>(batch) * D * 4));
   ws->mod = static_cast<float*>(take(static_cast<size_t>(batch) * (static_cast<size_t>(s->depth) * 6 * D + 2 * D) * 4));
   ws->sk_flags = static_cast<unsigned long long*>(take(static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8));
+  ws->head = static_cast<float*>(take((T + 1) * 32 * 4));
   ws->bytes = off;
 }
 
@@ -100,11 +109,11 @@ int conditioning(const B200LatteShape* s, const B200LatteWeights* w, const int64
   const int bf16 = s->dtype == B200_BF16;
   const long long mod_bs = static_cast<long long>(s->depth) * 6 * D + 2 * D;
   B200_PROF(PROF_OTHER, launch_timestep_freq(reinterpret_cast<const long long*>(t), tfreq, n, stream));
-  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, tfreq, th, n, D, 256, 0, 1, nullptr, nullptr, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, tfreq, th, n, D, 256, 0, 1, nullptr, nullptr, 0, stream));
   B200_PROF(PROF_OTHER, launch_gemv(w->t_w2, 32, 0, w->t_b2, th, c, n, D, D, 0, 0, s->num_embed > 0 ? w->y_table : nullptr,
-                       reinterpret_cast<const long long*>(y), stream));
+                       reinterpret_cast<const long long*>(y), s->num_embed, stream));
   B200_PROF(PROF_OTHER, launch_gemv(w->ada_w16, 16, bf16, w->ada_b, c, mod, n, static_cast<int>(mod_bs), D, 1, 0, nullptr,
-                       nullptr, stream));
+                       nullptr, 0, stream));
   return B200_OK;
 }
 
@@ -192,8 +201,8 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
 
   // ---- final layer + unpatchify (latte.py:374-376), then guidance (latte.py:394-398)
   const float* mf = ws.mod + static_cast<size_t>(depth) * 6 * D;  // [shift, scale]
-  B200_PROF(PROF_OTHER, launch_final_layer(ws.x, mf, mf + D, mod_bs, w->final_w, w->final_b, out, batch, F, grid, s->patch,
-                              s->out_channels, D, 0, stream));
+  B200_TRY(output_head(ws.x, ws.h, ws.head, mf, mf + D, mod_bs, w->final_w, w->final_w16, w->final_b, out, batch, F, grid, s->patch,
+                       s->out_channels, D, bf16, 0, ws.sk_flags, stream));
   if (cfg) {
     const long long per_sample = static_cast<long long>(F) * s->out_channels * s->input_size * s->input_size;
     B200_PROF(PROF_OTHER, launch_cfg_combine(out, batch, per_sample, F, s->out_channels, s->in_channels, s->input_size * s->input_size,
@@ -209,6 +218,7 @@ struct T2VWorkspace {
   uint16_t* text16; uint16_t* cap_h; uint16_t* cap_o; uint16_t* kv_all;
   float* ones; float* tfreq; float* th; float* emb; float* ts; float* mod;
   unsigned long long* sk_flags;
+  float* head;
   size_t bytes;
 };
 
@@ -253,6 +263,7 @@ void t2v_carve(const B200T2VShape* s, int batch, int text_len, void* base, T2VWo
   ws->ts = static_cast<float*>(take(static_cast<size_t>(batch) * 6 * D * 4));
   ws->mod = static_cast<float*>(take(static_cast<size_t>(batch) * (static_cast<size_t>(s->layers) * 2 * 6 * D + 2 * D) * 4));
   ws->sk_flags = static_cast<unsigned long long*>(take(static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8));
+  ws->head = static_cast<float*>(take((T + 1) * 32 * 4));
   ws->bytes = off;
 }
 
@@ -277,9 +288,9 @@ int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, 
   B200_CHECK_CUDA(cudaMemsetAsync(ws.sk_flags, 0, static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8, stream));
   // ---- conditioning (latte_t2v.py:782-784): emb = TimestepEmbedding(sincos(t)); ts = Linear(SiLU(emb)); tables + ts
   B200_PROF(PROF_OTHER, launch_timestep_freq(reinterpret_cast<const long long*>(t), ws.tfreq, batch, stream));
-  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, stream));
-  B200_PROF(PROF_OTHER, launch_gemv(w->t_w2, 32, 0, w->t_b2, ws.th, ws.emb, batch, D, D, 0, 0, nullptr, nullptr, stream));
-  B200_PROF(PROF_OTHER, launch_gemv(w->ada_w16, 16, bf16, w->ada_b, ws.emb, ws.ts, batch, 6 * D, D, 1, 0, nullptr, nullptr, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w0, 32, 0, w->t_b0, ws.tfreq, ws.th, batch, D, 256, 0, 1, nullptr, nullptr, 0, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->t_w2, 32, 0, w->t_b2, ws.th, ws.emb, batch, D, D, 0, 0, nullptr, nullptr, 0, stream));
+  B200_PROF(PROF_OTHER, launch_gemv(w->ada_w16, 16, bf16, w->ada_b, ws.emb, ws.ts, batch, 6 * D, D, 1, 0, nullptr, nullptr, 0, stream));
   B200_PROF(PROF_OTHER, launch_t2v_mod(w->tables, ws.ts, w->final_table, ws.emb, ws.mod, batch, 2 * L, D, stream));
   B200_PROF(PROF_OTHER, launch_fill(ws.ones, 1.0f, D, stream));
 
@@ -368,8 +379,29 @@ int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, 
 
   // ---- output head (latte_t2v.py:918-936): table + embedded_timestep -> shift, scale; LN; modulate; proj_out; unpatchify to (b c f h w)
   const float* mf = ws.mod + static_cast<size_t>(2 * L) * 6 * D;
-  B200_PROF(PROF_OTHER, launch_final_layer(ws.x, mf, mf + D, mod_bs, w->final_w, w->final_b, out, batch, F, grid, s->patch,
-                                           s->out_channels, D, 1, stream));
+  B200_TRY(output_head(ws.x, ws.h, ws.head, mf, mf + D, mod_bs, w->final_w, w->final_w16, w->final_b, out, batch, F, grid, s->patch,
+                       s->out_channels, D, bf16, 1, ws.sk_flags, stream));
+  return B200_OK;
+}
+
+int output_head(const float* x, uint16_t* h, float* head, const float* shift, const float* scale, long long mod_bs,
+                const float* w32, const void* w16, const float* bias, float* out, int batch, int F, int grid, int patch,
+                int out_ch, int D, int bf16, int channels_first, unsigned long long* sk_flags, cudaStream_t stream) {
+  const int n_out = patch * patch * out_ch;
+  const int T = batch * F * grid * grid;
+  if (w16 == nullptr || n_out != 32) {
+    B200_PROF(PROF_OTHER, launch_final_layer(x, shift, scale, mod_bs, w32, bias, out, batch, F, grid, patch, out_ch, D, channels_first, stream));
+    return B200_OK;
+  }
+  float* ones = head + static_cast<size_t>(T) * 32;
+  B200_CHECK_CUDA(cudaMemsetAsync(head, 0, static_cast<size_t>(T) * 32 * 4, stream));
+  B200_PROF(PROF_OTHER, launch_fill(ones, 1.0f, 32, stream));
+  B200_PROF(PROF_LN, launch_ln_modulate(x, shift, scale, mod_bs, F * grid * grid, h, T, D, bf16, stream));
+  GemmArgs g{};
+  g.A = h; g.W = w16; g.bias = bias; g.M = T; g.N = n_out; g.K = D; g.bf16 = bf16; g.epilogue = B200_EPI_GATE_RESIDUAL;
+  g.resid = head; g.gate = ones; g.gate_batch_stride = 0; g.rows_per_batch = T; g.sk_flags = sk_flags;
+  B200_PROF(PROF_GEMM, launch_gemm(g, stream));
+  B200_PROF(PROF_OTHER, launch_unpatchify(head, out, batch, F, grid, patch, out_ch, channels_first, stream));
   return B200_OK;
 }
 

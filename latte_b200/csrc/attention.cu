@@ -26,7 +26,7 @@ namespace b200 {
 namespace {
 
 constexpr int kThreads = 160;          // attn_long_kernel: warps 0-3 softmax/epilogue, warp 4 TMA + MMA issuer
-constexpr int kAttnDefaultImpl = 2;    // launch_mode: which kernel serves the <= 256-key modes (see B200_ATTN_IMPL)
+constexpr int kAttnDefaultImpl = 3;    // launch_mode: which kernel serves the <= 256-key modes (see B200_ATTN_IMPL)
 
 enum { MODE_FULL = 0, MODE_PACKED = 1, MODE_TEMPORAL = 2, MODE_CROSS = 3 };
 volatile int g_attn_impl = 0;   // b200_set_attention_impl: 0 = default / environment, 2 or 3 = forced (A/B tests)
@@ -46,7 +46,8 @@ struct AttnDev {
   int Lk;           // keys per tile: N (FULL, <= 256) or 128
   int tiles_per_seq;  // FULL: N / 128; TEMPORAL: N / G
   float scale_log2; // hd^-0.5 * log2(e)
-  int dbg;          // B200_ATTN_DBG bits: 1 no TMA*, 2 no softmax math*, 4 no output stores*, 8 no MMA* (* v2 only, wrong results), 16 v3: all exponentials on the MUFU pipe
+  int dbg;          // B200_ATTN_DBG bits: 1 no TMA*, 2 no softmax math*, 4 no output stores*, 8 no MMA* (* v2 only, wrong results);
+                    // v3: 4 no output stores*, 16 all exponentials on the MUFU pipe, 512 contiguous instead of strided work items
   const float* key_bias;  // CROSS: additive bias on the scores, fp32 [batch][128] (natural-log units, e.g. 0 / -10000), or nullptr
 };
 
@@ -476,7 +477,7 @@ __device__ __forceinline__ float sel8(const uint32_t* v, int g) {   // v[g], g i
   return __uint_as_float((g & 4) ? b1 : b0);
 }
 
-template <bool BF16, bool TAIL, int MODE, int LK>
+template <bool BF16, bool TAIL, int MODE, int LK, bool POLY>
 __global__ void __launch_bounds__(V3<LK>::THREADS, 1)
 attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
                const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt,
@@ -528,13 +529,20 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   pdl_launch_dependents();
   pdl_wait();   // qkv (written by the preceding GEMM) is visible from here
 
-  const int first = blockIdx.x, step = gridDim.x;
-  const int n_items = first < total_items ? (total_items - first + step - 1) / step : 0;
+  // work items (tile, head), head fastest: CTA c takes items c, c + grid, ...  (dbg bit 512, A/B: the contiguous run
+  // [c*total/grid, (c+1)*total/grid) instead -- consecutive heads of one tile on one SM.  Measured: no gain for temporal
+  // tiles, 13 % SLOWER for spatial ones, so strided stays.)
+  const bool strided = (p.dbg & 512) == 0;
+  const int item0 = strided ? static_cast<int>(blockIdx.x)
+                            : static_cast<int>(static_cast<long long>(blockIdx.x) * total_items / gridDim.x);
+  const int item1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_items / gridDim.x);
+  const int step = strided ? static_cast<int>(gridDim.x) : 1;
+  const int n_items = strided ? (item0 < total_items ? (total_items - item0 + step - 1) / step : 0) : item1 - item0;
 
   // tile coordinates of local work item i: the TMA coordinates of its Q rows / K,V rows / output rows
   struct Coord { int head, c2, c3, kv2; };
   auto coord = [&](int i) {
-    const int item = first + i * step;
+    const int item = item0 + i * step;
     Coord c;
     c.head = item % H;
     const int tile = item / H;
@@ -646,6 +654,10 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         umma_commit(o_full + sl);
       };
+      // Issue order S_0 .. S_{NSLOT-2}, then (S_{i+NSLOT-1}, PV_i) for every i: the S of a later tile is queued before the
+      // P V of the current one, so it runs on the tensor pipe while tile i is still in its softmax.  (A readiness-driven
+      // order -- PV first whenever its P is there -- measured SLOWER, 30.7 -> 33.7 us per spatial launch: delaying S starves
+      // the other slot's warpgroups more than an early PV helps this one's.)
       for (int j = 0; j < NSLOT - 1 && j < n_items; ++j) issue_s(j);
       for (int i = 0; i < n_items; ++i) {
         if (i + NSLOT - 1 < n_items) issue_s(i + NSLOT - 1);
@@ -685,7 +697,6 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int bar_id = 1 + sl;
     uint8_t* stage_out = smem + sl * sp.stage_bytes + sp.v_main;
     const int row_bytes = p.hd * 2;
-    const bool use_poly = !(p.dbg & 16);
 
     for (int i = sl; i < n_items; i += NSLOT) {
       const int u = i / NSLOT;
@@ -721,12 +732,14 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int k = 1; k < 16; ++k) mx = fmaxf(mx, xs[k]);
         const float ms = mx * p.scale_log2;
         uint32_t pk16[16];
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const float e = ex2(fmaf(xs[k], p.scale_log2, -ms));
-          sum += e;
+          part[k & 3] += e;
           pk16[k] = (g & 1) ? pack2<BF16>(0.f, e) : pack2<BF16>(e, 0.f);
         }
+        sum = (part[0] + part[1]) + (part[2] + part[3]);
         const int w = g >> 1;   // which of the group's 4 packed words holds the live key
 #pragma unroll
         for (int c = 0; c < 4; ++c) {     // 32 key columns = 16 packed words = 4 groups of 4 words
@@ -767,25 +780,32 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mx = fmaxf(mx, xmax[(h ^ 1) * 128 + r]);
         }
         const float ms = have_bias ? mx : mx * p.scale_log2;
+        // Straight-line and wide on purpose: all 16 scores of a chunk are scaled, THEN exponentiated, THEN summed into four
+        // independent partial sums -- the FFMA -> MUFU -> FADD chain of one element is ~30 clk deep, so the elements must be
+        // independent instructions for the scheduler (round-2 ncu: a per-element branch + one serial sum chain left each
+        // softmax warp at one instruction per 5.4 clk).
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
         auto emit = [&](const uint32_t (&v)[16], int c) {
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (MODE == MODE_CROSS && have_bias) x[j] = fmaf(__uint_as_float(v[j]), p.scale_log2, bias_s[c * 16 + j]) - ms;
+            else x[j] = fmaf(__uint_as_float(v[j]), p.scale_log2, -ms);
+          }
+          float e[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // every 4th exponential on the FMA pipe (spatial tiles only: their rows are 256 keys long): balances the
+            // 16/clk MUFU pipe against the issue slots the polynomial costs
+            if (POLY && (j & 3) == 3) e[j] = ex2_poly(x[j]);
+            else e[j] = ex2(x[j]);
+            if (!key_valid<MODE>(rkey, c * 16 + j, p.gshift)) e[j] = 0.f;
+          }
           uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float e[2];
+          for (int j = 0; j < 8; ++j) pk[j] = pack2<BF16>(e[2 * j], e[2 * j + 1]);
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int jj = 2 * j + t;
-              float x;
-              if (MODE == MODE_CROSS && have_bias) x = fmaf(__uint_as_float(v[jj]), p.scale_log2, bias_s[c * 16 + jj]) - ms;
-              else x = fmaf(__uint_as_float(v[jj]), p.scale_log2, -ms);
-              // 5 of 16 exponentials on the FMA pipe (spatial tiles only: their rows are 256 keys long)
-              if (MODE == MODE_FULL && use_poly && (jj % 3 == 2)) e[t] = ex2_poly(x);
-              else e[t] = ex2(x);
-              if (!key_valid<MODE>(rkey, c * 16 + jj, p.gshift)) e[t] = 0.f;
-              sum += e[t];
-            }
-            pk[j] = pack2<BF16>(e[0], e[1]);
-          }
+          for (int j = 0; j < 16; ++j) s4[j & 3] += e[j];
           tmem_st_32x32b_x8(t_s + c * 8, pk);
         };
         uint32_t va[16], vb[16];
@@ -800,6 +820,7 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           emit(vb, c + 1);
           tmem_ld_wait();
         }
+        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
       if constexpr (LK == 256) xsum[h * 128 + r] = sum;
       tmem_st_wait();
@@ -875,9 +896,9 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-template <bool BF16, bool TAIL, int MODE, int LK>
+template <bool BF16, bool TAIL, int MODE, int LK, bool POLY>
 int launch_v3_lk(const CUtensorMap* m, const AttnDev& p, int total, cudaStream_t stream) {
-  auto kern = attn_v3_kernel<BF16, TAIL, MODE, LK>;
+  auto kern = attn_v3_kernel<BF16, TAIL, MODE, LK, POLY>;
   const int smem_bytes = make_v3_plan(LK, TAIL).total;
   B200_SET_SMEM_ONCE(kern, smem_bytes);
   int sms = 148;
@@ -891,9 +912,12 @@ template <bool BF16, bool TAIL, int MODE>
 int launch_v3(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t stream) {
   const int total = static_cast<int>(grid.x * grid.y);
   if constexpr (MODE == MODE_FULL) {
-    if (p.Lk == 256) return launch_v3_lk<BF16, TAIL, MODE, 256>(m, p, total, stream);
+    if (p.Lk == 256) {
+      if (p.dbg & 16) return launch_v3_lk<BF16, TAIL, MODE, 256, false>(m, p, total, stream);   // A/B: all exponentials on the MUFU pipe
+      return launch_v3_lk<BF16, TAIL, MODE, 256, true>(m, p, total, stream);
+    }
   }
-  return launch_v3_lk<BF16, TAIL, MODE, 128>(m, p, total, stream);
+  return launch_v3_lk<BF16, TAIL, MODE, 128, false>(m, p, total, stream);
 }
 
 template <bool BF16, bool TAIL, int MODE>

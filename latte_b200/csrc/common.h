@@ -143,12 +143,14 @@ int launch_cast16(const float* in, void* out16, long long n, int bf16, cudaStrea
 int launch_fill(float* p, float v, long long n, cudaStream_t stream);
 // out[b][j] = act_out(W[j,:] . act_in(in[b,:]) + bias[j] (+ add[add_idx[b]][j]));  W fp32 (wbits=32) or 16-bit
 int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const float* in, float* out, int batch, int J,
-                int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx,
+                int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx, int add_rows,
                 cudaStream_t stream);
 int launch_timestep_freq(const long long* t, float* out, int batch, cudaStream_t stream);
 int launch_final_layer(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
                        const float* w, const float* b, float* out, int batch, int frames, int grid, int patch,
                        int out_ch, int dim, int channels_first, cudaStream_t stream);
+int launch_unpatchify(const float* y, float* out, int batch, int frames, int grid, int patch, int out_ch, int channels_first,
+                      cudaStream_t stream);
 int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, int out_ch, int guided_ch, int hw,
                        float scale, cudaStream_t stream);
 

@@ -27,7 +27,9 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 constexpr int LN_MAXV = 12;  // float4 per lane: dim <= 12*128 = 1536
 
 // One warp per row, the whole row in registers (NV float4 per lane, compile-time so nothing spills), two-pass
-// mean/variance in fp32, one read and one write of the data.  Work is split so that EVERY warp owns the same number of
+// mean/variance in fp32, one read and one write of the data.  (Round 2 tried one 16-byte store per lane per chunk of 8:
+// 80 registers instead of 64 cost a quarter of the resident warps and the kernel got SLOWER in the step, 0.91 -> 1.07 ms;
+// the 8-byte stores of a warp still fill whole 128-byte lines, so this form stays.)  Work is split so that EVERY warp owns the same number of
 // consecutive rows and all warps are resident at once (register-limited to 32 warps/SM): a grid-stride loop left a
 // half-empty second wave.  The block's shift/scale vectors are staged in shared memory once, so the only global latency
 // on a row's critical path is the row itself.
@@ -109,12 +111,15 @@ int ln_launch(cudaStream_t stream, const float* x, const float* shift, const flo
               uint16_t* out, int rows, int dim, int sms) {
   auto kern = ln_modulate_kernel<BF16, NV>;
   const size_t smem = static_cast<size_t>(dim) * 2 * sizeof(float);
-  static int blocks_per_sm = 0;   // per instantiation: what the register/smem footprint really allows
-  if (blocks_per_sm == 0) {
+  static int blocks_per_sm_dev[64] = {};   // per instantiation and device: what the register/smem footprint really allows
+  int dev = 0;
+  B200_TRY(current_device(&dev));
+  if (blocks_per_sm_dev[dev] == 0) {
     int n = 0;
     B200_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, smem));
-    blocks_per_sm = n > 0 ? n : 1;
+    blocks_per_sm_dev[dev] = n > 0 ? n : 1;
   }
+  const int blocks_per_sm = blocks_per_sm_dev[dev];
   // every warp gets the same number of consecutive rows and the whole grid is resident in one wave
   const int wpb = 4;
   const int resident_warps = sms * blocks_per_sm * wpb;
@@ -208,8 +213,15 @@ __global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ W, c
                                                    const float* __restrict__ in, float* __restrict__ out, int batch,
                                                    int J, int K, int silu_in, int silu_out,
                                                    const float* __restrict__ add_table,
-                                                   const long long* __restrict__ add_idx) {
+                                                   const long long* __restrict__ add_idx, int add_rows) {
   extern __shared__ float sin_[];  // [batch][K]
+  if (add_table && threadIdx.x < batch) {   // nn.Embedding asserts on an out-of-range index; so does this lookup
+    const long long idx = add_idx[threadIdx.x];
+    if (idx < 0 || idx >= add_rows) {
+      if (blockIdx.x == 0) printf("latte_b200: label %lld out of range [0, %d)\n", idx, add_rows);
+      __trap();
+    }
+  }
   for (int i = threadIdx.x; i < batch * K; i += blockDim.x) {
     const float v = in[i];
     sin_[i] = silu_in ? silu(v) : v;
@@ -355,6 +367,29 @@ __global__ void __launch_bounds__(512) final_layer_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------- unpatchify
+// y [T, n_out] fp32 (token-major output of the head GEMM, n_out = p*p*out_ch ordered (pi, qi, c)) -> the reference's
+// layout out[b][f][c][gh*p + pi][gw*p + qi] (latte.py:297-310) or [b][c][f][..] (LatteT2V).  One thread per output
+// element, indexed in OUTPUT order so the 4-byte stores coalesce; the gathers hit 128-byte rows of y that are L2-resident.
+__global__ void unpatchify_kernel(const float* __restrict__ y, float* __restrict__ out, long long total, int frames, int grid,
+                                  int patch, int out_ch, int n_out, long long osb, long long osf, long long osc) {
+  const int size = grid * patch;
+  const long long plane = static_cast<long long>(size) * size;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // i enumerates (bf, c, row, col) in the order of an [bf][c][H][W] tensor; osb/osf/osc place it in the real layout
+    const long long pix = i % plane;
+    const long long t1 = i / plane;
+    const int c = static_cast<int>(t1 % out_ch);
+    const long long bf = t1 / out_ch;
+    const int row = static_cast<int>(pix / size), col = static_cast<int>(pix % size);
+    const int gh = row / patch, pi = row % patch, gw = col / patch, qi = col % patch;
+    const long long tok = bf * grid * grid + static_cast<long long>(gh) * grid + gw;
+    const float v = y[tok * n_out + (pi * patch + qi) * out_ch + c];
+    out[(bf / frames) * osb + (bf % frames) * osf + c * osc + pix] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------- cfg combine
 __global__ void cfg_combine_kernel(float* __restrict__ out, int half_batch, long long per_sample, int out_ch,
                                    int guided_ch, int hw, float scale) {
@@ -493,7 +528,7 @@ int launch_timestep_freq(const long long* t, float* out, int batch, cudaStream_t
 }
 
 int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const float* in, float* out, int batch, int J,
-                int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx,
+                int K, int silu_in, int silu_out, const float* add_table, const long long* add_idx, int add_rows,
                 cudaStream_t stream) {
   B200_REQUIRE(K % 8 == 0 && J > 0, B200_ERR_SHAPE, "gemv: K=%d must be a multiple of 8", K);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, B200_ERR_ALIGN, "gemv: W must be 16-byte aligned");
@@ -511,11 +546,11 @@ int launch_gemv(const void* W, int wbits, int bf16, const float* bias, const flo
     float* outb = out + static_cast<size_t>(b0) * J;
     const long long* idx = add_idx ? add_idx + b0 : nullptr;
     if (wbits == 32)
-      gemv_kernel<32, false><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx);
+      gemv_kernel<32, false><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx, add_rows);
     else if (bf16)
-      gemv_kernel<16, true><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx);
+      gemv_kernel<16, true><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx, add_rows);
     else
-      gemv_kernel<16, false><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx);
+      gemv_kernel<16, false><<<blocks, warps * 32, smem, stream>>>(W, bias, inb, outb, nb, J, K, silu_in, silu_out, add_table, idx, add_rows);
     B200_CHECK_CUDA(cudaGetLastError());
   }
   return B200_OK;
@@ -528,11 +563,7 @@ int launch_final_layer(const float* x, const float* shift, const float* scale, l
   B200_REQUIRE(n_out <= FL_MAXO && dim % 4 == 0 && dim <= FL_MAXV * 128, B200_ERR_SHAPE,
                "final_layer: p*p*Cout = %d must be <= %d, dim %d <= %d", n_out, FL_MAXO, dim, FL_MAXV * 128);
   const size_t smem = static_cast<size_t>(n_out) * dim * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(final_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  B200_SET_SMEM_ONCE(final_layer_kernel, 200 * 1024);
   B200_REQUIRE(smem <= 200 * 1024, B200_ERR_SHAPE, "final_layer: weight tile %zu B exceeds shared memory", smem);
   int sms = 0;
   B200_TRY(device_sm_count(&sms));
@@ -546,6 +577,20 @@ int launch_final_layer(const float* x, const float* shift, const float* scale, l
   const long long sc = channels_first ? plane * frames : plane;
   final_layer_kernel<<<blocks, warps * 32, smem, stream>>>(x, shift, scale, mod_batch_stride, w, b, out, total, frames,
                                                             grid, patch, out_ch, dim, sb, sf, sc);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_unpatchify(const float* y, float* out, int batch, int frames, int grid, int patch, int out_ch, int channels_first,
+                      cudaStream_t stream) {
+  const long long plane = static_cast<long long>(grid * patch) * (grid * patch);
+  const long long total = static_cast<long long>(batch) * frames * out_ch * plane;
+  const long long sb = plane * out_ch * frames;
+  const long long sf = channels_first ? plane : plane * out_ch;
+  const long long sc = channels_first ? plane * frames : plane;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpatchify_kernel<<<blocks, 256, 0, stream>>>(y, out, total, frames, grid, patch, out_ch, patch * patch * out_ch, sb, sf, sc);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

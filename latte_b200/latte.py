@@ -246,6 +246,7 @@ class Latte(DeviceCacheMixin, nn.Module):
         T["fc2_b"] = cat32([b.mlp.fc2.bias for b in blocks])
         T["final_w"] = f32(self.final_layer.linear.weight)
         T["final_b"] = f32(self.final_layer.linear.bias)
+        T["final_w16"] = self.final_layer.linear.weight.detach().to(device=dev, dtype=od).contiguous()
 
         w = _lib.LatteWeights()
         for name in _lib.WEIGHT_FIELDS:

@@ -123,7 +123,7 @@ def gen_subops(ref, out_dir):
 
 TINY = dict(num_attention_heads=2, attention_head_dim=64, num_layers=2, sample_size=16, video_length=8, caption_channels=256)
 HD72 = dict(num_attention_heads=8, attention_head_dim=72, num_layers=2, sample_size=32, video_length=16, caption_channels=512)
-S64 = dict(num_attention_heads=4, attention_head_dim=72, num_layers=2, sample_size=64, video_length=16, caption_channels=256)
+S64 = dict(num_attention_heads=8, attention_head_dim=72, num_layers=2, sample_size=64, video_length=16, caption_channels=256)
 FULL = dict(num_attention_heads=16, attention_head_dim=72, num_layers=28, sample_size=64, video_length=16, caption_channels=4096)
 
 if __name__ == "__main__":

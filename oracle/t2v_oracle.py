@@ -220,6 +220,17 @@ def t2v_forward(sd, cfg: T2VConfig, x, t, text, dtype=torch.float32, enable_temp
     return h.reshape(B, Fr, cfg.out_channels, Hh, Ww).permute(0, 2, 1, 3, 4).contiguous()
 
 
+def gemm_flops_per_video(cfg: T2VConfig, text_len: int) -> float:
+    """The Linear-layer part of `algorithmic_flops_per_video` (everything the tcgen05 GEMM kernel executes)."""
+    D, N, Fr, L = cfg.inner_dim, cfg.num_patches, cfg.video_length, cfg.num_layers
+    T = N * Fr
+    sp_lin = 2.0 * T * (3 * D * D + D * D + 2 * D * D + 8 * D * D)
+    tm_lin = 2.0 * T * (3 * D * D + D * D + 8 * D * D)
+    kv = 2.0 * text_len * D * 2 * D
+    cap = 2.0 * text_len * (cfg.caption_channels * D + D * D)
+    return (sp_lin + tm_lin + kv) * L + cap
+
+
 def algorithmic_flops_per_video(cfg: T2VConfig, text_len: int) -> float:
     """text K/V projected once per sample."""
     D, N, Fr, L = cfg.inner_dim, cfg.num_patches, cfg.video_length, cfg.num_layers
