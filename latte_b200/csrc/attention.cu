@@ -1177,6 +1177,373 @@ int launch_long(const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t 
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Long spatial sequences (N = 512 / 1024 tokens per frame: LatteT2V at 512 px), round 2: a persistent, role-warp,
+// online-softmax kernel in the shape of the v3 kernel above.
+//   * work item = (frame, head, 256 query rows) = TWO 128-row query tiles that share every K/V byte the item streams;
+//     keys arrive in chunks of 128 through a 3-stage TMA ring {K, V};
+//   * TMEM: S_0 [0,128)  S_1 [128,256)  O_0 [256,336)  O_1 [336,416).  P_t (16-bit, packed) overwrites the start of S_t;
+//   * MMA issue order S_0(0) S_1(0) | PV_0(c) S_0(c+1) PV_1(c) S_1(c+1) | ...: while warpgroup 0 exponentiates S_0(c) the
+//     tensor pipe computes S_1(c) and P_1 V of the previous chunk -- two tiles ping-pong on one pipe;
+//   * online softmax with a LAZY running maximum: the row maximum m only moves (and O_t, l are rescaled, tcgen05.ld ->
+//     * alpha -> tcgen05.st) when the new chunk's maximum exceeds it by more than 2^8; until then P may grow up to 256,
+//     which 16-bit P and the fp32 accumulators hold exactly as well.  The rescale of a warp's 32 rows is skipped when no
+//     row needs it (warp vote), which is nearly always after the first chunks;
+//   * the epilogue stages O_t / l into the item's (dead) Q tile and leaves through one TMA bulk store per tile.
+// Warps: 0 = TMA producer K/V ring, 3 = TMA producer Q, 1 = MMA issuer (+ TMEM allocator), 2 = output store,
+//        4-7 = softmax/epilogue tile 0, 8-11 = tile 1.
+constexpr int ST_THREADS = 384;
+constexpr int ST_NST = 3;            // K/V ring depth
+constexpr int ST_CK = 128;           // keys per chunk
+constexpr float ST_TAU = 8.0f;       // lazy-maximum threshold, log2 units
+
+struct StPlan {
+  int q_buf, q_tile, q_tail, kv_stage, k_main, k_tail, v_main, v_tail, ring, bars, total;
+};
+__host__ __device__ inline StPlan make_st_plan(bool tail) {
+  StPlan s;
+  s.q_tile = 128 * 128 + (tail ? 128 * 32 : 0);     // one 128-row query tile (main + tail), also its output staging tile
+  s.q_tail = 128 * 128;
+  s.q_buf = 2 * s.q_tile;                           // Q_0, Q_1 of one item
+  s.k_main = 0;
+  s.k_tail = ST_CK * 128;
+  s.v_main = s.k_tail + (tail ? ST_CK * 32 : 0);
+  s.v_tail = s.v_main + ST_CK * 128;
+  s.kv_stage = s.v_tail + (tail ? ST_CK * 32 : 0);
+  s.ring = 2 * s.q_buf;
+  s.bars = s.ring + ST_NST * s.kv_stage;
+  s.total = s.bars + 512 + 1024;
+  return s;
+}
+
+template <bool BF16, bool TAIL>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+attn_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
+                   const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmKVt,
+                   const __grid_constant__ CUtensorMap tmO, const AttnDev p, const int total_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const StPlan sp = make_st_plan(TAIL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* q_full = bars + 0;              // [2] TMA: both query tiles of the item have landed
+  uint64_t* q_free = bars + 2;              // [2] store warp (2 arrivals): both output tiles have left the Q buffer
+  uint64_t* k_full = bars + 4;              // [NST]
+  uint64_t* v_full = bars + 4 + ST_NST;     // [NST]
+  uint64_t* k_free = bars + 4 + 2 * ST_NST; // [NST] MMA commit: S_1 of the chunk is done
+  uint64_t* v_free = bars + 4 + 3 * ST_NST; // [NST] MMA commit: P_1 V of the chunk is done
+  uint64_t* s_full = bars + 4 + 4 * ST_NST; // [2] MMA commit: S_t of a chunk is complete (and every earlier MMA)
+  uint64_t* p_full = s_full + 2;            // [2] softmax (128 arrivals): P_t written, O_t rescaled
+  uint64_t* o_full = s_full + 4;            // [2] MMA commit: O_t of the item is complete
+  uint64_t* o_free = s_full + 6;            // [2] epilogue (128 arrivals): O_t has been read out of TMEM
+  uint64_t* o_staged = s_full + 8;          // [2] epilogue (128 arrivals): the output tile is staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int H = p.heads;
+  const int C = p.tokens / ST_CK;                    // chunks per item
+  const int pairs_per_seq = p.tokens / 256;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i, 1);
+      mbar_init(q_free + i, 2);
+      mbar_init(s_full + i, 1);
+      mbar_init(p_full + i, 128);
+      mbar_init(o_full + i, 1);
+      mbar_init(o_free + i, 128);
+      mbar_init(o_staged + i, 128);
+    }
+    for (int i = 0; i < ST_NST; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(k_free + i, 1);
+      mbar_init(v_free + i, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int first = blockIdx.x, step = gridDim.x;
+  const int n_items = first < total_items ? (total_items - first + step - 1) / step : 0;
+  struct Coord { int head, q_row0, kv_row0; };
+  auto coord = [&](int n) {
+    const int item = first + n * step;
+    Coord c;
+    c.head = item % H;
+    const int qp = item / H;                       // (sequence, query pair)
+    c.kv_row0 = (qp / pairs_per_seq) * p.tokens;
+    c.q_row0 = c.kv_row0 + (qp % pairs_per_seq) * 256;
+    return c;
+  };
+
+  if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer: the item's two query tiles
+      const uint32_t q_bytes = 2 * (128 * 128 + (TAIL ? 128 * 32 : 0));
+      for (int n = 0; n < n_items; ++n) {
+        const int b = n & 1, u = n >> 1;
+        uint8_t* buf = smem + b * sp.q_buf;
+        const Coord c = coord(n);
+        if (u > 0) mbar_wait(q_free + b, (u - 1) & 1);
+        mbar_arrive_expect_tx(q_full + b, q_bytes);
+        for (int t = 0; t < 2; ++t) {
+          tma_load_3d(buf + t * sp.q_tile, &tmQ, q_full + b, 0, c.head, c.q_row0 + t * 128);
+          if constexpr (TAIL) tma_load_3d(buf + t * sp.q_tile + sp.q_tail, &tmQt, q_full + b, 64, c.head, c.q_row0 + t * 128);
+        }
+      }
+    }
+  } else if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer: K / V chunk ring
+      const uint32_t kb = ST_CK * 128 + (TAIL ? ST_CK * 32 : 0);
+      int g = 0;
+      for (int n = 0; n < n_items; ++n) {
+        const Coord c = coord(n);
+        for (int ch = 0; ch < C; ++ch, ++g) {
+          const int st = g % ST_NST, u = g / ST_NST;
+          uint8_t* buf = smem + sp.ring + st * sp.kv_stage;
+          const int row = c.kv_row0 + ch * ST_CK;
+          if (u > 0) mbar_wait(k_free + st, (u - 1) & 1);
+          mbar_arrive_expect_tx(k_full + st, kb);
+          tma_load_3d(buf + sp.k_main, &tmKV, k_full + st, 0, p.k_head0 + c.head, row);
+          if constexpr (TAIL) tma_load_3d(buf + sp.k_tail, &tmKVt, k_full + st, 64, p.k_head0 + c.head, row);
+          if (u > 0) mbar_wait(v_free + st, (u - 1) & 1);
+          mbar_arrive_expect_tx(v_full + st, kb);
+          tma_load_3d(buf + sp.v_main, &tmKV, v_full + st, 0, p.v_head0 + c.head, row);
+          if constexpr (TAIL) tma_load_3d(buf + sp.v_tail, &tmKVt, v_full + st, 64, p.v_head0 + c.head, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_s = umma_idesc_f16(BF16, 128, ST_CK, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_f16(BF16, 128, 64, false, true);    // B = V is MN-major ([key][hd] in smem)
+      constexpr uint32_t idesc_ot = umma_idesc_f16(BF16, 128, 16, false, true);
+      int g = 0;                                   // global chunk counter (ring position)
+      uint32_t sp_phase = 0;                       // phase of s_full / p_full: one completion per chunk, both tiles in step
+      auto issue_s = [&](const uint8_t* qbuf, const uint8_t* kbuf, int t) {
+        const uint32_t tS = tmem_base + t * 128;
+        const uint64_t dq = umma_smem_desc(smem_u32(qbuf + t * sp.q_tile), 0, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t dk = umma_smem_desc(smem_u32(kbuf + sp.k_main), 0, 1024, UMMA_LAYOUT_SW128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tS, umma_desc_advance(dq, k * 32), umma_desc_advance(dk, k * 32), idesc_s, k > 0 ? 1u : 0u);
+        if constexpr (TAIL) {
+          const uint64_t dqt = umma_smem_desc(smem_u32(qbuf + t * sp.q_tile + sp.q_tail), 0, 256, UMMA_LAYOUT_SW32);
+          const uint64_t dkt = umma_smem_desc(smem_u32(kbuf + sp.k_tail), 0, 256, UMMA_LAYOUT_SW32);
+          umma_f16_ss(tS, dqt, dkt, idesc_s, 1u);
+        }
+        umma_commit(s_full + t);
+      };
+      auto issue_pv = [&](const uint8_t* vbuf, int t, bool first_chunk) {
+        const uint32_t tP = tmem_base + t * 128;
+        const uint32_t tO = tmem_base + 256 + t * 80;
+        const uint64_t dv = umma_smem_desc(smem_u32(vbuf + sp.v_main), ST_CK * 128, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t dvt = umma_smem_desc(smem_u32(vbuf + sp.v_tail), ST_CK * 32, 256, UMMA_LAYOUT_SW32);
+#pragma unroll
+        for (int k = 0; k < ST_CK / 16; ++k) {
+          const uint32_t acc = (first_chunk && k == 0) ? 0u : 1u;
+          umma_f16_ts(tO, tP + k * 8, umma_desc_advance(dv, k * 16 * 128), idesc_o, acc);
+          if constexpr (TAIL) umma_f16_ts(tO + 64, tP + k * 8, umma_desc_advance(dvt, k * 16 * 32), idesc_ot, acc);
+        }
+      };
+      for (int n = 0; n < n_items; ++n) {
+        const int qb = n & 1;
+        const uint8_t* qbuf = smem + qb * sp.q_buf;
+        mbar_wait(q_full + qb, (n >> 1) & 1);
+        {   // S_0(0), S_1(0)
+          const int st = g % ST_NST;
+          const uint8_t* kv = smem + sp.ring + st * sp.kv_stage;
+          mbar_wait(k_full + st, (g / ST_NST) & 1);
+          tc_fence_after();
+          issue_s(qbuf, kv, 0);
+          issue_s(qbuf, kv, 1);
+          umma_commit(k_free + st);
+        }
+        for (int ch = 0; ch < C; ++ch, ++g) {
+          const int st = g % ST_NST;
+          const uint8_t* kv = smem + sp.ring + st * sp.kv_stage;
+          const int st_n = (g + 1) % ST_NST;
+          const uint8_t* kv_n = smem + sp.ring + st_n * sp.kv_stage;
+          const bool more = ch + 1 < C;
+          mbar_wait(v_full + st, (g / ST_NST) & 1);
+          if (more) mbar_wait(k_full + st_n, ((g + 1) / ST_NST) & 1);
+          for (int t = 0; t < 2; ++t) {
+            if (ch == 0 && n > 0) mbar_wait(o_free + t, (n - 1) & 1);   // the previous item's O_t has been read out
+            mbar_wait(p_full + t, sp_phase);
+            tc_fence_after();
+            issue_pv(kv, t, ch == 0);
+            if (more) issue_s(qbuf, kv_n, t);        // S_t(c+1) overwrites P_t(c): queued behind the P V that reads it
+            else umma_commit(o_full + t);
+          }
+          umma_commit(v_free + st);
+          if (more) umma_commit(k_free + st_n);
+          sp_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ output store
+      for (int n = 0; n < n_items; ++n) {
+        const int qb = n & 1;
+        const Coord c = coord(n);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(o_staged + t, n & 1);
+          if (!(p.dbg & 4)) {
+            tma_store_3d(&tmO, smem + qb * sp.q_buf + t * sp.q_tile, 0, c.head, c.q_row0 + t * 128);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          mbar_arrive(q_free + qb);
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax + epilogue: warpgroup t owns query tile t
+    const int t = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t t_s = tmem_base + t * 128 + lane_off;
+    const uint32_t t_o = tmem_base + 256 + t * 80 + lane_off;
+    const int row_bytes = p.hd * 2;
+    uint32_t phase = 0;
+    for (int n = 0; n < n_items; ++n) {
+      float m_run = -INFINITY, l_run = 0.f;      // running maximum (raw score units) and sum, this thread's row
+      for (int ch = 0; ch < C; ++ch) {
+        mbar_wait(s_full + t, phase);
+        tc_fence_after();
+        // pass 1: chunk maximum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(t_s + c * 32, va);
+          tmem_ld_32x32b_x32(t_s + (c + 1) * 32, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(va[j]), __uint_as_float(vb[j])));
+        }
+        // lazy running maximum: move it only when this chunk exceeds it by more than 2^TAU
+        float alpha = 1.0f;
+        const bool grow = (mx - m_run) * p.scale_log2 > ST_TAU;      // always true for the first chunk (m_run = -inf)
+        if (grow) {
+          alpha = ch == 0 ? 0.f : ex2((m_run - mx) * p.scale_log2);
+          m_run = mx;
+        }
+        if (ch > 0 && __any_sync(0xffffffffu, grow)) {               // O_t is stable: every MMA before S_t(ch) has completed
+          l_run *= alpha;
+#pragma unroll 1
+          for (int cc = 0; cc < (TAIL ? 5 : 4); ++cc) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_o + cc * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+            tmem_st_32x32b_x16(t_o + cc * 16, v);
+          }
+        }
+        const float ms = m_run * p.scale_log2;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        auto emit = [&](const uint32_t (&v)[16], int c) {
+          float e[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = fmaf(__uint_as_float(v[j]), p.scale_log2, -ms);
+            e[j] = (j & 3) == 3 ? ex2_poly(x) : ex2(x);        // x <= TAU: ex2_poly handles positive arguments too
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack2<BF16>(e[2 * j], e[2 * j + 1]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s4[j & 3] += e[j];
+          tmem_st_32x32b_x8(t_s + c * 8, pk);
+        };
+        uint32_t va[16], vb[16];
+        tmem_ld_32x32b_x16(t_s, va);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_32x32b_x16(t_s + (c + 1) * 16, vb);
+          emit(va, c);
+          tmem_ld_wait();
+          if (c + 2 < 8) tmem_ld_32x32b_x16(t_s + (c + 2) * 16, va);
+          emit(vb, c + 1);
+          tmem_ld_wait();
+        }
+        l_run += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full + t);
+        phase ^= 1;
+      }
+      // ---- epilogue of the item: O_t / l -> 16-bit -> staging tile (the item's Q_t smem) -> TMA store by warp 2
+      const float inv = 1.0f / l_run;
+      mbar_wait(o_full + t, n & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32], ot[16];
+      tmem_ld_32x32b_x32(t_o, o0);
+      tmem_ld_32x32b_x32(t_o + 32, o1);
+      if constexpr (TAIL) tmem_ld_32x32b_x16(t_o + 64, ot);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free + t);
+      uint8_t* drow = smem + (n & 1) * sp.q_buf + t * sp.q_tile + r * row_bytes;
+      auto put8 = [&](const uint32_t* o, int col) {
+        uint4 w;
+        w.x = pack2<BF16>(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        w.y = pack2<BF16>(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        w.z = pack2<BF16>(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        w.w = pack2<BF16>(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        *reinterpret_cast<uint4*>(drow + col * 2) = w;
+      };
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) { put8(o0 + 8 * i4, i4 * 8); put8(o1 + 8 * i4, 32 + i4 * 8); }
+      if constexpr (TAIL) {
+        const int tail8 = (p.hd - 64) / 8;
+#pragma unroll
+        for (int i4 = 0; i4 < 2; ++i4)
+          if (i4 < tail8) put8(ot + 8 * i4, 64 + i4 * 8);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(o_staged + t);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool BF16, bool TAIL>
+int launch_stream(const CUtensorMap* m, const AttnDev& p, int total_items, cudaStream_t stream) {
+  auto kern = attn_stream_kernel<BF16, TAIL>;
+  const int smem_bytes = make_st_plan(TAIL).total;
+  B200_SET_SMEM_ONCE(kern, smem_bytes);
+  int sms = 148;
+  B200_TRY(device_sm_count(&sms));
+  const int ctas = total_items < sms ? total_items : sms;
+  B200_CHECK_CUDA(launch_pdl(kern, dim3(ctas), dim3(ST_THREADS), static_cast<size_t>(smem_bytes), stream, m[0], m[1], m[2], m[3], m[4], p, total_items));
+  return B200_OK;
+}
+
 template <bool BF16, bool TAIL>
 int launch_tail(int mode, const CUtensorMap* m, const AttnDev& p, dim3 grid, cudaStream_t s) {
   switch (mode) {
@@ -1236,10 +1603,14 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     uint32_t kv_rows;
     if (a.tokens > 256) {
       B200_REQUIRE(a.tokens % 256 == 0, B200_ERR_UNSUPPORTED, "attention: spatial sequence length %d must be a multiple of 256", a.tokens);
+      static const int env_impl = env_int("B200_ATTN_IMPL", kAttnDefaultImpl);
+      const int forced = g_attn_impl;
+      const bool streaming = (forced ? forced : env_impl) != 2;     // impl 2 = the round-1 one-tile-per-CTA kernel (A/B)
       p.Lk = 256;
       p.tiles_per_seq = a.tokens / 128;
+      const uint32_t kv_rows = streaming ? 128u : 256u;
       const uint32_t boxQ[3] = {64, 1, 128}, boxQt[3] = {16, 1, 128};
-      const uint32_t boxK[3] = {64, 1, 256}, boxKt[3] = {16, 1, 256};
+      const uint32_t boxK[3] = {64, 1, kv_rows}, boxKt[3] = {16, 1, kv_rows};
       B200_TRY(make_tmap_16bit(&maps[0], a.qkv, 3, dims, str, boxQ, TMAP_SW_128));
       B200_TRY(make_tmap_16bit(&maps[2], a.qkv, 3, dims, str, boxK, TMAP_SW_128));
       if (tail) {
@@ -1248,6 +1619,15 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
       } else {
         maps[1] = maps[0];
         maps[3] = maps[2];
+      }
+      if (streaming) {
+        const uint64_t odims[3] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(T)};
+        const uint64_t ostr[2] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(D) * 2};
+        const uint32_t obox[3] = {static_cast<uint32_t>(hd), 1, 128};
+        B200_TRY(make_tmap_16bit(&maps[4], a.out, 3, odims, ostr, obox, TMAP_SW_NONE));
+        const int items = a.batch * a.frames * (a.tokens / 256) * H;
+        if (a.bf16) return tail ? launch_stream<true, true>(maps, p, items, stream) : launch_stream<true, false>(maps, p, items, stream);
+        return tail ? launch_stream<false, true>(maps, p, items, stream) : launch_stream<false, false>(maps, p, items, stream);
       }
       const dim3 lgrid(a.batch * a.frames * p.tiles_per_seq, H);
       if (a.bf16) return tail ? launch_long<true, true>(maps, p, lgrid, stream) : launch_long<true, false>(maps, p, lgrid, stream);

@@ -202,6 +202,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
+  __syncthreads();      // CTA-scope order for the allocator's write of tmem_slot (what compute-sanitizer's racecheck models;
+                        // the cluster barrier below already implies it)
   cluster_sync_all();   // barriers of both CTAs are initialised before any multicast / remote arrival can target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;

@@ -38,6 +38,13 @@ def gemm():
         gate = torch.randn(2, N, generator=g).to(dev)
         resid = torch.randn(M, N, generator=g).to(dev)
         fl = 2.0 * M * N * K
+        # library yardstick (cuBLAS through torch; never on the product path): the plain GEMM without any epilogue
+        Wt = W.t().contiguous()
+        for fl_on in (True, False):
+            best, mean = bench(lambda: torch.matmul(A, Wt), do_flush=fl_on)
+            print(f"cublas {name:4s} {M}x{N}x{K}       {'cold' if fl_on else 'warm'}: best {best:7.1f} us mean {mean:7.1f} us -> {fl / best / 1e6:7.1f} TFLOP/s (best)", flush=True)
+        best, mean = bench(lambda: torch.nn.functional.linear(A, W), do_flush=True)
+        print(f"cublas {name:4s} linear(A, W[N,K])        cold: best {best:7.1f} us mean {mean:7.1f} us -> {fl / best / 1e6:7.1f} TFLOP/s (best)", flush=True)
         for bn in (128, 192, 256):
             if mode == "resid":
                 fn = lambda: ops.linear_gate_residual_(resid, A, W, bias, gate, M // 2, block_n=bn)
@@ -65,6 +72,21 @@ def attn():
     lib.b200_set_attention_impl(0)
 
 
+def attn_long():
+    """LatteT2V @512 px: spatial attention over N = 1024 tokens per frame (B_model = 2, 16 frames, 16 heads x 72)."""
+    from latte_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    b, f, n, h, hd = 2, 16, 1024, 16, 72
+    qkv = torch.randn(b * f * n, 3 * h * hd, generator=g).to(dev).half()
+    for impl in [int(v) for v in os.environ.get('B200_MB_IMPLS', '2,3').split(',')]:
+        lib.b200_set_attention_impl(impl)
+        best, mean = bench(lambda: ops.attention(qkv, b, f, n, h, False), iters=10)
+        flops = 4.0 * n * n * f * h * hd * b
+        print(f"attn N=1024 v{impl}: best {best:7.1f} us mean {mean:7.1f} -> {flops / best / 1e6:6.1f} TFLOP/s", flush=True)
+    lib.b200_set_attention_impl(0)
+
+
 def ln():
     g = torch.Generator().manual_seed(2)
     T, D = 8192, 1152
@@ -79,4 +101,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "ln"]
     print(torch.cuda.get_device_name(0), flush=True)
     for w in which:
-        {"gemm": gemm, "attn": attn, "ln": ln}[w]()
+        {"gemm": gemm, "attn": attn, "ln": ln, "attn_long": attn_long}[w]()
