@@ -263,7 +263,7 @@ def run_video_leg(net, cfg, xd, yd, dev, world, barrier, sharding):
     fused sampler step) + AutoencoderKL.decode (SD-VAE topology, synthetic weights) + uint8 conversion, then the decoded
     frames of all ranks are gathered with NCCL (sharding.gather_frames: the ONE collective of the sampling path).
     Wall clock incl. host code, max over ranks; value = world * frames / that."""
-    from latte_b200 import AutoencoderKL
+    from latte_b200 import AutoencoderKL, ops
     from latte_b200.diffusion import create_diffusion
     vae = AutoencoderKL().to(dev).half().eval()
     n_steps = 250
@@ -276,8 +276,8 @@ def run_video_leg(net, cfg, xd, yd, dev, world, barrier, sharding):
             smp = diffusion.ddim_sample_loop(net.forward_with_cfg, zz.shape, zz, clip_denoised=False, model_kwargs=kw, device=dev)
             smp, _ = smp.chunk(2, dim=0)
             img = vae.decode(smp[0] / 0.18215).sample                                   # (16, 3, 256, 256)
-            u8 = ((img.float() * 0.5 + 0.5).clamp(0, 1) * 255).add_(0.5).to(torch.uint8)  # sample.py:116-117
-            return sharding.gather_frames(u8.permute(0, 2, 3, 1).contiguous()[None])    # [world, 16, 256, 256, 3]
+            u8 = ops.frames_to_uint8(img.contiguous(), "sample")                            # sample.py:122, fused with the permute
+            return sharding.gather_frames(u8[None])                                       # [world, 16, 256, 256, 3]
 
     one_video()                     # warm-up: graph capture, VAE packing, NCCL channel setup
     with torch.no_grad():

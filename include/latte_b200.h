@@ -41,7 +41,7 @@ enum {
   B200_ERR_UNSUPPORTED = -7
 };
 enum { B200_FP16 = 0, B200_BF16 = 1 };
-enum { B200_EPI_BIAS = 0, B200_EPI_BIAS_GELU = 1, B200_EPI_GATE_RESIDUAL = 2, B200_EPI_BIAS_ADD16 = 3 };
+enum { B200_EPI_BIAS = 0, B200_EPI_BIAS_GELU = 1, B200_EPI_GATE_RESIDUAL = 2, B200_EPI_BIAS_ADD16 = 3, B200_EPI_BIAS_MUL16 = 4 };
 
 /* Model geometry: the ctor arguments of reference `Latte` (models/latte.py:208-223). */
 typedef struct B200LatteShape {
@@ -165,6 +165,47 @@ B200_API int b200_t2v_forward(const B200T2VShape* shape, const B200T2VWeights* w
  * per key (broadcast over heads and queries); out [rows, heads*head_dim] 16-bit.                                  */
 B200_API int b200_cross_attention(const void* q, const void* kv, const float* key_bias, void* out, int batch, int q_rows_per_batch,
                                   int kv_len, int q_row_stride, int kv_row_stride, int heads, int head_dim, int dtype, void* stream);
+
+/* ---- T5 text encoder: the reference obtains prompt embeddings from transformers' T5EncoderModel
+ * (sample/pipeline_latte.py:214, `self.text_encoder(ids, attention_mask=mask)[0]`; t5-v1_1-xxl: d_model 4096, 64 heads x 64,
+ * d_ff 10240 gated-GELU, 24 layers, relative position bias shared by all layers, no biases, no attention scaling).
+ * Parity: oracle/t5_oracle.py is pinned to fixtures generated by transformers' own T5EncoderModel (oracle/make_golden_t5.py). */
+typedef struct B200T5Shape {
+  int32_t layers;
+  int32_t d_model;
+  int32_t heads;        /* d_kv is 64: inner = 64 * heads */
+  int32_t d_ff;
+  int32_t vocab;
+  int32_t dtype;        /* B200_FP16 / B200_BF16 operand type of the packed weights */
+  float eps;            /* layer_norm_epsilon (1e-6) */
+} B200T5Shape;
+
+typedef struct B200T5Weights {
+  const void* embed16;    /* shared.weight [vocab, d_model] 16-bit                                                   */
+  const void* qkv_w16;    /* block.l.layer.0.SelfAttention.q|k|v.weight stacked [l][3*inner, d_model]                */
+  const void* o_w16;      /* ...SelfAttention.o.weight [l][d_model, inner]                                           */
+  const float* ln0_w;     /* block.l.layer.0.layer_norm.weight [l][d_model] fp32                                     */
+  const void* wi0_w16;    /* block.l.layer.1.DenseReluDense.wi_0.weight [l][d_ff, d_model] (the GELU branch)         */
+  const void* wi1_w16;    /* ...wi_1.weight [l][d_ff, d_model]                                                       */
+  const void* wo_w16;     /* ...wo.weight [l][d_model, d_ff]                                                         */
+  const float* ln1_w;     /* block.l.layer.1.layer_norm.weight [l][d_model]                                          */
+  const float* final_w;   /* final_layer_norm.weight [d_model]                                                       */
+} B200T5Weights;
+
+B200_API size_t b200_t5_workspace_bytes(const B200T5Shape* shape, int batch);
+/* ids [batch, 128] int64 (sequences padded to 128 tokens; any valid id in the padding), key_bias [batch, 128] fp32 =
+ * 0 for kept tokens, a large negative number for masked ones (the extended attention mask), pos_bias [heads, 128, 128]
+ * fp32 = relative_attention_bias[bucket(j - i)][h] (evaluated by the caller once per model: it depends only on the
+ * weights).  out [batch, 128, d_model] fp32 = last_hidden_state (rows of padding tokens are computed but meaningless). */
+B200_API int b200_t5_encode(const B200T5Shape* shape, const B200T5Weights* w, const int64_t* ids, const float* key_bias,
+                            const float* pos_bias, int batch, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Decoded frames -> uint8 video, fused with the channels-last permute: video [n, c, h, w] in `dtype`
+ * (0 fp32, 1 fp16, 2 bf16) -> out [n, h, w, c] uint8 (device).  mode 0 = sample/pipeline_latte.py:775,796
+ * `((v / 2.0 + 0.5).clamp(0, 1) * 255).to(uint8)`; mode 1 = sample/sample.py:122, sample_ddp.py:172
+ * `((v * 0.5 + 0.5) * 255).add_(0.5).clamp_(0, 255).to(uint8)`.  Every intermediate is rounded to `dtype` as torch does,
+ * so the bytes are identical to the reference expression on the same tensor.                                          */
+B200_API int b200_frames_to_uint8(const void* video, int dtype, int n, int c, int h, int w, int mode, uint8_t* out, void* stream);
 
 /* ---- AutoencoderKL.decode (diffusers 0.24.0 SD-VAE decoder; reference call sites sample/sample.py:114,
  * sample_ddp.py:167, pipeline_latte.py:758,771).  Parity UNPINNED (diffusers absent offline).

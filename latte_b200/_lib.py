@@ -14,7 +14,7 @@ ABI_VERSION = 2
 GEMM_SK_FLAGS = 1024   # B200_GEMM_SK_FLAGS: u64 words of the stream-K flag buffer
 OK = 0
 FP16, BF16 = 0, 1
-EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL = 0, 1, 2
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_BIAS_ADD16, EPI_BIAS_MUL16 = 0, 1, 2, 3, 4
 ERR_NAMES = {-1: "SHAPE", -2: "DTYPE", -3: "ALIGN", -4: "ARCH", -5: "WORKSPACE", -6: "CUDA", -7: "UNSUPPORTED"}
 
 
@@ -51,6 +51,17 @@ T2V_WEIGHT_FIELDS = (
 
 class T2VWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in T2V_WEIGHT_FIELDS]
+
+
+class T5Shape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("layers", "d_model", "heads", "d_ff", "vocab", "dtype")] + [("eps", C.c_float)]
+
+
+T5_WEIGHT_FIELDS = ("embed16", "qkv_w16", "o_w16", "ln0_w", "wi0_w16", "wi1_w16", "wo_w16", "ln1_w", "final_w")
+
+
+class T5Weights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in T5_WEIGHT_FIELDS]
 
 
 class VaeResnet(C.Structure):
@@ -104,6 +115,10 @@ EXPORTS = {
                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200_cross_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b200_frames_to_uint8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b200_t5_workspace_bytes": (C.c_size_t, [C.POINTER(T5Shape), C.c_int]),
+    "b200_t5_encode": (C.c_int, [C.POINTER(T5Shape), C.POINTER(T5Weights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDecoder), C.c_int, C.c_int, C.c_int]),
     "b200_vae_decode": (C.c_int, [C.POINTER(VaeDecoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),

@@ -405,10 +405,113 @@ int output_head(const float* x, uint16_t* h, float* head, const float* shift, co
   return B200_OK;
 }
 
+// ====================================================================================================== T5 encoder
+struct T5Workspace {
+  float* x; uint16_t* h; uint16_t* qkv; uint16_t* att; uint16_t* g0; uint16_t* g; float* ones; unsigned long long* sk_flags;
+  size_t bytes;
+};
+
+int t5_shape_ok(const B200T5Shape* s, int batch) {
+  B200_REQUIRE(s != nullptr && batch > 0, B200_ERR_SHAPE, "t5: bad shape/batch");
+  B200_REQUIRE(s->layers > 0 && s->heads > 0 && s->vocab > 0, B200_ERR_SHAPE, "t5: layers/heads/vocab must be positive");
+  B200_REQUIRE(s->d_model % 64 == 0 && s->d_ff % 64 == 0, B200_ERR_UNSUPPORTED, "t5: d_model %d and d_ff %d must be multiples of 64", s->d_model, s->d_ff);
+  B200_REQUIRE(s->dtype == B200_FP16 || s->dtype == B200_BF16, B200_ERR_DTYPE, "t5: dtype %d unknown", s->dtype);
+  return B200_OK;
+}
+
+void t5_carve(const B200T5Shape* s, int batch, void* base, T5Workspace* ws) {
+  const size_t R = static_cast<size_t>(batch) * 128, D = s->d_model, I = static_cast<size_t>(s->heads) * 64, FF = s->d_ff;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  ws->x = static_cast<float*>(take(R * D * 4));
+  ws->h = static_cast<uint16_t*>(take(R * D * 2));
+  ws->qkv = static_cast<uint16_t*>(take(R * 3 * I * 2));
+  ws->att = static_cast<uint16_t*>(take(R * I * 2));
+  ws->g0 = static_cast<uint16_t*>(take(R * FF * 2));
+  ws->g = static_cast<uint16_t*>(take(R * FF * 2));
+  ws->ones = static_cast<float*>(take(D * 4));
+  ws->sk_flags = static_cast<unsigned long long*>(take(static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8));
+  ws->bytes = off;
+}
+
+// T5Stack.forward (encoder): embed -> [T5LayerSelfAttention, T5LayerFF] x layers -> final_layer_norm (transformers
+// modeling_t5.py; reached from sample/pipeline_latte.py:214).  Sequences are padded to 128 rows, so one attention tile is one
+// (sample, head); masked / padding keys carry a large negative key_bias.
+int t5_encode(const B200T5Shape* s, const B200T5Weights* w, const int64_t* ids, const float* key_bias, const float* pos_bias,
+              int batch, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  B200_TRY(t5_shape_ok(s, batch));
+  B200_REQUIRE(w && ids && pos_bias && out && workspace, B200_ERR_SHAPE, "t5: NULL argument");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, B200_ERR_ALIGN, "t5: workspace must be 1024-byte aligned");
+  B200_TRY(check_arch());
+  T5Workspace ws;
+  t5_carve(s, batch, workspace, &ws);
+  B200_REQUIRE(ws.bytes <= workspace_bytes, B200_ERR_WORKSPACE, "t5: workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+  const int R = batch * 128, D = s->d_model, H = s->heads, I = H * 64, FF = s->d_ff;
+  const int bf16 = s->dtype == B200_BF16;
+  B200_CHECK_CUDA(cudaMemsetAsync(ws.sk_flags, 0, static_cast<size_t>(B200_GEMM_SK_FLAGS) * 8, stream));
+  B200_TRY(launch_fill(ws.ones, 1.0f, D, stream));
+  B200_TRY(launch_embed(reinterpret_cast<const long long*>(ids), w->embed16, ws.x, R, D, s->vocab, bf16, stream));
+  auto linear16 = [&](const void* A, const void* W, int M, int N, int K, int epi, void* o16, const void* other) {
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = nullptr; a.M = M; a.N = N; a.K = K; a.bf16 = bf16; a.epilogue = epi; a.out16 = o16; a.add16 = other;
+    return launch_gemm(a, stream);
+  };
+  auto linear_resid = [&](const void* A, const void* W, int K) {
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = nullptr; a.M = R; a.N = D; a.K = K; a.bf16 = bf16; a.epilogue = B200_EPI_GATE_RESIDUAL;
+    a.resid = ws.x; a.gate = ws.ones; a.gate_batch_stride = 0; a.rows_per_batch = R; a.sk_flags = ws.sk_flags;
+    return launch_gemm(a, stream);
+  };
+  for (int l = 0; l < s->layers; ++l) {
+    const uint16_t* qkv_w = static_cast<const uint16_t*>(w->qkv_w16) + static_cast<size_t>(l) * 3 * I * D;
+    const uint16_t* o_w = static_cast<const uint16_t*>(w->o_w16) + static_cast<size_t>(l) * D * I;
+    const uint16_t* wi0 = static_cast<const uint16_t*>(w->wi0_w16) + static_cast<size_t>(l) * FF * D;
+    const uint16_t* wi1 = static_cast<const uint16_t*>(w->wi1_w16) + static_cast<size_t>(l) * FF * D;
+    const uint16_t* wo = static_cast<const uint16_t*>(w->wo_w16) + static_cast<size_t>(l) * D * FF;
+    // ---- T5LayerSelfAttention: x += o(attention(q, k, v of T5LayerNorm(x)) with position bias + mask, NO 1/sqrt(d) scale)
+    B200_TRY(launch_rms_norm(ws.x, w->ln0_w + static_cast<size_t>(l) * D, ws.h, nullptr, R, D, s->eps, bf16, stream));
+    B200_TRY(linear16(ws.h, qkv_w, R, 3 * I, D, B200_EPI_BIAS, ws.qkv, nullptr));
+    CrossAttnArgs ca{};
+    ca.q = ws.qkv; ca.kv = ws.qkv + I; ca.out = ws.att; ca.batch = batch; ca.q_rows_per_batch = 128; ca.kv_len = 128;
+    ca.kv_batch_rows = 128; ca.q_row_stride = 3 * I; ca.kv_row_stride = 3 * I; ca.heads = H; ca.head_dim = 64; ca.bf16 = bf16;
+    ca.key_bias = key_bias; ca.pos_bias = pos_bias; ca.scale = 1.0f;
+    B200_TRY(launch_cross_attention(ca, stream));
+    B200_TRY(linear_resid(ws.att, o_w, I));
+    // ---- T5LayerFF (gated-gelu): x += wo(gelu_new(wi_0 h) * wi_1 h), h = T5LayerNorm(x)
+    B200_TRY(launch_rms_norm(ws.x, w->ln1_w + static_cast<size_t>(l) * D, ws.h, nullptr, R, D, s->eps, bf16, stream));
+    B200_TRY(linear16(ws.h, wi0, R, FF, D, B200_EPI_BIAS_GELU, ws.g0, nullptr));
+    B200_TRY(linear16(ws.h, wi1, R, FF, D, B200_EPI_BIAS_MUL16, ws.g, ws.g0));
+    B200_TRY(linear_resid(ws.g, wo, FF));
+  }
+  B200_TRY(launch_rms_norm(ws.x, w->final_w, nullptr, out, R, D, s->eps, bf16, stream));
+  return B200_OK;
+}
+
 }  // namespace
 }  // namespace b200
 
 extern "C" {
+
+B200_API int b200_frames_to_uint8(const void* video, int dtype, int n, int c, int h, int w, int mode, uint8_t* out, void* stream) {
+  B200_TRY(b200::check_arch());
+  return b200::launch_frames_to_uint8(video, dtype, n, c, h, w, mode, out, static_cast<cudaStream_t>(stream));
+}
+
+B200_API size_t b200_t5_workspace_bytes(const B200T5Shape* shape, int batch) {
+  if (b200::t5_shape_ok(shape, batch) != B200_OK) return 0;
+  b200::T5Workspace ws;
+  b200::t5_carve(shape, batch, nullptr, &ws);
+  return ws.bytes;
+}
+
+B200_API int b200_t5_encode(const B200T5Shape* shape, const B200T5Weights* w, const int64_t* ids, const float* key_bias,
+                            const float* pos_bias, int batch, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::t5_encode(shape, w, ids, key_bias, pos_bias, batch, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
 
 B200_API int b200_sampler_step(const B200SamplerTables* tables, int method, int clip_denoised, const int64_t* t,
                                const float* x, const void* model_out, int model_out_dtype, const float* noise, int batch,

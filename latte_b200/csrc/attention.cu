@@ -49,6 +49,8 @@ struct AttnDev {
   int dbg;          // B200_ATTN_DBG bits: 1 no TMA*, 2 no softmax math*, 4 no output stores*, 8 no MMA* (* v2 only, wrong results);
                     // v3: 4 no output stores*, 16 all exponentials on the MUFU pipe, 512 contiguous instead of strided work items
   const float* key_bias;  // CROSS: additive bias on the scores, fp32 [batch][128] (natural-log units, e.g. 0 / -10000), or nullptr
+  const float* pos_bias;  // CROSS (v3 only): additive bias fp32 [heads][128][128] per (head, query row, key), or nullptr
+  int kv_valid;           // CROSS: number of valid keys per sample (<= kv_rows_per_batch)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -260,7 +262,7 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     const int nchunks = Lk / 32;
-    const int rkey = MODE == MODE_CROSS ? p.kv_rows_per_batch : row_key<MODE>(r, p.gshift);
+    const int rkey = MODE == MODE_CROSS ? p.kv_valid : row_key<MODE>(r, p.gshift);
     const uint32_t t_row = tmem_base + wg * 256 + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t_o = t_row + (Lk >> 1);
     int i = wg;
@@ -702,11 +704,13 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int u = i / NSLOT;
       float sum = 0.f;
       bool have_bias = false;
+      const float* prow = nullptr;          // T5: this (head, query row)'s 128 relative-position biases
       if constexpr (MODE == MODE_CROSS) {
-        have_bias = p.key_bias != nullptr;
+        have_bias = p.key_bias != nullptr || p.pos_bias != nullptr;
         if (have_bias) {        // this sample's additive key bias (natural-log units) -> smem, once per tile
           const Coord c = coord(i);
-          bias_s[r] = __ldg(p.key_bias + static_cast<size_t>(c.c3) * 128 + r) * 1.4426950408889634f;
+          bias_s[r] = p.key_bias ? __ldg(p.key_bias + static_cast<size_t>(c.c3) * 128 + r) * 1.4426950408889634f : 0.f;
+          if (p.pos_bias) prow = p.pos_bias + (static_cast<size_t>(c.head) * 128 + r) * 128;
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
       }
@@ -753,7 +757,7 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       } else {
         // ---- two passes over my 128 key columns: row maximum, then P = exp2(s * scale (+ bias) - max)
-        const int rkey = MODE == MODE_CROSS ? p.kv_rows_per_batch : row_key<MODE>(r, p.gshift);
+        const int rkey = MODE == MODE_CROSS ? p.kv_valid : row_key<MODE>(r, p.gshift);
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 4; c += 2) {
@@ -768,6 +772,10 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               if (have_bias) {
                 a = fmaf(a, p.scale_log2, bias_s[c * 32 + j]);
                 b = fmaf(b, p.scale_log2, bias_s[(c + 1) * 32 + j]);
+                if (prow) {
+                  a = fmaf(__ldg(prow + c * 32 + j), 1.4426950408889634f, a);
+                  b = fmaf(__ldg(prow + (c + 1) * 32 + j), 1.4426950408889634f, b);
+                }
               }
             }
             if (key_valid<MODE>(rkey, c * 32 + j, p.gshift)) mx = fmaxf(mx, a);
@@ -789,8 +797,12 @@ attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           float x[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (MODE == MODE_CROSS && have_bias) x[j] = fmaf(__uint_as_float(v[j]), p.scale_log2, bias_s[c * 16 + j]) - ms;
-            else x[j] = fmaf(__uint_as_float(v[j]), p.scale_log2, -ms);
+            if (MODE == MODE_CROSS && have_bias) {
+              x[j] = fmaf(__uint_as_float(v[j]), p.scale_log2, bias_s[c * 16 + j]) - ms;
+              if (prow) x[j] = fmaf(__ldg(prow + c * 16 + j), 1.4426950408889634f, x[j]);
+            } else {
+              x[j] = fmaf(__uint_as_float(v[j]), p.scale_log2, -ms);
+            }
           }
           float e[16];
 #pragma unroll
@@ -1585,6 +1597,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   static const int dbg = env_int("B200_ATTN_DBG", 0);
   p.dbg = dbg;
   p.key_bias = nullptr;
+  p.pos_bias = nullptr;
+  p.kv_valid = 0;
 
   p.group = 1;
   p.gshift = 0;
@@ -1719,13 +1733,19 @@ int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream) {
   B200_TRY(check_arch());
   const int H = a.heads, hd = a.head_dim, D = H * hd;
   const long long T = static_cast<long long>(a.batch) * a.q_rows_per_batch;
-  const long long R = static_cast<long long>(a.batch) * a.kv_len;
+  const long long R = static_cast<long long>(a.batch) * (a.kv_batch_rows > 0 ? a.kv_batch_rows : a.kv_len);
   const bool tail = hd > 64;
   AttnDev p{};
   p.out = a.out; p.T = static_cast<int>(T); p.D = D; p.heads = H; p.hd = hd;
   p.tokens = a.q_rows_per_batch; p.frames = 1; p.group = 1; p.gshift = 0; p.Lk = 128; p.tiles_per_seq = 1;
-  p.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
-  p.k_head0 = 0; p.v_head0 = H; p.kv_rows_per_batch = a.kv_len; p.q_rows_per_batch = a.q_rows_per_batch;
+  p.scale_log2 = (a.scale > 0.f ? a.scale : 1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
+  p.k_head0 = 0; p.v_head0 = H; p.q_rows_per_batch = a.q_rows_per_batch;
+  p.kv_rows_per_batch = a.kv_batch_rows > 0 ? a.kv_batch_rows : a.kv_len;
+  p.kv_valid = a.kv_len;
+  B200_REQUIRE(p.kv_rows_per_batch >= a.kv_len, B200_ERR_SHAPE, "cross attention: kv_batch_rows %d < kv_len %d", a.kv_batch_rows, a.kv_len);
+  B200_REQUIRE(!a.pos_bias || (a.q_rows_per_batch == 128 && (reinterpret_cast<uintptr_t>(a.pos_bias) & 15) == 0), B200_ERR_UNSUPPORTED,
+               "cross attention: pos_bias needs 128 query rows per sample (one tile) and 16-byte alignment");
+  p.pos_bias = a.pos_bias;
   static const int dbg = env_int("B200_ATTN_DBG", 0);
   p.dbg = dbg;
   B200_REQUIRE(!a.key_bias || (reinterpret_cast<uintptr_t>(a.key_bias) & 15) == 0, B200_ERR_ALIGN, "cross attention: key_bias must be 16-byte aligned");
@@ -1753,6 +1773,10 @@ int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream) {
     B200_TRY(make_tmap_16bit(&maps[4], a.out, 3, odims, ostr, obox, TMAP_SW_NONE));
   }
   const dim3 grid(static_cast<unsigned>(T / 128), H);
+  if (a.pos_bias) {   // the per-(head, row, key) bias exists in the v3 kernel only
+    if (a.bf16) return tail ? launch_v3<true, true, MODE_CROSS>(maps, p, grid, stream) : launch_v3<true, false, MODE_CROSS>(maps, p, grid, stream);
+    return tail ? launch_v3<false, true, MODE_CROSS>(maps, p, grid, stream) : launch_v3<false, false, MODE_CROSS>(maps, p, grid, stream);
+  }
   if (a.bf16) return tail ? launch_tail<true, true>(MODE_CROSS, maps, p, grid, stream) : launch_tail<true, false>(MODE_CROSS, maps, p, grid, stream);
   return tail ? launch_tail<false, true>(MODE_CROSS, maps, p, grid, stream) : launch_tail<false, false>(MODE_CROSS, maps, p, grid, stream);
 }

@@ -129,6 +129,10 @@ struct CrossAttnArgs {
   int bf16;
   const float* key_bias;  // optional [batch][128] fp32 additive score bias per key (encoder_attention_mask -> (1-m)*-10000,
                           // latte_t2v.py:766-771); entries >= kv_len are ignored
+  const float* pos_bias;  // optional [heads][128][128] fp32 additive score bias per (head, query row, key) -- T5's relative
+                          // position bias; needs q_rows_per_batch == 128 (one tile per sample)
+  float scale;            // score scale; 0 = head_dim^-0.5 (T5 attention is unscaled: 1.0)
+  int kv_batch_rows;      // rows of the K/V buffer per sample; 0 = kv_len (T5: sequences padded to 128 rows, kv_len valid)
 };
 int launch_cross_attention(const CrossAttnArgs& a, cudaStream_t stream);
 int set_attention_impl(int impl);
@@ -149,6 +153,10 @@ int launch_timestep_freq(const long long* t, float* out, int batch, cudaStream_t
 int launch_final_layer(const float* x, const float* shift, const float* scale, long long mod_batch_stride,
                        const float* w, const float* b, float* out, int batch, int frames, int grid, int patch,
                        int out_ch, int dim, int channels_first, cudaStream_t stream);
+int launch_rms_norm(const float* x, const float* w, void* out16, float* out32, int rows, int dim, float eps, int bf16,
+                    cudaStream_t stream);
+int launch_embed(const long long* ids, const void* table16, float* x, int rows, int dim, int vocab, int bf16, cudaStream_t stream);
+int launch_frames_to_uint8(const void* video, int dtype, int n, int c, int h, int w, int mode, uint8_t* out, cudaStream_t stream);
 int launch_unpatchify(const float* y, float* out, int batch, int frames, int grid, int patch, int out_ch, int channels_first,
                       cudaStream_t stream);
 int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, int out_ch, int guided_ch, int hw,

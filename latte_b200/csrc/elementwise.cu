@@ -141,11 +141,13 @@ int ln_dispatch(int nvmax, cudaStream_t stream, const float* x, const float* shi
 // ---------------------------------------------------------------------------------- patch_embed
 constexpr int PE_TOK = 16;
 
-// K = C*p*p is a template parameter (16 for the 4-channel, patch-2 latents every Latte config uses) so the per-d weight
-// row lives in K registers; a block computes PE_TOK tokens x all D outputs; the write of the fp32 residual stream
-// (the only real traffic: T*D*4 bytes) is coalesced over d.
+// K = C*p*p is a template parameter (16 for the 4-channel, patch-2 latents every Latte config uses).  A thread owns FOUR
+// consecutive output channels: their 4 x K weights live in registers, and for each of the block's PE_TOK tokens it does
+// 4 x K FMAs, one 16-byte read of pos_embed and ONE 16-byte store of the fp32 residual stream (the only real traffic:
+// T*D*4 bytes).  Round 1 stored 4 bytes per thread per token: 42 us for 37.7 MB; this form issues a quarter of the
+// load/store instructions.
 template <int K>
-__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ x, int x_batch_mod,
+__global__ void __launch_bounds__(320) patch_embed_kernel(const float* __restrict__ x, int x_batch_mod,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ pos, float* __restrict__ out,
                                                           int total_tokens, int frames, int chans, int size, int patch,
@@ -170,22 +172,29 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
     in[tl][k] = val;
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
-    float wk[K];
+  const int nv = dim >> 2;
+  for (int d4 = threadIdx.x; d4 < nv; d4 += blockDim.x) {
+    float wk[4][K];
 #pragma unroll
-    for (int k = 0; k < K; k += 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(d) * K + k));
-      wk[k] = t.x; wk[k + 1] = t.y; wk[k + 2] = t.z; wk[k + 3] = t.w;
-    }
-    const float bd = __ldg(bias + d);
-#pragma unroll 4
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int k = 0; k < K; k += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(d4 * 4 + r) * K + k));
+        wk[r][k] = t.x; wk[r][k + 1] = t.y; wk[r][k + 2] = t.z; wk[r][k + 3] = t.w;
+      }
+    const float4 bd = __ldg(reinterpret_cast<const float4*>(bias) + d4);
+#pragma unroll 2
     for (int tl = 0; tl < PE_TOK; ++tl) {
       const int tok = tok0 + tl;
       if (tok >= total_tokens) break;
-      float acc = bd;
+      const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(tok % N) * dim) + d4);
+      float a0 = bd.x, a1 = bd.y, a2 = bd.z, a3 = bd.w;
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc = fmaf(in[tl][k], wk[k], acc);
-      out[static_cast<size_t>(tok) * dim + d] = acc + __ldg(pos + static_cast<size_t>(tok % N) * dim + d);
+      for (int k = 0; k < K; ++k) {
+        const float v = in[tl][k];
+        a0 = fmaf(v, wk[0][k], a0); a1 = fmaf(v, wk[1][k], a1); a2 = fmaf(v, wk[2][k], a2); a3 = fmaf(v, wk[3][k], a3);
+      }
+      reinterpret_cast<float4*>(out + static_cast<size_t>(tok) * dim)[d4] = make_float4(a0 + pe.x, a1 + pe.y, a2 + pe.z, a3 + pe.w);
     }
   }
 }
@@ -367,6 +376,93 @@ __global__ void __launch_bounds__(512) final_layer_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------- T5 encoder pieces
+// T5LayerNorm (transformers modeling_t5.py): y = x * rsqrt(mean(x^2) + eps) * weight -- no mean subtraction, no bias;
+// the variance is taken in fp32.  One warp per row; out16 (GEMM operand) or out32 (the encoder's final_layer_norm).
+template <bool BF16>
+__global__ void __launch_bounds__(256) rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       uint16_t* __restrict__ out16, float* __restrict__ out32, int rows,
+                                                       int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
+  const int nv = dim >> 2;
+  float q = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = xr[i];
+    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  const float r = rsqrtf(warp_sum(q) / static_cast<float>(dim) + eps);
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = xr[i];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + i);
+    const float y0 = v.x * r * g.x, y1 = v.y * r * g.y, y2 = v.z * r * g.z, y3 = v.w * r * g.w;
+    if (out32) reinterpret_cast<float4*>(out32 + static_cast<size_t>(row) * dim)[i] = make_float4(y0, y1, y2, y3);
+    else reinterpret_cast<uint2*>(out16 + static_cast<size_t>(row) * dim)[i] = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
+  }
+}
+
+// x[r, :] = table[ids[r], :]  (nn.Embedding lookup of the token ids; 16-bit table -> fp32 residual stream)
+template <bool BF16>
+__global__ void __launch_bounds__(256) embed_kernel(const long long* __restrict__ ids, const uint16_t* __restrict__ table,
+                                                    float* __restrict__ x, int rows, int dim, int vocab) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const long long id = ids[row];
+  if (id < 0 || id >= vocab) {
+    if (threadIdx.x == 0) printf("latte_b200: token id %lld out of range [0, %d)\n", id, vocab);
+    __trap();
+  }
+  const uint2* src = reinterpret_cast<const uint2*>(table + static_cast<size_t>(id) * dim);
+  float4* dst = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * dim);
+  for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
+    const uint2 v = __ldg(src + i);
+    const float2 a = unpack2<BF16>(v.x), b = unpack2<BF16>(v.y);
+    dst[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+// ---------------------------------------------------------------------------------- decoded frames -> uint8
+// The two post-processing expressions of the reference, each with ITS rounding, fused with the NCHW -> NHWC permute:
+//   mode 0  pipeline_latte.py:775,796   ((v / 2.0 + 0.5).clamp(0, 1) * 255).to(uint8)           (truncation)
+//   mode 1  sample.py:122, sample_ddp.py:172   ((v * 0.5 + 0.5) * 255).add_(0.5).clamp_(0, 255).to(uint8)
+// torch evaluates every operator in the tensor's own dtype, so for 16-bit inputs each intermediate is rounded to that
+// type (`rnd`) -- the result is bit-identical to the reference expression on the same tensor.
+template <int DT>   // 0 fp32, 1 fp16, 2 bf16
+__device__ __forceinline__ float rnd(float v) {
+  if constexpr (DT == 1) return __half2float(__float2half_rn(v));
+  if constexpr (DT == 2) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+template <int DT>
+__global__ void __launch_bounds__(256) frames_to_uint8_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, long long total,
+                                                              int c, int hw, int mode) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // i enumerates the OUTPUT [n][h*w][c]; the input is [n][c][h*w]
+    const int ch = static_cast<int>(i % c);
+    const long long pix = (i / c) % hw;
+    const long long img = i / (static_cast<long long>(c) * hw);
+    const long long src = (img * c + ch) * hw + pix;
+    float v;
+    if constexpr (DT == 0) v = static_cast<const float*>(in)[src];
+    else if constexpr (DT == 1) v = __half2float(static_cast<const __half*>(in)[src]);
+    else v = __bfloat162float(static_cast<const __nv_bfloat16*>(in)[src]);
+    float r;
+    if (mode == 0) {
+      r = rnd<DT>(rnd<DT>(v / 2.0f) + 0.5f);
+      r = fminf(fmaxf(r, 0.f), 1.f);
+      r = rnd<DT>(r * 255.f);
+    } else {
+      r = rnd<DT>(rnd<DT>(rnd<DT>(v * 0.5f) + 0.5f) * 255.f);
+      r = rnd<DT>(r + 0.5f);
+      r = fminf(fmaxf(r, 0.f), 255.f);
+    }
+    out[i] = static_cast<uint8_t>(static_cast<int>(r));     // float -> uint8 conversion truncates toward zero, like torch
+  }
+}
+
 // ---------------------------------------------------------------------------------- unpatchify
 // y [T, n_out] fp32 (token-major output of the head GEMM, n_out = p*p*out_ch ordered (pi, qi, c)) -> the reference's
 // layout out[b][f][c][gh*p + pi][gw*p + qi] (latte.py:297-310) or [b][c][f][..] (LatteT2V).  One thread per output
@@ -508,7 +604,7 @@ int launch_patch_embed(const float* x, int x_batch_mod, const float* w, const fl
   const long long sb = plane * chans * frames;
   const long long sf = channels_first ? plane : plane * chans;
   const long long sc = channels_first ? plane * frames : plane;
-#define B200_PE(KK) patch_embed_kernel<KK><<<blocks, 256, 0, stream>>>(x, x_batch_mod, w, b, pos, out, total, frames, chans, size, patch, dim, sb, sf, sc)
+#define B200_PE(KK) patch_embed_kernel<KK><<<blocks, 320, 0, stream>>>(x, x_batch_mod, w, b, pos, out, total, frames, chans, size, patch, dim, sb, sf, sc)
   switch (K) {
     case 4: B200_PE(4); break;
     case 8: B200_PE(8); break;
@@ -577,6 +673,38 @@ int launch_final_layer(const float* x, const float* shift, const float* scale, l
   const long long sc = channels_first ? plane * frames : plane;
   final_layer_kernel<<<blocks, warps * 32, smem, stream>>>(x, shift, scale, mod_batch_stride, w, b, out, total, frames,
                                                             grid, patch, out_ch, dim, sb, sf, sc);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_rms_norm(const float* x, const float* w, void* out16, float* out32, int rows, int dim, float eps, int bf16,
+                    cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim % 4 == 0, B200_ERR_SHAPE, "rms_norm: dim %d must be a multiple of 4", dim);
+  B200_REQUIRE((out16 != nullptr) != (out32 != nullptr), B200_ERR_SHAPE, "rms_norm: exactly one of out16 / out32");
+  const int blocks = (rows + 7) / 8;
+  if (bf16) rms_norm_kernel<true><<<blocks, 256, 0, stream>>>(x, w, static_cast<uint16_t*>(out16), out32, rows, dim, eps);
+  else rms_norm_kernel<false><<<blocks, 256, 0, stream>>>(x, w, static_cast<uint16_t*>(out16), out32, rows, dim, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_embed(const long long* ids, const void* table16, float* x, int rows, int dim, int vocab, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim % 4 == 0, B200_ERR_SHAPE, "embed: dim %d must be a multiple of 4", dim);
+  if (bf16) embed_kernel<true><<<rows, 256, 0, stream>>>(ids, static_cast<const uint16_t*>(table16), x, rows, dim, vocab);
+  else embed_kernel<false><<<rows, 256, 0, stream>>>(ids, static_cast<const uint16_t*>(table16), x, rows, dim, vocab);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_frames_to_uint8(const void* video, int dtype, int n, int c, int h, int w, int mode, uint8_t* out, cudaStream_t stream) {
+  B200_REQUIRE(video && out && n > 0 && c > 0 && h > 0 && w > 0, B200_ERR_SHAPE, "frames_to_uint8: bad arguments");
+  B200_REQUIRE(dtype >= 0 && dtype <= 2 && (mode == 0 || mode == 1), B200_ERR_UNSUPPORTED, "frames_to_uint8: dtype %d / mode %d", dtype, mode);
+  const long long total = static_cast<long long>(n) * c * h * w;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == 0) frames_to_uint8_kernel<0><<<blocks, 256, 0, stream>>>(video, out, total, c, h * w, mode);
+  else if (dtype == 1) frames_to_uint8_kernel<1><<<blocks, 256, 0, stream>>>(video, out, total, c, h * w, mode);
+  else frames_to_uint8_kernel<2><<<blocks, 256, 0, stream>>>(video, out, total, c, h * w, mode);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

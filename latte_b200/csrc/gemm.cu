@@ -477,6 +477,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int row = m0 + rl;
               if (row < p.M) {
                 uint4 val = *reinterpret_cast<const uint4*>(buf + rl * 128 + ((ch_b ^ (rl & 7)) << 4));
+                if constexpr (EPI == B200_EPI_BIAS_MUL16) {   // gated feed-forward: (h wi_1^T) * gelu(h wi_0^T), the second factor read back in 16 bits
+                  const uint4 rs = __ldg(reinterpret_cast<const uint4*>(p.add16 + static_cast<size_t>(row) * p.N + col));
+                  const float2 a0 = unpack2<BF16>(val.x), a1 = unpack2<BF16>(val.y), a2 = unpack2<BF16>(val.z), a3 = unpack2<BF16>(val.w);
+                  const float2 r0 = unpack2<BF16>(rs.x), r1 = unpack2<BF16>(rs.y), r2 = unpack2<BF16>(rs.z), r3 = unpack2<BF16>(rs.w);
+                  val.x = pack2<BF16>(a0.x * r0.x, a0.y * r0.y);
+                  val.y = pack2<BF16>(a1.x * r1.x, a1.y * r1.y);
+                  val.z = pack2<BF16>(a2.x * r2.x, a2.y * r2.y);
+                  val.w = pack2<BF16>(a3.x * r3.x, a3.y * r3.y);
+                }
                 if constexpr (EPI == B200_EPI_BIAS_ADD16) {   // + shortcut, both already rounded to 16 bits like the reference
                   const uint4 rs = __ldg(reinterpret_cast<const uint4*>(p.add16 + static_cast<size_t>(row) * p.N + col));
                   const float2 a0 = unpack2<BF16>(val.x), a1 = unpack2<BF16>(val.y), a2 = unpack2<BF16>(val.z), a3 = unpack2<BF16>(val.w);
@@ -525,6 +534,7 @@ int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     case B200_EPI_BIAS_GELU: return launch_one<BN, B200_EPI_BIAS_GELU, BF16>(tmA, tmB, tmX, p, grid, s);
     case B200_EPI_GATE_RESIDUAL: return launch_one<BN, B200_EPI_GATE_RESIDUAL, BF16>(tmA, tmB, tmX, p, grid, s);
     case B200_EPI_BIAS_ADD16: return launch_one<BN, B200_EPI_BIAS_ADD16, BF16>(tmA, tmB, tmX, p, grid, s);
+    case B200_EPI_BIAS_MUL16: return launch_one<BN, B200_EPI_BIAS_MUL16, BF16>(tmA, tmB, tmX, p, grid, s);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return B200_ERR_UNSUPPORTED;
@@ -608,9 +618,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   B200_REQUIRE(a.K % BK == 0, B200_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", a.K, BK);
   B200_REQUIRE(a.N % 32 == 0, B200_ERR_SHAPE, "gemm: N=%d must be a multiple of 32", a.N);
   B200_REQUIRE(a.epilogue == B200_EPI_BIAS || a.epilogue == B200_EPI_BIAS_GELU || a.epilogue == B200_EPI_GATE_RESIDUAL ||
-                   a.epilogue == B200_EPI_BIAS_ADD16,
+                   a.epilogue == B200_EPI_BIAS_ADD16 || a.epilogue == B200_EPI_BIAS_MUL16,
                B200_ERR_UNSUPPORTED, "gemm: unknown epilogue %d", a.epilogue);
-  B200_REQUIRE(a.epilogue != B200_EPI_BIAS_ADD16 || (a.add16 && (reinterpret_cast<uintptr_t>(a.add16) & 15) == 0), B200_ERR_ALIGN,
+  B200_REQUIRE((a.epilogue != B200_EPI_BIAS_ADD16 && a.epilogue != B200_EPI_BIAS_MUL16) || (a.add16 && (reinterpret_cast<uintptr_t>(a.add16) & 15) == 0), B200_ERR_ALIGN,
                "gemm: add16 tensor missing or unaligned");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
                B200_ERR_ALIGN, "gemm: A and W must be 16-byte aligned");

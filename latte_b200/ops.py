@@ -112,3 +112,20 @@ def cross_attention(q: torch.Tensor, kv: torch.Tensor, batch: int, q_rows_per_ba
                                               q.shape[1], kv.shape[1], heads, D // heads, _dt(q), _stream(q))
     _lib.check(rc, "b200_cross_attention")
     return out
+
+
+_U8_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def frames_to_uint8(video: torch.Tensor, mode: str = "pipeline") -> torch.Tensor:
+    """Decoded frames [n, c, h, w] in [-1, 1] -> uint8 [n, h, w, c] on the device, byte-identical to the reference expression:
+    mode "pipeline" = pipeline_latte.py:775,796 (truncating), mode "sample" = sample.py:122 / sample_ddp.py:172 (+0.5 rounding)."""
+    _need_cuda(video)
+    assert video.dim() == 4 and video.is_contiguous() and video.dtype in _U8_DT
+    n, c, h, w = video.shape
+    out = torch.empty(n, h, w, c, dtype=torch.uint8, device=video.device)
+    with torch.cuda.device(video.device):
+        rc = _lib.load().b200_frames_to_uint8(video.data_ptr(), _U8_DT[video.dtype], n, c, h, w, {"pipeline": 0, "sample": 1}[mode],
+                                              out.data_ptr(), _stream(video))
+    _lib.check(rc, "b200_frames_to_uint8")
+    return out

@@ -132,3 +132,14 @@ def test_device_caches_are_not_pickled():
     d = create_diffusion("8")
     d._dev["x"] = _lib.SamplerTables()
     assert copy.deepcopy(d)._dev == {}
+
+
+def test_mask_text_embeddings_matches_pipeline_semantics():
+    """pipeline_latte.py:118-124: one prompt is trimmed to its kept tokens, a batch is zero-masked and keeps its length."""
+    from latte_b200.t5 import mask_text_embeddings
+    emb = torch.arange(2 * 1 * 6 * 4, dtype=torch.float32).reshape(2, 1, 6, 4) + 1
+    mask = torch.tensor([[1, 1, 1, 0, 0, 0], [1, 1, 1, 1, 1, 0]])
+    one, keep = mask_text_embeddings(emb[:1], mask[:1])
+    assert keep == 3 and one.shape == (1, 1, 3, 4) and torch.equal(one, emb[:1, :, :3])
+    both, length = mask_text_embeddings(emb, mask)
+    assert length == 6 and torch.equal(both[0, 0, 3:], torch.zeros(3, 4)) and torch.equal(both[1, 0, :5], emb[1, 0, :5])
