@@ -169,7 +169,7 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
     B200_PROF(PROF_LN, launch_ln_modulate(ws.x, m + 0 * D, m + 1 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
     GemmArgs ga{};
     ga.A = ws.h; ga.W = qkv_w; ga.bias = w->qkv_b + static_cast<size_t>(i) * 3 * D;
-    ga.M = T; ga.N = 3 * D; ga.K = D; ga.bf16 = bf16; ga.epilogue = B200_EPI_BIAS; ga.out16 = ws.qkv;
+    ga.M = T; ga.N = 3 * D; ga.K = D; ga.bf16 = bf16; ga.epilogue = B200_EPI_BIAS; ga.out16 = ws.qkv; ga.w_const = 1;
     B200_PROF(PROF_GEMM, launch_gemm(ga, stream));
 
     AttnArgs aa{};
@@ -179,19 +179,19 @@ int forward(const B200LatteShape* s, const B200LatteWeights* w, const float* x, 
 
     GemmArgs gp{};
     gp.A = ws.h; gp.W = proj_w; gp.bias = w->proj_b + static_cast<size_t>(i) * D;
-    gp.M = T; gp.N = D; gp.K = D; gp.bf16 = bf16; gp.epilogue = B200_EPI_GATE_RESIDUAL; gp.resid = ws.x;
+    gp.M = T; gp.N = D; gp.K = D; gp.bf16 = bf16; gp.epilogue = B200_EPI_GATE_RESIDUAL; gp.resid = ws.x; gp.w_const = 1;
     gp.gate = m + 2 * D; gp.gate_batch_stride = mod_bs; gp.rows_per_batch = rows_per_batch; gp.sk_flags = ws.sk_flags;
     B200_PROF(PROF_GEMM, launch_gemm(gp, stream));
 
     B200_PROF(PROF_LN, launch_ln_modulate(ws.x, m + 3 * D, m + 4 * D, mod_bs, rows_per_batch, ws.h, T, D, bf16, stream));
     GemmArgs g1{};
     g1.A = ws.h; g1.W = fc1_w; g1.bias = w->fc1_b + static_cast<size_t>(i) * HID;
-    g1.M = T; g1.N = HID; g1.K = D; g1.bf16 = bf16; g1.epilogue = B200_EPI_BIAS_GELU; g1.out16 = ws.g;
+    g1.M = T; g1.N = HID; g1.K = D; g1.bf16 = bf16; g1.epilogue = B200_EPI_BIAS_GELU; g1.out16 = ws.g; g1.w_const = 1;
     B200_PROF(PROF_GEMM, launch_gemm(g1, stream));
 
     GemmArgs g2{};
     g2.A = ws.g; g2.W = fc2_w; g2.bias = w->fc2_b + static_cast<size_t>(i) * D;
-    g2.M = T; g2.N = D; g2.K = HID; g2.bf16 = bf16; g2.epilogue = B200_EPI_GATE_RESIDUAL; g2.resid = ws.x;
+    g2.M = T; g2.N = D; g2.K = HID; g2.bf16 = bf16; g2.epilogue = B200_EPI_GATE_RESIDUAL; g2.resid = ws.x; g2.w_const = 1;
     g2.gate = m + 5 * D; g2.gate_batch_stride = mod_bs; g2.rows_per_batch = rows_per_batch; g2.sk_flags = ws.sk_flags;
     if (i == 0) {  // x = x + temp_embed before the first temporal block (latte.py:357-358), folded into block 0's last epilogue
       g2.row_add = w->temp_embed; g2.row_add_div = N; g2.row_add_period = F;
@@ -317,13 +317,13 @@ int t2v_forward(const B200T2VShape* s, const B200T2VWeights* w, const float* x, 
 
   auto linear16 = [&](const void* A, const void* W, const float* bias, int M, int Nn, int K, int epi, void* o16) {
     GemmArgs a{};
-    a.A = A; a.W = W; a.bias = bias; a.M = M; a.N = Nn; a.K = K; a.bf16 = bf16; a.epilogue = epi; a.out16 = o16;
+    a.A = A; a.W = W; a.bias = bias; a.M = M; a.N = Nn; a.K = K; a.bf16 = bf16; a.epilogue = epi; a.out16 = o16; a.w_const = 1;
     return launch_gemm(a, stream);
   };
   auto linear_resid = [&](const void* A, const void* W, const float* bias, int K, const float* gate, long long gate_bs,
                           const float* row_add) {
     GemmArgs a{};
-    a.A = A; a.W = W; a.bias = bias; a.M = T; a.N = D; a.K = K; a.bf16 = bf16; a.epilogue = B200_EPI_GATE_RESIDUAL;
+    a.A = A; a.W = W; a.bias = bias; a.M = T; a.N = D; a.K = K; a.bf16 = bf16; a.epilogue = B200_EPI_GATE_RESIDUAL; a.w_const = 1;
     a.resid = ws.x; a.gate = gate; a.gate_batch_stride = gate_bs; a.rows_per_batch = rows_per_batch; a.sk_flags = ws.sk_flags;
     if (row_add) { a.row_add = row_add; a.row_add_div = N; a.row_add_period = F; }
     return launch_gemm(a, stream);
@@ -398,7 +398,7 @@ int output_head(const float* x, uint16_t* h, float* head, const float* shift, co
   B200_PROF(PROF_OTHER, launch_fill(ones, 1.0f, 32, stream));
   B200_PROF(PROF_LN, launch_ln_modulate(x, shift, scale, mod_bs, F * grid * grid, h, T, D, bf16, stream));
   GemmArgs g{};
-  g.A = h; g.W = w16; g.bias = bias; g.M = T; g.N = n_out; g.K = D; g.bf16 = bf16; g.epilogue = B200_EPI_GATE_RESIDUAL;
+  g.A = h; g.W = w16; g.bias = bias; g.M = T; g.N = n_out; g.K = D; g.bf16 = bf16; g.epilogue = B200_EPI_GATE_RESIDUAL; g.w_const = 1;
   g.resid = head; g.gate = ones; g.gate_batch_stride = 0; g.rows_per_batch = T; g.sk_flags = sk_flags;
   B200_PROF(PROF_GEMM, launch_gemm(g, stream));
   B200_PROF(PROF_OTHER, launch_unpatchify(head, out, batch, F, grid, patch, out_ch, channels_first, stream));
@@ -457,12 +457,12 @@ int t5_encode(const B200T5Shape* s, const B200T5Weights* w, const int64_t* ids, 
   B200_TRY(launch_embed(reinterpret_cast<const long long*>(ids), w->embed16, ws.x, R, D, s->vocab, bf16, stream));
   auto linear16 = [&](const void* A, const void* W, int M, int N, int K, int epi, void* o16, const void* other) {
     GemmArgs a{};
-    a.A = A; a.W = W; a.bias = nullptr; a.M = M; a.N = N; a.K = K; a.bf16 = bf16; a.epilogue = epi; a.out16 = o16; a.add16 = other;
+    a.A = A; a.W = W; a.bias = nullptr; a.M = M; a.N = N; a.K = K; a.bf16 = bf16; a.epilogue = epi; a.out16 = o16; a.add16 = other; a.w_const = 1;
     return launch_gemm(a, stream);
   };
   auto linear_resid = [&](const void* A, const void* W, int K) {
     GemmArgs a{};
-    a.A = A; a.W = W; a.bias = nullptr; a.M = R; a.N = D; a.K = K; a.bf16 = bf16; a.epilogue = B200_EPI_GATE_RESIDUAL;
+    a.A = A; a.W = W; a.bias = nullptr; a.M = R; a.N = D; a.K = K; a.bf16 = bf16; a.epilogue = B200_EPI_GATE_RESIDUAL; a.w_const = 1;
     a.resid = ws.x; a.gate = ws.ones; a.gate_batch_stride = 0; a.rows_per_batch = R; a.sk_flags = ws.sk_flags;
     return launch_gemm(a, stream);
   };

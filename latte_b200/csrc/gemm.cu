@@ -78,6 +78,7 @@ struct GemmDev {
   // implicit-GEMM convolution: see GemmArgs
   int conv_taps, conv_cblk, conv_h, conv_w, conv_bw, conv_bh;
   int conv_dx[9], conv_dy[9], conv_dz[9];
+  int w_const;  // W is a weight (not produced by a kernel of the step): its first tiles may be fetched before griddepcontrol.wait
   int streamk;  // residual epilogue only: split the last partial wave of tiles along K across all pairs (see TileSched)
   // stream-K ordering flags (caller's workspace), one per (streamed tile, CTA rank, epilogue warpgroup): "k-blocks of the
   // tile already added into x".  All zero between launches: the segment that completes a tile resets its flag, so the
@@ -208,7 +209,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();   // the next kernel may begin its prologue as SMs drain
-  pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible from here
+  // griddepcontrol.wait (the predecessor's outputs become visible) is executed by each role that touches global memory --
+  // the producer only AFTER it has put the first W tiles in flight when W is a constant weight (see below)
 
   // pair-tile schedule: cluster k owns pair-tiles k, k + #clusters, ...; a pair-tile is two M-adjacent 128-row tiles of
   // one N column; this CTA takes row-tile 2 * pair_m + rank (it may lie past M: zero-filled loads, clipped stores)
@@ -226,6 +228,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // W tiles of the first k-blocks are fetched BEFORE the grid dependency resolves when W is a weight (never written by
+      // a kernel of the step): they come from DRAM (1.35 GB of weights stream through L2 every step), the A tiles from the
+      // L2 the predecessor just filled, so this takes the longer of the two latencies off the start of every GEMM.
+      int prefetched = 0;
+      if (p.w_const && !(p.dbg & 1)) {
+        TileSched s0(my_pair, num_pairs, num_tiles, num_kb, streamk);
+        int t0, k0, k1;
+        if (s0.next(t0, k0, k1)) {
+          const int n_blk = t0 % p.num_n;
+          const int n_live = ((p.N - n_blk * BN) < BN && !(p.dbg & 64)) ? (p.N - n_blk * BN) : BN;
+          const int w_row0 = n_blk * BN + static_cast<int>(rank) * (n_live / 2);
+          prefetched = (k1 - k0) < C::STAGES ? (k1 - k0) : C::STAGES;
+          for (int i = 0; i < prefetched; ++i) {
+            const uint32_t full_leader = mapa_u32(&full[i], 0);
+            if (leader) mbar_arrive_expect_tx(&full[i], 2 * C::STAGE_BYTES);
+            else mbar_arrive_cluster(full_leader);
+            tma_load_2d_pair(smem + i * C::STAGE_BYTES + C::A_BYTES, &tmB, full_leader, (k0 + i) * BK, w_row0);
+          }
+        }
+      }
+      pdl_wait();
       TileSched sched(my_pair, num_pairs, num_tiles, num_kb, streamk);
       int tile, kb0, kb1;
       while (sched.next(tile, kb0, kb1)) {
@@ -235,15 +258,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n_live = ((p.N - n_blk * BN) < BN && !(p.dbg & 64)) ? (p.N - n_blk * BN) : BN;
         const int w_row0 = n_blk * BN + static_cast<int>(rank) * (n_live / 2);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          const bool w_in_flight = prefetched > 0;     // this stage's expect_tx / arrival and W load were issued above
+          if (w_in_flight) --prefetched;
+          else mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           const uint32_t full_leader = mapa_u32(&full[stage], 0);
           if (p.dbg & 1) {
             if (leader) mbar_arrive(&full[stage]); else mbar_arrive_cluster(full_leader);
           } else {
             // both CTAs' bytes complete on the LEADER's barrier (cta_group::2 loads may signal the pair leader)
-            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
-            else mbar_arrive_cluster(full_leader);
+            if (!w_in_flight) {
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+              else mbar_arrive_cluster(full_leader);
+            }
             if (p.conv_taps > 0) {
               // implicit GEMM: this k-block is channels [cb*64, +64) of filter tap `tap`; the A tile is the tile's
               // conv_bh x conv_bw pixel patch shifted by the tap offset (borders zero-filled by TMA)
@@ -255,7 +282,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             } else {
               tma_load_2d_pair(sa, &tmA, full_leader, kb * BK, m_blk * BM);
             }
-            tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, w_row0);
+            if (!w_in_flight) tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, w_row0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -299,6 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // spare warp (kept so the warp-role layout is the same for every epilogue mode)
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..9
+    pdl_wait();                               // bias / gate / shortcut / residual stream: visible from here
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     const int row_a = q * 32 + lane;          // accumulator row of this thread
     const int wg = warp >= 6 ? 1 : 0;         // epilogue warpgroup
@@ -699,6 +727,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   for (int i = 0; i < 9; ++i) { p.conv_dx[i] = a.conv_dx[i]; p.conv_dy[i] = a.conv_dy[i]; p.conv_dz[i] = a.conv_dz[i]; }
   static const int dbg = env_int("B200_GEMM_DBG", 0);
   p.dbg = dbg;
+  static const int no_wprefetch = env_int("B200_GEMM_NO_WPREFETCH", 0);     // A/B switch
+  p.w_const = (a.w_const && !no_wprefetch && a.conv_taps == 0) ? 1 : 0;
   const int pair_tiles = plan.pair_tiles;
   const int grid = 2 * plan.pairs;
   {
