@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define B200_API __attribute__((visibility("default")))
 #else
@@ -318,6 +318,51 @@ B200_API int b200_set_attention_impl(int impl);
  * — replaces norm1/norm2 + modulate (latte.py:28-29, 166-168, 179-180). x fp32 [rows, dim].          */
 B200_API int b200_ln_modulate(const float* x, const float* shift, const float* scale, int64_t mod_batch_stride,
                      int rows_per_batch, void* out16, int rows, int dim, int dtype, void* stream);
+
+/* ---- training step (BASELINE config 5: train.py:206-222, fwd + bwd of models/latte.py under loss.backward()) -------------
+ * The reference differentiates Latte.forward with torch autograd; the replacement keeps the same forward kernels, stores the
+ * activations, and evaluates the analytic backward with b200_linear (every dgrad: A = dY, W = W^T; every wgrad: A = dY^T,
+ * W = X^T, B200_EPI_GATE_RESIDUAL with a unit gate accumulating into the fp32 gradient) plus the passes below.  Host side:
+ * latte_b200/training.py (TrainEngine).  All [rows, dim] matrices are row-major; "16" = fp16/bf16 per `dtype`.           */
+/* out16[cols, rows] = in16[rows, cols]^T (wgrad operands: the token dimension must be contiguous).                        */
+B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream);
+/* fp32 master parameter [rows, cols] -> 16-bit copy and (out16_t != NULL) its transpose [cols, rows], one read.           */
+B200_API int b200_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int dtype, void* stream);
+/* fp32 -> 16-bit elementwise (n % 4 == 0).                                                                                */
+B200_API int b200_cast16(const float* in, void* out16, int64_t n, int dtype, void* stream);
+/* out[r] = x[r] + gate[r / rows_per_batch] * m16[r] (+ row_add[(r / tokens) % frames] when row_add != NULL): the residual
+ * updates of TransformerBlock.forward (latte.py:179-180) with the branch output kept for the backward; row_add = temp_embed
+ * (latte.py:357-358).                                                                                                     */
+B200_API int b200_gate_residual(const float* x, const void* m16, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
+                                const float* row_add, int tokens, int frames, float* out, int rows, int dim, int dtype, void* stream);
+/* a16 = gelu_tanh(u16) (timm Mlp act, latte.py:169).                                                                      */
+B200_API int b200_gelu(const void* u16, void* a16, int64_t n, int dtype, void* stream);
+/* du16 = da16 * gelu_tanh'(u16); dbias[dim] (fp32, overwritten) = column sums of du = fc1.bias gradient.                  */
+B200_API int b200_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int dtype, void* stream);
+/* backward of out = x + gate[b] * m: dm16 = dx * gate[b]; dgate[b] (row stride dgate_batch_stride, overwritten) = sum over
+ * the sample's rows of dx * m; dbias[dim] (overwritten) = column sums of dm = the bias gradient of the Linear that made m. */
+B200_API int b200_gate_bwd(const float* dx, const void* m16, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
+                           void* dm16, float* dgate, int64_t dgate_batch_stride, float* dbias, int rows, int dim, int dtype,
+                           void* stream);
+/* out[dim] (fp32, overwritten) = column sums of a [rows, dim]; a_dtype: 0 fp32, 1 fp16, 2 bf16.                           */
+B200_API int b200_colsum(const void* a, int a_dtype, float* out, int rows, int dim, void* stream);
+/* backward of h = LayerNorm(x)(1 + scale[b]) + shift[b] (latte.py:28-29, eps 1e-6): dx (fp32, in place) += dL/dx;
+ * dshift[b], dscale[b] (row stride dmod_batch_stride, overwritten) = per-sample sums of dh and dh * xhat.
+ * rows_per_batch % 64 == 0.                                                                                              */
+B200_API int b200_ln_modulate_bwd(const void* dh16, const float* x, const float* scale, int64_t mod_batch_stride, int rows_per_batch,
+                                  float* dx, float* dshift, float* dscale, int64_t dmod_batch_stride, int rows, int dim, int dtype,
+                                  void* stream);
+/* backward of b200_attention: dqkv16 [T, 3*heads*head_dim] from qkv16, o16 (its output) and do16.  Scores are recomputed on
+ * mma.sync tensor cores (spatial: tokens % 64 == 0, head_dim 64 or 72; stats = 2 * batch*frames*heads*tokens floats of
+ * scratch) or in shared memory (temporal: frames <= 16; stats unused).                                                     */
+B200_API int b200_attention_bwd(const void* qkv16, const void* o16, const void* do16, void* dqkv16, float* stats, int batch,
+                                int frames, int tokens, int heads, int head_dim, int dtype, int temporal, void* stream);
+/* adaLN_modulation Linear on `batch` <= 8 conditioning rows (all blocks stacked, NA = depth*6*dim + 2*dim output features):
+ * dW[NA, dim] (fp32, overwritten) = dmod^T . sc16;  dsc[batch, dim] (fp32, overwritten) = dmod . W16.                     */
+B200_API int b200_ada_outer(const float* dmod, int64_t dmod_batch_stride, const void* sc16, float* dW, int batch, int NA, int dim,
+                            int dtype, void* stream);
+B200_API int b200_ada_dsc(const float* dmod, int64_t dmod_batch_stride, const void* w16, float* dsc, int batch, int NA, int dim,
+                          int dtype, void* stream);
 
 /* ---- sampler step: the fp32 arithmetic the reference's GaussianDiffusion does around every model
  * call, as ONE kernel with device-resident schedule tables.  Replaces p_mean_variance (diffusion/gaussian_diffusion.py:

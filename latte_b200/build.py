@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "liblatte_b200.so")
-SOURCES = ["runtime.cu", "gemm.cu", "attention.cu", "elementwise.cu", "vae.cu", "sampler.cu", "api.cu"]
+SOURCES = ["runtime.cu", "gemm.cu", "attention.cu", "elementwise.cu", "vae.cu", "sampler.cu", "train.cu", "api.cu"]
 HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "ptx.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "latte_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

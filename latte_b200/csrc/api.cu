@@ -657,4 +657,68 @@ B200_API int b200_ln_modulate(const float* x, const float* shift, const float* s
                                   dtype == B200_BF16, static_cast<cudaStream_t>(stream));
 }
 
+// ---- training-step passes (train.cu) ----
+#define B200_DT(dtype) B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype)
+B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream) {
+  return b200::launch_transpose16(in16, out16, rows, cols, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int dtype, void* stream) {
+  B200_DT(dtype);
+  return b200::launch_cast_transpose(in, out16, out16_t, rows, cols, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_cast16(const float* in, void* out16, int64_t n, int dtype, void* stream) {
+  B200_DT(dtype);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out16) & 7) == 0, B200_ERR_ALIGN, "cast16: misaligned pointer");
+  return b200::launch_cast16(in, out16, n, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_gate_residual(const float* x, const void* m16, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
+                                const float* row_add, int tokens, int frames, float* out, int rows, int dim, int dtype, void* stream) {
+  B200_DT(dtype);
+  return b200::launch_gate_residual(x, m16, gate, gate_batch_stride, rows_per_batch, row_add, tokens, frames, out, rows, dim,
+                                    dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_gelu(const void* u16, void* a16, int64_t n, int dtype, void* stream) {
+  B200_DT(dtype);
+  return b200::launch_gelu_fwd(u16, a16, n, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int dtype, void* stream) {
+  B200_DT(dtype);
+  return b200::launch_gelu_bwd(da16, u16, du16, dbias, rows, dim, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_gate_bwd(const float* dx, const void* m16, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
+                           void* dm16, float* dgate, int64_t dgate_batch_stride, float* dbias, int rows, int dim, int dtype,
+                           void* stream) {
+  B200_DT(dtype);
+  return b200::launch_gate_bwd(dx, m16, gate, gate_batch_stride, rows_per_batch, dm16, dgate, dgate_batch_stride, dbias, rows, dim,
+                               dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_colsum(const void* a, int a_dtype, float* out, int rows, int dim, void* stream) {
+  return b200::launch_colsum(a, a_dtype, out, rows, dim, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_ln_modulate_bwd(const void* dh16, const float* x, const float* scale, int64_t mod_batch_stride, int rows_per_batch,
+                                  float* dx, float* dshift, float* dscale, int64_t dmod_batch_stride, int rows, int dim, int dtype,
+                                  void* stream) {
+  B200_DT(dtype);
+  return b200::launch_ln_modulate_bwd(dh16, x, scale, mod_batch_stride, rows_per_batch, dx, dshift, dscale, dmod_batch_stride, rows,
+                                      dim, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_attention_bwd(const void* qkv16, const void* o16, const void* do16, void* dqkv16, float* stats, int batch,
+                                int frames, int tokens, int heads, int head_dim, int dtype, int temporal, void* stream) {
+  B200_DT(dtype);
+  B200_TRY(b200::check_arch());
+  return b200::launch_attention_bwd(qkv16, o16, do16, dqkv16, stats, batch, frames, tokens, heads, head_dim, dtype == B200_BF16,
+                                    temporal, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_ada_outer(const float* dmod, int64_t dmod_batch_stride, const void* sc16, float* dW, int batch, int NA, int dim,
+                            int dtype, void* stream) {
+  B200_DT(dtype);
+  return b200::launch_ada_outer(dmod, dmod_batch_stride, sc16, dW, batch, NA, dim, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_ada_dsc(const float* dmod, int64_t dmod_batch_stride, const void* w16, float* dsc, int batch, int NA, int dim,
+                          int dtype, void* stream) {
+  B200_DT(dtype);
+  return b200::launch_ada_dsc(dmod, dmod_batch_stride, w16, dsc, batch, NA, dim, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
+#undef B200_DT
+
 }  // extern "C"

@@ -164,6 +164,23 @@ int launch_unpatchify(const float* y, float* out, int batch, int frames, int gri
 int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, int out_ch, int guided_ch, int hw,
                        float scale, cudaStream_t stream);
 
+// training-step passes (train.cu)
+int launch_transpose16(const void* in, void* out, int rows, int cols, cudaStream_t stream);
+int launch_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int bf16, cudaStream_t stream);
+int launch_gate_residual(const float* x, const void* m16, const float* gate, long long gate_bs, int rows_per_batch,
+                         const float* row_add, int tokens, int frames, float* out, int rows, int dim, int bf16, cudaStream_t stream);
+int launch_gelu_fwd(const void* u16, void* a16, long long n, int bf16, cudaStream_t stream);
+int launch_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int bf16, cudaStream_t stream);
+int launch_gate_bwd(const float* dx, const void* m16, const float* gate, long long gate_bs, int rows_per_batch, void* dm16,
+                    float* dgate, long long dgate_bs, float* dbias, int rows, int dim, int bf16, cudaStream_t stream);
+int launch_colsum(const void* a, int dtype, float* out, int rows, int dim, cudaStream_t stream);
+int launch_ln_modulate_bwd(const void* dh16, const float* x, const float* scale, long long mod_bs, int rows_per_batch, float* dx,
+                           float* dshift, float* dscale, long long dmod_bs, int rows, int dim, int bf16, cudaStream_t stream);
+int launch_attention_bwd(const void* qkv, const void* o, const void* d_o, void* dqkv, float* stats, int batch, int frames, int tokens,
+                         int heads, int head_dim, int bf16, int temporal, cudaStream_t stream);
+int launch_ada_outer(const float* dmod, long long dmod_bs, const void* sc16, float* dW, int batch, int NA, int dim, int bf16, cudaStream_t stream);
+int launch_ada_dsc(const float* dmod, long long dmod_bs, const void* w16, float* dsc, int batch, int NA, int dim, int bf16, cudaStream_t stream);
+
 // VAE passes (vae.cu)
 int launch_gn(const void* x, float* part, const float* gamma, const float* beta, void* y, int n_img, int hw, int C, int groups,
               float eps, int do_silu, int bf16, cudaStream_t stream);

@@ -1,0 +1,956 @@
+// Backward-pass kernels of the training step (BASELINE config 5; reference train.py:206-222 -> autograd over models/latte.py).
+// Every GEMM of the backward (dgrad, wgrad) runs on the tcgen05 kernel of gemm.cu; this file holds what surrounds them:
+//   transpose16 / cast_transpose   16-bit [R,C] -> [C,R] operands for wgrad (K = tokens must be the contiguous dimension)
+//   gate_residual                  x_out = x + gate[b] * m (+ temp_embed row)          forward of latte.py:179-180 residuals
+//   gelu_fwd / gelu_bwd            tanh-GELU and its derivative, bias gradient (column sums) fused      (latte.py:169-171)
+//   gate_bwd                       dm = dx * gate[b]; dgate[b] = sum_rows dx * m; dbias = sum_rows dm   (latte.py:179-180)
+//   ln_modulate_bwd                d/dx of LN(x)(1+scale)+shift accumulated into dx; dshift, dscale per sample (latte.py:28-29)
+//   attn_bwd_dq / attn_bwd_dkv     softmax(QK^T hd^-1/2)V backward on mma.sync tensor cores, scores recomputed (latte.py:48-77)
+//   attn_bwd_temporal              same for the F <= 16 frame sequences (CUDA cores, HBM-bound)
+//   ada_outer / ada_dsc            gradients of the stacked adaLN_modulation Linear on B rows  (latte.py:160-163,192-195)
+// All are HBM-bound passes (one read, one write, fp32 math) except the attention backward (tensor cores, ~2 % of the FLOPs).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool BF16>
+__device__ __forceinline__ float cvt1(uint16_t u) {
+  if constexpr (BF16) return __uint_as_float(static_cast<uint32_t>(u) << 16);
+  else return __half2float(*reinterpret_cast<const __half*>(&u));
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t rnd1(float f) {
+  const uint32_t p = pack2<BF16>(f, 0.f);
+  return static_cast<uint16_t>(p & 0xffffu);
+}
+
+// ------------------------------------------------------------------------------------------------ transposes
+// 64x64 tile through shared memory; 4-byte global accesses on both sides.  R, C even.
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int R, int C) {
+  __shared__ uint16_t tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 64; r += 8) {
+    const int row = r0 + r, col = c0 + 2 * tx;
+    uint32_t v = 0;
+    if (row < R && col < C) v = *reinterpret_cast<const uint32_t*>(in + static_cast<size_t>(row) * C + col);
+    tile[r][2 * tx] = static_cast<uint16_t>(v & 0xffffu);
+    tile[r][2 * tx + 1] = static_cast<uint16_t>(v >> 16);
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8) {
+    const int orow = c0 + c, ocol = r0 + 2 * tx;
+    if (orow < C && ocol < R) {
+      const uint32_t v = static_cast<uint32_t>(tile[2 * tx][c]) | (static_cast<uint32_t>(tile[2 * tx + 1][c]) << 16);
+      *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(orow) * R + ocol) = v;
+    }
+  }
+}
+
+// fp32 [R,C] -> 16-bit [R,C] and 16-bit [C,R] in one read (weights: W for the forward GEMM, W^T as the dgrad weight operand)
+template <bool BF16>
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __restrict__ in, uint16_t* __restrict__ out,
+                                                             uint16_t* __restrict__ out_t, int R, int C) {
+  __shared__ uint16_t tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 64; r += 8) {
+    const int row = r0 + r, col = c0 + 2 * tx;
+    uint32_t v = 0;
+    if (row < R && col < C) {
+      const float2 f = *reinterpret_cast<const float2*>(in + static_cast<size_t>(row) * C + col);
+      v = pack2<BF16>(f.x, f.y);
+      *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row) * C + col) = v;
+    }
+    tile[r][2 * tx] = static_cast<uint16_t>(v & 0xffffu);
+    tile[r][2 * tx + 1] = static_cast<uint16_t>(v >> 16);
+  }
+  if (out_t == nullptr) return;
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8) {
+    const int orow = c0 + c, ocol = r0 + 2 * tx;
+    if (orow < C && ocol < R) {
+      const uint32_t v = static_cast<uint32_t>(tile[2 * tx][c]) | (static_cast<uint32_t>(tile[2 * tx + 1][c]) << 16);
+      *reinterpret_cast<uint32_t*>(out_t + static_cast<size_t>(orow) * R + ocol) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gate_residual (forward)
+// out[r, :] = x[r, :] + gate[r / rpb, :] * m[r, :] (+ row_add[(r / tokens) % frames, :]).  Thread = 4 columns.
+template <bool BF16>
+__global__ void __launch_bounds__(256) gate_residual_kernel(const float* __restrict__ x, const uint16_t* __restrict__ m,
+                                                            const float* __restrict__ gate, long long gate_bs, int rpb,
+                                                            const float* __restrict__ row_add, int tokens, int frames,
+                                                            float* __restrict__ out, int rows, int dim) {
+  const int nv = dim >> 2;
+  const long long total = static_cast<long long>(rows) * nv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / nv), c4 = static_cast<int>(i % nv);
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const uint2 mv = reinterpret_cast<const uint2*>(m)[i];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (row / rpb) * gate_bs) + c4);
+    const float2 m0 = unpack2<BF16>(mv.x), m1 = unpack2<BF16>(mv.y);
+    float4 o = make_float4(fmaf(g.x, m0.x, xv.x), fmaf(g.y, m0.y, xv.y), fmaf(g.z, m1.x, xv.z), fmaf(g.w, m1.y, xv.w));
+    if (row_add != nullptr) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(row_add + static_cast<size_t>((row / tokens) % frames) * dim) + c4);
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GELU (tanh form)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_f(float u) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * u * (1.0f + tanhf(k0 * (u + k1 * u * u * u)));
+}
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float th = tanhf(k0 * (u + k1 * u * u * u));
+  return 0.5f * (1.0f + th) + 0.5f * u * (1.0f - th * th) * k0 * (1.0f + 3.0f * k1 * u * u);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint16_t* __restrict__ u, uint16_t* __restrict__ a, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(u)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack2<BF16>(w[j]);
+      o[j] = pack2<BF16>(gelu_f(f.x), gelu_f(f.y));
+    }
+    reinterpret_cast<uint4*>(a)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// du = da * gelu'(u); dbias[c] += sum over the block's rows.  Block = 128 threads x 8 columns, `rs` rows per block.
+template <bool BF16>
+__global__ void __launch_bounds__(128) gelu_bwd_kernel(const uint16_t* __restrict__ da, const uint16_t* __restrict__ u,
+                                                       uint16_t* __restrict__ du, float* __restrict__ dbias, int rows, int dim, int rs) {
+  const int c8 = blockIdx.x * 128 + threadIdx.x;
+  if (c8 * 8 >= dim) return;
+  const int r0 = blockIdx.y * rs;
+  const int r1 = min(rows, r0 + rs);
+  float acc[8] = {};
+  const int nv = dim >> 3;
+  for (int r = r0; r < r1; ++r) {
+    const size_t idx = static_cast<size_t>(r) * nv + c8;
+    const uint4 a = reinterpret_cast<const uint4*>(da)[idx];
+    const uint4 b = reinterpret_cast<const uint4*>(u)[idx];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 g = unpack2<BF16>(aw[j]), uu = unpack2<BF16>(bw[j]);
+      const float d0 = g.x * gelu_grad(uu.x), d1 = g.y * gelu_grad(uu.y);
+      o[j] = pack2<BF16>(d0, d1);
+      acc[2 * j] += d0;
+      acc[2 * j + 1] += d1;
+    }
+    reinterpret_cast<uint4*>(du)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dbias + c8 * 8 + j, acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------------ gate_bwd
+// dm = dx * gate[b] (16-bit); dgate[b, c] += sum_rows dx * m; dbias[c] += sum_rows dm.  Thread = 4 columns, `rs` rows/block
+// (rs divides rows_per_batch, so a block stays inside one sample).
+template <bool BF16>
+__global__ void __launch_bounds__(128) gate_bwd_kernel(const float* __restrict__ dx, const uint16_t* __restrict__ m,
+                                                       const float* __restrict__ gate, long long gate_bs, int rpb,
+                                                       uint16_t* __restrict__ dm, float* __restrict__ dgate, long long dgate_bs,
+                                                       float* __restrict__ dbias, int rows, int dim, int rs) {
+  const int c4 = blockIdx.x * 128 + threadIdx.x;
+  const int nv = dim >> 2;
+  if (c4 >= nv) return;
+  const int r0 = blockIdx.y * rs;
+  const int r1 = min(rows, r0 + rs);
+  const int b = r0 / rpb;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gate + b * gate_bs) + c4);
+  float ag[4] = {}, ab[4] = {};
+  for (int r = r0; r < r1; ++r) {
+    const size_t idx = static_cast<size_t>(r) * nv + c4;
+    const float4 d = reinterpret_cast<const float4*>(dx)[idx];
+    const uint2 mv = reinterpret_cast<const uint2*>(m)[idx];
+    const float2 m0 = unpack2<BF16>(mv.x), m1 = unpack2<BF16>(mv.y);
+    const float o0 = d.x * g.x, o1 = d.y * g.y, o2 = d.z * g.z, o3 = d.w * g.w;
+    reinterpret_cast<uint2*>(dm)[idx] = make_uint2(pack2<BF16>(o0, o1), pack2<BF16>(o2, o3));
+    ag[0] += d.x * m0.x; ag[1] += d.y * m0.y; ag[2] += d.z * m1.x; ag[3] += d.w * m1.y;
+    ab[0] += o0; ab[1] += o1; ab[2] += o2; ab[3] += o3;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(dgate + b * dgate_bs + c4 * 4 + j, ag[j]);
+    atomicAdd(dbias + c4 * 4 + j, ab[j]);
+  }
+}
+
+// column sums of a [rows, dim] matrix (16-bit or fp32) into fp32 (pre-zeroed)
+template <int KIND>   // 0 fp32, 1 fp16, 2 bf16
+__global__ void __launch_bounds__(128) colsum_kernel(const void* __restrict__ a, float* __restrict__ out, int rows, int dim, int rs) {
+  const int c4 = blockIdx.x * 128 + threadIdx.x;
+  const int nv = dim >> 2;
+  if (c4 >= nv) return;
+  const int r0 = blockIdx.y * rs;
+  const int r1 = min(rows, r0 + rs);
+  float acc[4] = {};
+  for (int r = r0; r < r1; ++r) {
+    const size_t idx = static_cast<size_t>(r) * nv + c4;
+    if constexpr (KIND == 0) {
+      const float4 d = reinterpret_cast<const float4*>(a)[idx];
+      acc[0] += d.x; acc[1] += d.y; acc[2] += d.z; acc[3] += d.w;
+    } else {
+      const uint2 v = reinterpret_cast<const uint2*>(a)[idx];
+      const float2 f0 = unpack2<KIND == 2>(v.x), f1 = unpack2<KIND == 2>(v.y);
+      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) atomicAdd(out + c4 * 4 + j, acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------------ ln_modulate_bwd
+// h = xhat * (1 + scale[b]) + shift[b], xhat = (x - mean) * rstd.  Given dh:
+//   dshift[b] += sum_rows dh;  dscale[b] += sum_rows dh * xhat;  g = dh * (1 + scale[b]);
+//   dx += rstd * (g - mean(g) - xhat * mean(g * xhat)).
+// One warp per row (row in registers), LB_RPW consecutive rows per warp, the 4 warps of a block reduce their column sums
+// through shared memory before the atomics.  rows_per_batch % (4 * LB_RPW) == 0 keeps a block inside one sample.
+constexpr int LB_RPW = 16;
+template <bool BF16, int NV>
+__global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __restrict__ dh, const float* __restrict__ x,
+                                                              const float* __restrict__ scale, long long mod_bs, int rpb,
+                                                              float* __restrict__ dx, float* __restrict__ dshift,
+                                                              float* __restrict__ dscale, long long dmod_bs, int rows, int dim) {
+  extern __shared__ float s_red[];   // [4][2][dim]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = dim >> 2;
+  const int block_row0 = blockIdx.x * 4 * LB_RPW;
+  const int b = block_row0 / rpb;
+  const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
+  float4 a_sh[NV], a_sc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a_sh[i] = a_sc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_d = 1.0f / static_cast<float>(dim);
+  for (int rr = 0; rr < LB_RPW; ++rr) {
+    const int row = block_row0 + warp * LB_RPW + rr;
+    if (row >= rows) break;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
+    const uint2* dr = reinterpret_cast<const uint2*>(dh + static_cast<size_t>(row) * dim);
+    float4 v[NV], d[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        v[i] = xr[idx];
+        const uint2 t = dr[idx];
+        const float2 d0 = unpack2<BF16>(t.x), d1 = unpack2<BF16>(t.y);
+        d[i] = make_float4(d0.x, d0.y, d1.x, d1.y);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nv) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + 1e-6f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
+        a_sh[i].x += d[i].x; a_sh[i].y += d[i].y; a_sh[i].z += d[i].z; a_sh[i].w += d[i].w;
+        a_sc[i].x += d[i].x * v[i].x; a_sc[i].y += d[i].y * v[i].y; a_sc[i].z += d[i].z * v[i].z; a_sc[i].w += d[i].w * v[i].w;
+        const float4 c = __ldg(sc + idx);
+        d[i].x *= 1.0f + c.x; d[i].y *= 1.0f + c.y; d[i].z *= 1.0f + c.z; d[i].w *= 1.0f + c.w;   // g
+        s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+    float4* dxr = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * dim);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        float4 o = dxr[idx];
+        o.x += rstd * (d[i].x - s1 - v[i].x * s2);
+        o.y += rstd * (d[i].y - s1 - v[i].y * s2);
+        o.z += rstd * (d[i].z - s1 - v[i].z * s2);
+        o.w += rstd * (d[i].w - s1 - v[i].w * s2);
+        dxr[idx] = o;
+      }
+    }
+  }
+  float4* red = reinterpret_cast<float4*>(s_red);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      red[(warp * 2 + 0) * nv + idx] = a_sh[i];
+      red[(warp * 2 + 1) * nv + idx] = a_sc[i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) {
+    const int which = i / dim, c = i % dim;
+    const float t = s_red[(0 * 2 + which) * dim + c] + s_red[(1 * 2 + which) * dim + c] + s_red[(2 * 2 + which) * dim + c] +
+                    s_red[(3 * 2 + which) * dim + c];
+    atomicAdd((which == 0 ? dshift : dscale) + b * dmod_bs + c, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention backward (spatial)
+// mma.sync m16n8k16 building blocks.  Shared-memory tiles are [64 rows][HDP] 16-bit with HDP = KP + 8 (KP = head_dim rounded up
+// to 16; the pad columns [HD, KP) are zero so they add nothing to a k = head_dim contraction); the 8-element skew makes the
+// eight 16-byte rows of an ldmatrix land in distinct bank groups.
+template <bool BF16>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (BF16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__device__ __forceinline__ void ldsm_x2_t(uint32_t& r0, uint32_t& r1, uint32_t addr) {   // lanes 0-15 supply the row addresses
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+template <int HD>
+struct AB {
+  static constexpr int KP = (HD + 15) / 16 * 16;   // 64 or 80
+  static constexpr int KS = KP / 16;               // k-steps of a head_dim contraction
+  static constexpr int HDP = KP + 8;               // row pitch in elements
+  static constexpr int NT = HD / 8;                // n-tiles of a head_dim-wide output (8 or 9)
+  static constexpr int TILE = 64 * HDP;            // elements per 64-row tile
+};
+
+// copy a [64 x HD] block (rows `row0 + r*row_step`, columns col0..col0+HD) of a row-major 16-bit matrix into a shared tile
+template <int HD>
+__device__ __forceinline__ void load_tile64(uint16_t* s, const uint16_t* __restrict__ g, size_t row0, size_t row_step,
+                                            int ld, int col0, int nrows_valid) {
+  constexpr int CH = HD / 8;          // 16-byte chunks per row
+  constexpr int HDP = AB<HD>::HDP;
+  for (int i = threadIdx.x; i < 64 * CH; i += blockDim.x) {
+    const int r = i / CH, c = i % CH;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < nrows_valid) v = *reinterpret_cast<const uint4*>(g + (row0 + r * row_step) * ld + col0 + c * 8);
+    *reinterpret_cast<uint4*>(s + r * HDP + c * 8) = v;
+  }
+  if constexpr (AB<HD>::KP > HD) {
+    for (int r = threadIdx.x; r < 64; r += blockDim.x) *reinterpret_cast<uint4*>(s + r * HDP + HD) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// acc[16 x 64] = A[16 x KP] . tile[64 x KP]^T: A = rows [r0, r0+16) of shared tile sA (fragments fetched per k-step, so they
+// do not occupy registers across the loop), tile rows are the n dimension, its columns the contraction.
+template <bool BF16, int HD>
+__device__ __forceinline__ void mm_a_tileT(float (&acc)[8][4], const uint16_t* sA, int r0, const uint16_t* s) {
+  const int lane = threadIdx.x & 31;
+  const int arow = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int acol = (lane >> 4) * 8;
+  const int brow = (lane & 7) + (lane >> 4) * 8;
+  const int bcol = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int k = 0; k < AB<HD>::KS; ++k) {
+    uint32_t a[4];
+    ldsm_x4(a, smem_u32(sA + arow * AB<HD>::HDP + k * 16 + acol));
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4(b, smem_u32(s + (np * 16 + brow) * AB<HD>::HDP + k * 16 + bcol));
+      mma16816<BF16>(acc[2 * np], a, b[0], b[1]);
+      mma16816<BF16>(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// out[16 x HD] += P[16 x 64] . tile[64 x HD]   (P given as 4 k-steps of A fragments; tile rows are the contraction)
+template <bool BF16, int HD>
+__device__ __forceinline__ void mm_p_tile(float (&out)[AB<HD>::NT][4], const uint32_t (&p)[4][4], const uint16_t* s) {
+  const int lane = threadIdx.x & 31;
+  const int brow = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int bcol = (lane >> 4) * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int np = 0; np < AB<HD>::NT / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, smem_u32(s + (k * 16 + brow) * AB<HD>::HDP + np * 16 + bcol));
+      mma16816<BF16>(out[2 * np], p[k], b[0], b[1]);
+      mma16816<BF16>(out[2 * np + 1], p[k], b[2], b[3]);
+    }
+    if constexpr (AB<HD>::NT % 2 == 1) {     // last single n-tile (head_dim 72): columns [HD-8, HD)
+      uint32_t b0, b1;
+      ldsm_x2_t(b0, b1, smem_u32(s + (k * 16 + brow) * AB<HD>::HDP + (AB<HD>::NT - 1) * 8));
+      mma16816<BF16>(out[AB<HD>::NT - 1], p[k], b0, b1);
+    }
+  }
+}
+
+// pack a 16 x 64 fp32 accumulator block into 4 k-steps of A fragments
+template <bool BF16>
+__device__ __forceinline__ void acc_to_afrag(uint32_t (&p)[4][4], const float (&acc)[8][4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    p[k][0] = pack2<BF16>(acc[2 * k][0], acc[2 * k][1]);
+    p[k][1] = pack2<BF16>(acc[2 * k][2], acc[2 * k][3]);
+    p[k][2] = pack2<BF16>(acc[2 * k + 1][0], acc[2 * k + 1][1]);
+    p[k][3] = pack2<BF16>(acc[2 * k + 1][2], acc[2 * k + 1][3]);
+  }
+}
+
+// write a warp's [16 x HD] fp32 accumulator as 16-bit rows of the output (row pitch ld)
+template <bool BF16, int HD>
+__device__ __forceinline__ void store_rows(uint16_t* __restrict__ g, size_t row0, int ld, int col0, const float (&acc)[AB<HD>::NT][4],
+                                           int r_in_tile, int nvalid) {
+  const int lane = threadIdx.x & 31;
+  const int r = r_in_tile + (lane >> 2);
+#pragma unroll
+  for (int n = 0; n < AB<HD>::NT; ++n) {
+    const int c = col0 + n * 8 + (lane & 3) * 2;
+    if (r < nvalid) *reinterpret_cast<uint32_t*>(g + (row0 + r) * ld + c) = pack2<BF16>(acc[n][0], acc[n][1]);
+    if (r + 8 < nvalid) *reinterpret_cast<uint32_t*>(g + (row0 + r + 8) * ld + c) = pack2<BF16>(acc[n][2], acc[n][3]);
+  }
+}
+
+// Kernel A: one CTA = 64 query rows of one (sequence, head).  Pass 1 recomputes the row statistics (log-sum-exp in log2
+// units) and delta = sum_d dO.O, stores both for kernel B; pass 2 recomputes P, forms dS = P (dP - delta) * scale and
+// accumulates dQ = dS K.
+template <bool BF16, int HD>
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ o,
+                                                          const uint16_t* __restrict__ d_o, uint16_t* __restrict__ dqkv,
+                                                          float* __restrict__ lse, float* __restrict__ delta, int S, int heads,
+                                                          float scale_log2) {
+  using G = AB<HD>;
+  extern __shared__ __align__(16) uint16_t sm[];
+  uint16_t* sQ = sm;
+  uint16_t* sDO = sm + G::TILE;
+  uint16_t* sK = sm + 2 * G::TILE;
+  uint16_t* sV = sm + 3 * G::TILE;
+  const int qb = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
+  const int D = heads * HD, ld = 3 * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t seq_row0 = static_cast<size_t>(seq) * S;
+  const int q0 = qb * 64;
+  load_tile64<HD>(sQ, qkv, seq_row0 + q0, 1, ld, h * HD, 64);
+  load_tile64<HD>(sDO, d_o, seq_row0 + q0, 1, D, h * HD, 64);
+  load_tile64<HD>(sK, o, seq_row0 + q0, 1, D, h * HD, 64);     // O block, only for delta
+  __syncthreads();
+  // delta for this thread's two rows (quad lanes split the columns)
+  const int r_lo = warp * 16 + (lane >> 2);
+  float dl[2] = {0.f, 0.f};
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = r_lo + hh * 8;
+    for (int c = (lane & 3) * 2; c < HD; c += 8) {
+      const float2 a = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(sDO + r * G::HDP + c));
+      const float2 b = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(sK + r * G::HDP + c));
+      dl[hh] += a.x * b.x + a.y * b.y;
+    }
+    dl[hh] += __shfl_xor_sync(0xffffffffu, dl[hh], 1);
+    dl[hh] += __shfl_xor_sync(0xffffffffu, dl[hh], 2);
+  }
+  // ---- pass 1: row max / sum over all keys
+  float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
+  const int nkb = S / 64;
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();
+    load_tile64<HD>(sK, qkv, seq_row0 + kb * 64, 1, ld, D + h * HD, 64);
+    __syncthreads();
+    float acc[8][4] = {};
+    mm_a_tileT<BF16, HD>(acc, sQ, warp * 16, sK);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float m = mx[hh];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) m = fmaxf(m, fmaxf(acc[n][2 * hh], acc[n][2 * hh + 1]) * scale_log2);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float s = 0.f;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) s += exp2f(acc[n][2 * hh] * scale_log2 - m) + exp2f(acc[n][2 * hh + 1] * scale_log2 - m);
+      sum[hh] = sum[hh] * exp2f(mx[hh] - m) + s;
+      mx[hh] = m;
+    }
+  }
+  float l2[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float s = sum[hh];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    l2[hh] = mx[hh] + log2f(s);
+    if ((lane & 3) == 0) {
+      const size_t idx = (static_cast<size_t>(seq) * heads + h) * S + q0 + r_lo + hh * 8;
+      lse[idx] = l2[hh];
+      delta[idx] = dl[hh];
+    }
+  }
+  // ---- pass 2
+  const float scale = scale_log2 * 0.6931471805599453f;
+  float dq[G::NT][4] = {};
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();
+    load_tile64<HD>(sK, qkv, seq_row0 + kb * 64, 1, ld, D + h * HD, 64);
+    load_tile64<HD>(sV, qkv, seq_row0 + kb * 64, 1, ld, 2 * D + h * HD, 64);
+    __syncthreads();
+    float s_acc[8][4] = {}, p_acc[8][4] = {};
+    mm_a_tileT<BF16, HD>(s_acc, sQ, warp * 16, sK);
+    mm_a_tileT<BF16, HD>(p_acc, sDO, warp * 16, sV);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int hh = e >> 1;
+        const float p = exp2f(s_acc[n][e] * scale_log2 - l2[hh]);
+        s_acc[n][e] = p * (p_acc[n][e] - dl[hh]) * scale;
+      }
+    uint32_t pds[4][4];
+    acc_to_afrag<BF16>(pds, s_acc);
+    mm_p_tile<BF16, HD>(dq, pds, sK);
+  }
+  store_rows<BF16, HD>(dqkv, seq_row0 + q0, ld, h * HD, dq, warp * 16, 64);
+}
+
+// Kernel B: one CTA = 64 keys of one (sequence, head); loops over the query blocks with the statistics of kernel A.
+// S^T = K Q^T so that the warp's accumulator rows are keys: P^T and dS^T are then directly the A operands of
+// dV = P^T dO and dK = dS^T Q.
+template <bool BF16, int HD>
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ d_o,
+                                                           uint16_t* __restrict__ dqkv, const float* __restrict__ lse,
+                                                           const float* __restrict__ delta, int S, int heads, float scale_log2) {
+  using G = AB<HD>;
+  extern __shared__ __align__(16) uint16_t sm[];
+  uint16_t* sK = sm;
+  uint16_t* sV = sm + G::TILE;
+  uint16_t* sQ = sm + 2 * G::TILE;
+  uint16_t* sDO = sm + 3 * G::TILE;
+  float* sL = reinterpret_cast<float*>(sm + 4 * G::TILE);
+  float* sD = sL + 64;
+  const int kb = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
+  const int D = heads * HD, ld = 3 * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t seq_row0 = static_cast<size_t>(seq) * S;
+  const int k0 = kb * 64;
+  load_tile64<HD>(sK, qkv, seq_row0 + k0, 1, ld, D + h * HD, 64);
+  load_tile64<HD>(sV, qkv, seq_row0 + k0, 1, ld, 2 * D + h * HD, 64);
+  __syncthreads();
+  const float scale = scale_log2 * 0.6931471805599453f;
+  float dk[G::NT][4] = {}, dv[G::NT][4] = {};
+  const int nqb = S / 64;
+  for (int qb = 0; qb < nqb; ++qb) {
+    __syncthreads();
+    load_tile64<HD>(sQ, qkv, seq_row0 + qb * 64, 1, ld, h * HD, 64);
+    load_tile64<HD>(sDO, d_o, seq_row0 + qb * 64, 1, D, h * HD, 64);
+    if (threadIdx.x < 64) {
+      const size_t idx = (static_cast<size_t>(seq) * heads + h) * S + qb * 64 + threadIdx.x;
+      sL[threadIdx.x] = lse[idx];
+      sD[threadIdx.x] = delta[idx];
+    }
+    __syncthreads();
+    float s_acc[8][4] = {}, p_acc[8][4] = {};
+    mm_a_tileT<BF16, HD>(s_acc, sK, warp * 16, sQ);      // [16 keys x 64 queries]
+    mm_a_tileT<BF16, HD>(p_acc, sV, warp * 16, sDO);
+    uint32_t pp[4][4], pds[4][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = n * 8 + (lane & 3) * 2 + (e & 1);
+        const float p = exp2f(s_acc[n][e] * scale_log2 - sL[qi]);
+        p_acc[n][e] = p * (p_acc[n][e] - sD[qi]) * scale;
+        s_acc[n][e] = p;
+      }
+    acc_to_afrag<BF16>(pp, s_acc);
+    acc_to_afrag<BF16>(pds, p_acc);
+    mm_p_tile<BF16, HD>(dv, pp, sDO);
+    mm_p_tile<BF16, HD>(dk, pds, sQ);
+  }
+  store_rows<BF16, HD>(dqkv, seq_row0 + k0, ld, D + h * HD, dk, warp * 16, 64);
+  store_rows<BF16, HD>(dqkv, seq_row0 + k0, ld, 2 * D + h * HD, dv, warp * 16, 64);
+}
+
+// ------------------------------------------------------------------------------------------------ attention backward (temporal)
+// Sequences of F <= 16 frames at a fixed token: rows (b, f, n), f = 0..F-1 (row stride `tokens`).  One CTA of 128 threads per
+// (b, n, head); everything lives in shared memory as fp32.  HBM-bound (reads qkv + dO, writes dqkv).
+template <bool BF16>
+__global__ void __launch_bounds__(128) attn_bwd_temporal_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ d_o,
+                                                                uint16_t* __restrict__ dqkv, int frames, int tokens, int heads,
+                                                                int hd, float scale) {
+  extern __shared__ float sf[];
+  const int F = frames;
+  float* q = sf;                 // [F][hd]
+  float* k = q + F * hd;
+  float* v = k + F * hd;
+  float* g = v + F * hd;         // dO
+  float* P = g + F * hd;         // [F][F]
+  float* dS = P + F * F;         // [F][F]
+  const int n = blockIdx.x % tokens, b = blockIdx.x / tokens, h = blockIdx.y;
+  const int D = heads * hd, ld = 3 * D;
+  const size_t row0 = static_cast<size_t>(b) * F * tokens + n;
+  const int half = hd / 2;
+  for (int i = threadIdx.x; i < F * half; i += blockDim.x) {
+    const int f = i / half, c = (i % half) * 2;
+    const size_t r = row0 + static_cast<size_t>(f) * tokens;
+    const float2 a = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(qkv + r * ld + h * hd + c));
+    const float2 bb = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(qkv + r * ld + D + h * hd + c));
+    const float2 cc = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(qkv + r * ld + 2 * D + h * hd + c));
+    const float2 dd = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(d_o + r * D + h * hd + c));
+    q[f * hd + c] = a.x; q[f * hd + c + 1] = a.y;
+    k[f * hd + c] = bb.x; k[f * hd + c + 1] = bb.y;
+    v[f * hd + c] = cc.x; v[f * hd + c + 1] = cc.y;
+    g[f * hd + c] = dd.x; g[f * hd + c + 1] = dd.y;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * F; i += blockDim.x) {
+    const int a = i / F, c = i % F;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < hd; ++d) {
+      s += q[a * hd + d] * k[c * hd + d];
+      dp += g[a * hd + d] * v[c * hd + d];
+    }
+    P[i] = s * scale;
+    dS[i] = dp;
+  }
+  __syncthreads();
+  if (threadIdx.x < F) {
+    const int a = threadIdx.x;
+    float m = -INFINITY;
+    for (int c = 0; c < F; ++c) m = fmaxf(m, P[a * F + c]);
+    float s = 0.f;
+    for (int c = 0; c < F; ++c) { const float e = __expf(P[a * F + c] - m); P[a * F + c] = e; s += e; }
+    const float inv = 1.0f / s;
+    float dl = 0.f;
+    for (int c = 0; c < F; ++c) { P[a * F + c] *= inv; dl += P[a * F + c] * dS[a * F + c]; }
+    for (int c = 0; c < F; ++c) dS[a * F + c] = P[a * F + c] * (dS[a * F + c] - dl) * scale;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * half; i += blockDim.x) {
+    const int f = i / half, c = (i % half) * 2;
+    float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+    for (int j = 0; j < F; ++j) {
+      const float ds_fj = dS[f * F + j], ds_jf = dS[j * F + f], p_jf = P[j * F + f];
+      dq0 += ds_fj * k[j * hd + c]; dq1 += ds_fj * k[j * hd + c + 1];
+      dk0 += ds_jf * q[j * hd + c]; dk1 += ds_jf * q[j * hd + c + 1];
+      dv0 += p_jf * g[j * hd + c]; dv1 += p_jf * g[j * hd + c + 1];
+    }
+    const size_t r = row0 + static_cast<size_t>(f) * tokens;
+    *reinterpret_cast<uint32_t*>(dqkv + r * ld + h * hd + c) = pack2<BF16>(dq0, dq1);
+    *reinterpret_cast<uint32_t*>(dqkv + r * ld + D + h * hd + c) = pack2<BF16>(dk0, dk1);
+    *reinterpret_cast<uint32_t*>(dqkv + r * ld + 2 * D + h * hd + c) = pack2<BF16>(dv0, dv1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ adaLN gradients
+// dW[n, k] = sum_b dmod[b, n] * sc[b, k]   (B <= 8 rows; pure write bandwidth: the gradient buffer itself)
+template <bool BF16>
+__global__ void __launch_bounds__(256) ada_outer_kernel(const float* __restrict__ dmod, long long dmod_bs, const uint16_t* __restrict__ sc,
+                                                        float* __restrict__ dW, int batch, int NA, int dim) {
+  extern __shared__ float s_sc[];   // [batch][dim]
+  for (int i = threadIdx.x; i < batch * dim; i += blockDim.x) s_sc[i] = cvt1<BF16>(sc[i]);
+  __syncthreads();
+  const int nv = dim >> 2;
+  for (int n = blockIdx.x; n < NA; n += gridDim.x) {
+    float dm[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) dm[b] = b < batch ? dmod[b * dmod_bs + n] : 0.f;
+    float4* row = reinterpret_cast<float4*>(dW + static_cast<size_t>(n) * dim);
+    for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < batch) {
+          const float4 s = reinterpret_cast<const float4*>(s_sc + b * dim)[c];
+          a.x = fmaf(dm[b], s.x, a.x); a.y = fmaf(dm[b], s.y, a.y); a.z = fmaf(dm[b], s.z, a.z); a.w = fmaf(dm[b], s.w, a.w);
+        }
+      }
+      row[c] = a;
+    }
+  }
+}
+
+// dsc[b, k] += sum_{n in slab} dmod[b, n] * W[n, k]     (W 16-bit [NA, dim]; one read of the adaLN weights)
+template <bool BF16>
+__global__ void __launch_bounds__(256) ada_dsc_kernel(const float* __restrict__ dmod, long long dmod_bs, const uint16_t* __restrict__ w,
+                                                      float* __restrict__ dsc, int batch, int NA, int dim, int slab) {
+  const int n0 = blockIdx.x * slab;
+  const int n1 = min(NA, n0 + slab);
+  const int half = dim >> 1;
+  for (int c = threadIdx.x; c < half; c += blockDim.x) {
+    float acc[8][2] = {};
+    for (int n = n0; n < n1; ++n) {
+      const float2 wv = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(n) * dim + 2 * c));
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < batch) {
+          const float d = __ldg(dmod + b * dmod_bs + n);
+          acc[b][0] = fmaf(d, wv.x, acc[b][0]);
+          acc[b][1] = fmaf(d, wv.y, acc[b][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      if (b < batch) {
+        atomicAdd(dsc + static_cast<size_t>(b) * dim + 2 * c, acc[b][0]);
+        atomicAdd(dsc + static_cast<size_t>(b) * dim + 2 * c + 1, acc[b][1]);
+      }
+    }
+  }
+}
+
+inline int grid_for(long long items, int per_block, int cap) {
+  long long b = (items + per_block - 1) / per_block;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+// ================================================================================================ launchers
+#define ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+int launch_transpose16(const void* in, void* out, int rows, int cols, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && cols > 0 && rows % 2 == 0 && cols % 2 == 0, B200_ERR_SHAPE, "transpose16: %d x %d must be even", rows, cols);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, B200_ERR_ALIGN,
+               "transpose16: pointers must be 4-byte aligned");
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+  transpose16_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), rows, cols);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && cols > 0 && rows % 2 == 0 && cols % 2 == 0, B200_ERR_SHAPE, "cast_transpose: %d x %d must be even", rows, cols);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(out16) & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out16_t) & 3) == 0, B200_ERR_ALIGN, "cast_transpose: misaligned pointer");
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+  if (bf16) cast_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, static_cast<uint16_t*>(out16), static_cast<uint16_t*>(out16_t), rows, cols);
+  else cast_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, static_cast<uint16_t*>(out16), static_cast<uint16_t*>(out16_t), rows, cols);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_gate_residual(const float* x, const void* m16, const float* gate, long long gate_bs, int rows_per_batch,
+                         const float* row_add, int tokens, int frames, float* out, int rows, int dim, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && rows_per_batch > 0 && gate_bs % 4 == 0, B200_ERR_SHAPE, "gate_residual: bad shape");
+  B200_REQUIRE(row_add == nullptr || (tokens > 0 && frames > 0), B200_ERR_SHAPE, "gate_residual: row_add needs tokens and frames");
+  B200_REQUIRE(ALIGNED16(x) && ALIGNED16(gate) && ALIGNED16(out) && (reinterpret_cast<uintptr_t>(m16) & 7) == 0 &&
+                   (row_add == nullptr || ALIGNED16(row_add)), B200_ERR_ALIGN, "gate_residual: misaligned pointer");
+  const long long total = static_cast<long long>(rows) * (dim / 4);
+  const int blocks = grid_for(total, 256, 148 * 16);
+  const uint16_t* m = static_cast<const uint16_t*>(m16);
+  if (bf16) gate_residual_kernel<true><<<blocks, 256, 0, stream>>>(x, m, gate, gate_bs, rows_per_batch, row_add, tokens, frames, out, rows, dim);
+  else gate_residual_kernel<false><<<blocks, 256, 0, stream>>>(x, m, gate, gate_bs, rows_per_batch, row_add, tokens, frames, out, rows, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_gelu_fwd(const void* u16, void* a16, long long n, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(n > 0 && n % 8 == 0, B200_ERR_SHAPE, "gelu: element count %lld must be a multiple of 8", n);
+  B200_REQUIRE(ALIGNED16(u16) && ALIGNED16(a16), B200_ERR_ALIGN, "gelu: pointers must be 16-byte aligned");
+  const int blocks = grid_for(n / 8, 256, 148 * 16);
+  if (bf16) gelu_fwd_kernel<true><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(u16), static_cast<uint16_t*>(a16), n / 8);
+  else gelu_fwd_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(u16), static_cast<uint16_t*>(a16), n / 8);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0, B200_ERR_SHAPE, "gelu_bwd: dim %d must be a multiple of 8", dim);
+  B200_REQUIRE(ALIGNED16(da16) && ALIGNED16(u16) && ALIGNED16(du16), B200_ERR_ALIGN, "gelu_bwd: pointers must be 16-byte aligned");
+  B200_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * dim, stream));
+  const int rs = 32;
+  dim3 grid((dim / 8 + 127) / 128, (rows + rs - 1) / rs);
+  const uint16_t *a = static_cast<const uint16_t*>(da16), *u = static_cast<const uint16_t*>(u16);
+  if (bf16) gelu_bwd_kernel<true><<<grid, 128, 0, stream>>>(a, u, static_cast<uint16_t*>(du16), dbias, rows, dim, rs);
+  else gelu_bwd_kernel<false><<<grid, 128, 0, stream>>>(a, u, static_cast<uint16_t*>(du16), dbias, rows, dim, rs);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_gate_bwd(const float* dx, const void* m16, const float* gate, long long gate_bs, int rows_per_batch, void* dm16,
+                    float* dgate, long long dgate_bs, float* dbias, int rows, int dim, int bf16, cudaStream_t stream) {
+  const int rs = 32;
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && rows_per_batch % rs == 0 && gate_bs % 4 == 0, B200_ERR_SHAPE,
+               "gate_bwd: dim %% 4 and rows_per_batch %% %d must be 0", rs);
+  B200_REQUIRE(ALIGNED16(dx) && ALIGNED16(gate) && (reinterpret_cast<uintptr_t>(m16) & 7) == 0 && (reinterpret_cast<uintptr_t>(dm16) & 7) == 0,
+               B200_ERR_ALIGN, "gate_bwd: misaligned pointer");
+  const int batch = (rows + rows_per_batch - 1) / rows_per_batch;
+  for (int b = 0; b < batch; ++b) B200_CHECK_CUDA(cudaMemsetAsync(dgate + b * dgate_bs, 0, sizeof(float) * dim, stream));
+  B200_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * dim, stream));
+  dim3 grid((dim / 4 + 127) / 128, (rows + rs - 1) / rs);
+  const uint16_t* m = static_cast<const uint16_t*>(m16);
+  if (bf16) gate_bwd_kernel<true><<<grid, 128, 0, stream>>>(dx, m, gate, gate_bs, rows_per_batch, static_cast<uint16_t*>(dm16), dgate, dgate_bs, dbias, rows, dim, rs);
+  else gate_bwd_kernel<false><<<grid, 128, 0, stream>>>(dx, m, gate, gate_bs, rows_per_batch, static_cast<uint16_t*>(dm16), dgate, dgate_bs, dbias, rows, dim, rs);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_colsum(const void* a, int dtype, float* out, int rows, int dim, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dtype >= 0 && dtype <= 2, B200_ERR_SHAPE, "colsum: bad shape / dtype");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(a) & (dtype == 0 ? 15 : 7)) == 0, B200_ERR_ALIGN, "colsum: misaligned input");
+  B200_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * dim, stream));
+  const int rs = 64;
+  dim3 grid((dim / 4 + 127) / 128, (rows + rs - 1) / rs);
+  if (dtype == 0) colsum_kernel<0><<<grid, 128, 0, stream>>>(a, out, rows, dim, rs);
+  else if (dtype == 1) colsum_kernel<1><<<grid, 128, 0, stream>>>(a, out, rows, dim, rs);
+  else colsum_kernel<2><<<grid, 128, 0, stream>>>(a, out, rows, dim, rs);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <bool BF16, int NV>
+static int lnb_launch(cudaStream_t stream, const uint16_t* dh, const float* x, const float* scale, long long mod_bs, int rpb, float* dx,
+                      float* dshift, float* dscale, long long dmod_bs, int rows, int dim) {
+  auto kern = ln_modulate_bwd_kernel<BF16, NV>;
+  const size_t smem = static_cast<size_t>(dim) * 8 * sizeof(float);
+  B200_SET_SMEM_ONCE(kern, static_cast<int>(smem));
+  const int blocks = (rows + 4 * LB_RPW - 1) / (4 * LB_RPW);
+  kern<<<blocks, 128, smem, stream>>>(dh, x, scale, mod_bs, rpb, dx, dshift, dscale, dmod_bs, rows, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_ln_modulate_bwd(const void* dh16, const float* x, const float* scale, long long mod_bs, int rows_per_batch, float* dx,
+                           float* dshift, float* dscale, long long dmod_bs, int rows, int dim, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 12 * 128, B200_ERR_SHAPE, "ln_modulate_bwd: dim %d must be a multiple of 4 and <= 1536", dim);
+  B200_REQUIRE(rows_per_batch % (4 * LB_RPW) == 0 && mod_bs % 4 == 0, B200_ERR_SHAPE, "ln_modulate_bwd: rows_per_batch must be a multiple of %d", 4 * LB_RPW);
+  B200_REQUIRE(ALIGNED16(x) && ALIGNED16(scale) && ALIGNED16(dx) && (reinterpret_cast<uintptr_t>(dh16) & 7) == 0, B200_ERR_ALIGN,
+               "ln_modulate_bwd: misaligned pointer");
+  const int batch = (rows + rows_per_batch - 1) / rows_per_batch;
+  for (int b = 0; b < batch; ++b) {
+    B200_CHECK_CUDA(cudaMemsetAsync(dshift + b * dmod_bs, 0, sizeof(float) * dim, stream));
+    B200_CHECK_CUDA(cudaMemsetAsync(dscale + b * dmod_bs, 0, sizeof(float) * dim, stream));
+  }
+  const int nvmax = (dim / 4 + 31) / 32;
+  const uint16_t* dh = static_cast<const uint16_t*>(dh16);
+#define LNB(BF, NVV) return lnb_launch<BF, NVV>(stream, dh, x, scale, mod_bs, rows_per_batch, dx, dshift, dscale, dmod_bs, rows, dim)
+  if (bf16) {
+    if (nvmax <= 3) LNB(true, 3);
+    if (nvmax <= 6) LNB(true, 6);
+    if (nvmax <= 9) LNB(true, 9);
+    LNB(true, 12);
+  }
+  if (nvmax <= 3) LNB(false, 3);
+  if (nvmax <= 6) LNB(false, 6);
+  if (nvmax <= 9) LNB(false, 9);
+  LNB(false, 12);
+#undef LNB
+}
+
+template <bool BF16, int HD>
+static int attn_bwd_spatial(const uint16_t* qkv, const uint16_t* o, const uint16_t* d_o, uint16_t* dqkv, float* lse, float* delta,
+                            int nseq, int S, int heads, cudaStream_t stream) {
+  using G = AB<HD>;
+  auto ka = attn_bwd_dq_kernel<BF16, HD>;
+  auto kb = attn_bwd_dkv_kernel<BF16, HD>;
+  const size_t smem_a = static_cast<size_t>(4) * G::TILE * 2;
+  const size_t smem_b = smem_a + 128 * sizeof(float);
+  B200_SET_SMEM_ONCE(ka, static_cast<int>(smem_a));
+  B200_SET_SMEM_ONCE(kb, static_cast<int>(smem_b));
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  dim3 grid(S / 64, heads, nseq);
+  ka<<<grid, 128, smem_a, stream>>>(qkv, o, d_o, dqkv, lse, delta, S, heads, scale_log2);
+  B200_CHECK_CUDA(cudaGetLastError());
+  kb<<<grid, 128, smem_b, stream>>>(qkv, d_o, dqkv, lse, delta, S, heads, scale_log2);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_attention_bwd(const void* qkv, const void* o, const void* d_o, void* dqkv, float* stats, int batch, int frames, int tokens,
+                         int heads, int head_dim, int bf16, int temporal, cudaStream_t stream) {
+  B200_REQUIRE(batch > 0 && frames > 0 && tokens > 0 && heads > 0, B200_ERR_SHAPE, "attention_bwd: bad shape");
+  B200_REQUIRE(ALIGNED16(qkv) && ALIGNED16(o) && ALIGNED16(d_o) && ALIGNED16(dqkv), B200_ERR_ALIGN, "attention_bwd: pointers must be 16-byte aligned");
+  const uint16_t *q = static_cast<const uint16_t*>(qkv), *oo = static_cast<const uint16_t*>(o), *g = static_cast<const uint16_t*>(d_o);
+  uint16_t* dq = static_cast<uint16_t*>(dqkv);
+  if (temporal) {
+    B200_REQUIRE(frames <= 16 && head_dim % 2 == 0 && head_dim <= 128, B200_ERR_UNSUPPORTED, "attention_bwd: temporal sequences of <= 16 frames only (got %d)", frames);
+    const size_t smem = (static_cast<size_t>(4) * frames * head_dim + 2 * frames * frames) * sizeof(float);
+    const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+    dim3 grid(batch * tokens, heads);
+    if (bf16) attn_bwd_temporal_kernel<true><<<grid, 128, smem, stream>>>(q, g, dq, frames, tokens, heads, head_dim, scale);
+    else attn_bwd_temporal_kernel<false><<<grid, 128, smem, stream>>>(q, g, dq, frames, tokens, heads, head_dim, scale);
+    B200_CHECK_CUDA(cudaGetLastError());
+    return B200_OK;
+  }
+  B200_REQUIRE(tokens % 64 == 0, B200_ERR_UNSUPPORTED, "attention_bwd: tokens per frame (%d) must be a multiple of 64", tokens);
+  B200_REQUIRE(head_dim == 64 || head_dim == 72, B200_ERR_UNSUPPORTED, "attention_bwd: head_dim %d not built (64, 72)", head_dim);
+  B200_REQUIRE(stats != nullptr && ALIGNED16(stats), B200_ERR_ALIGN, "attention_bwd: stats workspace missing");
+  const int nseq = batch * frames;
+  float* lse = stats;
+  float* delta = stats + static_cast<size_t>(nseq) * heads * tokens;
+  if (head_dim == 72) {
+    if (bf16) return attn_bwd_spatial<true, 72>(q, oo, g, dq, lse, delta, nseq, tokens, heads, stream);
+    return attn_bwd_spatial<false, 72>(q, oo, g, dq, lse, delta, nseq, tokens, heads, stream);
+  }
+  if (bf16) return attn_bwd_spatial<true, 64>(q, oo, g, dq, lse, delta, nseq, tokens, heads, stream);
+  return attn_bwd_spatial<false, 64>(q, oo, g, dq, lse, delta, nseq, tokens, heads, stream);
+}
+
+int launch_ada_outer(const float* dmod, long long dmod_bs, const void* sc16, float* dW, int batch, int NA, int dim, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(batch > 0 && batch <= 8 && NA > 0 && dim > 0 && dim % 4 == 0, B200_ERR_SHAPE, "ada_outer: batch <= 8, dim %% 4 == 0");
+  B200_REQUIRE(ALIGNED16(dW), B200_ERR_ALIGN, "ada_outer: dW must be 16-byte aligned");
+  const size_t smem = static_cast<size_t>(batch) * dim * sizeof(float);
+  B200_REQUIRE(smem <= 48 * 1024, B200_ERR_UNSUPPORTED, "ada_outer: batch * dim too large for the staging buffer");
+  const int blocks = NA < 148 * 8 ? NA : 148 * 8;
+  if (bf16) ada_outer_kernel<true><<<blocks, 256, smem, stream>>>(dmod, dmod_bs, static_cast<const uint16_t*>(sc16), dW, batch, NA, dim);
+  else ada_outer_kernel<false><<<blocks, 256, smem, stream>>>(dmod, dmod_bs, static_cast<const uint16_t*>(sc16), dW, batch, NA, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_ada_dsc(const float* dmod, long long dmod_bs, const void* w16, float* dsc, int batch, int NA, int dim, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(batch > 0 && batch <= 8 && NA > 0 && dim > 0 && dim % 2 == 0, B200_ERR_SHAPE, "ada_dsc: batch <= 8, dim even");
+  B200_CHECK_CUDA(cudaMemsetAsync(dsc, 0, sizeof(float) * batch * dim, stream));
+  const int slab = 128;
+  const int blocks = (NA + slab - 1) / slab;
+  if (bf16) ada_dsc_kernel<true><<<blocks, 256, 0, stream>>>(dmod, dmod_bs, static_cast<const uint16_t*>(w16), dsc, batch, NA, dim, slab);
+  else ada_dsc_kernel<false><<<blocks, 256, 0, stream>>>(dmod, dmod_bs, static_cast<const uint16_t*>(w16), dsc, batch, NA, dim, slab);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -12,7 +12,9 @@ sampling loop never synchronises the host with the GPU.  The per-step `randn_lik
 reference consumes RNG at eta = 0 too, gaussian_diffusion.py:555).
 
 CUDA tensors only -- there is no CPU path (the CPU truth is oracle/sampler_oracle.py, test infrastructure).
-Not built (raise NotImplementedError): cond_fn / denoised_fn hooks, predict_xstart, fixed-variance models, training_losses.
+`training_losses` (MSE + learned-range VB, the objective train.py uses) is torch elementwise math with autograd around the
+native forward/backward of the denoiser.  Not built (raise NotImplementedError): cond_fn / denoised_fn hooks, predict_xstart,
+fixed-variance models.
 """
 from __future__ import annotations
 
@@ -247,8 +249,65 @@ class SpacedDiffusion:
             pass
         return final["sample"]
 
-    def training_losses(self, *a, **k):
-        raise NotImplementedError("training_losses is not built in latte_b200.diffusion (sampling path only)")
+    # ------------------------------------------------------------------ training objective (train.py:131,221)
+    def _gather(self, name, t, ndim):
+        """_extract_into_tensor (gaussian_diffusion.py:869-881): float64 table -> device gather -> .float(), broadcastable."""
+        key = ("tab", name, t.device)
+        tab = self._dev.get(key)
+        if tab is None:
+            arr = np.log(self.betas) if name == "log_betas" else getattr(self, name)
+            tab = self._dev[key] = torch.from_numpy(np.asarray(arr, dtype=np.float64)).to(t.device)
+        return tab[t].float().view(-1, *([1] * (ndim - 1)))
+
+    def q_sample(self, x_start, t, noise=None):
+        """x_t = sqrt(abar_t) x_0 + sqrt(1 - abar_t) noise (gaussian_diffusion.py:223-236)."""
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        return (self._gather("sqrt_alphas_cumprod", t, x_start.dim()) * x_start
+                + self._gather("sqrt_one_minus_alphas_cumprod", t, x_start.dim()) * noise)
+
+    def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
+        """LossType.MSE with LEARNED_RANGE variance (gaussian_diffusion.py:719-795, the only objective create_diffusion builds):
+        loss = mean((noise - eps)^2) + L_vb(eps.detach(), var_values), with L_vb = KL(q(x_{t-1}|x_t,x_0) || p) in bits and the
+        discretised decoder NLL at t == 0 (:686-716; diffusion_utils.py:10-88).  The model is called with the ORIGINAL timestep
+        (respace.py:125-130).  Elementwise fp32 torch ops on (B, F, C, h, w) -- 65 k elements per video -- with autograd; the
+        denoiser underneath is latte_b200.Latte's native forward/backward (latte_b200/training.py)."""
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        nd = x_start.dim()
+        x_t = self.q_sample(x_start, t, noise)
+        mo = self._call_model(model, x_t, t, model_kwargs)
+        if isinstance(mo, tuple):
+            mo = mo[0]
+        Cc = x_t.shape[2]
+        if tuple(mo.shape) != (x_t.shape[0], x_t.shape[1], 2 * Cc, *x_t.shape[3:]):
+            raise ValueError(f"model output {tuple(mo.shape)} is not the learn_sigma layout of x {tuple(x_t.shape)}")
+        mo = mo.float()
+        eps, var_values = torch.split(mo, Cc, dim=2)
+        flat = lambda v: v.mean(dim=list(range(1, v.dim())))   # noqa: E731  mean_flat
+        # --- variational bound term on a frozen mean (:757-765)
+        eps_f = eps.detach()
+        min_log = self._gather("posterior_log_variance_clipped", t, nd)
+        max_log = self._gather("log_betas", t, nd)
+        frac = (var_values + 1) / 2
+        log_var = frac * max_log + (1 - frac) * min_log
+        pred_x0 = self._gather("sqrt_recip_alphas_cumprod", t, nd) * x_t - self._gather("sqrt_recipm1_alphas_cumprod", t, nd) * eps_f
+        c1, c2 = self._gather("posterior_mean_coef1", t, nd), self._gather("posterior_mean_coef2", t, nd)
+        mean = c1 * pred_x0 + c2 * x_t
+        true_mean = c1 * x_start + c2 * x_t
+        kl = 0.5 * (-1.0 + log_var - min_log + torch.exp(min_log - log_var) + (true_mean - mean) ** 2 * torch.exp(-log_var))
+        kl = flat(kl) / np.log(2.0)
+        centered = x_start - mean
+        inv_std = torch.exp(-0.5 * log_var)
+        cdf = lambda v: 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (v + 0.044715 * torch.pow(v, 3))))   # noqa: E731
+        cdf_plus, cdf_min = cdf(inv_std * (centered + 1.0 / 255.0)), cdf(inv_std * (centered - 1.0 / 255.0))
+        log_probs = torch.where(x_start < -0.999, torch.log(cdf_plus.clamp(min=1e-12)),
+                                torch.where(x_start > 0.999, torch.log((1.0 - cdf_min).clamp(min=1e-12)),
+                                            torch.log((cdf_plus - cdf_min).clamp(min=1e-12))))
+        nll = flat(-log_probs) / np.log(2.0)
+        vb = torch.where(t.to(kl.device) == 0, nll, kl)
+        mse = flat((noise - eps) ** 2)
+        return {"loss": mse + vb, "mse": mse, "vb": vb}
 
 
 def create_diffusion(timestep_respacing, noise_schedule="linear", use_kl=False, sigma_small=False, predict_xstart=False,

@@ -132,6 +132,8 @@ class Latte(DeviceCacheMixin, nn.Module):
         self.attention_mode = attention_mode
         #: tensor-core operand type used when the parameters are fp32 (fp16 = the reference's `use_fp16` path)
         self.compute_dtype = torch.float16
+        #: operand type of the training step with fp32 parameters outside autocast (train.py runs under bf16 autocast)
+        self.train_dtype = torch.bfloat16
 
         self.x_embedder = _PatchEmbedParams(input_size, patch_size, in_channels, hidden_size)
         self.t_embedder = _TimestepParams(hidden_size)
@@ -277,8 +279,10 @@ class Latte(DeviceCacheMixin, nn.Module):
         if not x.is_cuda:
             raise RuntimeError("latte_b200.Latte runs on CUDA (sm_100a) only; there is no CPU fallback "
                                "(the CPU truth lives in oracle/, which is test infrastructure)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("latte_b200: the backward pass is not built yet; call under torch.no_grad() / .eval()")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            if use_cfg or trajectory_step is not None:
+                raise NotImplementedError("latte_b200: forward_with_cfg / trajectory conditioning are sampling-only; train through forward()")
+            return self._run_train(x, t, y)
         if x.dim() != 5 or x.shape[1] != self.num_frames or x.shape[2] != self.in_channels \
                 or x.shape[3] != self.input_size or x.shape[4] != self.input_size:
             raise ValueError(f"x must be (B, {self.num_frames}, {self.in_channels}, {self.input_size}, {self.input_size}), got {tuple(x.shape)}")
@@ -319,6 +323,40 @@ class Latte(DeviceCacheMixin, nn.Module):
                              torch.cuda.current_stream(dev).cuda_stream)
         pd = self.blocks[0].attn.qkv.weight.dtype
         return out if pd == torch.float32 else out.to(pd)
+
+    def _run_train(self, x, t, y):
+        """Training-mode forward (`model.train()` with grad enabled, train.py:206-222): the native forward that keeps its
+        activations, with the hand-written backward attached as one autograd node (latte_b200/training.py), so the reference's
+        `loss.backward()`, optimizer, `clip_grad_norm_` and DistributedDataParallel work unchanged.  Operands are bf16 under
+        `torch.autocast(bfloat16)` / fp32 parameters (the reference's mixed-precision recipe) or the parameter dtype if that is
+        16-bit; accumulation, the residual stream, LayerNorm statistics and every gradient buffer are fp32."""
+        from . import training, train_ops
+        if x.dim() != 5 or x.shape[1] != self.num_frames or x.shape[2] != self.in_channels \
+                or x.shape[3] != self.input_size or x.shape[4] != self.input_size:
+            raise ValueError(f"x must be (B, {self.num_frames}, {self.in_channels}, {self.input_size}, {self.input_size}), got {tuple(x.shape)}")
+        dev = x.device
+        if self.pos_embed.device != dev:
+            raise RuntimeError(f"model is on {self.pos_embed.device}, input on {dev}")
+        _lib.load()
+        pd = self.blocks[0].attn.qkv.weight.dtype
+        od = pd if pd in (torch.float16, torch.bfloat16) else self.train_dtype
+        if torch.is_autocast_enabled("cuda"):
+            od = torch.get_autocast_dtype("cuda")
+            if od not in (torch.float16, torch.bfloat16):
+                raise TypeError(f"latte_b200: autocast dtype {od} is not a tensor-core operand type")
+        B = x.shape[0]
+        tt = t.to(device=dev, dtype=torch.int64)
+        yy = None
+        if self.extras == 2:
+            if y is None:
+                raise ValueError("class-conditional model (extras=2) needs labels y")
+            yy = y.to(device=dev, dtype=torch.int64)
+            if self.y_embedder.dropout_prob > 0:                        # token_drop, latte.py:137-146
+                drop = torch.rand(B, device=dev) < self.y_embedder.dropout_prob
+                yy = torch.where(drop, torch.full_like(yy, self.y_embedder.num_classes), yy)
+        with torch.autocast("cuda", enabled=False):
+            c = training.conditioning(self, tt, yy)
+            return training.train_forward(self, train_ops.NativeOps(od), od, x.float(), c)
 
     def _launch(self, lib, shape, w, xf, tt, yy, mod, B, use_cfg, cfg_scale, out, base, need, stream):
         """ONE C-ABI call = the whole forward (203 kernel launches for XL/2) enqueued on `stream`."""

@@ -1,0 +1,290 @@
+"""Training step of `Latte` (BASELINE config 5: train.py:206-222 — forward + backward under `loss.backward()`).
+
+The reference trains through torch autograd over ~1000 eager kernels per forward.  Here the forward keeps the activations the
+backward needs and the backward is written out explicitly, op by op, over the same hand-written kernels as the sampling path
+(the tcgen05 GEMM does every dgrad and wgrad; wgrads accumulate in fp32 straight into the gradient buffers through the
+residual epilogue) plus the kernels of csrc/train.cu (LayerNorm-modulate backward, gate / GELU backward with the bias and
+per-sample reductions fused, attention backward on tensor cores, 16-bit transposes, adaLN outer products).
+
+Derivatives follow the reference forward (models/latte.py): block :177-181, modulate :28-29, attention 'math' :48-77, Mlp
+:169-171, FinalLayer :197-201, PatchEmbed + pos_embed :330-331, temp_embed :357-358.  Rows stay in (b, f, n) order for
+spatial AND temporal blocks (the regrouping of :355/:368 is index arithmetic inside the attention kernels), so every
+per-sample adaLN vector addresses `rows_per_batch = F*N` consecutive rows.
+
+`TrainEngine` is backend-agnostic: the product backend is latte_b200.train_ops.NativeOps (C ABI, CUDA only, raises without
+the extension); tests drive the same orchestration through oracle/train_ops_oracle.TorchOps on the CPU and compare with
+gradients produced by the unmodified reference (tests/golden/train_tiny64.npz).
+"""
+from __future__ import annotations
+
+import torch
+
+_BLOCK_LINEARS = ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2")
+
+
+class TrainEngine:
+    def __init__(self, model, ops, dtype):
+        self.m = model
+        self.ops = ops
+        self.dtype = dtype
+        self.saved = None
+        self.w = None
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def prepare(self):
+        """Operand copies of the current parameters: W and W^T in the compute type (dgrad reads W^T as its weight operand),
+        the adaLN weights of all blocks + final layer stacked, zero-padded patch-embed / final-layer operands (K = 16 and 32
+        are below the GEMM's 64-element k-block)."""
+        m, ops = self.m, self.ops
+        D = m.hidden_size
+        W = {}
+        for i, blk in enumerate(m.blocks):
+            for name in _BLOCK_LINEARS:
+                lin = blk
+                for part in name.split("."):
+                    lin = getattr(lin, part)
+                W[f"{i}.{name}"] = ops.cast(lin.weight) + (lin.bias.detach().float().contiguous(),)
+        ada_w = torch.cat([b.adaLN_modulation[1].weight.detach() for b in m.blocks] + [m.final_layer.adaLN_modulation[1].weight.detach()])
+        W["ada_w"] = ops.cast(ada_w)[0]
+        W["ada_b"] = torch.cat([b.adaLN_modulation[1].bias.detach() for b in m.blocks] +
+                               [m.final_layer.adaLN_modulation[1].bias.detach()]).float().contiguous()
+        dev = ada_w.device
+        pw = m.x_embedder.proj.weight.detach().reshape(D, -1)
+        self.kp = pw.shape[1]
+        pad = torch.zeros(D, 64, dtype=torch.float32, device=dev)
+        pad[:, : self.kp] = pw
+        W["patch_w"] = ops.cast(pad)[0]
+        W["patch_b"] = m.x_embedder.proj.bias.detach().float().contiguous()
+        fw = m.final_layer.linear.weight.detach()                     # [p*p*Cout, D]
+        self.nf = fw.shape[0]
+        W["final_w"] = ops.cast(fw)[0]
+        padt = torch.zeros(D, 64, dtype=torch.float32, device=dev)
+        padt[:, : self.nf] = fw.t()
+        W["final_wt"] = ops.cast(padt)[0]                             # dgrad weight operand [N = D, K = 64]
+        W["final_b"] = m.final_layer.linear.bias.detach().float().contiguous()
+        self.w = W
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _patchify(self, x):
+        """(B, F, C, H, W) -> rows (b, f, gh, gw) x columns (c, i, j): timm PatchEmbed's Conv2d(k = s = p) as a GEMM operand."""
+        m = self.m
+        B, Fr, C, H, Wd = x.shape
+        p = m.patch_size
+        xx = x.reshape(B * Fr, C, H // p, p, Wd // p, p).permute(0, 2, 4, 1, 3, 5)
+        return xx.reshape(B * Fr * (H // p) * (Wd // p), C * p * p)
+
+    def _unpatchify(self, tok, B):
+        """rows (b, f, h, w) x (p, q, c) -> (B, F, c, h*p, w*q) (latte.py:297-310, :375-376)."""
+        m = self.m
+        c, p = m.out_channels, m.patch_size
+        g = m.input_size // p
+        t = tok.view(B * m.num_frames, g, g, p, p, c).permute(0, 5, 1, 3, 2, 4)
+        return t.reshape(B, m.num_frames, c, g * p, g * p)
+
+    def _patchify_out(self, dout):
+        m = self.m
+        c, p = m.out_channels, m.patch_size
+        g = m.input_size // p
+        B = dout.shape[0]
+        t = dout.reshape(B * m.num_frames, c, g, p, g, p).permute(0, 2, 4, 3, 5, 1)
+        return t.reshape(B * m.num_frames * g * g, p * p * c).contiguous()
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def forward(self, x, c):
+        """x (B, F, C, H, W) fp32, c (B, D) fp32 = t_embedder(t) + y_embedder(y) (latte.py:332-348) -> (B, F, 2C, H, W) fp32."""
+        if self.w is None:
+            self.prepare()
+        m, ops, W = self.m, self.ops, self.w
+        B = x.shape[0]
+        D, Fr, N, H = m.hidden_size, m.num_frames, m.x_embedder.num_patches, m.num_heads
+        T, rpb = B * Fr * N, Fr * N
+        dev = x.device
+        sc = ops.to_operand(torch.nn.functional.silu(c.float()).contiguous())            # adaLN_modulation[0], final too
+        mod = ops.linear(sc, W["ada_w"], W["ada_b"]).float()                               # (B, depth*6D + 2D)
+        S = {"B": B, "c": c, "sc": sc, "mod": mod, "blocks": []}
+
+        xp = torch.zeros(T, 64, dtype=torch.float32, device=dev)
+        xp[:, : self.kp] = self._patchify(x.float())
+        xp = ops.to_operand(xp)
+        xs = m.pos_embed.detach().float().reshape(1, N, D).expand(B * Fr, N, D).reshape(T, D).contiguous()
+        ops.linear_accum(xs, xp, W["patch_w"], W["patch_b"])
+        S["xp"] = xp
+        temp = m.temp_embed.detach().float().reshape(Fr, D).contiguous()
+        for i in range(m.depth):
+            mv = mod[:, i * 6 * D:(i + 1) * 6 * D]
+            sh1, sc1, g1, sh2, sc2, g2 = (mv[:, k * D:(k + 1) * D] for k in range(6))
+            temporal = bool(i % 2)
+            wq, wp, w1, w2 = (W[f"{i}.{n}"] for n in _BLOCK_LINEARS)
+            h1 = ops.ln_modulate(xs, sh1, sc1, rpb)
+            qkv = ops.linear(h1, wq[0], wq[2])
+            o = ops.attention(qkv, B, Fr, N, H, temporal)
+            m1 = ops.linear(o, wp[0], wp[2])
+            xm = ops.gate_residual(xs, m1, g1, rpb)
+            h2 = ops.ln_modulate(xm, sh2, sc2, rpb)
+            u = ops.linear(h2, w1[0], w1[2])
+            a = ops.gelu(u)
+            m2 = ops.linear(a, w2[0], w2[2])
+            del a
+            xo = ops.gate_residual(xm, m2, g2, rpb, row_add=temp if i == 0 else None, tokens=N)
+            S["blocks"].append((xs, h1, qkv, o, m1, xm, h2, u, m2))
+            xs = xo
+        base = m.depth * 6 * D
+        shf, scf = mod[:, base:base + D], mod[:, base + D:base + 2 * D]
+        hf = ops.ln_modulate(xs, shf, scf, rpb)
+        tok = torch.zeros(T, self.nf, dtype=torch.float32, device=dev)
+        ops.linear_accum(tok, hf, W["final_w"], W["final_b"])
+        S["x_last"], S["hf"] = xs, hf
+        self.saved = S
+        return self._unpatchify(tok, B)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def backward(self, dout):
+        """dout (B, F, 2C, H, W) -> (grads: {parameter name: fp32 tensor}, dc (B, D) fp32).  Frees the saved activations."""
+        m, ops, W, S = self.m, self.ops, self.w, self.saved
+        self.saved = None
+        B = S["B"]
+        D, Fr, N, H = m.hidden_size, m.num_frames, m.x_embedder.num_patches, m.num_heads
+        T, rpb = B * Fr * N, Fr * N
+        dev = dout.device
+        mod = S["mod"]
+        G = {}
+        dmod = torch.zeros_like(mod)
+
+        def wgrad(n_out, dy_t, x_t):
+            g = torch.zeros(n_out, x_t.shape[0], dtype=torch.float32, device=dev)
+            ops.linear_accum(g, dy_t, x_t)
+            return g
+
+        # ---- final layer (latte.py:197-201) ----
+        dtok = self._patchify_out(dout.float())                                         # (T, nf) fp32
+        G["final_layer.linear.bias"] = ops.colsum(dtok)
+        dtok16 = ops.to_operand(dtok)
+        G["final_layer.linear.weight"] = wgrad(self.nf, ops.transpose(dtok16), ops.transpose(S["hf"]))
+        dtp = torch.zeros(T, 64, dtype=torch.float32, device=dev)
+        dtp[:, : self.nf] = dtok
+        dhf = ops.linear(ops.to_operand(dtp), W["final_wt"])
+        dx = torch.zeros(T, D, dtype=torch.float32, device=dev)
+        base = m.depth * 6 * D
+        dsh, dsc_ = ops.ln_modulate_bwd(dhf, S["x_last"], mod[:, base:base + D], mod[:, base + D:base + 2 * D], rpb, dx)
+        dmod[:, base:base + D], dmod[:, base + D:base + 2 * D] = dsh, dsc_
+        del dhf, dtp, dtok16
+
+        # ---- blocks, last to first (latte.py:177-181) ----
+        for i in reversed(range(m.depth)):
+            xs, h1, qkv, o, m1, xm, h2, u, m2 = S["blocks"].pop()
+            mv = mod[:, i * 6 * D:(i + 1) * 6 * D]
+            sh1, sc1, g1, sh2, sc2, g2 = (mv[:, k * D:(k + 1) * D] for k in range(6))
+            dv = dmod[:, i * 6 * D:(i + 1) * 6 * D]
+            temporal = bool(i % 2)
+            wq, wp, w1, w2 = (W[f"{i}.{n}"] for n in _BLOCK_LINEARS)
+            p = f"blocks.{i}."
+            # x_out = x_mid + g2 * fc2(gelu(fc1(LNmod(x_mid))))
+            dm2, dg2, G[p + "mlp.fc2.bias"] = ops.gate_bwd(dx, m2, g2, rpb)
+            a = ops.gelu(u)
+            dm2_t = ops.transpose(dm2)
+            G[p + "mlp.fc2.weight"] = wgrad(D, dm2_t, ops.transpose(a))
+            del a, dm2_t
+            da = ops.linear(dm2, w2[1])
+            du, G[p + "mlp.fc1.bias"] = ops.gelu_bwd(da, u)
+            del da, dm2
+            G[p + "mlp.fc1.weight"] = wgrad(m.mlp_hidden, ops.transpose(du), ops.transpose(h2))
+            dh2 = ops.linear(du, w1[1])
+            del du
+            dsh2, dsc2 = ops.ln_modulate_bwd(dh2, xm, sh2, sc2, rpb, dx)
+            del dh2
+            # x_mid = x_in + g1 * proj(attn(qkv(LNmod(x_in))))
+            dm1, dg1, G[p + "attn.proj.bias"] = ops.gate_bwd(dx, m1, g1, rpb)
+            G[p + "attn.proj.weight"] = wgrad(D, ops.transpose(dm1), ops.transpose(o))
+            do = ops.linear(dm1, wp[1])
+            del dm1
+            dqkv = ops.attention_bwd(qkv, o, do, B, Fr, N, H, temporal)
+            del do
+            G[p + "attn.qkv.bias"] = ops.colsum(dqkv)
+            G[p + "attn.qkv.weight"] = wgrad(3 * D, ops.transpose(dqkv), ops.transpose(h1))
+            dh1 = ops.linear(dqkv, wq[1])
+            del dqkv
+            dsh1, dsc1 = ops.ln_modulate_bwd(dh1, xs, sh1, sc1, rpb, dx)
+            del dh1
+            for k, t in enumerate((dsh1, dsc1, dg1, dsh2, dsc2, dg2)):
+                dv[:, k * D:(k + 1) * D] = t
+            del xs, h1, qkv, o, m1, xm, h2, u, m2
+
+        # ---- patch embedding (latte.py:330-331; pos_embed / temp_embed are frozen, :246-247) ----
+        G["x_embedder.proj.bias"] = ops.colsum(dx)
+        gpe = wgrad(D, ops.transpose(ops.to_operand(dx)), ops.transpose(S["xp"]))
+        G["x_embedder.proj.weight"] = gpe[:, : self.kp].reshape(m.x_embedder.proj.weight.shape).contiguous()
+
+        # ---- adaLN_modulation of every block + final layer: mod = Linear(SiLU(c)) (latte.py:160-163, 192-195) ----
+        dW = ops.ada_outer(dmod, S["sc"])                                               # (depth*6D + 2D, D)
+        db = dmod.sum(0)
+        for i in range(m.depth):
+            G[f"blocks.{i}.adaLN_modulation.1.weight"] = dW[i * 6 * D:(i + 1) * 6 * D]
+            G[f"blocks.{i}.adaLN_modulation.1.bias"] = db[i * 6 * D:(i + 1) * 6 * D]
+        G["final_layer.adaLN_modulation.1.weight"] = dW[base:base + 2 * D]
+        G["final_layer.adaLN_modulation.1.bias"] = db[base:base + 2 * D]
+        dsc = ops.ada_dsc(dmod, W["ada_w"])
+        c = S["c"].float()
+        sg = torch.sigmoid(c)
+        dc = dsc * (sg * (1 + c * (1 - sg)))                                            # d silu
+        return G, dc
+
+
+def trainable_names(model):
+    """Names, in a fixed order, of the parameters the engine produces gradients for (everything except the embedders that
+    feed `c`, whose few-kilobyte graph stays on torch autograd, and the frozen sin-cos tables)."""
+    names = ["x_embedder.proj.weight", "x_embedder.proj.bias"]
+    for i in range(model.depth):
+        for n in _BLOCK_LINEARS:
+            names += [f"blocks.{i}.{n}.weight", f"blocks.{i}.{n}.bias"]
+        names += [f"blocks.{i}.adaLN_modulation.1.weight", f"blocks.{i}.adaLN_modulation.1.bias"]
+    names += ["final_layer.linear.weight", "final_layer.linear.bias",
+              "final_layer.adaLN_modulation.1.weight", "final_layer.adaLN_modulation.1.bias"]
+    return names
+
+
+class _LatteTrainFn(torch.autograd.Function):
+    """Autograd boundary: inputs (x, c, *parameters) -> output; backward hands each parameter its gradient, so optimizers,
+    `clip_grad_norm_`, gradient accumulation and DistributedDataParallel's bucketed all-reduce hooks see ordinary `.grad`s."""
+
+    @staticmethod
+    def forward(ctx, engine, names, x, c, *params):
+        ctx.engine, ctx.names = engine, names
+        ctx.dtypes = [p.dtype for p in params]
+        with torch.no_grad():
+            engine.prepare()
+            out = engine.forward(x.detach(), c.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng = ctx.engine
+        if eng.saved is None:
+            raise RuntimeError("latte_b200: backward called twice on one training forward (activations are freed after the first)")
+        with torch.no_grad():
+            G, dc = eng.backward(dout.contiguous())
+        grads = tuple(G[n].to(dt) if G[n].dtype != dt else G[n] for n, dt in zip(ctx.names, ctx.dtypes))
+        return (None, None, None, dc) + grads
+
+
+def train_forward(model, ops, dtype, x, c):
+    """Forward of one training step with the backward attached.  c = t_embedder(t) + y_embedder(y), computed by the caller with
+    torch autograd (a (B, D) graph)."""
+    eng = TrainEngine(model, ops, dtype)
+    names = trainable_names(model)
+    named = dict(model.named_parameters())
+    params = [named[n] for n in names]
+    return _LatteTrainFn.apply(eng, names, x, c, *params)
+
+
+def conditioning(model, t, y):
+    """c = t_embedder(t) [+ y_embedder(y)] with torch autograd (latte.py:98-123 sincos + MLP, :148-153 table lookup): a
+    (B, D) graph of a handful of kernels whose parameters get their gradients from `dc`."""
+    import math
+    half = model.t_embedder.frequency_embedding_size // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    c = model.t_embedder.mlp(emb.to(model.t_embedder.mlp[0].weight.dtype)).float()
+    if model.extras == 2:
+        c = c + model.y_embedder.embedding_table(y).float()
+    return c

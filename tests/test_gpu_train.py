@@ -1,0 +1,220 @@
+"""GPU: the training step (BASELINE config 5).  (1) every kernel of csrc/train.cu against the torch restatement of the same op
+(oracle/train_ops_oracle.TorchOps: fp32 math on the same 16-bit inputs, one rounding at the output); (2) the whole native
+forward + backward through `model(x, t, y)` / `loss.backward()` against the gradients of the UNMODIFIED reference
+(tests/golden/train_tiny64.npz) and, at the XL head geometry (head_dim 72, 256 tokens, 16 frames), against the same engine
+driven through TorchOps in fp32 on the GPU.  Tolerances: 16-bit operand rounding (fp16 2^-11, bf16 2^-8 relative per operand)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DTS = [torch.float16, torch.bfloat16]
+EPS = {torch.float16: 1e-3, torch.bfloat16: 8e-3}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _ops(dt):
+    from latte_b200.train_ops import NativeOps
+    from oracle.train_ops_oracle import TorchOps
+    return NativeOps(dt), TorchOps(dt)
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _close(a, b, tol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item() + 1e-12
+    assert err <= tol * scale, f"{what}: max-abs {err:.3e} vs scale {scale:.3e} (tol {tol})"
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_transpose_cast_colsum(dev, dt):
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(1)
+    for R, Cc in [(1536, 128), (4096, 1152), (512, 32), (130, 66)]:
+        a = torch.randn(R, Cc, generator=g).to(dev).to(dt)
+        assert torch.equal(nat.transpose(a), a.t().contiguous())
+        _close(nat.colsum(a), ref.colsum(a), 1e-5, "colsum16")
+    w = torch.randn(384, 1152, generator=g).to(dev)
+    w16, wt16 = nat.cast(w)
+    assert torch.equal(w16, w.to(dt)) and torch.equal(wt16, w.to(dt).t().contiguous())
+    x = torch.randn(2048, 384, generator=g).to(dev)
+    assert torch.equal(nat.to_operand(x), x.to(dt))
+    _close(nat.colsum(x), x.sum(0), 1e-5, "colsum32")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_linear_accum_small_and_wgrad_shapes(dev, dt):
+    """wgrad = dY^T . X through the residual epilogue with a unit gate (fp32 accumulate into the gradient), incl. M = 32
+    (final layer), N = 64 (patch embed) and M = 5 (adaLN rows through the 16-bit epilogue)."""
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(2)
+    for M, N, K in [(32, 1152, 2048), (1152, 64, 4096), (384, 128, 1536), (3456, 1152, 8192)]:
+        a = torch.randn(M, K, generator=g).to(dev).to(dt)
+        w = torch.randn(N, K, generator=g).to(dev).to(dt)
+        base = torch.randn(M, N, generator=g).to(dev)
+        got = nat.linear_accum(base.clone(), a, w)
+        want = ref.linear_accum(base.clone(), a, w)
+        _close(got, want, 2e-5, f"linear_accum {M}x{N}x{K}")
+    a = torch.randn(5, 1152, generator=g).to(dev).to(dt)
+    w = (torch.randn(6912 + 2304, 1152, generator=g) / 34).to(dev).to(dt)
+    b = torch.randn(6912 + 2304, generator=g).to(dev)
+    _close(nat.linear(a, w, b), ref.linear(a, w, b), EPS[dt], "linear M=5")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_elementwise_forward_ops(dev, dt):
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(3)
+    B, Fr, N, D = 3, 8, 64, 384
+    T, rpb = B * Fr * N, Fr * N
+    x = torch.randn(T, D, generator=g).to(dev)
+    m = torch.randn(T, D, generator=g).to(dev).to(dt)
+    mod = torch.randn(B, 6 * D, generator=g).to(dev)
+    gate = mod[:, 2 * D:3 * D]
+    temp = torch.randn(Fr, D, generator=g).to(dev)
+    _close(nat.gate_residual(x, m, gate, rpb), ref.gate_residual(x, m, gate, rpb), 1e-6, "gate_residual")
+    _close(nat.gate_residual(x, m, gate, rpb, row_add=temp, tokens=N), ref.gate_residual(x, m, gate, rpb, row_add=temp, tokens=N),
+           1e-6, "gate_residual+temp")
+    u = (torch.randn(T, 4 * D, generator=g) * 2).to(dev).to(dt)
+    _close(nat.gelu(u), ref.gelu(u), EPS[dt], "gelu")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_elementwise_backward_ops(dev, dt):
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(4)
+    B, Fr, N, D = 3, 8, 64, 384
+    T, rpb = B * Fr * N, Fr * N
+    dx = torch.randn(T, D, generator=g).to(dev)
+    m = torch.randn(T, D, generator=g).to(dev).to(dt)
+    mod = torch.randn(B, 6 * D, generator=g).to(dev)
+    gate, shift, scale = mod[:, 2 * D:3 * D], mod[:, 0:D], mod[:, D:2 * D]
+    for got, want, name in zip(nat.gate_bwd(dx, m, gate, rpb), ref.gate_bwd(dx, m, gate, rpb), ("dm", "dgate", "dbias")):
+        _close(got, want, EPS[dt] if name == "dm" else 2e-5, "gate_bwd " + name)
+    u = (torch.randn(T, 4 * D, generator=g) * 2).to(dev).to(dt)
+    da = torch.randn(T, 4 * D, generator=g).to(dev).to(dt)
+    du, db = nat.gelu_bwd(da, u)
+    du_r, db_r = ref.gelu_bwd(da, u)
+    _close(du, du_r, EPS[dt], "gelu_bwd du")
+    _close(db, db_r, 3e-3, "gelu_bwd dbias")      # sum of fp32 values vs sum of the same values: order only
+    x = (torch.randn(T, D, generator=g) * 3 + 1).to(dev)
+    dh = torch.randn(T, D, generator=g).to(dev).to(dt)
+    acc0 = torch.randn(T, D, generator=g).to(dev)
+    acc_n, acc_r = acc0.clone(), acc0.clone()
+    ds_n = nat.ln_modulate_bwd(dh, x, shift, scale, rpb, acc_n)
+    ds_r = ref.ln_modulate_bwd(dh, x, shift, scale, rpb, acc_r)
+    _close(acc_n, acc_r, 2e-5, "ln_modulate_bwd dx")
+    _close(ds_n[0], ds_r[0], 2e-5, "ln_modulate_bwd dshift")
+    _close(ds_n[1], ds_r[1], 2e-5, "ln_modulate_bwd dscale")
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("geom", [(2, 8, 64, 2, 64), (1, 16, 256, 8, 72), (2, 16, 128, 3, 72), (1, 8, 1024, 2, 72)])
+@pytest.mark.parametrize("temporal", [False, True])
+def test_attention_backward(dev, dt, geom, temporal):
+    """dqkv of softmax(QK^T hd^-1/2)V (latte.py:48-77) for spatial sequences (tensor cores, scores recomputed) and temporal
+    sequences (F <= 16), at head_dim 64 and 72; the forward output comes from the sampling path's attention kernel."""
+    nat, ref = _ops(dt)
+    B, Fr, N, H, hd = geom
+    g = torch.Generator().manual_seed(B * 1000 + N + hd)
+    T, D = B * Fr * N, H * hd
+    qkv = torch.randn(T, 3 * D, generator=g).to(dev).to(dt)
+    do = torch.randn(T, D, generator=g).to(dev).to(dt)
+    o = nat.attention(qkv, B, Fr, N, H, temporal)
+    got = nat.attention_bwd(qkv, o, do, B, Fr, N, H, temporal)
+    want = ref.attention_bwd(qkv, o, do, B, Fr, N, H, temporal)
+    for k, name in enumerate(("dq", "dk", "dv")):
+        e = _rel(got[:, k * D:(k + 1) * D], want[:, k * D:(k + 1) * D])
+        assert e < 3 * EPS[dt], f"{name}: relative Frobenius error {e:.3e}"
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_adaln_gradients(dev, dt):
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(6)
+    B, D, NA = 5, 384, 4 * 6 * 384 + 2 * 384
+    dmod = torch.randn(B, NA, generator=g).to(dev)
+    sc = torch.randn(B, D, generator=g).to(dev).to(dt)
+    w = (torch.randn(NA, D, generator=g) / 20).to(dev).to(dt)
+    _close(nat.ada_outer(dmod, sc), ref.ada_outer(dmod, sc), 2e-5, "ada_outer")
+    _close(nat.ada_dsc(dmod, w), ref.ada_dsc(dmod, w), 2e-5, "ada_dsc")
+
+
+def _golden_model(golden_dir, dev):
+    from latte_b200 import Latte
+    from oracle import latte_oracle as O
+    g = np.load(os.path.join(golden_dir, "train_tiny64.npz"))
+    cfg = O.make_config("Latte-tiny64/2", input_size=16, num_frames=8)
+    m = Latte(input_size=16, hidden_size=128, depth=2, num_heads=2, num_frames=8, num_classes=101, extras=2)
+    m.load_state_dict(O.make_weights(cfg, 21), strict=True)
+    return g, m.to(dev)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_training_step_matches_reference_gradients(dev, golden_dir, dt):
+    """model.train() + diffusion.training_losses + loss.backward() -- the reference's train.py:206-222 -- on the native path."""
+    from latte_b200.diffusion import create_diffusion
+    g, m = _golden_model(golden_dir, dev)
+    m.train()
+    m.y_embedder.dropout_prob = 0.0          # the golden was generated without label dropout (no RNG in the comparison)
+    m.train_dtype = dt
+    d = create_diffusion(timestep_respacing="")
+    x0, noise = torch.from_numpy(g["x0"]).to(dev), torch.from_numpy(g["noise"]).to(dev)
+    t, y = torch.from_numpy(g["t"]).to(dev), torch.from_numpy(g["y"]).to(dev)
+    terms = d.training_losses(m, x0, t, dict(y=y), noise=noise)
+    loss = terms["loss"].mean()
+    assert abs(loss.item() - float(g["loss"])) < 3 * EPS[dt] * abs(float(g["loss"]))
+    loss.backward()
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, want in zip([str(n) for n in g["grad_names"]], g["grad_norms"]):
+        got = named[k].grad.double().norm().item()
+        worst = max(worst, abs(got - want) / want)
+        assert abs(got - want) <= 10 * EPS[dt] * want, (k, got, want)
+    for key in g.files:
+        if key.startswith("grad::"):
+            ref = torch.from_numpy(g[key]).to(dev)
+            e = _rel(named[key[6:]].grad, ref)
+            assert e < 10 * EPS[dt], (key, e)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_training_step_xl_head_geometry(dev, dt):
+    """head_dim 72, 256 tokens, 16 frames, depth 4 (Latte-tiny72/2): native engine vs the same engine through TorchOps in fp32."""
+    from latte_b200 import Latte, training
+    from latte_b200.train_ops import NativeOps
+    from oracle import latte_oracle as O
+    from oracle.train_ops_oracle import TorchOps
+    cfg = O.make_config("Latte-tiny72/2", input_size=32, num_frames=16)
+    m = Latte(input_size=32, hidden_size=576, depth=4, num_heads=8, num_frames=16, num_classes=101, extras=2)
+    m.load_state_dict(O.make_weights(cfg, 5), strict=True)
+    m = m.to(dev)
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 16, 4, 32, 32, generator=gen).to(dev)
+    t = torch.tensor([3, 700], device=dev)
+    y = torch.tensor([4, 101], device=dev)
+    dout = torch.randn(2, 16, 8, 32, 32, generator=gen).to(dev)
+    grads = []
+    for ops, od in ((NativeOps(dt), dt), (TorchOps(torch.float32), torch.float32)):
+        m.zero_grad(set_to_none=True)
+        out = training.train_forward(m, ops, od, x, training.conditioning(m, t, y))
+        out.backward(dout)
+        grads.append(({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}, out.detach()))
+    (gn, on), (gr, orf) = grads
+    assert _rel(on, orf) < 3 * EPS[dt]
+    assert set(gn) == set(gr)
+    for k in gr:
+        e = _rel(gn[k], gr[k])
+        assert e < 8 * EPS[dt], (k, e)

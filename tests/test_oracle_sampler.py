@@ -63,8 +63,6 @@ def test_mirror_rejects_what_is_not_built():
     with pytest.raises(NotImplementedError):
         create_diffusion("250", predict_xstart=True)
     d = create_diffusion("8")
-    with pytest.raises(NotImplementedError):
-        d.training_losses(None, None, None)
     with pytest.raises(RuntimeError):   # no CPU path
         d.ddim_sample(lambda x, t: torch.cat([x, x], 2), torch.zeros(1, 2, 4, 4, 4), torch.zeros(1, dtype=torch.long))
 
@@ -79,3 +77,10 @@ def test_training_losses_equal_reference(golden_dir):
                             torch.from_numpy(g["train_noise"]))
     for k in ("loss", "mse", "vb"):
         assert np.array_equal(out[k].numpy(), g["train_" + k]), k
+    # the product's own training_losses (latte_b200/diffusion: torch elementwise math around the native denoiser) on the same
+    # toy model: same numbers up to the association of a few fp32 products
+    from latte_b200.diffusion import create_diffusion
+    got = create_diffusion(timestep_respacing="").training_losses(
+        S.toy_model, torch.from_numpy(g["train_x0"]), torch.from_numpy(g["train_t"]), noise=torch.from_numpy(g["train_noise"]))
+    for k in ("loss", "mse", "vb"):
+        np.testing.assert_allclose(got[k].numpy(), g["train_" + k], rtol=2e-5, atol=1e-6, err_msg=k)
