@@ -324,7 +324,13 @@ B200_API int b200_ln_modulate(const float* x, const float* shift, const float* s
  * activations, and evaluates the analytic backward with b200_linear (every dgrad: A = dY, W = W^T; every wgrad: A = dY^T,
  * W = X^T, B200_EPI_GATE_RESIDUAL with a unit gate accumulating into the fp32 gradient) plus the passes below.  Host side:
  * latte_b200/training.py (TrainEngine).  All [rows, dim] matrices are row-major; "16" = fp16/bf16 per `dtype`.           */
-/* out16[cols, rows] = in16[rows, cols]^T (wgrad operands: the token dimension must be contiguous).                        */
+/* dW[n_out, n_in] (fp32, in place) += col_scale[n_in] * (dY16[rows, n_out]^T . X16[rows, n_in]) -- the weight gradient of
+ * Y = X W^T, reading both activations as they lie in memory (the GEMM's MN-major operand mode: no transposed copies),
+ * accumulated in fp32 through the residual epilogue (sk_flags as in b200_linear).  col_scale: n_in floats, 1.0 for a plain
+ * gradient (a loss-scale / per-column factor otherwise).  rows % 64 == 0, n_out % 8 == 0, n_in % 128 == 0.                */
+B200_API int b200_wgrad(const void* dy16, const void* x16, const float* col_scale, float* dW, int rows, int n_out, int n_in,
+                        int dtype, void* sk_flags, void* stream);
+/* out16[cols, rows] = in16[rows, cols]^T (wgrad operands of shapes b200_wgrad does not take).                               */
 B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream);
 /* fp32 master parameter [rows, cols] -> 16-bit copy and (out16_t != NULL) its transpose [cols, rows], one read.           */
 B200_API int b200_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int dtype, void* stream);

@@ -659,6 +659,17 @@ B200_API int b200_ln_modulate(const float* x, const float* shift, const float* s
 
 // ---- training-step passes (train.cu) ----
 #define B200_DT(dtype) B200_REQUIRE(dtype == B200_FP16 || dtype == B200_BF16, B200_ERR_DTYPE, "dtype %d unknown", dtype)
+B200_API int b200_wgrad(const void* dy16, const void* x16, const float* col_scale, float* dW, int rows, int n_out, int n_in, int dtype,
+                        void* sk_flags, void* stream) {
+  B200_DT(dtype);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(sk_flags) & 7) == 0, B200_ERR_ALIGN, "sk_flags must be 8-byte aligned");
+  B200_REQUIRE(col_scale != nullptr, B200_ERR_SHAPE, "wgrad: col_scale (n_in floats, 1.0 for a plain gradient) is required");
+  b200::GemmArgs a{};
+  a.A = dy16; a.W = x16; a.M = n_out; a.N = n_in; a.K = rows; a.bf16 = dtype == B200_BF16; a.epilogue = B200_EPI_GATE_RESIDUAL;
+  a.resid = dW; a.gate = col_scale; a.gate_batch_stride = 0; a.rows_per_batch = n_out; a.mn_major = 1;
+  a.sk_flags = static_cast<unsigned long long*>(sk_flags);
+  return b200::launch_gemm(a, static_cast<cudaStream_t>(stream));
+}
 B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream) {
   return b200::launch_transpose16(in16, out16, rows, cols, static_cast<cudaStream_t>(stream));
 }

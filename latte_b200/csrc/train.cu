@@ -111,11 +111,6 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ GELU (tanh form)
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ float gelu_f(float u) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * u * (1.0f + tanhf(k0 * (u + k1 * u * u * u)));
@@ -152,6 +147,7 @@ __global__ void __launch_bounds__(128) gelu_bwd_kernel(const uint16_t* __restric
   const int r1 = min(rows, r0 + rs);
   float acc[8] = {};
   const int nv = dim >> 3;
+#pragma unroll 4
   for (int r = r0; r < r1; ++r) {
     const size_t idx = static_cast<size_t>(r) * nv + c8;
     const uint4 a = reinterpret_cast<const uint4*>(da)[idx];
@@ -188,6 +184,7 @@ __global__ void __launch_bounds__(128) gate_bwd_kernel(const float* __restrict__
   const int b = r0 / rpb;
   const float4 g = __ldg(reinterpret_cast<const float4*>(gate + b * gate_bs) + c4);
   float ag[4] = {}, ab[4] = {};
+#pragma unroll 8
   for (int r = r0; r < r1; ++r) {
     const size_t idx = static_cast<size_t>(r) * nv + c4;
     const float4 d = reinterpret_cast<const float4*>(dx)[idx];
@@ -214,6 +211,7 @@ __global__ void __launch_bounds__(128) colsum_kernel(const void* __restrict__ a,
   const int r0 = blockIdx.y * rs;
   const int r1 = min(rows, r0 + rs);
   float acc[4] = {};
+#pragma unroll 8
   for (int r = r0; r < r1; ++r) {
     const size_t idx = static_cast<size_t>(r) * nv + c4;
     if constexpr (KIND == 0) {
@@ -241,31 +239,34 @@ __global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __
                                                               const float* __restrict__ scale, long long mod_bs, int rpb,
                                                               float* __restrict__ dx, float* __restrict__ dshift,
                                                               float* __restrict__ dscale, long long dmod_bs, int rows, int dim) {
-  extern __shared__ float s_red[];   // [4][2][dim]
+  extern __shared__ float s_red[];   // [4 warps][2][dim]: per-warp column sums of dh and dh * xhat (each lane owns its columns)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = dim >> 2;
   const int block_row0 = blockIdx.x * 4 * LB_RPW;
   const int b = block_row0 / rpb;
   const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
-  float4 a_sh[NV], a_sc[NV];
+  float4* red_sh = reinterpret_cast<float4*>(s_red) + (warp * 2 + 0) * nv;
+  float4* red_sc = reinterpret_cast<float4*>(s_red) + (warp * 2 + 1) * nv;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) a_sh[i] = a_sc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) red_sh[idx] = red_sc[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const float inv_d = 1.0f / static_cast<float>(dim);
   for (int rr = 0; rr < LB_RPW; ++rr) {
     const int row = block_row0 + warp * LB_RPW + rr;
     if (row >= rows) break;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
     const uint2* dr = reinterpret_cast<const uint2*>(dh + static_cast<size_t>(row) * dim);
-    float4 v[NV], d[NV];
+    float4 v[NV];
+    uint2 dpk[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = lane + i * 32;
       if (idx < nv) {
         v[i] = xr[idx];
-        const uint2 t = dr[idx];
-        const float2 d0 = unpack2<BF16>(t.x), d1 = unpack2<BF16>(t.y);
-        d[i] = make_float4(d0.x, d0.y, d1.x, d1.y);
+        dpk[i] = dr[idx];
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
     }
@@ -285,12 +286,16 @@ __global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __
       const int idx = lane + i * 32;
       if (idx < nv) {
         v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
-        a_sh[i].x += d[i].x; a_sh[i].y += d[i].y; a_sh[i].z += d[i].z; a_sh[i].w += d[i].w;
-        a_sc[i].x += d[i].x * v[i].x; a_sc[i].y += d[i].y * v[i].y; a_sc[i].z += d[i].z * v[i].z; a_sc[i].w += d[i].w * v[i].w;
+        const float2 d0 = unpack2<BF16>(dpk[i].x), d1 = unpack2<BF16>(dpk[i].y);
+        float4 a = red_sh[idx], c2 = red_sc[idx];
+        a.x += d0.x; a.y += d0.y; a.z += d1.x; a.w += d1.y;
+        c2.x += d0.x * v[i].x; c2.y += d0.y * v[i].y; c2.z += d1.x * v[i].z; c2.w += d1.y * v[i].w;
+        red_sh[idx] = a;
+        red_sc[idx] = c2;
         const float4 c = __ldg(sc + idx);
-        d[i].x *= 1.0f + c.x; d[i].y *= 1.0f + c.y; d[i].z *= 1.0f + c.z; d[i].w *= 1.0f + c.w;   // g
-        s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
-        s2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+        const float g0 = d0.x * (1.0f + c.x), g1 = d0.y * (1.0f + c.y), g2 = d1.x * (1.0f + c.z), g3 = d1.y * (1.0f + c.w);
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * v[i].x + g1 * v[i].y) + (g2 * v[i].z + g3 * v[i].w);
       }
     }
     s1 = warp_sum(s1) * inv_d;
@@ -300,22 +305,15 @@ __global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __
     for (int i = 0; i < NV; ++i) {
       const int idx = lane + i * 32;
       if (idx < nv) {
+        const float2 d0 = unpack2<BF16>(dpk[i].x), d1 = unpack2<BF16>(dpk[i].y);
+        const float4 c = __ldg(sc + idx);
         float4 o = dxr[idx];
-        o.x += rstd * (d[i].x - s1 - v[i].x * s2);
-        o.y += rstd * (d[i].y - s1 - v[i].y * s2);
-        o.z += rstd * (d[i].z - s1 - v[i].z * s2);
-        o.w += rstd * (d[i].w - s1 - v[i].w * s2);
+        o.x += rstd * (d0.x * (1.0f + c.x) - s1 - v[i].x * s2);
+        o.y += rstd * (d0.y * (1.0f + c.y) - s1 - v[i].y * s2);
+        o.z += rstd * (d1.x * (1.0f + c.z) - s1 - v[i].z * s2);
+        o.w += rstd * (d1.y * (1.0f + c.w) - s1 - v[i].w * s2);
         dxr[idx] = o;
       }
-    }
-  }
-  float4* red = reinterpret_cast<float4*>(s_red);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      red[(warp * 2 + 0) * nv + idx] = a_sh[i];
-      red[(warp * 2 + 1) * nv + idx] = a_sc[i];
     }
   }
   __syncthreads();
@@ -365,20 +363,28 @@ struct AB {
   static constexpr int TILE = 64 * HDP;            // elements per 64-row tile
 };
 
-// copy a [64 x HD] block (rows `row0 + r*row_step`, columns col0..col0+HD) of a row-major 16-bit matrix into a shared tile
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous copy of a [64 x HD] block (rows row0.., columns col0..col0+HD) of a row-major 16-bit matrix into a shared tile
 template <int HD>
-__device__ __forceinline__ void load_tile64(uint16_t* s, const uint16_t* __restrict__ g, size_t row0, size_t row_step,
-                                            int ld, int col0, int nrows_valid) {
+__device__ __forceinline__ void load_tile64(uint16_t* s, const uint16_t* __restrict__ g, size_t row0, int ld, int col0) {
   constexpr int CH = HD / 8;          // 16-byte chunks per row
   constexpr int HDP = AB<HD>::HDP;
   for (int i = threadIdx.x; i < 64 * CH; i += blockDim.x) {
     const int r = i / CH, c = i % CH;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < nrows_valid) v = *reinterpret_cast<const uint4*>(g + (row0 + r * row_step) * ld + col0 + c * 8);
-    *reinterpret_cast<uint4*>(s + r * HDP + c * 8) = v;
+    cp_async16(s + r * HDP + c * 8, g + (row0 + r) * ld + col0 + c * 8);
   }
+}
+// zero the pad columns [HD, KP) of `ntiles` consecutive tiles once (the copies above never touch them)
+template <int HD>
+__device__ __forceinline__ void zero_pads(uint16_t* s, int ntiles) {
   if constexpr (AB<HD>::KP > HD) {
-    for (int r = threadIdx.x; r < 64; r += blockDim.x) *reinterpret_cast<uint4*>(s + r * HDP + HD) = make_uint4(0, 0, 0, 0);
+    for (int r = threadIdx.x; r < 64 * ntiles; r += blockDim.x) *reinterpret_cast<uint4*>(s + r * AB<HD>::HDP + HD) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -456,7 +462,7 @@ __device__ __forceinline__ void store_rows(uint16_t* __restrict__ g, size_t row0
 
 // Kernel A: one CTA = 64 query rows of one (sequence, head).  Pass 1 recomputes the row statistics (log-sum-exp in log2
 // units) and delta = sum_d dO.O, stores both for kernel B; pass 2 recomputes P, forms dS = P (dP - delta) * scale and
-// accumulates dQ = dS K.
+// accumulates dQ = dS K.  K / V blocks are double-buffered with cp.async so the next block streams in under the MMAs.
 template <bool BF16, int HD>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ o,
                                                           const uint16_t* __restrict__ d_o, uint16_t* __restrict__ dqkv,
@@ -466,16 +472,21 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const uint16_t* __rest
   extern __shared__ __align__(16) uint16_t sm[];
   uint16_t* sQ = sm;
   uint16_t* sDO = sm + G::TILE;
-  uint16_t* sK = sm + 2 * G::TILE;
-  uint16_t* sV = sm + 3 * G::TILE;
+  uint16_t* sK = sm + 2 * G::TILE;      // [2] buffers
+  uint16_t* sV = sm + 4 * G::TILE;      // [2] buffers
   const int qb = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
   const int D = heads * HD, ld = 3 * D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t seq_row0 = static_cast<size_t>(seq) * S;
   const int q0 = qb * 64;
-  load_tile64<HD>(sQ, qkv, seq_row0 + q0, 1, ld, h * HD, 64);
-  load_tile64<HD>(sDO, d_o, seq_row0 + q0, 1, D, h * HD, 64);
-  load_tile64<HD>(sK, o, seq_row0 + q0, 1, D, h * HD, 64);     // O block, only for delta
+  const int nkb = S / 64;
+  zero_pads<HD>(sm, 6);
+  load_tile64<HD>(sQ, qkv, seq_row0 + q0, ld, h * HD);
+  load_tile64<HD>(sDO, d_o, seq_row0 + q0, D, h * HD);
+  load_tile64<HD>(sV, o, seq_row0 + q0, D, h * HD);            // O block, only for delta
+  load_tile64<HD>(sK, qkv, seq_row0, ld, D + h * HD);          // K block 0
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   // delta for this thread's two rows (quad lanes split the columns)
   const int r_lo = warp * 16 + (lane >> 2);
@@ -485,7 +496,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const uint16_t* __rest
     const int r = r_lo + hh * 8;
     for (int c = (lane & 3) * 2; c < HD; c += 8) {
       const float2 a = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(sDO + r * G::HDP + c));
-      const float2 b = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(sK + r * G::HDP + c));
+      const float2 b = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(sV + r * G::HDP + c));
       dl[hh] += a.x * b.x + a.y * b.y;
     }
     dl[hh] += __shfl_xor_sync(0xffffffffu, dl[hh], 1);
@@ -493,13 +504,15 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const uint16_t* __rest
   }
   // ---- pass 1: row max / sum over all keys
   float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
-  const int nkb = S / 64;
   for (int kb = 0; kb < nkb; ++kb) {
-    __syncthreads();
-    load_tile64<HD>(sK, qkv, seq_row0 + kb * 64, 1, ld, D + h * HD, 64);
-    __syncthreads();
+    const uint16_t* cK = sK + (kb & 1) * G::TILE;
+    if (kb + 1 < nkb) load_tile64<HD>(sK + ((kb + 1) & 1) * G::TILE, qkv, seq_row0 + (kb + 1) * 64, ld, D + h * HD);
+    else {                                     // last block of pass 1: start pass 2's first K / V block (V buffer 0 held O, now consumed)
+      if (nkb > 1) load_tile64<HD>(sK + ((kb + 1) & 1) * G::TILE, qkv, seq_row0, ld, D + h * HD);
+    }
+    cp_async_commit();
     float acc[8][4] = {};
-    mm_a_tileT<BF16, HD>(acc, sQ, warp * 16, sK);
+    mm_a_tileT<BF16, HD>(acc, sQ, warp * 16, cK);
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float m = mx[hh];
@@ -507,55 +520,68 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const uint16_t* __rest
       for (int n = 0; n < 8; ++n) m = fmaxf(m, fmaxf(acc[n][2 * hh], acc[n][2 * hh + 1]) * scale_log2);
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-      float s = 0.f;
+      float sacc = 0.f;
 #pragma unroll
-      for (int n = 0; n < 8; ++n) s += exp2f(acc[n][2 * hh] * scale_log2 - m) + exp2f(acc[n][2 * hh + 1] * scale_log2 - m);
-      sum[hh] = sum[hh] * exp2f(mx[hh] - m) + s;
+      for (int n = 0; n < 8; ++n) sacc += exp2f(acc[n][2 * hh] * scale_log2 - m) + exp2f(acc[n][2 * hh + 1] * scale_log2 - m);
+      sum[hh] = sum[hh] * exp2f(mx[hh] - m) + sacc;
       mx[hh] = m;
     }
+    cp_async_wait<0>();
+    __syncthreads();
   }
   float l2[2];
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
-    float s = sum[hh];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    l2[hh] = mx[hh] + log2f(s);
+    float t = sum[hh];
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    l2[hh] = mx[hh] + log2f(t);
     if ((lane & 3) == 0) {
       const size_t idx = (static_cast<size_t>(seq) * heads + h) * S + q0 + r_lo + hh * 8;
       lse[idx] = l2[hh];
       delta[idx] = dl[hh];
     }
   }
-  // ---- pass 2
+  // ---- pass 2.  K block 0 sits in K buffer (nkb & 1) when nkb > 1 (prefetched above), else still in buffer 0.
+  const int kbase = nkb > 1 ? (nkb & 1) : 0;
+  load_tile64<HD>(sV + kbase * G::TILE, qkv, seq_row0, ld, 2 * D + h * HD);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
   const float scale = scale_log2 * 0.6931471805599453f;
   float dq[G::NT][4] = {};
   for (int kb = 0; kb < nkb; ++kb) {
-    __syncthreads();
-    load_tile64<HD>(sK, qkv, seq_row0 + kb * 64, 1, ld, D + h * HD, 64);
-    load_tile64<HD>(sV, qkv, seq_row0 + kb * 64, 1, ld, 2 * D + h * HD, 64);
-    __syncthreads();
+    const int cur = (kbase + kb) & 1, nxt = cur ^ 1;
+    if (kb + 1 < nkb) {
+      load_tile64<HD>(sK + nxt * G::TILE, qkv, seq_row0 + (kb + 1) * 64, ld, D + h * HD);
+      load_tile64<HD>(sV + nxt * G::TILE, qkv, seq_row0 + (kb + 1) * 64, ld, 2 * D + h * HD);
+    }
+    cp_async_commit();
+    const uint16_t* cK = sK + cur * G::TILE;
+    const uint16_t* cV = sV + cur * G::TILE;
     float s_acc[8][4] = {}, p_acc[8][4] = {};
-    mm_a_tileT<BF16, HD>(s_acc, sQ, warp * 16, sK);
-    mm_a_tileT<BF16, HD>(p_acc, sDO, warp * 16, sV);
+    mm_a_tileT<BF16, HD>(s_acc, sQ, warp * 16, cK);
+    mm_a_tileT<BF16, HD>(p_acc, sDO, warp * 16, cV);
 #pragma unroll
     for (int n = 0; n < 8; ++n)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int hh = e >> 1;
-        const float p = exp2f(s_acc[n][e] * scale_log2 - l2[hh]);
-        s_acc[n][e] = p * (p_acc[n][e] - dl[hh]) * scale;
+        const float pr = exp2f(s_acc[n][e] * scale_log2 - l2[hh]);
+        s_acc[n][e] = pr * (p_acc[n][e] - dl[hh]) * scale;
       }
     uint32_t pds[4][4];
     acc_to_afrag<BF16>(pds, s_acc);
-    mm_p_tile<BF16, HD>(dq, pds, sK);
+    mm_p_tile<BF16, HD>(dq, pds, cK);
+    cp_async_wait<0>();
+    __syncthreads();
   }
   store_rows<BF16, HD>(dqkv, seq_row0 + q0, ld, h * HD, dq, warp * 16, 64);
 }
 
 // Kernel B: one CTA = 64 keys of one (sequence, head); loops over the query blocks with the statistics of kernel A.
 // S^T = K Q^T so that the warp's accumulator rows are keys: P^T and dS^T are then directly the A operands of
-// dV = P^T dO and dK = dS^T Q.
+// dV = P^T dO and dK = dS^T Q.  Q / dO blocks (and their statistics) are double-buffered with cp.async.
 template <bool BF16, int HD>
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ d_o,
                                                            uint16_t* __restrict__ dqkv, const float* __restrict__ lse,
@@ -564,48 +590,59 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const uint16_t* __res
   extern __shared__ __align__(16) uint16_t sm[];
   uint16_t* sK = sm;
   uint16_t* sV = sm + G::TILE;
-  uint16_t* sQ = sm + 2 * G::TILE;
-  uint16_t* sDO = sm + 3 * G::TILE;
-  float* sL = reinterpret_cast<float*>(sm + 4 * G::TILE);
-  float* sD = sL + 64;
+  uint16_t* sQ = sm + 2 * G::TILE;      // [2]
+  uint16_t* sDO = sm + 4 * G::TILE;     // [2]
+  float* sL = reinterpret_cast<float*>(sm + 6 * G::TILE);   // [2][64] lse, then [2][64] delta
+  float* sD = sL + 128;
   const int kb = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
   const int D = heads * HD, ld = 3 * D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t seq_row0 = static_cast<size_t>(seq) * S;
+  const size_t stat0 = (static_cast<size_t>(seq) * heads + h) * S;
   const int k0 = kb * 64;
-  load_tile64<HD>(sK, qkv, seq_row0 + k0, 1, ld, D + h * HD, 64);
-  load_tile64<HD>(sV, qkv, seq_row0 + k0, 1, ld, 2 * D + h * HD, 64);
+  const int nqb = S / 64;
+  auto load_q = [&](int qb, int buf) {
+    load_tile64<HD>(sQ + buf * G::TILE, qkv, seq_row0 + qb * 64, ld, h * HD);
+    load_tile64<HD>(sDO + buf * G::TILE, d_o, seq_row0 + qb * 64, D, h * HD);
+    if (threadIdx.x < 16) cp_async16(sL + buf * 64 + threadIdx.x * 4, lse + stat0 + qb * 64 + threadIdx.x * 4);
+    else if (threadIdx.x < 32) cp_async16(sD + buf * 64 + (threadIdx.x - 16) * 4, delta + stat0 + qb * 64 + (threadIdx.x - 16) * 4);
+  };
+  zero_pads<HD>(sm, 6);
+  load_tile64<HD>(sK, qkv, seq_row0 + k0, ld, D + h * HD);
+  load_tile64<HD>(sV, qkv, seq_row0 + k0, ld, 2 * D + h * HD);
+  load_q(0, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   const float scale = scale_log2 * 0.6931471805599453f;
   float dk[G::NT][4] = {}, dv[G::NT][4] = {};
-  const int nqb = S / 64;
   for (int qb = 0; qb < nqb; ++qb) {
-    __syncthreads();
-    load_tile64<HD>(sQ, qkv, seq_row0 + qb * 64, 1, ld, h * HD, 64);
-    load_tile64<HD>(sDO, d_o, seq_row0 + qb * 64, 1, D, h * HD, 64);
-    if (threadIdx.x < 64) {
-      const size_t idx = (static_cast<size_t>(seq) * heads + h) * S + qb * 64 + threadIdx.x;
-      sL[threadIdx.x] = lse[idx];
-      sD[threadIdx.x] = delta[idx];
-    }
-    __syncthreads();
+    const int cur = qb & 1;
+    if (qb + 1 < nqb) load_q(qb + 1, cur ^ 1);
+    cp_async_commit();
+    const uint16_t* cQ = sQ + cur * G::TILE;
+    const uint16_t* cDO = sDO + cur * G::TILE;
+    const float* cL = sL + cur * 64;
+    const float* cD = sD + cur * 64;
     float s_acc[8][4] = {}, p_acc[8][4] = {};
-    mm_a_tileT<BF16, HD>(s_acc, sK, warp * 16, sQ);      // [16 keys x 64 queries]
-    mm_a_tileT<BF16, HD>(p_acc, sV, warp * 16, sDO);
+    mm_a_tileT<BF16, HD>(s_acc, sK, warp * 16, cQ);      // [16 keys x 64 queries]
+    mm_a_tileT<BF16, HD>(p_acc, sV, warp * 16, cDO);
     uint32_t pp[4][4], pds[4][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int qi = n * 8 + (lane & 3) * 2 + (e & 1);
-        const float p = exp2f(s_acc[n][e] * scale_log2 - sL[qi]);
-        p_acc[n][e] = p * (p_acc[n][e] - sD[qi]) * scale;
-        s_acc[n][e] = p;
+        const float pr = exp2f(s_acc[n][e] * scale_log2 - cL[qi]);
+        p_acc[n][e] = pr * (p_acc[n][e] - cD[qi]) * scale;
+        s_acc[n][e] = pr;
       }
     acc_to_afrag<BF16>(pp, s_acc);
     acc_to_afrag<BF16>(pds, p_acc);
-    mm_p_tile<BF16, HD>(dv, pp, sDO);
-    mm_p_tile<BF16, HD>(dk, pds, sQ);
+    mm_p_tile<BF16, HD>(dv, pp, cDO);
+    mm_p_tile<BF16, HD>(dk, pds, cQ);
+    cp_async_wait<0>();
+    __syncthreads();
   }
   store_rows<BF16, HD>(dqkv, seq_row0 + k0, ld, D + h * HD, dk, warp * 16, 64);
   store_rows<BF16, HD>(dqkv, seq_row0 + k0, ld, 2 * D + h * HD, dv, warp * 16, 64);
@@ -620,37 +657,41 @@ __global__ void __launch_bounds__(128) attn_bwd_temporal_kernel(const uint16_t* 
                                                                 int hd, float scale) {
   extern __shared__ float sf[];
   const int F = frames;
-  float* q = sf;                 // [F][hd]
-  float* k = q + F * hd;
-  float* v = k + F * hd;
-  float* g = v + F * hd;         // dO
-  float* P = g + F * hd;         // [F][F]
+  const int hdp = hd + 1;        // odd pitch: the F x F score loop reads rows of q/k/v/g at stride hdp -> conflict-free
+  float* q = sf;                 // [F][hdp]
+  float* k = q + F * hdp;
+  float* v = k + F * hdp;
+  float* g = v + F * hdp;        // dO
+  float* P = g + F * hdp;        // [F][F]
   float* dS = P + F * F;         // [F][F]
   const int n = blockIdx.x % tokens, b = blockIdx.x / tokens, h = blockIdx.y;
   const int D = heads * hd, ld = 3 * D;
   const size_t row0 = static_cast<size_t>(b) * F * tokens + n;
-  const int half = hd / 2;
-  for (int i = threadIdx.x; i < F * half; i += blockDim.x) {
-    const int f = i / half, c = (i % half) * 2;
+  const int c8n = hd / 8;        // 16-byte chunks per row
+  for (int i = threadIdx.x; i < 4 * F * c8n; i += blockDim.x) {
+    const int which = i / (F * c8n), rem = i % (F * c8n);
+    const int f = rem / c8n, c = (rem % c8n) * 8;
     const size_t r = row0 + static_cast<size_t>(f) * tokens;
-    const float2 a = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(qkv + r * ld + h * hd + c));
-    const float2 bb = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(qkv + r * ld + D + h * hd + c));
-    const float2 cc = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(qkv + r * ld + 2 * D + h * hd + c));
-    const float2 dd = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(d_o + r * D + h * hd + c));
-    q[f * hd + c] = a.x; q[f * hd + c + 1] = a.y;
-    k[f * hd + c] = bb.x; k[f * hd + c + 1] = bb.y;
-    v[f * hd + c] = cc.x; v[f * hd + c + 1] = cc.y;
-    g[f * hd + c] = dd.x; g[f * hd + c + 1] = dd.y;
+    const uint16_t* src = which < 3 ? qkv + r * ld + which * D + h * hd + c : d_o + r * D + h * hd + c;
+    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    float* dst = sf + which * F * hdp + f * hdp + c;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack2<BF16>(w[j]);
+      dst[2 * j] = t.x;
+      dst[2 * j + 1] = t.y;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < F * F; i += blockDim.x) {
     const int a = i / F, c = i % F;
-    float s = 0.f, dp = 0.f;
+    float sacc = 0.f, dp = 0.f;
     for (int d = 0; d < hd; ++d) {
-      s += q[a * hd + d] * k[c * hd + d];
-      dp += g[a * hd + d] * v[c * hd + d];
+      sacc += q[a * hdp + d] * k[c * hdp + d];
+      dp += g[a * hdp + d] * v[c * hdp + d];
     }
-    P[i] = s * scale;
+    P[i] = sacc * scale;
     dS[i] = dp;
   }
   __syncthreads();
@@ -658,27 +699,28 @@ __global__ void __launch_bounds__(128) attn_bwd_temporal_kernel(const uint16_t* 
     const int a = threadIdx.x;
     float m = -INFINITY;
     for (int c = 0; c < F; ++c) m = fmaxf(m, P[a * F + c]);
-    float s = 0.f;
-    for (int c = 0; c < F; ++c) { const float e = __expf(P[a * F + c] - m); P[a * F + c] = e; s += e; }
-    const float inv = 1.0f / s;
+    float t = 0.f;
+    for (int c = 0; c < F; ++c) { const float e = __expf(P[a * F + c] - m); P[a * F + c] = e; t += e; }
+    const float inv = 1.0f / t;
     float dl = 0.f;
     for (int c = 0; c < F; ++c) { P[a * F + c] *= inv; dl += P[a * F + c] * dS[a * F + c]; }
     for (int c = 0; c < F; ++c) dS[a * F + c] = P[a * F + c] * (dS[a * F + c] - dl) * scale;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < F * half; i += blockDim.x) {
-    const int f = i / half, c = (i % half) * 2;
-    float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+  for (int i = threadIdx.x; i < 3 * F * c8n; i += blockDim.x) {
+    const int which = i / (F * c8n), rem = i % (F * c8n);
+    const int f = rem / c8n, c = (rem % c8n) * 8;
+    float acc[8] = {};
     for (int j = 0; j < F; ++j) {
-      const float ds_fj = dS[f * F + j], ds_jf = dS[j * F + f], p_jf = P[j * F + f];
-      dq0 += ds_fj * k[j * hd + c]; dq1 += ds_fj * k[j * hd + c + 1];
-      dk0 += ds_jf * q[j * hd + c]; dk1 += ds_jf * q[j * hd + c + 1];
-      dv0 += p_jf * g[j * hd + c]; dv1 += p_jf * g[j * hd + c + 1];
+      // dq_f = sum_j dS[f][j] k_j;  dk_f = sum_j dS[j][f] q_j;  dv_f = sum_j P[j][f] dO_j
+      const float wgt = which == 0 ? dS[f * F + j] : (which == 1 ? dS[j * F + f] : P[j * F + f]);
+      const float* src = (which == 0 ? k : (which == 1 ? q : g)) + j * hdp + c;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, src[e], acc[e]);
     }
     const size_t r = row0 + static_cast<size_t>(f) * tokens;
-    *reinterpret_cast<uint32_t*>(dqkv + r * ld + h * hd + c) = pack2<BF16>(dq0, dq1);
-    *reinterpret_cast<uint32_t*>(dqkv + r * ld + D + h * hd + c) = pack2<BF16>(dk0, dk1);
-    *reinterpret_cast<uint32_t*>(dqkv + r * ld + 2 * D + h * hd + c) = pack2<BF16>(dv0, dv1);
+    *reinterpret_cast<uint4*>(dqkv + r * ld + which * D + h * hd + c) =
+        make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]), pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
   }
 }
 
@@ -887,8 +929,8 @@ static int attn_bwd_spatial(const uint16_t* qkv, const uint16_t* o, const uint16
   using G = AB<HD>;
   auto ka = attn_bwd_dq_kernel<BF16, HD>;
   auto kb = attn_bwd_dkv_kernel<BF16, HD>;
-  const size_t smem_a = static_cast<size_t>(4) * G::TILE * 2;
-  const size_t smem_b = smem_a + 128 * sizeof(float);
+  const size_t smem_a = static_cast<size_t>(6) * G::TILE * 2;
+  const size_t smem_b = smem_a + 256 * sizeof(float);
   B200_SET_SMEM_ONCE(ka, static_cast<int>(smem_a));
   B200_SET_SMEM_ONCE(kb, static_cast<int>(smem_b));
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
@@ -907,8 +949,8 @@ int launch_attention_bwd(const void* qkv, const void* o, const void* d_o, void* 
   const uint16_t *q = static_cast<const uint16_t*>(qkv), *oo = static_cast<const uint16_t*>(o), *g = static_cast<const uint16_t*>(d_o);
   uint16_t* dq = static_cast<uint16_t*>(dqkv);
   if (temporal) {
-    B200_REQUIRE(frames <= 16 && head_dim % 2 == 0 && head_dim <= 128, B200_ERR_UNSUPPORTED, "attention_bwd: temporal sequences of <= 16 frames only (got %d)", frames);
-    const size_t smem = (static_cast<size_t>(4) * frames * head_dim + 2 * frames * frames) * sizeof(float);
+    B200_REQUIRE(frames <= 16 && head_dim % 8 == 0 && head_dim <= 128, B200_ERR_UNSUPPORTED, "attention_bwd: temporal sequences of <= 16 frames, head_dim %% 8 == 0 (got %d, %d)", frames, head_dim);
+    const size_t smem = (static_cast<size_t>(4) * frames * (head_dim + 1) + 2 * frames * frames) * sizeof(float);
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
     dim3 grid(batch * tokens, heads);
     if (bf16) attn_bwd_temporal_kernel<true><<<grid, 128, smem, stream>>>(q, g, dq, frames, tokens, heads, head_dim, scale);

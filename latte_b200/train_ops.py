@@ -45,6 +45,21 @@ class NativeOps:
         """out32 [M, N] += a [M, K] @ w [N, K]^T (+ bias): the GEMM's residual epilogue with a unit gate (ordered stream-K)."""
         return ops.linear_gate_residual_(out32, a, w, bias, self._unit_gate(out32.shape[1], out32.device), max(out32.shape[0], 1))
 
+    def wgrad(self, dW32, dy, x):
+        """dW32 [n_out, n_in] += dy [rows, n_out]^T @ x [rows, n_in]: the GEMM reads both activations untransposed (MN-major
+        operand mode); shapes it does not take (n_in not a multiple of 128) go through explicit 16-bit transposes."""
+        self._cuda(dW32, dy, x)
+        rows, n_out = dy.shape
+        n_in = x.shape[1]
+        if n_in % 128 == 0 and n_out % 8 == 0 and rows % 64 == 0:
+            assert dy.is_contiguous() and x.is_contiguous() and dW32.is_contiguous() and dW32.dtype == torch.float32
+            with torch.cuda.device(dy.device):
+                rc = _lib.load().b200_wgrad(dy.data_ptr(), x.data_ptr(), self._unit_gate(n_in, dy.device).data_ptr(), dW32.data_ptr(),
+                                            rows, n_out, n_in, self.dt, ops._sk_flags(dy.device).data_ptr(), _s(dy))
+            _lib.check(rc, "b200_wgrad")
+            return dW32
+        return self.linear_accum(dW32, self.transpose(dy), self.transpose(x))
+
     def attention(self, qkv, B, Fr, N, H, temporal):
         return ops.attention(qkv, B, Fr, N, H, temporal)
 

@@ -150,16 +150,15 @@ class TrainEngine:
         G = {}
         dmod = torch.zeros_like(mod)
 
-        def wgrad(n_out, dy_t, x_t):
-            g = torch.zeros(n_out, x_t.shape[0], dtype=torch.float32, device=dev)
-            ops.linear_accum(g, dy_t, x_t)
-            return g
+        def wgrad(dy, x):
+            g = torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=dev)
+            return ops.wgrad(g, dy, x)
 
         # ---- final layer (latte.py:197-201) ----
         dtok = self._patchify_out(dout.float())                                         # (T, nf) fp32
         G["final_layer.linear.bias"] = ops.colsum(dtok)
         dtok16 = ops.to_operand(dtok)
-        G["final_layer.linear.weight"] = wgrad(self.nf, ops.transpose(dtok16), ops.transpose(S["hf"]))
+        G["final_layer.linear.weight"] = wgrad(dtok16, S["hf"])
         dtp = torch.zeros(T, 64, dtype=torch.float32, device=dev)
         dtp[:, : self.nf] = dtok
         dhf = ops.linear(ops.to_operand(dtp), W["final_wt"])
@@ -181,26 +180,25 @@ class TrainEngine:
             # x_out = x_mid + g2 * fc2(gelu(fc1(LNmod(x_mid))))
             dm2, dg2, G[p + "mlp.fc2.bias"] = ops.gate_bwd(dx, m2, g2, rpb)
             a = ops.gelu(u)
-            dm2_t = ops.transpose(dm2)
-            G[p + "mlp.fc2.weight"] = wgrad(D, dm2_t, ops.transpose(a))
-            del a, dm2_t
+            G[p + "mlp.fc2.weight"] = wgrad(dm2, a)
+            del a
             da = ops.linear(dm2, w2[1])
             du, G[p + "mlp.fc1.bias"] = ops.gelu_bwd(da, u)
             del da, dm2
-            G[p + "mlp.fc1.weight"] = wgrad(m.mlp_hidden, ops.transpose(du), ops.transpose(h2))
+            G[p + "mlp.fc1.weight"] = wgrad(du, h2)
             dh2 = ops.linear(du, w1[1])
             del du
             dsh2, dsc2 = ops.ln_modulate_bwd(dh2, xm, sh2, sc2, rpb, dx)
             del dh2
             # x_mid = x_in + g1 * proj(attn(qkv(LNmod(x_in))))
             dm1, dg1, G[p + "attn.proj.bias"] = ops.gate_bwd(dx, m1, g1, rpb)
-            G[p + "attn.proj.weight"] = wgrad(D, ops.transpose(dm1), ops.transpose(o))
+            G[p + "attn.proj.weight"] = wgrad(dm1, o)
             do = ops.linear(dm1, wp[1])
             del dm1
             dqkv = ops.attention_bwd(qkv, o, do, B, Fr, N, H, temporal)
             del do
             G[p + "attn.qkv.bias"] = ops.colsum(dqkv)
-            G[p + "attn.qkv.weight"] = wgrad(3 * D, ops.transpose(dqkv), ops.transpose(h1))
+            G[p + "attn.qkv.weight"] = wgrad(dqkv, h1)
             dh1 = ops.linear(dqkv, wq[1])
             del dqkv
             dsh1, dsc1 = ops.ln_modulate_bwd(dh1, xs, sh1, sc1, rpb, dx)
@@ -211,7 +209,7 @@ class TrainEngine:
 
         # ---- patch embedding (latte.py:330-331; pos_embed / temp_embed are frozen, :246-247) ----
         G["x_embedder.proj.bias"] = ops.colsum(dx)
-        gpe = wgrad(D, ops.transpose(ops.to_operand(dx)), ops.transpose(S["xp"]))
+        gpe = wgrad(ops.to_operand(dx), S["xp"])
         G["x_embedder.proj.weight"] = gpe[:, : self.kp].reshape(m.x_embedder.proj.weight.shape).contiguous()
 
         # ---- adaLN_modulation of every block + final layer: mod = Linear(SiLU(c)) (latte.py:160-163, 192-195) ----

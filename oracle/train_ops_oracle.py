@@ -46,6 +46,11 @@ class TorchOps:
         out32 += r
         return out32
 
+    def wgrad(self, dW32, dy, x):
+        """dW [n_out, n_in] += dy [rows, n_out]^T @ x [rows, n_in]."""
+        dW32 += dy.float().t() @ x.float()
+        return dW32
+
     @staticmethod
     def _split(qkv, B, Fr, N, H, temporal):
         T, D3 = qkv.shape

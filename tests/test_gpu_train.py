@@ -42,7 +42,7 @@ def _close(a, b, tol, what=""):
 def test_transpose_cast_colsum(dev, dt):
     nat, ref = _ops(dt)
     g = torch.Generator().manual_seed(1)
-    for R, Cc in [(1536, 128), (4096, 1152), (512, 32), (130, 66)]:
+    for R, Cc in [(1536, 128), (4096, 1152), (512, 32), (130, 68)]:
         a = torch.randn(R, Cc, generator=g).to(dev).to(dt)
         assert torch.equal(nat.transpose(a), a.t().contiguous())
         _close(nat.colsum(a), ref.colsum(a), 1e-5, "colsum16")
@@ -71,6 +71,24 @@ def test_linear_accum_small_and_wgrad_shapes(dev, dt):
     w = (torch.randn(6912 + 2304, 1152, generator=g) / 34).to(dev).to(dt)
     b = torch.randn(6912 + 2304, generator=g).to(dev)
     _close(nat.linear(a, w, b), ref.linear(a, w, b), EPS[dt], "linear M=5")
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_wgrad_reads_untransposed_operands(dev, dt):
+    """dW += dY^T X with both activations as they lie in memory (the GEMM's MN-major UMMA descriptors, 64-wide chunk loads):
+    full tiles, the half-width edge tile (n_in = 1152 = 4.5 x 256), ragged n_out (32, 1152 = 4.5 x 256 rows), stream-K."""
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(7)
+    for rows, n_out, n_in in [(2048, 32, 1152), (4096, 1152, 128), (1536, 384, 128), (8192, 3456, 1152), (20480, 1152, 4608),
+                              (4096, 512, 256), (2048, 1152, 576)]:
+        dy = torch.randn(rows, n_out, generator=g).to(dev).to(dt)
+        x = torch.randn(rows, n_in, generator=g).to(dev).to(dt)
+        base = torch.randn(n_out, n_in, generator=g).to(dev)
+        got = nat.wgrad(base.clone(), dy, x)
+        want = ref.wgrad(base.clone(), dy, x)
+        _close(got, want, 3e-5, f"wgrad {rows}x{n_out}x{n_in}")
+        again = nat.wgrad(base.clone(), dy, x)
+        assert torch.equal(got, again), "ordered stream-K must be bit-reproducible"
 
 
 @pytest.mark.parametrize("dt", DTS)
