@@ -343,18 +343,18 @@ B200_API int b200_gate_residual(const float* x, const void* m16, const float* ga
                                 const float* row_add, int tokens, int frames, float* out, int rows, int dim, int dtype, void* stream);
 /* a16 = gelu_tanh(u16) (timm Mlp act, latte.py:169).                                                                      */
 B200_API int b200_gelu(const void* u16, void* a16, int64_t n, int dtype, void* stream);
-/* du16 = da16 * gelu_tanh'(u16); dbias[dim] (fp32, overwritten) = column sums of du = fc1.bias gradient.                  */
+/* du16 = da16 * gelu_tanh'(u16); dbias[dim] (fp32) += column sums of du = fc1.bias gradient.  (Every reduction output of the
+ * training passes ACCUMULATES: the caller zeroes its gradient buffers once per step, so no pass issues a memset.)          */
 B200_API int b200_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int dtype, void* stream);
-/* backward of out = x + gate[b] * m: dm16 = dx * gate[b]; dgate[b] (row stride dgate_batch_stride, overwritten) = sum over
- * the sample's rows of dx * m; dbias[dim] (overwritten) = column sums of dm = the bias gradient of the Linear that made m. */
+/* backward of out = x + gate[b] * m: dm16 = dx * gate[b]; dgate[b] (row stride dgate_batch_stride) += sum over the sample's
+ * rows of dx * m; dbias[dim] += column sums of dm = the bias gradient of the Linear that made m.                          */
 B200_API int b200_gate_bwd(const float* dx, const void* m16, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
                            void* dm16, float* dgate, int64_t dgate_batch_stride, float* dbias, int rows, int dim, int dtype,
                            void* stream);
-/* out[dim] (fp32, overwritten) = column sums of a [rows, dim]; a_dtype: 0 fp32, 1 fp16, 2 bf16.                           */
+/* out[dim] (fp32) += column sums of a [rows, dim]; a_dtype: 0 fp32, 1 fp16, 2 bf16.                                       */
 B200_API int b200_colsum(const void* a, int a_dtype, float* out, int rows, int dim, void* stream);
 /* backward of h = LayerNorm(x)(1 + scale[b]) + shift[b] (latte.py:28-29, eps 1e-6): dx (fp32, in place) += dL/dx;
- * dshift[b], dscale[b] (row stride dmod_batch_stride, overwritten) = per-sample sums of dh and dh * xhat.
- * rows_per_batch % 64 == 0.                                                                                              */
+ * dshift[b], dscale[b] (row stride dmod_batch_stride) += per-sample sums of dh and dh * xhat.  rows_per_batch % 64 == 0. */
 B200_API int b200_ln_modulate_bwd(const void* dh16, const float* x, const float* scale, int64_t mod_batch_stride, int rows_per_batch,
                                   float* dx, float* dshift, float* dscale, int64_t dmod_batch_stride, int rows, int dim, int dtype,
                                   void* stream);

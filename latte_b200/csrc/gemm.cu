@@ -618,7 +618,7 @@ int pick_block_n(int M, int N, int K, bool resid, int sms) {
 
 // The scheduling decisions of one launch (shared by launch_gemm and the schedule dump the CPU tests read).
 struct GemmPlan { int bn, pairs, pair_tiles, num_kb, streamk; };
-GemmPlan plan_gemm(int M, int N, int K, bool resid, int block_n, int sms) {
+GemmPlan plan_gemm(int M, int N, int K, bool resid, int block_n, int sms, bool split_small = false) {
   static const bool no_sk = env_int("B200_GEMM_NO_STREAMK", 0) != 0;
   GemmPlan g;
   g.bn = block_n ? block_n : pick_block_n(M, N, K, resid, sms);
@@ -628,6 +628,14 @@ GemmPlan plan_gemm(int M, int N, int K, bool resid, int block_n, int sms) {
   g.pairs = grid / 2;
   g.num_kb = K / BK;
   g.streamk = (resid && !no_sk && g.pair_tiles > g.pairs && g.pair_tiles % g.pairs != 0 && g.num_kb >= streamk_min_kb()) ? 1 : 0;
+  // weight gradients: a small output (fewer tiles than CTA pairs) under a very long contraction (K = tokens).  All tiles are
+  // streamed: the (tile, k-block) units are cut into one equal share per pair, a tile's partial sums are reduce-added in k
+  // order through the same flags (a chain of waits only ever points from pair p+1 to pair p, and every pair is resident).
+  if (split_small && resid && !no_sk && g.pair_tiles <= sms / 2 && g.pair_tiles % (sms / 2) != 0 &&
+      static_cast<long long>(g.pair_tiles) * g.num_kb >= static_cast<long long>(sms / 2) * streamk_min_kb()) {
+    g.pairs = sms / 2;
+    g.streamk = 1;
+  }
   return g;
 }
 
@@ -688,7 +696,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
                  B200_ERR_UNSUPPORTED, "gemm (transposed operands): M %% 8 == 0, N %% 128 == 0, block_n 128 or 256 (M=%d N=%d)", a.M, a.N);
   }
   const GemmPlan plan = plan_gemm(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL,
-                                  a.mn_major && a.block_n == 0 ? (a.N % 256 == 0 || a.N > 1024 ? 256 : 128) : a.block_n, sms);
+                                  a.mn_major && a.block_n == 0 ? (a.N % 256 == 0 || a.N > 1024 ? 256 : 128) : a.block_n, sms,
+                                  a.mn_major != 0);
   const int bn = plan.bn;
 
   CUtensorMap tmA, tmB, tmX;

@@ -85,6 +85,38 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __rest
   }
 }
 
+// wide version for R % 4 == 0 and C % 4 == 0 (every weight matrix): 16-byte reads, 8-byte writes on both outputs
+template <bool BF16>
+__global__ void __launch_bounds__(256) cast_transpose4_kernel(const float* __restrict__ in, uint16_t* __restrict__ out,
+                                                              uint16_t* __restrict__ out_t, int R, int C) {
+  __shared__ uint16_t tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int r = ty; r < 64; r += 16) {
+    const int row = r0 + r, col = c0 + 4 * tx;
+    uint2 v = make_uint2(0, 0);
+    if (row < R && col < C) {
+      const float4 f = *reinterpret_cast<const float4*>(in + static_cast<size_t>(row) * C + col);
+      v = make_uint2(pack2<BF16>(f.x, f.y), pack2<BF16>(f.z, f.w));
+      *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C + col) = v;
+    }
+    *reinterpret_cast<uint32_t*>(&tile[r][4 * tx]) = v.x;
+    *reinterpret_cast<uint32_t*>(&tile[r][4 * tx + 2]) = v.y;
+  }
+  if (out_t == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int c = ty; c < 64; c += 16) {
+    const int orow = c0 + c, ocol = r0 + 4 * tx;
+    if (orow < C && ocol < R) {
+      const uint32_t lo = static_cast<uint32_t>(tile[4 * tx][c]) | (static_cast<uint32_t>(tile[4 * tx + 1][c]) << 16);
+      const uint32_t hi = static_cast<uint32_t>(tile[4 * tx + 2][c]) | (static_cast<uint32_t>(tile[4 * tx + 3][c]) << 16);
+      *reinterpret_cast<uint2*>(out_t + static_cast<size_t>(orow) * R + ocol) = make_uint2(lo, hi);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gate_residual (forward)
 // out[r, :] = x[r, :] + gate[r / rpb, :] * m[r, :] (+ row_add[(r / tokens) % frames, :]).  Thread = 4 columns.
 template <bool BF16>
@@ -111,14 +143,24 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ GELU (tanh form)
+// one MUFU op per element (tanh.approx, relative error 2^-11 -- below the 16-bit rounding of the result), as in the GEMM's
+// GELU epilogue: with libm's tanhf the backward pass was ALU-bound (~60 instructions per element on 94 M elements per call)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_f(float u) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * u * (1.0f + tanhf(k0 * (u + k1 * u * u * u)));
+  const float hu = 0.5f * u;
+  return fmaf(hu, tanh_fast(k0 * fmaf(k1 * u * u, u, u)), hu);
 }
 __device__ __forceinline__ float gelu_grad(float u) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float th = tanhf(k0 * (u + k1 * u * u * u));
-  return 0.5f * (1.0f + th) + 0.5f * u * (1.0f - th * th) * k0 * (1.0f + 3.0f * k1 * u * u);
+  const float u2 = u * u;
+  const float th = tanh_fast(k0 * fmaf(k1 * u2, u, u));
+  const float sech2 = fmaf(-th, th, 1.0f);
+  return fmaf(0.5f * u * sech2, k0 * fmaf(3.0f * k1, u2, 1.0f), fmaf(0.5f, th, 0.5f));
 }
 
 template <bool BF16>
@@ -233,7 +275,7 @@ __global__ void __launch_bounds__(128) colsum_kernel(const void* __restrict__ a,
 //   dx += rstd * (g - mean(g) - xhat * mean(g * xhat)).
 // One warp per row (row in registers), LB_RPW consecutive rows per warp, the 4 warps of a block reduce their column sums
 // through shared memory before the atomics.  rows_per_batch % (4 * LB_RPW) == 0 keeps a block inside one sample.
-constexpr int LB_RPW = 16;
+constexpr int LB_RPW = 8;
 template <bool BF16, int NV>
 __global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __restrict__ dh, const float* __restrict__ x,
                                                               const float* __restrict__ scale, long long mod_bs, int rpb,
@@ -724,6 +766,179 @@ __global__ void __launch_bounds__(128) attn_bwd_temporal_kernel(const uint16_t* 
   }
 }
 
+// Tensor-core version of the above for head_dim 64 / 72: ONE WARP per (b, n, head), four heads per CTA, no block-level
+// synchronisation.  The F <= 16 frames of q, k, v, dO sit in a [16 x HDP] shared tile each (rows >= F zero); S = Q K^T and
+// dP = dO V^T are one 16x16 accumulator pair, and the transposed pair (K Q^T, V dO^T) is recomputed so that P^T / dS^T come
+// out directly as the A operands of dV = P^T dO and dK = dS^T Q (as in the spatial kernel B).  Row statistics go through 32
+// floats of shared memory.  Results are staged in the tiles they came from and written back with 16-byte stores.
+template <bool BF16, int HD>
+__global__ void __launch_bounds__(128) attn_bwd_temporal_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ d_o,
+                                                                    uint16_t* __restrict__ dqkv, int frames, int tokens, int heads,
+                                                                    float scale_log2) {
+  using G = AB<HD>;
+  constexpr int T16 = 16 * G::HDP;                 // elements per 16-row tile
+  extern __shared__ __align__(16) uint16_t sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y * 4 + warp;
+  if (h >= heads) return;
+  uint16_t* sQ = sm + warp * (4 * T16 + 64);       // + 64 elements = 32 floats of statistics per warp
+  uint16_t* sK = sQ + T16;
+  uint16_t* sV = sK + T16;
+  uint16_t* sG = sV + T16;
+  float* sL = reinterpret_cast<float*>(sG + T16);  // [16] lse (log2 units), [16] delta
+  const int F = frames;
+  const int n = blockIdx.x % tokens, b = blockIdx.x / tokens;
+  const int D = heads * HD, ld = 3 * D;
+  const size_t row0 = static_cast<size_t>(b) * F * tokens + n;
+  constexpr int CH = HD / 8;
+  for (int i = lane; i < 4 * 16 * (G::HDP / 8); i += 32) {          // whole tiles incl. pad columns: zero where nothing is loaded
+    const int which = i / (16 * (G::HDP / 8)), rem = i % (16 * (G::HDP / 8));
+    const int f = rem / (G::HDP / 8), c = rem % (G::HDP / 8);
+    uint16_t* dst = sQ + which * T16 + f * G::HDP + c * 8;
+    if (f < F && c < CH) {
+      const size_t r = row0 + static_cast<size_t>(f) * tokens;
+      const uint16_t* src = which < 3 ? qkv + r * ld + which * D + h * HD + c * 8 : d_o + r * D + h * HD + c * 8;
+      cp_async16(dst, src);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncwarp();
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;      // A-fragment lane address
+  const int brow = (lane & 7) + (lane >> 4) * 8, bcol = ((lane >> 3) & 1) * 8;      // B-fragment ([n][k] tile) lane address
+  auto mm16 = [&](float (&acc)[2][4], const uint16_t* sA, const uint16_t* sB) {     // acc[16 x 16] = A[16 x KP] . B[16 x KP]^T
+#pragma unroll
+    for (int k = 0; k < G::KS; ++k) {
+      uint32_t a[4], bb[4];
+      ldsm_x4(a, smem_u32(sA + arow * G::HDP + k * 16 + acol));
+      ldsm_x4(bb, smem_u32(sB + brow * G::HDP + k * 16 + bcol));
+      mma16816<BF16>(acc[0], a, bb[0], bb[1]);
+      mma16816<BF16>(acc[1], a, bb[2], bb[3]);
+    }
+  };
+  const float scale = scale_log2 * 0.6931471805599453f;
+  const int c_lo = (lane & 3) * 2;                 // this thread's columns: c_lo, c_lo+1 (n-tile 0), +8 (n-tile 1)
+  // ---- orientation 1: rows = queries
+  float s[2][4] = {}, dp[2][4] = {};
+  mm16(s, sQ, sK);
+  mm16(dp, sG, sV);
+  float l2[2], dl[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = t * 8 + c_lo + e;
+        float& v = s[t][2 * hh + e];
+        v = col < F ? v * scale_log2 : -INFINITY;
+        m = fmaxf(m, v);
+      }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) sum += exp2f(s[t][2 * hh + e] - m);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    l2[hh] = m + log2f(sum);
+    float d = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float pr = exp2f(s[t][2 * hh + e] - l2[hh]);      // exp2(-inf) = 0 for masked keys
+        s[t][2 * hh + e] = pr;
+        d += pr * dp[t][2 * hh + e];
+      }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    dl[hh] = d;
+    if ((lane & 3) == 0) {
+      sL[(lane >> 2) + hh * 8] = l2[hh];
+      sL[16 + (lane >> 2) + hh * 8] = d;
+    }
+  }
+  uint32_t ds_a[4];
+  {
+    float t0[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) t0[t][e] = s[t][e] * (dp[t][e] - dl[e >> 1]) * scale;
+    ds_a[0] = pack2<BF16>(t0[0][0], t0[0][1]); ds_a[1] = pack2<BF16>(t0[0][2], t0[0][3]);
+    ds_a[2] = pack2<BF16>(t0[1][0], t0[1][1]); ds_a[3] = pack2<BF16>(t0[1][2], t0[1][3]);
+  }
+  __syncwarp();
+  // out[16 x HD] = A-frag(16 x 16) . tile[16 x HD]   (tile rows = contraction)
+  auto mm_out = [&](float (&out)[G::NT][4], const uint32_t (&a)[4], const uint16_t* sB) {
+#pragma unroll
+    for (int np = 0; np < G::NT / 2; ++np) {
+      uint32_t bb[4];
+      ldsm_x4_t(bb, smem_u32(sB + arow * G::HDP + np * 16 + acol));
+      mma16816<BF16>(out[2 * np], a, bb[0], bb[1]);
+      mma16816<BF16>(out[2 * np + 1], a, bb[2], bb[3]);
+    }
+    if constexpr (G::NT % 2 == 1) {
+      uint32_t b0, b1;
+      ldsm_x2_t(b0, b1, smem_u32(sB + arow * G::HDP + (G::NT - 1) * 8));
+      mma16816<BF16>(out[G::NT - 1], a, b0, b1);
+    }
+  };
+  float dq[G::NT][4] = {};
+  mm_out(dq, ds_a, sK);
+  // ---- orientation 2: rows = keys
+  float st[2][4] = {}, dpt[2][4] = {};
+  mm16(st, sK, sQ);
+  mm16(dpt, sV, sG);
+  uint32_t pt_a[4], dst_a[4];
+  {
+    float pv[2][4], dv_[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = t * 8 + c_lo + (e & 1);
+        const float pr = exp2f(st[t][e] * scale_log2 - sL[qi]);
+        pv[t][e] = pr;
+        dv_[t][e] = pr * (dpt[t][e] - sL[16 + qi]) * scale;
+      }
+    pt_a[0] = pack2<BF16>(pv[0][0], pv[0][1]); pt_a[1] = pack2<BF16>(pv[0][2], pv[0][3]);
+    pt_a[2] = pack2<BF16>(pv[1][0], pv[1][1]); pt_a[3] = pack2<BF16>(pv[1][2], pv[1][3]);
+    dst_a[0] = pack2<BF16>(dv_[0][0], dv_[0][1]); dst_a[1] = pack2<BF16>(dv_[0][2], dv_[0][3]);
+    dst_a[2] = pack2<BF16>(dv_[1][0], dv_[1][1]); dst_a[3] = pack2<BF16>(dv_[1][2], dv_[1][3]);
+  }
+  float dk[G::NT][4] = {}, dv[G::NT][4] = {};
+  mm_out(dv, pt_a, sG);
+  mm_out(dk, dst_a, sQ);
+  __syncwarp();
+  // ---- stage the three results in the q / k / v tiles, then 16-byte stores
+  auto stage = [&](uint16_t* tile, const float (&acc)[G::NT][4]) {
+    const int r = lane >> 2;
+#pragma unroll
+    for (int nn = 0; nn < G::NT; ++nn) {
+      *reinterpret_cast<uint32_t*>(tile + r * G::HDP + nn * 8 + c_lo) = pack2<BF16>(acc[nn][0], acc[nn][1]);
+      *reinterpret_cast<uint32_t*>(tile + (r + 8) * G::HDP + nn * 8 + c_lo) = pack2<BF16>(acc[nn][2], acc[nn][3]);
+    }
+  };
+  stage(sQ, dq);
+  stage(sK, dk);
+  stage(sV, dv);
+  __syncwarp();
+  for (int i = lane; i < 3 * F * CH; i += 32) {
+    const int which = i / (F * CH), rem = i % (F * CH);
+    const int f = rem / CH, c = rem % CH;
+    const size_t r = row0 + static_cast<size_t>(f) * tokens;
+    *reinterpret_cast<uint4*>(dqkv + r * ld + which * D + h * HD + c * 8) =
+        *reinterpret_cast<const uint4*>(sQ + which * T16 + f * G::HDP + c * 8);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ adaLN gradients
 // dW[n, k] = sum_b dmod[b, n] * sc[b, k]   (B <= 8 rows; pure write bandwidth: the gradient buffer itself)
 template <bool BF16>
@@ -809,8 +1024,14 @@ int launch_cast_transpose(const float* in, void* out16, void* out16_t, int rows,
   B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(out16) & 3) == 0 &&
                    (reinterpret_cast<uintptr_t>(out16_t) & 3) == 0, B200_ERR_ALIGN, "cast_transpose: misaligned pointer");
   dim3 grid((cols + 63) / 64, (rows + 63) / 64);
-  if (bf16) cast_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, static_cast<uint16_t*>(out16), static_cast<uint16_t*>(out16_t), rows, cols);
-  else cast_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, static_cast<uint16_t*>(out16), static_cast<uint16_t*>(out16_t), rows, cols);
+  uint16_t *o = static_cast<uint16_t*>(out16), *ot = static_cast<uint16_t*>(out16_t);
+  const bool wide = rows % 4 == 0 && cols % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0 &&
+                    (reinterpret_cast<uintptr_t>(ot) & 7) == 0;
+  if (wide) {
+    if (bf16) cast_transpose4_kernel<true><<<grid, 256, 0, stream>>>(in, o, ot, rows, cols);
+    else cast_transpose4_kernel<false><<<grid, 256, 0, stream>>>(in, o, ot, rows, cols);
+  } else if (bf16) cast_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, o, ot, rows, cols);
+  else cast_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, o, ot, rows, cols);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -843,7 +1064,6 @@ int launch_gelu_fwd(const void* u16, void* a16, long long n, int bf16, cudaStrea
 int launch_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int bf16, cudaStream_t stream) {
   B200_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0, B200_ERR_SHAPE, "gelu_bwd: dim %d must be a multiple of 8", dim);
   B200_REQUIRE(ALIGNED16(da16) && ALIGNED16(u16) && ALIGNED16(du16), B200_ERR_ALIGN, "gelu_bwd: pointers must be 16-byte aligned");
-  B200_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * dim, stream));
   const int rs = 32;
   dim3 grid((dim / 8 + 127) / 128, (rows + rs - 1) / rs);
   const uint16_t *a = static_cast<const uint16_t*>(da16), *u = static_cast<const uint16_t*>(u16);
@@ -860,9 +1080,6 @@ int launch_gate_bwd(const float* dx, const void* m16, const float* gate, long lo
                "gate_bwd: dim %% 4 and rows_per_batch %% %d must be 0", rs);
   B200_REQUIRE(ALIGNED16(dx) && ALIGNED16(gate) && (reinterpret_cast<uintptr_t>(m16) & 7) == 0 && (reinterpret_cast<uintptr_t>(dm16) & 7) == 0,
                B200_ERR_ALIGN, "gate_bwd: misaligned pointer");
-  const int batch = (rows + rows_per_batch - 1) / rows_per_batch;
-  for (int b = 0; b < batch; ++b) B200_CHECK_CUDA(cudaMemsetAsync(dgate + b * dgate_bs, 0, sizeof(float) * dim, stream));
-  B200_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * dim, stream));
   dim3 grid((dim / 4 + 127) / 128, (rows + rs - 1) / rs);
   const uint16_t* m = static_cast<const uint16_t*>(m16);
   if (bf16) gate_bwd_kernel<true><<<grid, 128, 0, stream>>>(dx, m, gate, gate_bs, rows_per_batch, static_cast<uint16_t*>(dm16), dgate, dgate_bs, dbias, rows, dim, rs);
@@ -874,7 +1091,6 @@ int launch_gate_bwd(const float* dx, const void* m16, const float* gate, long lo
 int launch_colsum(const void* a, int dtype, float* out, int rows, int dim, cudaStream_t stream) {
   B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dtype >= 0 && dtype <= 2, B200_ERR_SHAPE, "colsum: bad shape / dtype");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(a) & (dtype == 0 ? 15 : 7)) == 0, B200_ERR_ALIGN, "colsum: misaligned input");
-  B200_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * dim, stream));
   const int rs = 64;
   dim3 grid((dim / 4 + 127) / 128, (rows + rs - 1) / rs);
   if (dtype == 0) colsum_kernel<0><<<grid, 128, 0, stream>>>(a, out, rows, dim, rs);
@@ -902,11 +1118,6 @@ int launch_ln_modulate_bwd(const void* dh16, const float* x, const float* scale,
   B200_REQUIRE(rows_per_batch % (4 * LB_RPW) == 0 && mod_bs % 4 == 0, B200_ERR_SHAPE, "ln_modulate_bwd: rows_per_batch must be a multiple of %d", 4 * LB_RPW);
   B200_REQUIRE(ALIGNED16(x) && ALIGNED16(scale) && ALIGNED16(dx) && (reinterpret_cast<uintptr_t>(dh16) & 7) == 0, B200_ERR_ALIGN,
                "ln_modulate_bwd: misaligned pointer");
-  const int batch = (rows + rows_per_batch - 1) / rows_per_batch;
-  for (int b = 0; b < batch; ++b) {
-    B200_CHECK_CUDA(cudaMemsetAsync(dshift + b * dmod_bs, 0, sizeof(float) * dim, stream));
-    B200_CHECK_CUDA(cudaMemsetAsync(dscale + b * dmod_bs, 0, sizeof(float) * dim, stream));
-  }
   const int nvmax = (dim / 4 + 31) / 32;
   const uint16_t* dh = static_cast<const uint16_t*>(dh16);
 #define LNB(BF, NVV) return lnb_launch<BF, NVV>(stream, dh, x, scale, mod_bs, rows_per_batch, dx, dshift, dscale, dmod_bs, rows, dim)
@@ -950,6 +1161,23 @@ int launch_attention_bwd(const void* qkv, const void* o, const void* d_o, void* 
   uint16_t* dq = static_cast<uint16_t*>(dqkv);
   if (temporal) {
     B200_REQUIRE(frames <= 16 && head_dim % 8 == 0 && head_dim <= 128, B200_ERR_UNSUPPORTED, "attention_bwd: temporal sequences of <= 16 frames, head_dim %% 8 == 0 (got %d, %d)", frames, head_dim);
+    if (head_dim == 64 || head_dim == 72) {       // tensor-core kernel: one warp per (b, n, head)
+      const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+      dim3 grid_w(batch * tokens, (heads + 3) / 4);
+      const int hdp = (head_dim + 15) / 16 * 16 + 8;
+      const size_t smem_w = static_cast<size_t>(4) * (4 * 16 * hdp + 64) * 2;
+#define TMMA(BF, HDV)                                                                                                          \
+      do {                                                                                                                      \
+        auto kern = attn_bwd_temporal_mma_kernel<BF, HDV>;                                                                      \
+        B200_SET_SMEM_ONCE(kern, static_cast<int>(smem_w));                                                                     \
+        kern<<<grid_w, 128, smem_w, stream>>>(q, g, dq, frames, tokens, heads, scale_log2);                                     \
+      } while (0)
+      if (head_dim == 72) { if (bf16) TMMA(true, 72); else TMMA(false, 72); }
+      else { if (bf16) TMMA(true, 64); else TMMA(false, 64); }
+#undef TMMA
+      B200_CHECK_CUDA(cudaGetLastError());
+      return B200_OK;
+    }
     const size_t smem = (static_cast<size_t>(4) * frames * (head_dim + 1) + 2 * frames * frames) * sizeof(float);
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
     dim3 grid(batch * tokens, heads);

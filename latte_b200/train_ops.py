@@ -84,41 +84,36 @@ class NativeOps:
         return a
 
     # ------------------------------------------------------------------ backward ops
-    def gate_bwd(self, dx, m, gate, rpb):
-        self._cuda(dx, m, gate)
-        assert dx.dtype == torch.float32 and dx.is_contiguous() and m.is_contiguous()
+    # Reduction outputs (dgate, dbias, dshift, dscale, column sums) ACCUMULATE into the fp32 views the engine hands in -- slices of
+    # gradient buffers it zeroed once for the step -- so no pass needs a memset or a copy of its result.
+    def gate_bwd(self, dx, m, gate, rpb, dgate, dbias):
+        self._cuda(dx, m, gate, dgate, dbias)
+        assert dx.dtype == torch.float32 and dx.is_contiguous() and m.is_contiguous() and dgate.stride(1) == 1
         T, D = dx.shape
-        B = T // rpb
         dm = torch.empty(T, D, dtype=self.dtype, device=dx.device)
-        dgate = torch.empty(B, D, dtype=torch.float32, device=dx.device)
-        dbias = torch.empty(D, dtype=torch.float32, device=dx.device)
         with torch.cuda.device(dx.device):
             rc = _lib.load().b200_gate_bwd(dx.data_ptr(), m.data_ptr(), gate.data_ptr(), gate.stride(0), rpb, dm.data_ptr(),
-                                           dgate.data_ptr(), D, dbias.data_ptr(), T, D, self.dt, _s(dx))
+                                           dgate.data_ptr(), dgate.stride(0), dbias.data_ptr(), T, D, self.dt, _s(dx))
         _lib.check(rc, "b200_gate_bwd")
-        return dm, dgate, dbias
+        return dm
 
-    def gelu_bwd(self, da, u):
-        self._cuda(da, u)
+    def gelu_bwd(self, da, u, dbias):
+        self._cuda(da, u, dbias)
         T, D = u.shape
         du = torch.empty_like(u)
-        dbias = torch.empty(D, dtype=torch.float32, device=u.device)
         with torch.cuda.device(u.device):
             rc = _lib.load().b200_gelu_bwd(da.data_ptr(), u.data_ptr(), du.data_ptr(), dbias.data_ptr(), T, D, self.dt, _s(u))
         _lib.check(rc, "b200_gelu_bwd")
-        return du, dbias
+        return du
 
-    def ln_modulate_bwd(self, dh, x, shift, scale, rpb, dx):
-        self._cuda(dh, x, scale, dx)
+    def ln_modulate_bwd(self, dh, x, shift, scale, rpb, dx, dshift, dscale):
+        self._cuda(dh, x, scale, dx, dshift, dscale)
+        assert dshift.stride(0) == dscale.stride(0) and dshift.stride(1) == 1
         T, D = x.shape
-        B = T // rpb
-        dshift = torch.empty(B, D, dtype=torch.float32, device=x.device)
-        dscale = torch.empty(B, D, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             rc = _lib.load().b200_ln_modulate_bwd(dh.data_ptr(), x.data_ptr(), scale.data_ptr(), scale.stride(0), rpb, dx.data_ptr(),
-                                                  dshift.data_ptr(), dscale.data_ptr(), D, T, D, self.dt, _s(x))
+                                                  dshift.data_ptr(), dscale.data_ptr(), dshift.stride(0), T, D, self.dt, _s(x))
         _lib.check(rc, "b200_ln_modulate_bwd")
-        return dshift, dscale
 
     def attention_bwd(self, qkv, o, do, B, Fr, N, H, temporal):
         self._cuda(qkv, o, do)
@@ -132,10 +127,9 @@ class NativeOps:
         _lib.check(rc, "b200_attention_bwd")
         return dqkv
 
-    def colsum(self, a):
-        self._cuda(a)
-        assert a.is_contiguous()
-        out = torch.empty(a.shape[1], dtype=torch.float32, device=a.device)
+    def colsum(self, a, out):
+        self._cuda(a, out)
+        assert a.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
         with torch.cuda.device(a.device):
             rc = _lib.load().b200_colsum(a.data_ptr(), _KIND[a.dtype], out.data_ptr(), a.shape[0], a.shape[1], _s(a))
         _lib.check(rc, "b200_colsum")

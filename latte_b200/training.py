@@ -124,9 +124,8 @@ class TrainEngine:
             u = ops.linear(h2, w1[0], w1[2])
             a = ops.gelu(u)
             m2 = ops.linear(a, w2[0], w2[2])
-            del a
             xo = ops.gate_residual(xm, m2, g2, rpb, row_add=temp if i == 0 else None, tokens=N)
-            S["blocks"].append((xs, h1, qkv, o, m1, xm, h2, u, m2))
+            S["blocks"].append((xs, h1, qkv, o, m1, xm, h2, u, a, m2))
             xs = xo
         base = m.depth * 6 * D
         shf, scf = mod[:, base:base + D], mod[:, base + D:base + 2 * D]
@@ -139,16 +138,24 @@ class TrainEngine:
 
     # ---------------------------------------------------------------------------------------------------------------
     def backward(self, dout):
-        """dout (B, F, 2C, H, W) -> (grads: {parameter name: fp32 tensor}, dc (B, D) fp32).  Frees the saved activations."""
+        """dout (B, F, 2C, H, W) -> (grads: {parameter name: fp32 tensor}, dc (B, D) fp32).  Frees the saved activations.
+        Bias gradients, the per-sample adaLN gradients (dmod) and every weight gradient are views of buffers zeroed once here;
+        the kernels accumulate into them (wgrad through the GEMM's fp32 residual epilogue, reductions with atomics)."""
         m, ops, W, S = self.m, self.ops, self.w, self.saved
         self.saved = None
         B = S["B"]
-        D, Fr, N, H = m.hidden_size, m.num_frames, m.x_embedder.num_patches, m.num_heads
+        D, Fr, N, H, Hm = m.hidden_size, m.num_frames, m.x_embedder.num_patches, m.num_heads, m.mlp_hidden
         T, rpb = B * Fr * N, Fr * N
         dev = dout.device
         mod = S["mod"]
         G = {}
         dmod = torch.zeros_like(mod)
+        # all bias gradients in one zeroed buffer: per block [qkv 3D | proj D | fc1 Hm | fc2 D], then final (nf), patch (D)
+        per_blk = 3 * D + D + Hm + D
+        bias_flat = torch.zeros(m.depth * per_blk + self.nf + D, dtype=torch.float32, device=dev)
+
+        def bias_view(i, off, n):
+            return bias_flat[i * per_blk + off: i * per_blk + off + n]
 
         def wgrad(dy, x):
             g = torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=dev)
@@ -156,7 +163,7 @@ class TrainEngine:
 
         # ---- final layer (latte.py:197-201) ----
         dtok = self._patchify_out(dout.float())                                         # (T, nf) fp32
-        G["final_layer.linear.bias"] = ops.colsum(dtok)
+        G["final_layer.linear.bias"] = ops.colsum(dtok, bias_flat[m.depth * per_blk: m.depth * per_blk + self.nf])
         dtok16 = ops.to_operand(dtok)
         G["final_layer.linear.weight"] = wgrad(dtok16, S["hf"])
         dtp = torch.zeros(T, 64, dtype=torch.float32, device=dev)
@@ -164,51 +171,50 @@ class TrainEngine:
         dhf = ops.linear(ops.to_operand(dtp), W["final_wt"])
         dx = torch.zeros(T, D, dtype=torch.float32, device=dev)
         base = m.depth * 6 * D
-        dsh, dsc_ = ops.ln_modulate_bwd(dhf, S["x_last"], mod[:, base:base + D], mod[:, base + D:base + 2 * D], rpb, dx)
-        dmod[:, base:base + D], dmod[:, base + D:base + 2 * D] = dsh, dsc_
+        ops.ln_modulate_bwd(dhf, S["x_last"], mod[:, base:base + D], mod[:, base + D:base + 2 * D], rpb, dx,
+                            dmod[:, base:base + D], dmod[:, base + D:base + 2 * D])
         del dhf, dtp, dtok16
 
         # ---- blocks, last to first (latte.py:177-181) ----
         for i in reversed(range(m.depth)):
-            xs, h1, qkv, o, m1, xm, h2, u, m2 = S["blocks"].pop()
+            xs, h1, qkv, o, m1, xm, h2, u, a, m2 = S["blocks"].pop()
             mv = mod[:, i * 6 * D:(i + 1) * 6 * D]
             sh1, sc1, g1, sh2, sc2, g2 = (mv[:, k * D:(k + 1) * D] for k in range(6))
             dv = dmod[:, i * 6 * D:(i + 1) * 6 * D]
+            dsh1, dsc1, dg1, dsh2, dsc2, dg2 = (dv[:, k * D:(k + 1) * D] for k in range(6))
             temporal = bool(i % 2)
             wq, wp, w1, w2 = (W[f"{i}.{n}"] for n in _BLOCK_LINEARS)
             p = f"blocks.{i}."
+            G[p + "attn.qkv.bias"], G[p + "attn.proj.bias"] = bias_view(i, 0, 3 * D), bias_view(i, 3 * D, D)
+            G[p + "mlp.fc1.bias"], G[p + "mlp.fc2.bias"] = bias_view(i, 4 * D, Hm), bias_view(i, 4 * D + Hm, D)
             # x_out = x_mid + g2 * fc2(gelu(fc1(LNmod(x_mid))))
-            dm2, dg2, G[p + "mlp.fc2.bias"] = ops.gate_bwd(dx, m2, g2, rpb)
-            a = ops.gelu(u)
+            dm2 = ops.gate_bwd(dx, m2, g2, rpb, dg2, G[p + "mlp.fc2.bias"])
             G[p + "mlp.fc2.weight"] = wgrad(dm2, a)
             del a
             da = ops.linear(dm2, w2[1])
-            du, G[p + "mlp.fc1.bias"] = ops.gelu_bwd(da, u)
+            du = ops.gelu_bwd(da, u, G[p + "mlp.fc1.bias"])
             del da, dm2
             G[p + "mlp.fc1.weight"] = wgrad(du, h2)
             dh2 = ops.linear(du, w1[1])
             del du
-            dsh2, dsc2 = ops.ln_modulate_bwd(dh2, xm, sh2, sc2, rpb, dx)
+            ops.ln_modulate_bwd(dh2, xm, sh2, sc2, rpb, dx, dsh2, dsc2)
             del dh2
             # x_mid = x_in + g1 * proj(attn(qkv(LNmod(x_in))))
-            dm1, dg1, G[p + "attn.proj.bias"] = ops.gate_bwd(dx, m1, g1, rpb)
+            dm1 = ops.gate_bwd(dx, m1, g1, rpb, dg1, G[p + "attn.proj.bias"])
             G[p + "attn.proj.weight"] = wgrad(dm1, o)
             do = ops.linear(dm1, wp[1])
             del dm1
             dqkv = ops.attention_bwd(qkv, o, do, B, Fr, N, H, temporal)
             del do
-            G[p + "attn.qkv.bias"] = ops.colsum(dqkv)
+            ops.colsum(dqkv, G[p + "attn.qkv.bias"])
             G[p + "attn.qkv.weight"] = wgrad(dqkv, h1)
             dh1 = ops.linear(dqkv, wq[1])
             del dqkv
-            dsh1, dsc1 = ops.ln_modulate_bwd(dh1, xs, sh1, sc1, rpb, dx)
-            del dh1
-            for k, t in enumerate((dsh1, dsc1, dg1, dsh2, dsc2, dg2)):
-                dv[:, k * D:(k + 1) * D] = t
-            del xs, h1, qkv, o, m1, xm, h2, u, m2
+            ops.ln_modulate_bwd(dh1, xs, sh1, sc1, rpb, dx, dsh1, dsc1)
+            del dh1, xs, h1, qkv, o, m1, xm, h2, u, m2
 
         # ---- patch embedding (latte.py:330-331; pos_embed / temp_embed are frozen, :246-247) ----
-        G["x_embedder.proj.bias"] = ops.colsum(dx)
+        G["x_embedder.proj.bias"] = ops.colsum(dx, bias_flat[m.depth * per_blk + self.nf:])
         gpe = wgrad(ops.to_operand(dx), S["xp"])
         G["x_embedder.proj.weight"] = gpe[:, : self.kp].reshape(m.x_embedder.proj.weight.shape).contiguous()
 

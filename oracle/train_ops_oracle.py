@@ -88,22 +88,25 @@ class TorchOps:
         return F.gelu(u.float(), approximate="tanh").to(self.dtype)
 
     # ------------------------------------------------------------------ backward ops
-    def gate_bwd(self, dx, m, gate, rpb):
+    # reduction outputs accumulate (+=) into the views handed in, like the kernels
+    def gate_bwd(self, dx, m, gate, rpb, dgate, dbias):
         B = dx.shape[0] // rpb
         d = dx.view(B, rpb, -1)
         dm = d * gate.float()[:, None]
-        dgate = (d * m.float().view(B, rpb, -1)).sum(1)
-        return dm.reshape(dx.shape).to(self.dtype), dgate, dm.sum((0, 1))
+        dgate += (d * m.float().view(B, rpb, -1)).sum(1)
+        dbias += dm.sum((0, 1))
+        return dm.reshape(dx.shape).to(self.dtype)
 
-    def gelu_bwd(self, da, u):
+    def gelu_bwd(self, da, u, dbias):
         uf = u.float()
         k0, k1 = math.sqrt(2.0 / math.pi), 0.044715
         th = torch.tanh(k0 * (uf + k1 * uf ** 3))
         dg = 0.5 * (1 + th) + 0.5 * uf * (1 - th * th) * k0 * (1 + 3 * k1 * uf * uf)
         du = da.float() * dg
-        return du.to(self.dtype), du.sum(0)
+        dbias += du.sum(0)
+        return du.to(self.dtype)
 
-    def ln_modulate_bwd(self, dh, x, shift, scale, rpb, dx):
+    def ln_modulate_bwd(self, dh, x, shift, scale, rpb, dx, dshift, dscale):
         B = x.shape[0] // rpb
         xf = x.float().view(B, rpb, -1)
         mu = xf.mean(-1, keepdim=True)
@@ -111,12 +114,11 @@ class TorchOps:
         rstd = 1.0 / torch.sqrt(var + 1e-6)
         xh = (xf - mu) * rstd
         d = dh.float().view(B, rpb, -1)
-        dshift = d.sum(1)
-        dscale = (d * xh).sum(1)
+        dshift += d.sum(1)
+        dscale += (d * xh).sum(1)
         g = d * (1 + scale.float()[:, None])
         dxr = rstd * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
         dx += dxr.reshape(dx.shape)
-        return dshift, dscale
 
     def attention_bwd(self, qkv, o, do, B, Fr, N, H, temporal):
         q, k, v, hd = self._split(qkv, B, Fr, N, H, temporal)
@@ -134,8 +136,9 @@ class TorchOps:
         parts = [self._merge(t, B, Fr, N, H, temporal) for t in (dq, dk, dv)]
         return torch.cat(parts, dim=1).to(self.dtype)
 
-    def colsum(self, a):
-        return a.float().sum(0)
+    def colsum(self, a, out):
+        out += a.float().sum(0)
+        return out
 
     def transpose(self, a):
         return a.t().contiguous()

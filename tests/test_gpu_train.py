@@ -45,13 +45,14 @@ def test_transpose_cast_colsum(dev, dt):
     for R, Cc in [(1536, 128), (4096, 1152), (512, 32), (130, 68)]:
         a = torch.randn(R, Cc, generator=g).to(dev).to(dt)
         assert torch.equal(nat.transpose(a), a.t().contiguous())
-        _close(nat.colsum(a), ref.colsum(a), 1e-5, "colsum16")
+        base = torch.randn(Cc, generator=g).to(dev)                      # reductions accumulate into the buffer handed in
+        _close(nat.colsum(a, base.clone()), ref.colsum(a, base.clone()), 1e-5, "colsum16")
     w = torch.randn(384, 1152, generator=g).to(dev)
     w16, wt16 = nat.cast(w)
     assert torch.equal(w16, w.to(dt)) and torch.equal(wt16, w.to(dt).t().contiguous())
     x = torch.randn(2048, 384, generator=g).to(dev)
     assert torch.equal(nat.to_operand(x), x.to(dt))
-    _close(nat.colsum(x), x.sum(0), 1e-5, "colsum32")
+    _close(nat.colsum(x, torch.zeros(384, device=dev)), x.sum(0), 1e-5, "colsum32")
 
 
 @pytest.mark.parametrize("dt", DTS)
@@ -119,23 +120,30 @@ def test_elementwise_backward_ops(dev, dt):
     m = torch.randn(T, D, generator=g).to(dev).to(dt)
     mod = torch.randn(B, 6 * D, generator=g).to(dev)
     gate, shift, scale = mod[:, 2 * D:3 * D], mod[:, 0:D], mod[:, D:2 * D]
-    for got, want, name in zip(nat.gate_bwd(dx, m, gate, rpb), ref.gate_bwd(dx, m, gate, rpb), ("dm", "dgate", "dbias")):
+    dmod0 = torch.randn(B, 6 * D, generator=g).to(dev)               # outputs accumulate into strided views of a dmod-like buffer
+    outs = []
+    for o in (nat, ref):
+        dmod, dbias = dmod0.clone(), torch.ones(D, device=dev)
+        dm = o.gate_bwd(dx, m, gate, rpb, dmod[:, 2 * D:3 * D], dbias)
+        outs.append((dm, dmod, dbias))
+    for got, want, name in zip(outs[0], outs[1], ("dm", "dgate", "dbias")):
         _close(got, want, EPS[dt] if name == "dm" else 2e-5, "gate_bwd " + name)
     u = (torch.randn(T, 4 * D, generator=g) * 2).to(dev).to(dt)
     da = torch.randn(T, 4 * D, generator=g).to(dev).to(dt)
-    du, db = nat.gelu_bwd(da, u)
-    du_r, db_r = ref.gelu_bwd(da, u)
+    db, db_r = torch.zeros(4 * D, device=dev), torch.zeros(4 * D, device=dev)
+    du = nat.gelu_bwd(da, u, db)
+    du_r = ref.gelu_bwd(da, u, db_r)
     _close(du, du_r, EPS[dt], "gelu_bwd du")
     _close(db, db_r, 3e-3, "gelu_bwd dbias")      # sum of fp32 values vs sum of the same values: order only
     x = (torch.randn(T, D, generator=g) * 3 + 1).to(dev)
     dh = torch.randn(T, D, generator=g).to(dev).to(dt)
     acc0 = torch.randn(T, D, generator=g).to(dev)
     acc_n, acc_r = acc0.clone(), acc0.clone()
-    ds_n = nat.ln_modulate_bwd(dh, x, shift, scale, rpb, acc_n)
-    ds_r = ref.ln_modulate_bwd(dh, x, shift, scale, rpb, acc_r)
+    dm_n, dm_r = dmod0.clone(), dmod0.clone()
+    nat.ln_modulate_bwd(dh, x, shift, scale, rpb, acc_n, dm_n[:, 0:D], dm_n[:, D:2 * D])
+    ref.ln_modulate_bwd(dh, x, shift, scale, rpb, acc_r, dm_r[:, 0:D], dm_r[:, D:2 * D])
     _close(acc_n, acc_r, 2e-5, "ln_modulate_bwd dx")
-    _close(ds_n[0], ds_r[0], 2e-5, "ln_modulate_bwd dshift")
-    _close(ds_n[1], ds_r[1], 2e-5, "ln_modulate_bwd dscale")
+    _close(dm_n, dm_r, 2e-5, "ln_modulate_bwd dshift / dscale")
 
 
 @pytest.mark.parametrize("dt", DTS)
