@@ -330,7 +330,10 @@ B200_API int b200_ln_modulate(const float* x, const float* shift, const float* s
  * gradient (a loss-scale / per-column factor otherwise).  rows % 64 == 0, n_out % 8 == 0, n_in % 128 == 0.                */
 B200_API int b200_wgrad(const void* dy16, const void* x16, const float* col_scale, float* dW, int rows, int n_out, int n_in,
                         int dtype, void* sk_flags, void* stream);
-/* out16[cols, rows] = in16[rows, cols]^T (wgrad operands of shapes b200_wgrad does not take).                               */
+/* dX16[rows, n_in] = dY16[rows, n_out] . W16[n_out, n_in] -- the input gradient of Y = X W^T with the weight in its nn.Linear
+ * [out, in] layout (MN-major W operand: no transposed weight copy).  n_out % 64 == 0, n_in % 128 == 0.                     */
+B200_API int b200_dgrad(const void* dy16, const void* w16, void* dx16, int rows, int n_out, int n_in, int dtype, void* stream);
+/* out16[cols, rows] = in16[rows, cols]^T (operands of shapes b200_wgrad / b200_dgrad do not take).                          */
 B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream);
 /* fp32 master parameter [rows, cols] -> 16-bit copy and (out16_t != NULL) its transpose [cols, rows], one read.           */
 B200_API int b200_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int dtype, void* stream);

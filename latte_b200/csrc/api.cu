@@ -666,8 +666,15 @@ B200_API int b200_wgrad(const void* dy16, const void* x16, const float* col_scal
   B200_REQUIRE(col_scale != nullptr, B200_ERR_SHAPE, "wgrad: col_scale (n_in floats, 1.0 for a plain gradient) is required");
   b200::GemmArgs a{};
   a.A = dy16; a.W = x16; a.M = n_out; a.N = n_in; a.K = rows; a.bf16 = dtype == B200_BF16; a.epilogue = B200_EPI_GATE_RESIDUAL;
-  a.resid = dW; a.gate = col_scale; a.gate_batch_stride = 0; a.rows_per_batch = n_out; a.mn_major = 1;
+  a.resid = dW; a.gate = col_scale; a.gate_batch_stride = 0; a.rows_per_batch = n_out; a.mn_major = 3;
   a.sk_flags = static_cast<unsigned long long*>(sk_flags);
+  return b200::launch_gemm(a, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_dgrad(const void* dy16, const void* w16, void* dx16, int rows, int n_out, int n_in, int dtype, void* stream) {
+  B200_DT(dtype);
+  b200::GemmArgs a{};
+  a.A = dy16; a.W = w16; a.M = rows; a.N = n_in; a.K = n_out; a.bf16 = dtype == B200_BF16; a.epilogue = B200_EPI_BIAS;
+  a.out16 = dx16; a.mn_major = 2;
   return b200::launch_gemm(a, static_cast<cudaStream_t>(stream));
 }
 B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream) {

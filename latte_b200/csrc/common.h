@@ -101,7 +101,8 @@ struct GemmArgs {
   int block_n;          // 0 = auto
   int w_const;          // 1: W is a constant weight matrix (never written during the step) -> its first tiles are prefetched
                         // before the grid dependency resolves; 0 (default): W may be an activation of the preceding kernel
-  int mn_major;         // 1: A is stored [K, M] and W is stored [K, N] (wgrad: dW[M, N] += dY[K, M]^T X[K, N]); N % 128 == 0
+  int mn_major;         // bit 0: A is stored [K, M]; bit 1: W is stored [K, N] (N % 128 == 0).  3 = wgrad (dW[M, N] += dY[K, M]^T X[K, N]),
+                        // 2 = dgrad (dX[M, N] = dY[M, K] W[K, N] with the weight in its nn.Linear [out, in] layout)
   unsigned long long* sk_flags;  // B200_GEMM_SK_FLAGS zeroed u64 (caller's workspace) or nullptr: enables ordered stream-K
   const void* add16;    // EPI_BIAS_ADD16: [M, N] 16-bit tensor added to the result (resnet shortcut)
   // implicit-GEMM convolution (conv_taps > 0): A is an NHWC activation [conv_n, conv_h, conv_w, conv_c] (16-bit), M =

@@ -79,8 +79,9 @@ struct GemmDev {
   int conv_taps, conv_cblk, conv_h, conv_w, conv_bw, conv_bh;
   int conv_dx[9], conv_dy[9], conv_dz[9];
   int w_const;  // W is a weight (not produced by a kernel of the step): its first tiles may be fetched before griddepcontrol.wait
-  int mn_major; // wgrad mode: A is stored [K, M] and W is stored [K, N] (the contraction dimension is the ROW index of both):
-                // tiles are fetched as 64-wide MN chunks x 64 k-rows and multiplied with MN-major UMMA descriptors
+  int mn_major; // bit 0: A is stored [K, M]; bit 1: W is stored [K, N] (the contraction dimension is the ROW index): such an
+                // operand is fetched as 64-wide MN chunks x 64 k-rows and multiplied through an MN-major UMMA descriptor.
+                // wgrad sets both (dW = dY^T X), dgrad only bit 1 (dX = dY W with W in its [out, in] layout).
   int streamk;  // residual epilogue only: split the last partial wave of tiles along K across all pairs (see TileSched)
   // stream-K ordering flags (caller's workspace), one per (streamed tile, CTA rank, epilogue warpgroup): "k-blocks of the
   // tile already added into x".  All zero between launches: the segment that completes a tile resets its flag, so the
@@ -281,18 +282,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int hw = p.conv_h * p.conv_w;
               const int img = pix0 / hw, rem = pix0 % hw;
               tma_load_4d_pair(sa, &tmA, full_leader, cb * BK, rem % p.conv_w + p.conv_dx[tap], rem / p.conv_w + p.conv_dy[tap], img + p.conv_dz[tap]);
-            } else if (p.mn_major) {
-              // operands stored [K][MN]: one box = 64 MN elements (a 128-byte swizzle row) x 64 k-rows = 8 KiB, the canonical
+            } else if (p.mn_major & 1) {
+              // operand stored [K][MN]: one box = 64 MN elements (a 128-byte swizzle row) x 64 k-rows = 8 KiB, the canonical
               // MN-major SW128 chunk; chunks past the live columns / rows are zero-filled by TMA and still count their bytes
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tmA, full_leader, m_blk * BM + j * 64, kb * BK);
-#pragma unroll
-              for (int j = 0; j < BN / 128; ++j)
-                tma_load_2d_pair(sa + C::A_BYTES + j * 8192, &tmB, full_leader, w_row0 + j * 64, kb * BK);
             } else {
               tma_load_2d_pair(sa, &tmA, full_leader, kb * BK, m_blk * BM);
             }
-            if (!w_in_flight && !p.mn_major) tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, w_row0);
+            if (p.mn_major & 2) {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_2d_pair(sa + C::A_BYTES + j * 8192, &tmB, full_leader, w_row0 + j * 64, kb * BK);
+            } else if (!w_in_flight) {
+              tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_leader, kb * BK, w_row0);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -313,21 +317,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // edge tile: only the live columns (a multiple of 32) are multiplied -- no tensor work / energy on zero padding
         const int n0 = (tile % p.num_n) * BN;
         const int n_live = ((p.N - n0) < BN && !(p.dbg & 64)) ? (p.N - n0) : BN;   // dbg bit 6: A/B switch (full-width edge tiles)
-        const bool mn = p.mn_major != 0;
-        const uint32_t idesc = (n_live == BN && !mn) ? idesc_full : umma_idesc_f16(BF16, 2 * BM, static_cast<uint32_t>(n_live), mn, mn);
+        const bool a_mn = (p.mn_major & 1) != 0, b_mn = (p.mn_major & 2) != 0;
+        const uint32_t idesc = (n_live == BN && !p.mn_major) ? idesc_full
+                                                             : umma_idesc_f16(BF16, 2 * BM, static_cast<uint32_t>(n_live), a_mn, b_mn);
         // K-major: 8-row groups 1024 B apart, a k-step of 16 elements = 32 B inside the swizzle row.  MN-major: 64-wide MN
         // chunks 8192 B apart (leading offset), 8-k-row groups 1024 B apart, a k-step of 16 k-rows = 2048 B.
-        const uint32_t lbo = mn ? 8192u : 0u, kstep = mn ? 2048u : 32u;
+        const uint32_t lbo_a = a_mn ? 8192u : 0u, kstep_a = a_mn ? 2048u : 32u;
+        const uint32_t lbo_b = b_mn ? 8192u : 0u, kstep_b = b_mn ? 2048u : 32u;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);            // both CTAs' operands landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint64_t da = umma_smem_desc(sa, lbo, 1024, UMMA_LAYOUT_SW128);
-          const uint64_t db = umma_smem_desc(sa + C::A_BYTES, lbo, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t da = umma_smem_desc(sa, lbo_a, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t db = umma_smem_desc(sa + C::A_BYTES, lbo_b, 1024, UMMA_LAYOUT_SW128);
           if (!(p.dbg & 2))
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss_pair(d_tmem, umma_desc_advance(da, k * kstep), umma_desc_advance(db, k * kstep), idesc,
+            umma_f16_ss_pair(d_tmem, umma_desc_advance(da, k * kstep_a), umma_desc_advance(db, k * kstep_b), idesc,
                              (kb != kb0 || k != 0) ? 1u : 0u);
           umma_commit_pair(&empty[stage], 0x3);  // slot reusable in BOTH CTAs once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -691,13 +697,17 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
 
   B200_REQUIRE(a.block_n == 0 || a.block_n == 128 || a.block_n == 192 || a.block_n == 256, B200_ERR_UNSUPPORTED,
                "gemm: block_n must be 128, 192 or 256 (got %d)", a.block_n);
+  int block_n = a.block_n;
   if (a.mn_major) {
-    B200_REQUIRE(a.conv_taps == 0 && a.M % 8 == 0 && a.N % 128 == 0 && (a.block_n == 0 || a.block_n == 128 || a.block_n == 256),
+    B200_REQUIRE(a.mn_major >= 1 && a.mn_major <= 3 && a.conv_taps == 0 && (!(a.mn_major & 1) || a.M % 8 == 0) &&
+                     (!(a.mn_major & 2) || a.N % 128 == 0) && (a.block_n == 0 || a.block_n == 128 || a.block_n == 256),
                  B200_ERR_UNSUPPORTED, "gemm (transposed operands): M %% 8 == 0, N %% 128 == 0, block_n 128 or 256 (M=%d N=%d)", a.M, a.N);
+    if (block_n == 0) {
+      block_n = pick_block_n(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL, sms);
+      if (block_n == 192) block_n = (a.N % 256 == 0 || a.N > 1024) ? 256 : 128;     // W chunks are 64 wide per CTA: 128 or 256 only
+    }
   }
-  const GemmPlan plan = plan_gemm(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL,
-                                  a.mn_major && a.block_n == 0 ? (a.N % 256 == 0 || a.N > 1024 ? 256 : 128) : a.block_n, sms,
-                                  a.mn_major != 0);
+  const GemmPlan plan = plan_gemm(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL, block_n, sms, a.mn_major == 3);
   const int bn = plan.bn;
 
   CUtensorMap tmA, tmB, tmX;
@@ -717,7 +727,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
                                 static_cast<uint64_t>(a.conv_c) * 2 * a.conv_w * a.conv_h};
       const uint32_t boxA[4] = {BK, static_cast<uint32_t>(conv_bw), static_cast<uint32_t>(conv_bh), 1};
       B200_TRY(make_tmap_16bit(&tmA, a.A, 4, dimsA, strA, boxA, TMAP_SW_128));
-    } else if (a.mn_major) {
+    } else if (a.mn_major & 1) {
       const uint64_t dimsA[2] = {static_cast<uint64_t>(a.M), static_cast<uint64_t>(a.K)};      // stored [K][M]
       const uint64_t strA[1] = {static_cast<uint64_t>(a.M) * 2};
       const uint32_t boxA[2] = {64, BK};
@@ -728,7 +738,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
       const uint32_t boxA[2] = {BK, BM};
       B200_TRY(make_tmap_16bit(&tmA, a.A, 2, dimsA, strA, boxA, TMAP_SW_128));
     }
-    if (a.mn_major) {
+    if (a.mn_major & 2) {
       const uint64_t dimsB[2] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K)};      // stored [K][N]
       const uint64_t strB[1] = {static_cast<uint64_t>(a.N) * 2};
       const uint32_t boxB[2] = {64, BK};
@@ -769,7 +779,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.dbg = dbg;
   static const int no_wprefetch = env_int("B200_GEMM_NO_WPREFETCH", 0);     // A/B switch
   p.w_const = (a.w_const && !no_wprefetch && a.conv_taps == 0 && !a.mn_major) ? 1 : 0;
-  p.mn_major = a.mn_major ? 1 : 0;
+  p.mn_major = a.mn_major;
   const int pair_tiles = plan.pair_tiles;
   const int grid = 2 * plan.pairs;
   {

@@ -182,15 +182,18 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint16_t* __restric
 // du = da * gelu'(u); dbias[c] += sum over the block's rows.  Block = 128 threads x 8 columns, `rs` rows per block.
 template <bool BF16>
 __global__ void __launch_bounds__(128) gelu_bwd_kernel(const uint16_t* __restrict__ da, const uint16_t* __restrict__ u,
-                                                       uint16_t* __restrict__ du, float* __restrict__ dbias, int rows, int dim, int rs) {
+                                                       uint16_t* __restrict__ du, float* __restrict__ dbias, int rows, int dim, int rs, int dbg) {
+  // Rows are dealt round-robin to the gridDim.y row-lanes (lane y takes rows y, y + G, ...): at any moment the whole grid
+  // works inside one sliding window of G consecutive rows, which DRAM serves far better than G far-apart row slabs
+  // (measured: 165 -> see profiles/r02_train_micro.txt).  `rs` = rows per lane.
   const int c8 = blockIdx.x * 128 + threadIdx.x;
   if (c8 * 8 >= dim) return;
-  const int r0 = blockIdx.y * rs;
-  const int r1 = min(rows, r0 + rs);
+  const int G = gridDim.y;
   float acc[8] = {};
   const int nv = dim >> 3;
+  (void)rs;
 #pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
+  for (int r = blockIdx.y; r < rows; r += G) {
     const size_t idx = static_cast<size_t>(r) * nv + c8;
     const uint4 a = reinterpret_cast<const uint4*>(da)[idx];
     const uint4 b = reinterpret_cast<const uint4*>(u)[idx];
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(128) gelu_bwd_kernel(const uint16_t* __restric
     }
     reinterpret_cast<uint4*>(du)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
   }
+  if (dbg & 1) return;
 #pragma unroll
   for (int j = 0; j < 8; ++j) atomicAdd(dbias + c8 * 8 + j, acc[j]);
 }
@@ -217,17 +221,20 @@ template <bool BF16>
 __global__ void __launch_bounds__(128) gate_bwd_kernel(const float* __restrict__ dx, const uint16_t* __restrict__ m,
                                                        const float* __restrict__ gate, long long gate_bs, int rpb,
                                                        uint16_t* __restrict__ dm, float* __restrict__ dgate, long long dgate_bs,
-                                                       float* __restrict__ dbias, int rows, int dim, int rs) {
+                                                       float* __restrict__ dbias, int rows, int dim, int rs, int dbg) {
+  // grid (column strips, G row-lanes, samples): lane y of sample b takes rows b*rpb + y, + G, ... (sliding window, see gelu_bwd)
   const int c4 = blockIdx.x * 128 + threadIdx.x;
   const int nv = dim >> 2;
   if (c4 >= nv) return;
-  const int r0 = blockIdx.y * rs;
-  const int r1 = min(rows, r0 + rs);
-  const int b = r0 / rpb;
+  const int G = gridDim.y;
+  const int b = blockIdx.z;
+  const int r0 = b * rpb + blockIdx.y;
+  const int r1 = min(rows, (b + 1) * rpb);
+  (void)rs;
   const float4 g = __ldg(reinterpret_cast<const float4*>(gate + b * gate_bs) + c4);
   float ag[4] = {}, ab[4] = {};
 #pragma unroll 8
-  for (int r = r0; r < r1; ++r) {
+  for (int r = r0; r < r1; r += G) {
     const size_t idx = static_cast<size_t>(r) * nv + c4;
     const float4 d = reinterpret_cast<const float4*>(dx)[idx];
     const uint2 mv = reinterpret_cast<const uint2*>(m)[idx];
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(128) gate_bwd_kernel(const float* __restrict__
     ag[0] += d.x * m0.x; ag[1] += d.y * m0.y; ag[2] += d.z * m1.x; ag[3] += d.w * m1.y;
     ab[0] += o0; ab[1] += o1; ab[2] += o2; ab[3] += o3;
   }
+  if (dbg & 1) return;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     atomicAdd(dgate + b * dgate_bs + c4 * 4 + j, ag[j]);
@@ -250,11 +258,11 @@ __global__ void __launch_bounds__(128) colsum_kernel(const void* __restrict__ a,
   const int c4 = blockIdx.x * 128 + threadIdx.x;
   const int nv = dim >> 2;
   if (c4 >= nv) return;
-  const int r0 = blockIdx.y * rs;
-  const int r1 = min(rows, r0 + rs);
+  const int G = gridDim.y;
+  (void)rs;
   float acc[4] = {};
 #pragma unroll 8
-  for (int r = r0; r < r1; ++r) {
+  for (int r = blockIdx.y; r < rows; r += G) {
     const size_t idx = static_cast<size_t>(r) * nv + c4;
     if constexpr (KIND == 0) {
       const float4 d = reinterpret_cast<const float4*>(a)[idx];
@@ -275,17 +283,22 @@ __global__ void __launch_bounds__(128) colsum_kernel(const void* __restrict__ a,
 //   dx += rstd * (g - mean(g) - xhat * mean(g * xhat)).
 // One warp per row (row in registers), LB_RPW consecutive rows per warp, the 4 warps of a block reduce their column sums
 // through shared memory before the atomics.  rows_per_batch % (4 * LB_RPW) == 0 keeps a block inside one sample.
-constexpr int LB_RPW = 8;
+
 template <bool BF16, int NV>
-__global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __restrict__ dh, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const uint16_t* __restrict__ dh, const float* __restrict__ x,
                                                               const float* __restrict__ scale, long long mod_bs, int rpb,
                                                               float* __restrict__ dx, float* __restrict__ dshift,
-                                                              float* __restrict__ dscale, long long dmod_bs, int rows, int dim) {
-  extern __shared__ float s_red[];   // [4 warps][2][dim]: per-warp column sums of dh and dh * xhat (each lane owns its columns)
+                                                              float* __restrict__ dscale, long long dmod_bs, int rows, int dim,
+                                                              int rpw, int dbg) {
+  extern __shared__ float s_red[];   // [warps][2][dim]: per-warp column sums of dh and dh * xhat (each lane owns its columns)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
   const int nv = dim >> 2;
-  const int block_row0 = blockIdx.x * 4 * LB_RPW;
-  const int b = block_row0 / rpb;
+  // grid (blocks per sample, samples).  The warps of a sample take its rows round-robin (warp gw: rows gw, gw + W, ...), so the
+  // grid sweeps every sample front to back inside a window of W consecutive rows (DRAM locality, see gelu_bwd).
+  const int b = blockIdx.y;
+  const int W = gridDim.x * nw;
+  const int gw = blockIdx.x * nw + warp;
   const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
   float4* red_sh = reinterpret_cast<float4*>(s_red) + (warp * 2 + 0) * nv;
   float4* red_sc = reinterpret_cast<float4*>(s_red) + (warp * 2 + 1) * nv;
@@ -295,23 +308,28 @@ __global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __
     if (idx < nv) red_sh[idx] = red_sc[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float inv_d = 1.0f / static_cast<float>(dim);
-  for (int rr = 0; rr < LB_RPW; ++rr) {
-    const int row = block_row0 + warp * LB_RPW + rr;
+  (void)rpw;
+  for (int rr = gw; rr < rpb; rr += W) {
+    const int row = b * rpb + rr;
     if (row >= rows) break;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
     const uint2* dr = reinterpret_cast<const uint2*>(dh + static_cast<size_t>(row) * dim);
-    float4 v[NV];
+    float4* dxr = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * dim);
+    float4 v[NV], o[NV];
     uint2 dpk[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int i = 0; i < NV; ++i) {           // all three streams of the row are requested up front
       const int idx = lane + i * 32;
       if (idx < nv) {
         v[i] = xr[idx];
         dpk[i] = dr[idx];
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        o[i] = dxr[idx];
       }
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) * inv_d;
     float q = 0.f;
 #pragma unroll
@@ -342,27 +360,27 @@ __global__ void __launch_bounds__(128) ln_modulate_bwd_kernel(const uint16_t* __
     }
     s1 = warp_sum(s1) * inv_d;
     s2 = warp_sum(s2) * inv_d;
-    float4* dxr = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * dim);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = lane + i * 32;
       if (idx < nv) {
         const float2 d0 = unpack2<BF16>(dpk[i].x), d1 = unpack2<BF16>(dpk[i].y);
         const float4 c = __ldg(sc + idx);
-        float4 o = dxr[idx];
-        o.x += rstd * (d0.x * (1.0f + c.x) - s1 - v[i].x * s2);
-        o.y += rstd * (d0.y * (1.0f + c.y) - s1 - v[i].y * s2);
-        o.z += rstd * (d1.x * (1.0f + c.z) - s1 - v[i].z * s2);
-        o.w += rstd * (d1.y * (1.0f + c.w) - s1 - v[i].w * s2);
-        dxr[idx] = o;
+        float4 r = o[i];
+        r.x += rstd * (d0.x * (1.0f + c.x) - s1 - v[i].x * s2);
+        r.y += rstd * (d0.y * (1.0f + c.y) - s1 - v[i].y * s2);
+        r.z += rstd * (d1.x * (1.0f + c.z) - s1 - v[i].z * s2);
+        r.w += rstd * (d1.y * (1.0f + c.w) - s1 - v[i].w * s2);
+        dxr[idx] = r;
       }
     }
   }
   __syncthreads();
+  if (dbg & 1) return;
   for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) {
     const int which = i / dim, c = i % dim;
-    const float t = s_red[(0 * 2 + which) * dim + c] + s_red[(1 * 2 + which) * dim + c] + s_red[(2 * 2 + which) * dim + c] +
-                    s_red[(3 * 2 + which) * dim + c];
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += s_red[(w * 2 + which) * dim + c];
     atomicAdd((which == 0 ? dshift : dscale) + b * dmod_bs + c, t);
   }
 }
@@ -1064,26 +1082,27 @@ int launch_gelu_fwd(const void* u16, void* a16, long long n, int bf16, cudaStrea
 int launch_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int bf16, cudaStream_t stream) {
   B200_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0, B200_ERR_SHAPE, "gelu_bwd: dim %d must be a multiple of 8", dim);
   B200_REQUIRE(ALIGNED16(da16) && ALIGNED16(u16) && ALIGNED16(du16), B200_ERR_ALIGN, "gelu_bwd: pointers must be 16-byte aligned");
-  const int rs = 32;
+  static const int rs = env_int("B200_TRAIN_RS_GELU", 32), dbg = env_int("B200_TRAIN_DBG", 0);
   dim3 grid((dim / 8 + 127) / 128, (rows + rs - 1) / rs);
   const uint16_t *a = static_cast<const uint16_t*>(da16), *u = static_cast<const uint16_t*>(u16);
-  if (bf16) gelu_bwd_kernel<true><<<grid, 128, 0, stream>>>(a, u, static_cast<uint16_t*>(du16), dbias, rows, dim, rs);
-  else gelu_bwd_kernel<false><<<grid, 128, 0, stream>>>(a, u, static_cast<uint16_t*>(du16), dbias, rows, dim, rs);
+  if (bf16) gelu_bwd_kernel<true><<<grid, 128, 0, stream>>>(a, u, static_cast<uint16_t*>(du16), dbias, rows, dim, rs, dbg);
+  else gelu_bwd_kernel<false><<<grid, 128, 0, stream>>>(a, u, static_cast<uint16_t*>(du16), dbias, rows, dim, rs, dbg);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
 
 int launch_gate_bwd(const float* dx, const void* m16, const float* gate, long long gate_bs, int rows_per_batch, void* dm16,
                     float* dgate, long long dgate_bs, float* dbias, int rows, int dim, int bf16, cudaStream_t stream) {
-  const int rs = 32;
-  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && rows_per_batch % rs == 0 && gate_bs % 4 == 0, B200_ERR_SHAPE,
-               "gate_bwd: dim %% 4 and rows_per_batch %% %d must be 0", rs);
+  static const int rs_env = env_int("B200_TRAIN_RS_GATE", 32), dbg = env_int("B200_TRAIN_DBG", 0);
+  const int rs = rs_env > 0 ? rs_env : 32;
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && rows_per_batch > 0 && gate_bs % 4 == 0, B200_ERR_SHAPE, "gate_bwd: bad shape");
   B200_REQUIRE(ALIGNED16(dx) && ALIGNED16(gate) && (reinterpret_cast<uintptr_t>(m16) & 7) == 0 && (reinterpret_cast<uintptr_t>(dm16) & 7) == 0,
                B200_ERR_ALIGN, "gate_bwd: misaligned pointer");
-  dim3 grid((dim / 4 + 127) / 128, (rows + rs - 1) / rs);
+  const int batch = (rows + rows_per_batch - 1) / rows_per_batch;
+  dim3 grid((dim / 4 + 127) / 128, (rows_per_batch + rs - 1) / rs, batch);
   const uint16_t* m = static_cast<const uint16_t*>(m16);
-  if (bf16) gate_bwd_kernel<true><<<grid, 128, 0, stream>>>(dx, m, gate, gate_bs, rows_per_batch, static_cast<uint16_t*>(dm16), dgate, dgate_bs, dbias, rows, dim, rs);
-  else gate_bwd_kernel<false><<<grid, 128, 0, stream>>>(dx, m, gate, gate_bs, rows_per_batch, static_cast<uint16_t*>(dm16), dgate, dgate_bs, dbias, rows, dim, rs);
+  if (bf16) gate_bwd_kernel<true><<<grid, 128, 0, stream>>>(dx, m, gate, gate_bs, rows_per_batch, static_cast<uint16_t*>(dm16), dgate, dgate_bs, dbias, rows, dim, rs, dbg);
+  else gate_bwd_kernel<false><<<grid, 128, 0, stream>>>(dx, m, gate, gate_bs, rows_per_batch, static_cast<uint16_t*>(dm16), dgate, dgate_bs, dbias, rows, dim, rs, dbg);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -1091,7 +1110,7 @@ int launch_gate_bwd(const float* dx, const void* m16, const float* gate, long lo
 int launch_colsum(const void* a, int dtype, float* out, int rows, int dim, cudaStream_t stream) {
   B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dtype >= 0 && dtype <= 2, B200_ERR_SHAPE, "colsum: bad shape / dtype");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(a) & (dtype == 0 ? 15 : 7)) == 0, B200_ERR_ALIGN, "colsum: misaligned input");
-  const int rs = 64;
+  static const int rs = env_int("B200_TRAIN_RS_COLSUM", 64);
   dim3 grid((dim / 4 + 127) / 128, (rows + rs - 1) / rs);
   if (dtype == 0) colsum_kernel<0><<<grid, 128, 0, stream>>>(a, out, rows, dim, rs);
   else if (dtype == 1) colsum_kernel<1><<<grid, 128, 0, stream>>>(a, out, rows, dim, rs);
@@ -1104,10 +1123,13 @@ template <bool BF16, int NV>
 static int lnb_launch(cudaStream_t stream, const uint16_t* dh, const float* x, const float* scale, long long mod_bs, int rpb, float* dx,
                       float* dshift, float* dscale, long long dmod_bs, int rows, int dim) {
   auto kern = ln_modulate_bwd_kernel<BF16, NV>;
-  const size_t smem = static_cast<size_t>(dim) * 8 * sizeof(float);
-  B200_SET_SMEM_ONCE(kern, static_cast<int>(smem));
-  const int blocks = (rows + 4 * LB_RPW - 1) / (4 * LB_RPW);
-  kern<<<blocks, 128, smem, stream>>>(dh, x, scale, mod_bs, rpb, dx, dshift, dscale, dmod_bs, rows, dim);
+  static const int warps = env_int("B200_LNB_WARPS", 4), rpw_env = env_int("B200_LNB_RPW", 8), dbg = env_int("B200_TRAIN_DBG", 0);
+  const int nw = (warps == 8 || warps == 2) ? warps : 4, rpw = rpw_env > 0 ? rpw_env : 8;
+  const size_t smem = static_cast<size_t>(dim) * 2 * nw * sizeof(float);
+  B200_SET_SMEM_ONCE(kern, static_cast<int>(static_cast<size_t>(dim) * 16 * sizeof(float)));
+  const int batch = (rows + rpb - 1) / rpb;
+  dim3 grid((rpb + nw * rpw - 1) / (nw * rpw), batch);
+  kern<<<grid, nw * 32, smem, stream>>>(dh, x, scale, mod_bs, rpb, dx, dshift, dscale, dmod_bs, rows, dim, rpw, dbg);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -1115,7 +1137,7 @@ static int lnb_launch(cudaStream_t stream, const uint16_t* dh, const float* x, c
 int launch_ln_modulate_bwd(const void* dh16, const float* x, const float* scale, long long mod_bs, int rows_per_batch, float* dx,
                            float* dshift, float* dscale, long long dmod_bs, int rows, int dim, int bf16, cudaStream_t stream) {
   B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 12 * 128, B200_ERR_SHAPE, "ln_modulate_bwd: dim %d must be a multiple of 4 and <= 1536", dim);
-  B200_REQUIRE(rows_per_batch % (4 * LB_RPW) == 0 && mod_bs % 4 == 0, B200_ERR_SHAPE, "ln_modulate_bwd: rows_per_batch must be a multiple of %d", 4 * LB_RPW);
+  B200_REQUIRE(rows_per_batch > 0 && mod_bs % 4 == 0, B200_ERR_SHAPE, "ln_modulate_bwd: bad batch geometry");
   B200_REQUIRE(ALIGNED16(x) && ALIGNED16(scale) && ALIGNED16(dx) && (reinterpret_cast<uintptr_t>(dh16) & 7) == 0, B200_ERR_ALIGN,
                "ln_modulate_bwd: misaligned pointer");
   const int nvmax = (dim / 4 + 31) / 32;

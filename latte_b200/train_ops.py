@@ -60,6 +60,20 @@ class NativeOps:
             return dW32
         return self.linear_accum(dW32, self.transpose(dy), self.transpose(x))
 
+    def dgrad(self, dy, w):
+        """dx [rows, n_in] = dy [rows, n_out] @ w [n_out, n_in] with the weight in its nn.Linear layout (MN-major W operand)."""
+        self._cuda(dy, w)
+        rows, n_out = dy.shape
+        n_in = w.shape[1]
+        if n_in % 128 == 0 and n_out % 64 == 0:
+            assert dy.is_contiguous() and w.is_contiguous() and dy.dtype == w.dtype
+            dx = torch.empty(rows, n_in, dtype=dy.dtype, device=dy.device)
+            with torch.cuda.device(dy.device):
+                rc = _lib.load().b200_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), rows, n_out, n_in, self.dt, _s(dy))
+            _lib.check(rc, "b200_dgrad")
+            return dx
+        return self.linear(dy, self.transpose(w))
+
     def attention(self, qkv, B, Fr, N, H, temporal):
         return ops.attention(qkv, B, Fr, N, H, temporal)
 
@@ -149,11 +163,10 @@ class NativeOps:
         w32 = w32.detach().float().contiguous()
         R, Cc = w32.shape
         w = torch.empty(R, Cc, dtype=self.dtype, device=w32.device)
-        wt = torch.empty(Cc, R, dtype=self.dtype, device=w32.device)
         with torch.cuda.device(w32.device):
-            rc = _lib.load().b200_cast_transpose(w32.data_ptr(), w.data_ptr(), wt.data_ptr(), R, Cc, self.dt, _s(w32))
+            rc = _lib.load().b200_cast_transpose(w32.data_ptr(), w.data_ptr(), None, R, Cc, self.dt, _s(w32))
         _lib.check(rc, "b200_cast_transpose")
-        return w, wt
+        return w
 
     def to_operand(self, x32):
         self._cuda(x32)

@@ -32,9 +32,9 @@ class TrainEngine:
 
     # ---------------------------------------------------------------------------------------------------------------
     def prepare(self):
-        """Operand copies of the current parameters: W and W^T in the compute type (dgrad reads W^T as its weight operand),
-        the adaLN weights of all blocks + final layer stacked, zero-padded patch-embed / final-layer operands (K = 16 and 32
-        are below the GEMM's 64-element k-block)."""
+        """Operand copies of the current parameters in the compute type -- ONE copy per weight: the forward GEMM reads it as
+        [N][K], dgrad reads the same memory as an MN-major operand -- the adaLN weights of all blocks + final layer stacked, and
+        zero-padded patch-embed / final-layer operands (K = 16 and 32 are below the GEMM's 64-element k-block)."""
         m, ops = self.m, self.ops
         D = m.hidden_size
         W = {}
@@ -43,9 +43,9 @@ class TrainEngine:
                 lin = blk
                 for part in name.split("."):
                     lin = getattr(lin, part)
-                W[f"{i}.{name}"] = ops.cast(lin.weight) + (lin.bias.detach().float().contiguous(),)
+                W[f"{i}.{name}"] = (ops.cast(lin.weight), lin.bias.detach().float().contiguous())
         ada_w = torch.cat([b.adaLN_modulation[1].weight.detach() for b in m.blocks] + [m.final_layer.adaLN_modulation[1].weight.detach()])
-        W["ada_w"] = ops.cast(ada_w)[0]
+        W["ada_w"] = ops.cast(ada_w)
         W["ada_b"] = torch.cat([b.adaLN_modulation[1].bias.detach() for b in m.blocks] +
                                [m.final_layer.adaLN_modulation[1].bias.detach()]).float().contiguous()
         dev = ada_w.device
@@ -53,14 +53,14 @@ class TrainEngine:
         self.kp = pw.shape[1]
         pad = torch.zeros(D, 64, dtype=torch.float32, device=dev)
         pad[:, : self.kp] = pw
-        W["patch_w"] = ops.cast(pad)[0]
+        W["patch_w"] = ops.cast(pad)
         W["patch_b"] = m.x_embedder.proj.bias.detach().float().contiguous()
         fw = m.final_layer.linear.weight.detach()                     # [p*p*Cout, D]
         self.nf = fw.shape[0]
-        W["final_w"] = ops.cast(fw)[0]
-        padt = torch.zeros(D, 64, dtype=torch.float32, device=dev)
-        padt[:, : self.nf] = fw.t()
-        W["final_wt"] = ops.cast(padt)[0]                             # dgrad weight operand [N = D, K = 64]
+        W["final_w"] = ops.cast(fw)
+        padk = torch.zeros(64, D, dtype=torch.float32, device=dev)
+        padk[: self.nf] = fw
+        W["final_wk"] = ops.cast(padk)                                # dgrad weight [n_out padded to 64, D]
         W["final_b"] = m.final_layer.linear.bias.detach().float().contiguous()
         self.w = W
 
@@ -116,14 +116,14 @@ class TrainEngine:
             temporal = bool(i % 2)
             wq, wp, w1, w2 = (W[f"{i}.{n}"] for n in _BLOCK_LINEARS)
             h1 = ops.ln_modulate(xs, sh1, sc1, rpb)
-            qkv = ops.linear(h1, wq[0], wq[2])
+            qkv = ops.linear(h1, wq[0], wq[1])
             o = ops.attention(qkv, B, Fr, N, H, temporal)
-            m1 = ops.linear(o, wp[0], wp[2])
+            m1 = ops.linear(o, wp[0], wp[1])
             xm = ops.gate_residual(xs, m1, g1, rpb)
             h2 = ops.ln_modulate(xm, sh2, sc2, rpb)
-            u = ops.linear(h2, w1[0], w1[2])
+            u = ops.linear(h2, w1[0], w1[1])
             a = ops.gelu(u)
-            m2 = ops.linear(a, w2[0], w2[2])
+            m2 = ops.linear(a, w2[0], w2[1])
             xo = ops.gate_residual(xm, m2, g2, rpb, row_add=temp if i == 0 else None, tokens=N)
             S["blocks"].append((xs, h1, qkv, o, m1, xm, h2, u, a, m2))
             xs = xo
@@ -168,7 +168,7 @@ class TrainEngine:
         G["final_layer.linear.weight"] = wgrad(dtok16, S["hf"])
         dtp = torch.zeros(T, 64, dtype=torch.float32, device=dev)
         dtp[:, : self.nf] = dtok
-        dhf = ops.linear(ops.to_operand(dtp), W["final_wt"])
+        dhf = ops.dgrad(ops.to_operand(dtp), W["final_wk"])
         dx = torch.zeros(T, D, dtype=torch.float32, device=dev)
         base = m.depth * 6 * D
         ops.ln_modulate_bwd(dhf, S["x_last"], mod[:, base:base + D], mod[:, base + D:base + 2 * D], rpb, dx,
@@ -191,24 +191,24 @@ class TrainEngine:
             dm2 = ops.gate_bwd(dx, m2, g2, rpb, dg2, G[p + "mlp.fc2.bias"])
             G[p + "mlp.fc2.weight"] = wgrad(dm2, a)
             del a
-            da = ops.linear(dm2, w2[1])
+            da = ops.dgrad(dm2, w2[0])
             du = ops.gelu_bwd(da, u, G[p + "mlp.fc1.bias"])
             del da, dm2
             G[p + "mlp.fc1.weight"] = wgrad(du, h2)
-            dh2 = ops.linear(du, w1[1])
+            dh2 = ops.dgrad(du, w1[0])
             del du
             ops.ln_modulate_bwd(dh2, xm, sh2, sc2, rpb, dx, dsh2, dsc2)
             del dh2
             # x_mid = x_in + g1 * proj(attn(qkv(LNmod(x_in))))
             dm1 = ops.gate_bwd(dx, m1, g1, rpb, dg1, G[p + "attn.proj.bias"])
             G[p + "attn.proj.weight"] = wgrad(dm1, o)
-            do = ops.linear(dm1, wp[1])
+            do = ops.dgrad(dm1, wp[0])
             del dm1
             dqkv = ops.attention_bwd(qkv, o, do, B, Fr, N, H, temporal)
             del do
             ops.colsum(dqkv, G[p + "attn.qkv.bias"])
             G[p + "attn.qkv.weight"] = wgrad(dqkv, h1)
-            dh1 = ops.linear(dqkv, wq[1])
+            dh1 = ops.dgrad(dqkv, wq[0])
             del dqkv
             ops.ln_modulate_bwd(dh1, xs, sh1, sc1, rpb, dx, dsh1, dsc1)
             del dh1, xs, h1, qkv, o, m1, xm, h2, u, m2

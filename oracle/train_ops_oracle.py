@@ -46,6 +46,10 @@ class TorchOps:
         out32 += r
         return out32
 
+    def dgrad(self, dy, w):
+        """dx [rows, n_in] = dy [rows, n_out] @ w [n_out, n_in]."""
+        return (dy.float() @ w.float()).to(self.dtype)
+
     def wgrad(self, dW32, dy, x):
         """dW [n_out, n_in] += dy [rows, n_out]^T @ x [rows, n_in]."""
         dW32 += dy.float().t() @ x.float()
@@ -144,8 +148,7 @@ class TorchOps:
         return a.t().contiguous()
 
     def cast(self, w32):
-        w = w32.detach().to(self.dtype).contiguous()
-        return w, w.t().contiguous()
+        return w32.detach().to(self.dtype).contiguous()
 
     def to_operand(self, x32):
         return x32.to(self.dtype)

@@ -48,8 +48,7 @@ def test_transpose_cast_colsum(dev, dt):
         base = torch.randn(Cc, generator=g).to(dev)                      # reductions accumulate into the buffer handed in
         _close(nat.colsum(a, base.clone()), ref.colsum(a, base.clone()), 1e-5, "colsum16")
     w = torch.randn(384, 1152, generator=g).to(dev)
-    w16, wt16 = nat.cast(w)
-    assert torch.equal(w16, w.to(dt)) and torch.equal(wt16, w.to(dt).t().contiguous())
+    assert torch.equal(nat.cast(w), w.to(dt))
     x = torch.randn(2048, 384, generator=g).to(dev)
     assert torch.equal(nat.to_operand(x), x.to(dt))
     _close(nat.colsum(x, torch.zeros(384, device=dev)), x.sum(0), 1e-5, "colsum32")
@@ -90,6 +89,19 @@ def test_wgrad_reads_untransposed_operands(dev, dt):
         _close(got, want, 3e-5, f"wgrad {rows}x{n_out}x{n_in}")
         again = nat.wgrad(base.clone(), dy, x)
         assert torch.equal(got, again), "ordered stream-K must be bit-reproducible"
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_dgrad_reads_the_weight_in_place(dev, dt):
+    """dX = dY W with W in its nn.Linear [out, in] layout: A K-major, W through an MN-major UMMA descriptor (no W^T copy);
+    n_in = 576 takes the explicit-transpose fallback."""
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(8)
+    for rows, n_out, n_in in [(4096, 1152, 1152), (2048, 4608, 1152), (2048, 1152, 4608), (1536, 384, 128), (2048, 64, 1152),
+                              (20480, 3456, 1152), (1024, 576, 576), (200, 128, 256)]:
+        dy = torch.randn(rows, n_out, generator=g).to(dev).to(dt)
+        w = (torch.randn(n_out, n_in, generator=g) / n_out ** 0.5).to(dev).to(dt)
+        _close(nat.dgrad(dy, w), ref.dgrad(dy, w), EPS[dt], f"dgrad {rows}x{n_out}x{n_in}")
 
 
 @pytest.mark.parametrize("dt", DTS)
