@@ -338,6 +338,10 @@ B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols,
 /* fp32 master parameter [rows, cols] -> 16-bit copy and (out16_t != NULL) its transpose [cols, rows], one read.           */
 B200_API int b200_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int dtype, void* stream);
 /* fp32 -> 16-bit elementwise (n % 4 == 0).                                                                                */
+/* The same for many tensors in ONE launch (all parameters at the start of a step).  table: device array of n_entries records
+ * of four int64 {src fp32 pointer (16-byte aligned), dst 16-bit pointer (8-byte aligned), n4 = element count / 4, first_chunk}
+ * with first_chunk[0] = 0, first_chunk[e+1] = first_chunk[e] + ceil(n4[e] / 1024); total_chunks = the sum.                 */
+B200_API int b200_multi_cast(const void* table, int n_entries, int64_t total_chunks, int dtype, void* stream);
 B200_API int b200_cast16(const float* in, void* out16, int64_t n, int dtype, void* stream);
 /* out[r] = x[r] + gate[r / rows_per_batch] * m16[r] (+ row_add[(r / tokens) % frames] when row_add != NULL): the residual
  * updates of TransformerBlock.forward (latte.py:179-180) with the branch output kept for the backward; row_add = temp_embed

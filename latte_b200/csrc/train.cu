@@ -117,6 +117,33 @@ __global__ void __launch_bounds__(256) cast_transpose4_kernel(const float* __res
   }
 }
 
+// fp32 -> 16-bit cast of MANY tensors in one launch (the operand copies of all parameters at the start of a training step:
+// 116 weights = 116 launches of a few microseconds each otherwise, which left the GPU waiting for the host).
+// table[e] = {src, dst, n4 = float4 count, first_chunk}; a chunk = 1024 float4.  Chunks are dealt to blocks grid-stride; the
+// owning entry is found by binary search on first_chunk.
+struct MultiCastEntry { const float* src; uint16_t* dst; long long n4; long long first_chunk; };
+constexpr int MC_CHUNK = 1024;
+template <bool BF16>
+__global__ void __launch_bounds__(256) multi_cast_kernel(const MultiCastEntry* __restrict__ tab, int n_entries, long long total_chunks) {
+  for (long long c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tab[mid].first_chunk <= c) lo = mid; else hi = mid - 1;
+    }
+    const MultiCastEntry e = tab[lo];
+    const long long base = (c - e.first_chunk) * MC_CHUNK;
+#pragma unroll
+    for (int j = 0; j < MC_CHUNK / 256; ++j) {
+      const long long i = base + j * 256 + threadIdx.x;
+      if (i < e.n4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(e.src) + i);
+        reinterpret_cast<uint2*>(e.dst)[i] = make_uint2(pack2<BF16>(f.x, f.y), pack2<BF16>(f.z, f.w));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gate_residual (forward)
 // out[r, :] = x[r, :] + gate[r / rpb, :] * m[r, :] (+ row_add[(r / tokens) % frames, :]).  Thread = 4 columns.
 template <bool BF16>
@@ -192,22 +219,37 @@ __global__ void __launch_bounds__(128) gelu_bwd_kernel(const uint16_t* __restric
   float acc[8] = {};
   const int nv = dim >> 3;
   (void)rs;
-#pragma unroll 4
-  for (int r = blockIdx.y; r < rows; r += G) {
-    const size_t idx = static_cast<size_t>(r) * nv + c8;
-    const uint4 a = reinterpret_cast<const uint4*>(da)[idx];
-    const uint4 b = reinterpret_cast<const uint4*>(u)[idx];
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-    uint32_t o[4];
+  // explicit load batches: U rows of both streams are requested before any of them is consumed (left to itself the compiler
+  // interleaves load -> math -> store per row and keeps ~2 rows in flight per thread)
+  constexpr int U = 4;
+  for (int r = blockIdx.y; r < rows; r += U * G) {
+    uint4 av[U], bv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 g = unpack2<BF16>(aw[j]), uu = unpack2<BF16>(bw[j]);
-      const float d0 = g.x * gelu_grad(uu.x), d1 = g.y * gelu_grad(uu.y);
-      o[j] = pack2<BF16>(d0, d1);
-      acc[2 * j] += d0;
-      acc[2 * j + 1] += d1;
+    for (int t = 0; t < U; ++t) {
+      const int rt = r + t * G;
+      if (rt < rows) {
+        const size_t idx = static_cast<size_t>(rt) * nv + c8;
+        av[t] = __ldg(reinterpret_cast<const uint4*>(da) + idx);
+        bv[t] = __ldg(reinterpret_cast<const uint4*>(u) + idx);
+      }
     }
-    reinterpret_cast<uint4*>(du)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int rt = r + t * G;
+      if (rt < rows) {
+        const uint32_t aw[4] = {av[t].x, av[t].y, av[t].z, av[t].w}, bw[4] = {bv[t].x, bv[t].y, bv[t].z, bv[t].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 g = unpack2<BF16>(aw[j]), uu = unpack2<BF16>(bw[j]);
+          const float d0 = g.x * gelu_grad(uu.x), d1 = g.y * gelu_grad(uu.y);
+          o[j] = pack2<BF16>(d0, d1);
+          acc[2 * j] += d0;
+          acc[2 * j + 1] += d1;
+        }
+        reinterpret_cast<uint4*>(du)[static_cast<size_t>(rt) * nv + c8] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
   }
   if (dbg & 1) return;
 #pragma unroll
@@ -233,16 +275,31 @@ __global__ void __launch_bounds__(128) gate_bwd_kernel(const float* __restrict__
   (void)rs;
   const float4 g = __ldg(reinterpret_cast<const float4*>(gate + b * gate_bs) + c4);
   float ag[4] = {}, ab[4] = {};
-#pragma unroll 8
-  for (int r = r0; r < r1; r += G) {
-    const size_t idx = static_cast<size_t>(r) * nv + c4;
-    const float4 d = reinterpret_cast<const float4*>(dx)[idx];
-    const uint2 mv = reinterpret_cast<const uint2*>(m)[idx];
-    const float2 m0 = unpack2<BF16>(mv.x), m1 = unpack2<BF16>(mv.y);
-    const float o0 = d.x * g.x, o1 = d.y * g.y, o2 = d.z * g.z, o3 = d.w * g.w;
-    reinterpret_cast<uint2*>(dm)[idx] = make_uint2(pack2<BF16>(o0, o1), pack2<BF16>(o2, o3));
-    ag[0] += d.x * m0.x; ag[1] += d.y * m0.y; ag[2] += d.z * m1.x; ag[3] += d.w * m1.y;
-    ab[0] += o0; ab[1] += o1; ab[2] += o2; ab[3] += o3;
+  constexpr int U = 8;            // explicit load batches, see gelu_bwd
+  for (int r = r0; r < r1; r += U * G) {
+    float4 dv[U];
+    uint2 mv[U];
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int rt = r + t * G;
+      if (rt < r1) {
+        const size_t idx = static_cast<size_t>(rt) * nv + c4;
+        dv[t] = __ldg(reinterpret_cast<const float4*>(dx) + idx);
+        mv[t] = __ldg(reinterpret_cast<const uint2*>(m) + idx);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int rt = r + t * G;
+      if (rt < r1) {
+        const float4 d = dv[t];
+        const float2 m0 = unpack2<BF16>(mv[t].x), m1 = unpack2<BF16>(mv[t].y);
+        const float o0 = d.x * g.x, o1 = d.y * g.y, o2 = d.z * g.z, o3 = d.w * g.w;
+        reinterpret_cast<uint2*>(dm)[static_cast<size_t>(rt) * nv + c4] = make_uint2(pack2<BF16>(o0, o1), pack2<BF16>(o2, o3));
+        ag[0] += d.x * m0.x; ag[1] += d.y * m0.y; ag[2] += d.z * m1.x; ag[3] += d.w * m1.y;
+        ab[0] += o0; ab[1] += o1; ab[2] += o2; ab[3] += o3;
+      }
+    }
   }
   if (dbg & 1) return;
 #pragma unroll
@@ -261,16 +318,27 @@ __global__ void __launch_bounds__(128) colsum_kernel(const void* __restrict__ a,
   const int G = gridDim.y;
   (void)rs;
   float acc[4] = {};
-#pragma unroll 8
-  for (int r = blockIdx.y; r < rows; r += G) {
-    const size_t idx = static_cast<size_t>(r) * nv + c4;
+  constexpr int U = 8;            // explicit load batches, see gelu_bwd
+  for (int r = blockIdx.y; r < rows; r += U * G) {
     if constexpr (KIND == 0) {
-      const float4 d = reinterpret_cast<const float4*>(a)[idx];
-      acc[0] += d.x; acc[1] += d.y; acc[2] += d.z; acc[3] += d.w;
+      float4 d[U];
+#pragma unroll
+      for (int t = 0; t < U; ++t)
+        if (r + t * G < rows) d[t] = __ldg(reinterpret_cast<const float4*>(a) + static_cast<size_t>(r + t * G) * nv + c4);
+#pragma unroll
+      for (int t = 0; t < U; ++t)
+        if (r + t * G < rows) { acc[0] += d[t].x; acc[1] += d[t].y; acc[2] += d[t].z; acc[3] += d[t].w; }
     } else {
-      const uint2 v = reinterpret_cast<const uint2*>(a)[idx];
-      const float2 f0 = unpack2<KIND == 2>(v.x), f1 = unpack2<KIND == 2>(v.y);
-      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+      uint2 v[U];
+#pragma unroll
+      for (int t = 0; t < U; ++t)
+        if (r + t * G < rows) v[t] = __ldg(reinterpret_cast<const uint2*>(a) + static_cast<size_t>(r + t * G) * nv + c4);
+#pragma unroll
+      for (int t = 0; t < U; ++t)
+        if (r + t * G < rows) {
+          const float2 f0 = unpack2<KIND == 2>(v[t].x), f1 = unpack2<KIND == 2>(v[t].y);
+          acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+        }
     }
   }
 #pragma unroll
@@ -1050,6 +1118,17 @@ int launch_cast_transpose(const float* in, void* out16, void* out16_t, int rows,
     else cast_transpose4_kernel<false><<<grid, 256, 0, stream>>>(in, o, ot, rows, cols);
   } else if (bf16) cast_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, o, ot, rows, cols);
   else cast_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, o, ot, rows, cols);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_multi_cast(const void* table, int n_entries, long long total_chunks, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(table != nullptr && n_entries > 0 && total_chunks > 0, B200_ERR_SHAPE, "multi_cast: empty table");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(table) & 7) == 0, B200_ERR_ALIGN, "multi_cast: table must be 8-byte aligned");
+  const int blocks = static_cast<int>(total_chunks < 148 * 8 ? total_chunks : 148 * 8);
+  const MultiCastEntry* tab = static_cast<const MultiCastEntry*>(table);
+  if (bf16) multi_cast_kernel<true><<<blocks, 256, 0, stream>>>(tab, n_entries, total_chunks);
+  else multi_cast_kernel<false><<<blocks, 256, 0, stream>>>(tab, n_entries, total_chunks);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

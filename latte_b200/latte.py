@@ -151,6 +151,8 @@ class Latte(DeviceCacheMixin, nn.Module):
         self._workspace = None
         self._graphs = None
         self._frozen = None
+        self._train_backend = None
+        self._train_operands = None
         #: eval-mode calls replay a CUDA graph of the whole forward (captured per (batch, cfg) signature on its second
         #: use; results are bit-identical to the eager launch sequence).  Set False to always launch eagerly.
         self.use_cuda_graphs = True
@@ -354,9 +356,14 @@ class Latte(DeviceCacheMixin, nn.Module):
             if self.y_embedder.dropout_prob > 0:                        # token_drop, latte.py:137-146
                 drop = torch.rand(B, device=dev) < self.y_embedder.dropout_prob
                 yy = torch.where(drop, torch.full_like(yy, self.y_embedder.num_classes), yy)
+        ops = self._train_backend.get(od) if self._train_backend else None
+        if ops is None:                         # one backend object per operand type: it caches the multi-cast pointer table
+            if self._train_backend is None:
+                self._train_backend = {}
+            ops = self._train_backend[od] = train_ops.NativeOps(od)
         with torch.autocast("cuda", enabled=False):
             c = training.conditioning(self, tt, yy)
-            return training.train_forward(self, train_ops.NativeOps(od), od, x.float(), c)
+            return training.train_forward(self, ops, od, x.float(), c)
 
     def _launch(self, lib, shape, w, xf, tt, yy, mod, B, use_cfg, cfg_scale, out, base, need, stream):
         """ONE C-ABI call = the whole forward (203 kernel launches for XL/2) enqueued on `stream`."""

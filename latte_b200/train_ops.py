@@ -168,6 +168,27 @@ class NativeOps:
         _lib.check(rc, "b200_cast_transpose")
         return w
 
+    def cast_into(self, srcs, dsts):
+        """dsts[i] (16-bit, contiguous) = srcs[i] (fp32, contiguous) for all i in ONE launch; the pointer table is cached for as
+        long as the tensors stay where they are (parameters are updated in place by the optimizers)."""
+        key = tuple(t.data_ptr() for t in srcs) + tuple(t.data_ptr() for t in dsts)
+        st = getattr(self, "_mc", None)
+        if st is None or st[0] != key:
+            rows, first = [], 0
+            for a, b in zip(srcs, dsts):
+                self._cuda(a, b)
+                assert a.dtype == torch.float32 and b.dtype == self.dtype and a.is_contiguous() and b.is_contiguous()
+                assert a.numel() == b.numel() and a.numel() % 4 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 8 == 0
+                n4 = a.numel() // 4
+                rows.append([a.data_ptr(), b.data_ptr(), n4, first])
+                first += (n4 + 1023) // 1024
+            table = torch.tensor(rows, dtype=torch.int64).to(srcs[0].device)
+            st = self._mc = (key, table, first, len(rows))
+        _, table, total, n = st
+        with torch.cuda.device(table.device):
+            rc = _lib.load().b200_multi_cast(table.data_ptr(), n, total, self.dt, _s(table))
+        _lib.check(rc, "b200_multi_cast")
+
     def to_operand(self, x32):
         self._cuda(x32)
         x32 = x32.contiguous()

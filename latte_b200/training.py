@@ -33,34 +33,57 @@ class TrainEngine:
     # ---------------------------------------------------------------------------------------------------------------
     def prepare(self):
         """Operand copies of the current parameters in the compute type -- ONE copy per weight: the forward GEMM reads it as
-        [N][K], dgrad reads the same memory as an MN-major operand -- the adaLN weights of all blocks + final layer stacked, and
-        zero-padded patch-embed / final-layer operands (K = 16 and 32 are below the GEMM's 64-element k-block)."""
+        [N][K], dgrad reads the same memory as an MN-major operand.  The 16-bit buffers persist on the model between steps
+        (`model._train_operands`); a step refreshes all of them with one multi-tensor cast launch.  adaLN weights of all blocks
+        + final layer land in one stacked buffer; patch-embed / final-layer operands are zero-padded to the GEMM's 64-element
+        k-block (K = 16 and 32)."""
         m, ops = self.m, self.ops
         D = m.hidden_size
+        dev = m.pos_embed.device
+        lin = lambda blk, name: (getattr(getattr(blk, name.split(".")[0]), name.split(".")[1]))   # noqa: E731
+        ada = [b.adaLN_modulation[1] for b in m.blocks] + [m.final_layer.adaLN_modulation[1]]
+        cache = getattr(m, "_train_operands", None)
+        key = (self.dtype, dev, type(ops).__name__)
+        if cache is None or cache["key"] != key:
+            NA = sum(a.weight.shape[0] for a in ada)
+            cache = {"key": key, "ada_w": torch.empty(NA, D, dtype=self.dtype, device=dev), "w": {}}
+            for i, blk in enumerate(m.blocks):
+                for name in _BLOCK_LINEARS:
+                    cache["w"][f"{i}.{name}"] = torch.empty(lin(blk, name).weight.shape, dtype=self.dtype, device=dev)
+            m._train_operands = cache
+        srcs, dsts = [], []
+        for i, blk in enumerate(m.blocks):
+            for name in _BLOCK_LINEARS:
+                srcs.append(lin(blk, name).weight.detach())
+                dsts.append(cache["w"][f"{i}.{name}"])
+        row = 0
+        for a in ada:
+            srcs.append(a.weight.detach())
+            dsts.append(cache["ada_w"][row:row + a.weight.shape[0]])
+            row += a.weight.shape[0]
+        if all(t.dtype == torch.float32 and t.is_contiguous() for t in srcs):
+            ops.cast_into(srcs, dsts)
+        else:                                   # 16-bit or non-contiguous parameters: plain copies
+            for a, b in zip(srcs, dsts):
+                b.copy_(a)
         W = {}
         for i, blk in enumerate(m.blocks):
             for name in _BLOCK_LINEARS:
-                lin = blk
-                for part in name.split("."):
-                    lin = getattr(lin, part)
-                W[f"{i}.{name}"] = (ops.cast(lin.weight), lin.bias.detach().float().contiguous())
-        ada_w = torch.cat([b.adaLN_modulation[1].weight.detach() for b in m.blocks] + [m.final_layer.adaLN_modulation[1].weight.detach()])
-        W["ada_w"] = ops.cast(ada_w)
-        W["ada_b"] = torch.cat([b.adaLN_modulation[1].bias.detach() for b in m.blocks] +
-                               [m.final_layer.adaLN_modulation[1].bias.detach()]).float().contiguous()
-        dev = ada_w.device
-        pw = m.x_embedder.proj.weight.detach().reshape(D, -1)
+                W[f"{i}.{name}"] = (cache["w"][f"{i}.{name}"], lin(blk, name).bias.detach().float().contiguous())
+        W["ada_w"] = cache["ada_w"]
+        W["ada_b"] = torch.cat([a.bias.detach() for a in ada]).float().contiguous()
+        pw = m.x_embedder.proj.weight.detach().reshape(D, -1).float()
         self.kp = pw.shape[1]
         pad = torch.zeros(D, 64, dtype=torch.float32, device=dev)
         pad[:, : self.kp] = pw
         W["patch_w"] = ops.cast(pad)
         W["patch_b"] = m.x_embedder.proj.bias.detach().float().contiguous()
-        fw = m.final_layer.linear.weight.detach()                     # [p*p*Cout, D]
+        fw = m.final_layer.linear.weight.detach().float()             # [p*p*Cout, D]
         self.nf = fw.shape[0]
-        W["final_w"] = ops.cast(fw)
         padk = torch.zeros(64, D, dtype=torch.float32, device=dev)
         padk[: self.nf] = fw
-        W["final_wk"] = ops.cast(padk)                                # dgrad weight [n_out padded to 64, D]
+        W["final_wk"] = ops.cast(padk)                                # rows [0, nf) = the weight (forward), all 64 rows = dgrad operand
+        W["final_w"] = W["final_wk"][: self.nf]
         W["final_b"] = m.final_layer.linear.bias.detach().float().contiguous()
         self.w = W
 

@@ -150,6 +150,10 @@ class TorchOps:
     def cast(self, w32):
         return w32.detach().to(self.dtype).contiguous()
 
+    def cast_into(self, srcs, dsts):
+        for a, b in zip(srcs, dsts):
+            b.copy_(a.detach())
+
     def to_operand(self, x32):
         return x32.to(self.dtype)
 

@@ -22,6 +22,8 @@ def wrap(name, fn):
         if name in ("linear", "linear_accum"):
             M = a[0].shape[0]; N = a[1].shape[0] if name == "linear" else a[0].shape[1]; K = a[1].shape[1] if name == "linear" else a[1].shape[1]
             tag = f"{name} {M}x{N}x{K}"
+        if name == "dgrad":
+            tag = f"dgrad {a[0].shape[0]}x{a[0].shape[1]}x{a[1].shape[1]}"
         if name == "wgrad":
             tag = f"wgrad {a[1].shape[0]}x{a[1].shape[1]}x{a[2].shape[1]}"
         if name == "attention_bwd":
@@ -30,7 +32,7 @@ def wrap(name, fn):
         return r
     return inner
 for n in ("ln_modulate", "linear", "linear_accum", "attention", "gate_residual", "gelu", "gate_bwd", "gelu_bwd", "ln_modulate_bwd",
-          "attention_bwd", "wgrad", "colsum", "transpose", "cast", "to_operand", "ada_outer", "ada_dsc"):
+          "attention_bwd", "wgrad", "dgrad", "cast_into", "colsum", "transpose", "cast", "to_operand", "ada_outer", "ada_dsc"):
     setattr(ops, n, wrap(n, getattr(ops, n)))
 x = torch.randn(B, 16, 4, 32, 32, device=dev)
 t = torch.randint(0, 1000, (B,), device=dev)
