@@ -325,6 +325,81 @@ def run_ddp_batch_leg(net, cfg, args, dev, world, rank, barrier, sharding, steps
             "steps": steps, "videos_per_step": 2 * world}
 
 
+def run_train_leg(args, dev, world, rank, barrier, sharding, steps=5, local_batch=5):
+    """BASELINE configs[4]: Latte-XL/2 training step as train.py:206-222 runs it -- fp32 parameters,
+    `torch.autocast(bfloat16)`, `diffusion.training_losses` (MSE + VB), `loss.backward()` -- local batch 5 of synthetic
+    latents (VAE encode skipped, as the config says), DistributedDataParallel gradient all-reduce at N > 1.  Metric: fwd+bwd
+    steps/s (no optimizer step, per the config).  At N = 1 the UNMODIFIED reference module is timed the same way on this GPU."""
+    import torch.distributed as dist
+    from latte_b200 import Latte_models
+    from latte_b200.diffusion import create_diffusion
+    torch.manual_seed(1234 + rank)
+    model = Latte_models[args.model](input_size=32, num_classes=101, num_frames=16, learn_sigma=True, extras=2).to(dev)
+    with torch.no_grad():
+        for p in model.parameters():                      # adaLN-Zero / final layer start at zero: give every parameter a gradient
+            if p.requires_grad and float(p.abs().max()) == 0.0:
+                p.normal_(0, 0.02)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()} if world == 1 else None
+    model.train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if world > 1 else model
+    diffusion = create_diffusion(timestep_respacing="")
+    x = torch.randn(local_batch, 16, 4, 32, 32, device=dev)
+    y = torch.randint(0, 101, (local_batch,), device=dev)
+
+    def step(module, diff):
+        t = torch.randint(0, diff.num_timesteps, (local_batch,), device=dev)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = diff.training_losses(module, x, t, dict(y=y))["loss"].mean()
+        module.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss
+
+    def timed(module, diff, n):
+        for _ in range(2):
+            step(module, diff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            loss = step(module, diff)
+        e1.record()
+        barrier()
+        return sharding.max_over_ranks(e0.elapsed_time(e1), dev) / n, float(loss.detach())
+
+    ms, loss = timed(net, diffusion, steps)
+    flops = 3.0 * 3.7256e12 * local_batch                  # fwd + 2x for dgrad/wgrad, SURVEY App. A per-video forward FLOPs
+    res = {"value": world * 1000.0 / ms, "unit": "fwd+bwd steps/s (local batch 5 per GPU)", "ms_per_step": ms, "steps": steps,
+           "local_batch": local_batch, "global_batch": local_batch * world, "dtype": "bf16 operands, fp32 master parameters / gradients",
+           "loss": loss, "algorithmic_tflops_achieved": flops / (ms * 1e-3) / 1e12,
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+           "grad_sync": "DistributedDataParallel (NCCL all-reduce, bucketed, overlapped with the backward)" if world > 1 else "none (1 GPU)"}
+    del net, model
+    torch.cuda.empty_cache()
+    if world == 1:
+        try:
+            from oracle import ref_loader
+            import types
+            ref_model = ref_loader.build_latte(args.model, types.SimpleNamespace(input_size=32, num_classes=101, num_frames=16,
+                                                                                  learn_sigma=True, extras=2), sd)
+            if ref_model is not None:
+                ref_model = ref_model.to(dev).train()
+                ref_diffusion = ref_loader.load_diffusion().create_diffusion(timestep_respacing="")
+                torch.backends.cuda.matmul.allow_tf32 = True
+                torch.backends.cudnn.allow_tf32 = True
+                ms_ref, loss_ref = timed(ref_model, ref_diffusion, max(2, steps // 2))
+                res["gpu_eager_baseline"] = {"value": 1000.0 / ms_ref, "unit": "fwd+bwd steps/s", "ms_per_step": ms_ref, "loss": loss_ref,
+                                             "kind": "reference (unmodified models/latte.py + diffusion/ from oracle/_ref, PyTorch eager "
+                                                     "autograd under bf16 autocast on this GPU, as train.py runs it)",
+                                             "speedup": ms_ref / ms}
+                del ref_model
+            else:
+                res["gpu_eager_baseline"] = {"unavailable": "oracle/_ref not present on this box"}
+        except Exception as e:  # noqa: BLE001
+            res["gpu_eager_baseline"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -430,7 +505,7 @@ def main():
         _lib.profile_enable(False)
 
     # ---- legs every rank takes part in (they end in a collective): frames/s end to end and the sample_ddp batch
-    video_leg, ddp_leg = None, None
+    video_leg, ddp_leg, train_leg = None, None, None
     if not args.no_video:
         try:
             video_leg = run_video_leg(net, cfg, xd, yd, dev, world, barrier, sharding)
@@ -440,6 +515,12 @@ def main():
             ddp_leg = run_ddp_batch_leg(net, cfg, args, dev, world, rank, barrier, sharding, max(K // 2, 5))
         except Exception as e:  # noqa: BLE001
             ddp_leg = {"error": repr(e)[:300]}
+        try:
+            net._graphs = None                   # release the sampling path's graph scratch before the training leg allocates
+            torch.cuda.empty_cache()
+            train_leg = run_train_leg(args, dev, world, rank, barrier, sharding)
+        except Exception as e:  # noqa: BLE001
+            train_leg = {"error": repr(e)[:300]}
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -490,6 +571,8 @@ def main():
         res["frames_per_sec_e2e"] = video_leg
     if ddp_leg is not None:
         res["sample_ddp_batch"] = ddp_leg
+    if train_leg is not None:
+        res["train_fwd_bwd"] = train_leg
     if world == 1 and not args.no_video:
         # The reference's own 1-GPU path (north_star's ">= 5x" denominator): the UNMODIFIED reference module run as PyTorch
         # eager on this GPU exactly as sample.py does (model.half(), use_fp16=True, tf32 allowed, 'math' attention) when
