@@ -342,6 +342,15 @@ B200_API int b200_cast_transpose(const float* in, void* out16, void* out16_t, in
  * of four int64 {src fp32 pointer (16-byte aligned), dst 16-bit pointer (8-byte aligned), n4 = element count / 4, first_chunk}
  * with first_chunk[0] = 0, first_chunk[e+1] = first_chunk[e] + ceil(n4[e] / 1024); total_chunks = the sum.                 */
 B200_API int b200_multi_cast(const void* table, int n_entries, int64_t total_chunks, int dtype, void* stream);
+/* fp32 passes over a LIST of tensors in one launch -- replaces the per-parameter python loops of the reference's
+ * `clip_grad_norm_` (utils.py:72-125) and `update_ema` (utils.py:190-200).  table: records of four int64 {src, dst, n elements,
+ * first_chunk} with a chunk = 4096 elements (first_chunk as in b200_multi_cast).
+ *   B200_MT_SUMSQ  *accum (double, device) += sum over all src of src^2        (dst unused)
+ *   B200_MT_SCALE  dst *= *scalar (device float: the clamped clip coefficient, no host sync)   (src unused)
+ *   B200_MT_AXPBY  dst = a * dst + b * src                                      (EMA: a = decay, b = 1 - decay)               */
+enum { B200_MT_SUMSQ = 1, B200_MT_SCALE = 2, B200_MT_AXPBY = 3 };
+B200_API int b200_multi_tensor(const void* table, int n_entries, int64_t total_chunks, int op, float a, float b, const float* scalar,
+                               double* accum, void* stream);
 B200_API int b200_cast16(const float* in, void* out16, int64_t n, int dtype, void* stream);
 /* out[r] = x[r] + gate[r / rows_per_batch] * m16[r] (+ row_add[(r / tokens) % frames] when row_add != NULL): the residual
  * updates of TransformerBlock.forward (latte.py:179-180) with the branch output kept for the backward; row_add = temp_embed

@@ -688,6 +688,10 @@ B200_API int b200_multi_cast(const void* table, int n_entries, int64_t total_chu
   B200_DT(dtype);
   return b200::launch_multi_cast(table, n_entries, total_chunks, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
 }
+B200_API int b200_multi_tensor(const void* table, int n_entries, int64_t total_chunks, int op, float a, float b, const float* scalar,
+                               double* accum, void* stream) {
+  return b200::launch_multi_tensor(table, n_entries, total_chunks, op, a, b, scalar, accum, static_cast<cudaStream_t>(stream));
+}
 B200_API int b200_cast16(const float* in, void* out16, int64_t n, int dtype, void* stream) {
   B200_DT(dtype);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out16) & 7) == 0, B200_ERR_ALIGN, "cast16: misaligned pointer");

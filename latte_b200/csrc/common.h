@@ -169,6 +169,8 @@ int launch_cfg_combine(float* out, int batch, long long per_sample, int frames, 
 // training-step passes (train.cu)
 int launch_transpose16(const void* in, void* out, int rows, int cols, cudaStream_t stream);
 int launch_multi_cast(const void* table, int n_entries, long long total_chunks, int bf16, cudaStream_t stream);
+int launch_multi_tensor(const void* table, int n_entries, long long total_chunks, int op, float a, float b, const float* scalar,
+                        double* accum, cudaStream_t stream);
 int launch_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int bf16, cudaStream_t stream);
 int launch_gate_residual(const float* x, const void* m16, const float* gate, long long gate_bs, int rows_per_batch,
                          const float* row_add, int tokens, int frames, float* out, int rows, int dim, int bf16, cudaStream_t stream);

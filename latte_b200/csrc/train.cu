@@ -144,6 +144,65 @@ __global__ void __launch_bounds__(256) multi_cast_kernel(const MultiCastEntry* _
   }
 }
 
+// Multi-tensor fp32 passes over lists of parameters / gradients (the reference's python loops `clip_grad_norm_`,
+// utils.py:72-125, and `update_ema`, utils.py:190-200: two tiny kernels per parameter tensor = ~1200 launches per step for
+// XL/2's 293 tensors).  Same table layout as multi_cast ({src, dst, n elements, first_chunk}, a chunk = 4096 elements).
+//   MT_SUMSQ  *accum (double) += sum src^2          MT_SCALE  dst *= *scalar          MT_AXPBY  dst = a * dst + b * src
+enum { MT_SUMSQ = 1, MT_SCALE = 2, MT_AXPBY = 3 };
+struct MultiTensorEntry { const float* src; float* dst; long long n; long long first_chunk; };
+constexpr int MT_CHUNK = 4096;
+template <int OP>
+__global__ void __launch_bounds__(256) multi_tensor_kernel(const MultiTensorEntry* __restrict__ tab, int n_entries, long long total_chunks,
+                                                           float a, float b, const float* __restrict__ scalar, double* __restrict__ accum) {
+  float local = 0.f;
+  const float sc = (OP == MT_SCALE) ? __ldg(scalar) : 0.f;
+  for (long long c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tab[mid].first_chunk <= c) lo = mid; else hi = mid - 1;
+    }
+    const MultiTensorEntry e = tab[lo];
+    const long long base = (c - e.first_chunk) * MT_CHUNK;
+    const long long end = min(e.n, base + MT_CHUNK);
+    const bool vec = ((reinterpret_cast<uintptr_t>(e.src) | reinterpret_cast<uintptr_t>(e.dst)) & 15) == 0;
+    if (vec) {
+      const long long v0 = base >> 2, v1 = end >> 2;       // base is a multiple of 4096
+      for (long long i = v0 + threadIdx.x; i < v1; i += 256) {
+        if constexpr (OP == MT_SUMSQ) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(e.src) + i);
+          local += (f.x * f.x + f.y * f.y) + (f.z * f.z + f.w * f.w);
+        } else if constexpr (OP == MT_SCALE) {
+          float4 d = reinterpret_cast<float4*>(e.dst)[i];
+          d.x *= sc; d.y *= sc; d.z *= sc; d.w *= sc;
+          reinterpret_cast<float4*>(e.dst)[i] = d;
+        } else {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(e.src) + i);
+          float4 d = reinterpret_cast<float4*>(e.dst)[i];
+          d.x = a * d.x + b * f.x; d.y = a * d.y + b * f.y; d.z = a * d.z + b * f.z; d.w = a * d.w + b * f.w;
+          reinterpret_cast<float4*>(e.dst)[i] = d;
+        }
+      }
+    }
+    for (long long i = (vec ? (end & ~3LL) : base) + threadIdx.x; i < end; i += 256) {     // tail / unaligned tensors
+      if constexpr (OP == MT_SUMSQ) { const float f = e.src[i]; local += f * f; }
+      else if constexpr (OP == MT_SCALE) e.dst[i] *= sc;
+      else e.dst[i] = a * e.dst[i] + b * e.src[i];
+    }
+  }
+  if constexpr (OP == MT_SUMSQ) {
+    __shared__ float red[8];
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += static_cast<double>(red[w]);
+      atomicAdd(accum, t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gate_residual (forward)
 // out[r, :] = x[r, :] + gate[r / rpb, :] * m[r, :] (+ row_add[(r / tokens) % frames, :]).  Thread = 4 columns.
 template <bool BF16>
@@ -1129,6 +1188,22 @@ int launch_multi_cast(const void* table, int n_entries, long long total_chunks, 
   const MultiCastEntry* tab = static_cast<const MultiCastEntry*>(table);
   if (bf16) multi_cast_kernel<true><<<blocks, 256, 0, stream>>>(tab, n_entries, total_chunks);
   else multi_cast_kernel<false><<<blocks, 256, 0, stream>>>(tab, n_entries, total_chunks);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_multi_tensor(const void* table, int n_entries, long long total_chunks, int op, float a, float b, const float* scalar,
+                        double* accum, cudaStream_t stream) {
+  B200_REQUIRE(table != nullptr && n_entries > 0 && total_chunks > 0, B200_ERR_SHAPE, "multi_tensor: empty table");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(table) & 7) == 0, B200_ERR_ALIGN, "multi_tensor: table must be 8-byte aligned");
+  B200_REQUIRE(op == MT_SUMSQ || op == MT_SCALE || op == MT_AXPBY, B200_ERR_UNSUPPORTED, "multi_tensor: op %d unknown", op);
+  B200_REQUIRE(op != MT_SUMSQ || (accum != nullptr && (reinterpret_cast<uintptr_t>(accum) & 7) == 0), B200_ERR_ALIGN, "multi_tensor: accum missing");
+  B200_REQUIRE(op != MT_SCALE || scalar != nullptr, B200_ERR_SHAPE, "multi_tensor: scalar missing");
+  const int blocks = static_cast<int>(total_chunks < 148 * 8 ? total_chunks : 148 * 8);
+  const MultiTensorEntry* tab = static_cast<const MultiTensorEntry*>(table);
+  if (op == MT_SUMSQ) multi_tensor_kernel<MT_SUMSQ><<<blocks, 256, 0, stream>>>(tab, n_entries, total_chunks, a, b, scalar, accum);
+  else if (op == MT_SCALE) multi_tensor_kernel<MT_SCALE><<<blocks, 256, 0, stream>>>(tab, n_entries, total_chunks, a, b, scalar, accum);
+  else multi_tensor_kernel<MT_AXPBY><<<blocks, 256, 0, stream>>>(tab, n_entries, total_chunks, a, b, scalar, accum);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

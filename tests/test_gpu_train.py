@@ -256,3 +256,76 @@ def test_training_step_xl_head_geometry(dev, dt):
     for k in gr:
         e = _rel(gn[k], gr[k])
         assert e < 8 * EPS[dt], (k, e)
+
+
+def test_clip_grad_norm_and_update_ema(dev):
+    """latte_b200.utils (utils.py:72-125, 190-200 of the reference): one multi-tensor launch each, same numbers as the python loops."""
+    from latte_b200 import utils as U
+    g = torch.Generator().manual_seed(11)
+    shapes = [(1152, 1152), (4608,), (7,), (33, 5), (1153,), (102, 1152), (1, 16, 1152)]
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g).to(dev)) for s in shapes]
+    for p in params:
+        p.grad = torch.randn(p.shape, generator=g).to(dev) * 3
+    params.append(torch.nn.Parameter(torch.zeros(5, device=dev)))          # no grad: skipped like the reference does
+    want_grads = [p.grad.clone() for p in params[:-1]]
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in params[:-1]]
+    for p, gr in zip(ref_params, want_grads):
+        p.grad = gr.clone()
+    want_norm = torch.nn.utils.clip_grad_norm_(ref_params, 1.5)
+    got_norm = U.clip_grad_norm_(params, 1.5)
+    assert got_norm.dim() == 0 and abs(got_norm.item() - want_norm.item()) < 1e-5 * want_norm.item()
+    for p, r in zip(params[:-1], ref_params):
+        assert torch.allclose(p.grad, r.grad, rtol=1e-5, atol=1e-7)
+    before = [p.grad.clone() for p in params[:-1]]
+    n2 = U.clip_grad_norm_(params, 1.5, clip_grad=False)                    # train.py:226 -- measure only
+    assert abs(n2.item() - 1.5) < 1e-3 and all(torch.equal(a, p.grad) for a, p in zip(before, params[:-1]))
+    assert U.clip_grad_norm_(params, 1e9).item() == pytest.approx(n2.item(), rel=1e-6)   # coefficient clamped to 1: unchanged
+    assert all(torch.equal(a, p.grad) for a, p in zip(before, params[:-1]))
+
+    net = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Linear(17, 5)).to(dev)
+    import copy
+    ema = copy.deepcopy(net)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn(p.shape, generator=g).to(dev))
+    want = [e.detach() * 0.99 + p.detach() * 0.01 for e, p in zip(ema.parameters(), net.parameters())]
+    U.update_ema(ema, net, decay=0.99)
+    for e, w in zip(ema.parameters(), want):
+        assert torch.allclose(e, w, rtol=1e-6, atol=1e-7)
+    U.update_ema(ema, net, decay=0)                                         # train.py:163 -- initialise the EMA with the weights
+    for e, p in zip(ema.parameters(), net.parameters()):
+        assert torch.equal(e, p)
+
+
+def test_train_loop_like_train_py(dev):
+    """train.py:206-235 in miniature on the native path: training_losses under bf16 autocast, backward, clip, AdamW, EMA; the
+    loss on a fixed batch must go down and everything stays finite."""
+    import copy
+    from latte_b200 import Latte, utils as U
+    from latte_b200.diffusion import create_diffusion
+    torch.manual_seed(0)
+    m = Latte(input_size=16, hidden_size=128, depth=2, num_heads=2, num_frames=8, num_classes=11, extras=2).to(dev)
+    ema = copy.deepcopy(m)
+    U.requires_grad(ema, False)
+    U.update_ema(ema, m, decay=0)
+    m.train()
+    opt = torch.optim.AdamW(m.parameters(), lr=2e-3, weight_decay=0)
+    d = create_diffusion(timestep_respacing="")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 8, 4, 16, 16, generator=g).to(dev)
+    y = torch.randint(0, 11, (4,), generator=g).to(dev)
+    t = torch.tensor([50, 300, 600, 900], device=dev)
+    noise = torch.randn(x.shape, generator=g).to(dev)
+    losses = []
+    for _ in range(12):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = d.training_losses(m, x, t, dict(y=y), noise=noise)["mse"].mean()
+        loss.backward()
+        norm = U.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        U.update_ema(ema, m)
+        assert torch.isfinite(loss) and torch.isfinite(norm)
+        losses.append(loss.item())
+    assert losses[-1] < 0.9 * losses[0], losses
+    assert all(torch.isfinite(p).all() for p in ema.parameters())

@@ -143,3 +143,21 @@ def test_mask_text_embeddings_matches_pipeline_semantics():
     assert keep == 3 and one.shape == (1, 1, 3, 4) and torch.equal(one, emb[:1, :, :3])
     both, length = mask_text_embeddings(emb, mask)
     assert length == 6 and torch.equal(both[0, 0, 3:], torch.zeros(3, 4)) and torch.equal(both[1, 0, :5], emb[1, 0, :5])
+
+
+def test_utils_surface_and_no_cpu_fallback():
+    """latte_b200.utils mirrors the reference's utils.clip_grad_norm_ / update_ema / requires_grad (train.py:36-38)."""
+    import inspect
+    from latte_b200 import utils as U
+    assert list(inspect.signature(U.clip_grad_norm_).parameters) == ["parameters", "max_norm", "norm_type", "error_if_nonfinite", "clip_grad"]
+    assert list(inspect.signature(U.update_ema).parameters) == ["ema_model", "model", "decay"]
+    p = torch.nn.Parameter(torch.ones(8))
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        U.clip_grad_norm_([p], 1.0)
+    with pytest.raises(NotImplementedError):
+        U.clip_grad_norm_([p], 1.0, norm_type=float("inf"))
+    assert U.clip_grad_norm_([torch.nn.Parameter(torch.ones(2))], 1.0).item() == 0.0      # no gradients at all
+    net = torch.nn.Linear(2, 2)
+    U.requires_grad(net, False)
+    assert not any(q.requires_grad for q in net.parameters())
