@@ -255,6 +255,36 @@ B200_API int b200_vae_decode(const B200VaeDecoder* d, const float* z, int n_img,
 B200_API int b200_vae_decode_temporal(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, int num_frames, float* out,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- AutoencoderKL.encode (train.py:206-211 `vae.encode(x).latent_dist.sample().mul_(0.18215)`): the
+ * diffusers 0.24.0 Encoder -- conv_in, n_down DownEncoderBlock2D (2 resnets each, pad (0,1,0,1) + stride-2 conv except the last),
+ * mid block (resnet, 1-head attention, resnet), GroupNorm + SiLU, conv_out -- then quant_conv; the result is the moments tensor
+ * [n, 2L, h/f, w/f] (mean | log-variance) of DiagonalGaussianDistribution.  Same kernels as the decoder; a stride-2 conv is a
+ * space-to-depth pass + a 2x2-tap implicit GEMM over 4C channels (weights repacked by the host, see latte_b200/vae.py).       */
+typedef struct B200VaeEncoder {
+  int32_t in_channels;          /* 3 */
+  int32_t n_down;               /* 4 */
+  int32_t down_channels[4];     /* 128, 256, 512, 512 */
+  int32_t groups;               /* 32 */
+  int32_t dtype;
+  float eps;                    /* 1e-6 */
+  int32_t latent_channels;      /* L = 4: conv_out and quant_conv produce 2L channels */
+  const float* conv_in_w; const float* conv_in_b;   /* [C0, in, 3, 3] fp32 */
+  B200VaeResnet down[8];                            /* [block][resnet] row-major, 2 per block */
+  const void* down_w16[3]; const float* down_b[3];  /* stride-2 convs: [Cout][tap = oy*2+ox][phase = py*2+px][Cin], 16-bit */
+  B200VaeResnet mid[2];
+  const float* attn_gn_g; const float* attn_gn_b;
+  const void* attn_q_w16; const float* attn_q_b; const void* attn_k_w16; const float* attn_k_b;
+  const void* attn_v_w16;                           /* v bias folded into attn_o_b by the packer */
+  const void* attn_o_w16; const float* attn_o_b;
+  const float* norm_out_g; const float* norm_out_b;
+  const void* conv_out_w16; const float* conv_out_b; /* rows padded to 32: [32][9][C_last], bias [32] */
+  const float* quant_w; const float* quant_b;        /* quant_conv [2L, 2L] fp32, NULL to skip */
+} B200VaeEncoder;
+B200_API size_t b200_vae_encode_workspace_bytes(const B200VaeEncoder* e, int n_img, int h, int w);
+/* x [n_img, in_channels, h, w] fp32 -> moments [n_img, 2L, h/f, w/f] fp32, f = 2^(n_down-1) */
+B200_API int b200_vae_encode(const B200VaeEncoder* e, const float* x, int n_img, int h, int w, float* moments, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Thread-local description of the last failure on this thread ("" if none). */
 B200_API const char* b200_last_error(void);
 B200_API int b200_abi_version(void);

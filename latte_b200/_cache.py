@@ -10,7 +10,7 @@ from __future__ import annotations
 
 class DeviceCacheMixin:
     _CACHE_ATTRS = {"_packed": None, "_packed_key": None, "_workspace": None, "_trajectory": None, "_graphs": None,
-                    "_frozen": None, "_train_backend": None, "_train_operands": None}
+                    "_frozen": None, "_train_backend": None, "_train_operands": None, "_packed_enc": None}
 
     def __getstate__(self):
         state = dict(self.__dict__)

@@ -83,6 +83,19 @@ class VaeDecoder(C.Structure):
                 ("out_channels", C.c_int32), ("temporal_eps", C.c_float), ("time_conv_w", C.c_void_p), ("time_conv_b", C.c_void_p)]
 
 
+class VaeEncoder(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("n_down", C.c_int32), ("down_channels", C.c_int32 * 4), ("groups", C.c_int32),
+                ("dtype", C.c_int32), ("eps", C.c_float), ("latent_channels", C.c_int32),
+                ("conv_in_w", C.c_void_p), ("conv_in_b", C.c_void_p),
+                ("down", VaeResnet * 8), ("down_w16", C.c_void_p * 3), ("down_b", C.c_void_p * 3),
+                ("mid", VaeResnet * 2),
+                ("attn_gn_g", C.c_void_p), ("attn_gn_b", C.c_void_p), ("attn_q_w16", C.c_void_p), ("attn_q_b", C.c_void_p),
+                ("attn_k_w16", C.c_void_p), ("attn_k_b", C.c_void_p), ("attn_v_w16", C.c_void_p), ("attn_o_w16", C.c_void_p),
+                ("attn_o_b", C.c_void_p),
+                ("norm_out_g", C.c_void_p), ("norm_out_b", C.c_void_p), ("conv_out_w16", C.c_void_p), ("conv_out_b", C.c_void_p),
+                ("quant_w", C.c_void_p), ("quant_b", C.c_void_p)]
+
+
 class SamplerTables(C.Structure):
     _fields_ = [("num_timesteps", C.c_int)] + [(n, C.c_void_p) for n in (
         "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
@@ -121,6 +134,9 @@ EXPORTS = {
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDecoder), C.c_int, C.c_int, C.c_int]),
     "b200_vae_decode": (C.c_int, [C.POINTER(VaeDecoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
+    "b200_vae_encode_workspace_bytes": (C.c_size_t, [C.POINTER(VaeEncoder), C.c_int, C.c_int, C.c_int]),
+    "b200_vae_encode": (C.c_int, [C.POINTER(VaeEncoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
     "b200_vae_decode_temporal": (C.c_int, [C.POINTER(VaeDecoder), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_size_t, C.c_void_p]),

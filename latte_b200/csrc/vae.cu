@@ -238,6 +238,48 @@ __global__ void __launch_bounds__(256) time_conv_kernel(const float* __restrict_
   }
 }
 
+// Encoder downsampling (diffusers Downsample2D: pad (0,1,0,1) then Conv2d 3x3 stride 2) as a stride-1 convolution: the input
+// [n, H, W, C] is regrouped into its four pixel phases, out[n, y, x, (py*2+px)*C + c] = in[n, 2y+py, 2x+px, c]; input pixel
+// (2y+dy, 2x+dx), dy,dx in 0..2, is then phase (dy&1, dx&1) at offset (dy>>1, dx>>1), i.e. a 2x2-tap convolution over 4C
+// channels whose (phase 1, offset 1) weights are zero (host packer), and the bottom / right zero padding is the TMA box
+// running past the edge.  One 16-byte chunk (8 channels) per thread.
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n_img, int h, int w, int c8n) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = static_cast<long long>(n_img) * ho * wo * 4 * c8n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8n);
+    const int ph = static_cast<int>((i / c8n) % 4);
+    const long long p = i / (4LL * c8n);
+    const int ox = static_cast<int>(p % wo), oy = static_cast<int>((p / wo) % ho);
+    const int img = static_cast<int>(p / (static_cast<long long>(wo) * ho));
+    y[i] = x[((static_cast<long long>(img) * h + 2 * oy + (ph >> 1)) * w + 2 * ox + (ph & 1)) * c8n + c];
+  }
+}
+
+// conv_out result [pixels, 32] 16-bit NHWC (first M = 2 * latent channels valid) -> quant_conv (1x1, M -> M, fp32, optional)
+// -> moments [n_img, M, h, w] fp32 (mean channels first, then log-variance: DiagonalGaussianDistribution's chunk(2, dim=1))
+template <bool BF16>
+__global__ void __launch_bounds__(256) moments_kernel(const uint16_t* __restrict__ x, const float* __restrict__ qw, const float* __restrict__ qb,
+                                                      float* __restrict__ out, int n_img, int M, int hw) {
+  const long long total = static_cast<long long>(n_img) * hw;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < M ? unpack2<BF16>(static_cast<uint32_t>(x[p * 32 + j])).x : 0.f;
+    const int img = static_cast<int>(p / hw), pix = static_cast<int>(p % hw);
+    for (int o = 0; o < M; ++o) {
+      float acc = v[o];
+      if (qw != nullptr) {
+        acc = qb[o];
+        for (int j = 0; j < M; ++j) acc = fmaf(qw[o * M + j], v[j], acc);
+      }
+      out[(static_cast<long long>(img) * M + o) * hw + pix] = acc;
+    }
+  }
+}
+
 inline int grid_for(long long n, int cap = 148 * 16) {
   long long b = (n + 255) / 256;
   return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
@@ -314,6 +356,23 @@ int launch_to_nchw(const void* x, float* y, int n_img, int c, int cpad, int hw, 
 }
 
 
+int launch_space_to_depth(const void* x, void* y, int n_img, int h, int w, int C, cudaStream_t stream) {
+  B200_REQUIRE(C % 8 == 0 && h % 2 == 0 && w % 2 == 0, B200_ERR_SHAPE, "space_to_depth: C %% 8, even h and w required");
+  const long long total = static_cast<long long>(n_img) * (h / 2) * (w / 2) * 4 * (C / 8);
+  space_to_depth_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), n_img, h, w, C / 8);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_moments(const void* x, const float* qw, const float* qb, float* out, int n_img, int M, int hw, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(M > 0 && M <= 8, B200_ERR_UNSUPPORTED, "moments: %d channels (<= 8 built)", M);
+  const long long total = static_cast<long long>(n_img) * hw;
+  if (bf16) moments_kernel<true><<<grid_for(total), 256, 0, stream>>>(static_cast<const uint16_t*>(x), qw, qb, out, n_img, M, hw);
+  else moments_kernel<false><<<grid_for(total), 256, 0, stream>>>(static_cast<const uint16_t*>(x), qw, qb, out, n_img, M, hw);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
 // ====================================================================================================== decode
 namespace {
 
@@ -378,6 +437,8 @@ int vae_ok(const B200VaeDecoder* d, int n_img, int h, int w) {
 struct VaeCtx {
   const B200VaeDecoder* d;
   VaeWs ws;
+  int groups;
+  float eps, temporal_eps;
   int n_img, bf16;
   int frames;     // > 0: temporal decoder, the n_img frames form n_img / frames clips
   cudaStream_t stream;
@@ -418,9 +479,9 @@ int resnet(VaeCtx& c, const B200VaeResnet& r, int xi, int h, int w, int* out_idx
   uint8_t* t2 = c.ws.buf[free_[1]];
   uint8_t* sc = c.ws.buf[free_[2]];
   const int hw = h * w;
-  B200_TRY(launch_gn(x, c.ws.part, r.gn1_g, r.gn1_b, t1, c.n_img, hw, r.cin, c.d->groups, c.d->eps, 1, c.bf16, c.stream));
+  B200_TRY(launch_gn(x, c.ws.part, r.gn1_g, r.gn1_b, t1, c.n_img, hw, r.cin, c.groups, c.eps, 1, c.bf16, c.stream));
   B200_TRY(conv3x3(c, t1, r.conv1_w16, r.conv1_b, t2, h, w, r.cin, r.cout, nullptr));
-  B200_TRY(launch_gn(t2, c.ws.part, r.gn2_g, r.gn2_b, t1, c.n_img, hw, r.cout, c.d->groups, c.d->eps, 1, c.bf16, c.stream));
+  B200_TRY(launch_gn(t2, c.ws.part, r.gn2_g, r.gn2_b, t1, c.n_img, hw, r.cout, c.groups, c.eps, 1, c.bf16, c.stream));
   const void* shortcut = x;
   if (r.short_w16) {
     B200_TRY(gemm16(c, x, r.short_w16, r.short_b, c.n_img * hw, r.cout, r.cin, sc, nullptr));
@@ -435,12 +496,50 @@ int resnet(VaeCtx& c, const B200VaeResnet& r, int xi, int h, int w, int* out_idx
     uint8_t* xs = t2;
     uint8_t* u1 = t1;
     uint8_t* u2 = x;     // the block input is dead by now
-    B200_TRY(launch_gn(xs, c.ws.part, r.t_gn1_g, r.t_gn1_b, u1, clips, c.frames * hw, r.cout, c.d->groups, c.d->temporal_eps, 1, c.bf16, c.stream));
+    B200_TRY(launch_gn(xs, c.ws.part, r.t_gn1_g, r.t_gn1_b, u1, clips, c.frames * hw, r.cout, c.groups, c.temporal_eps, 1, c.bf16, c.stream));
     B200_TRY(conv_t3(c, u1, r.t_conv1_w16, r.t_conv1_b, u2, h, w, r.cout, nullptr));
-    B200_TRY(launch_gn(u2, c.ws.part, r.t_gn2_g, r.t_gn2_b, u1, clips, c.frames * hw, r.cout, c.d->groups, c.d->temporal_eps, 1, c.bf16, c.stream));
+    B200_TRY(launch_gn(u2, c.ws.part, r.t_gn2_g, r.t_gn2_b, u1, clips, c.frames * hw, r.cout, c.groups, c.temporal_eps, 1, c.bf16, c.stream));
     B200_TRY(conv_t3(c, u1, r.t_conv2_w16, r.t_conv2_b, u2, h, w, r.cout, xs));
     *out_idx = xi;
   }
+  return B200_OK;
+}
+
+// mid-block attention (1 head over the h*w positions of each image): x + to_out(softmax(q k^T / sqrt(C)) v), GroupNorm first
+struct MidAttn {
+  const float* gn_g; const float* gn_b;
+  const void* q_w16; const float* q_b; const void* k_w16; const float* k_b;
+  const void* v_w16;                    // v bias folded into o_b by the packer
+  const void* o_w16; const float* o_b;
+};
+int mid_attention(VaeCtx& c, const MidAttn& a, int C0, int xi, int h, int w, int* out_idx) {
+  const int hw = h * w, n_img = c.n_img;
+  cudaStream_t stream = c.stream;
+  int fr[3], nf = 0;
+  for (int i = 0; i < 4; ++i) if (i != xi) fr[nf++] = i;
+  uint8_t* x = c.ws.buf[xi];
+  uint8_t* xg = c.ws.buf[fr[0]];
+  uint8_t* o = c.ws.buf[fr[1]];
+  B200_TRY(launch_gn(x, c.ws.part, a.gn_g, a.gn_b, xg, n_img, hw, C0, c.groups, c.eps, 0, c.bf16, stream));
+  B200_TRY(gemm16(c, xg, a.q_w16, a.q_b, n_img * hw, C0, C0, c.ws.q, nullptr));
+  B200_TRY(gemm16(c, xg, a.k_w16, a.k_b, n_img * hw, C0, C0, c.ws.k, nullptr));
+  B200_TRY(launch_fill(c.ws.ones, 1.0f, hw, stream));
+  const float scale = 1.0f / sqrtf(static_cast<float>(C0));
+  for (int f = 0; f < n_img; ++f) {
+    const size_t off = static_cast<size_t>(f) * hw * C0 * 2;
+    // V^T [C0, hw] = Wv [C0, C0] . xg_f^T  (bias of v is folded into the output projection bias by the packer)
+    B200_TRY(gemm16(c, a.v_w16, xg + off, nullptr, C0, hw, C0, c.ws.vt, nullptr));
+    // fp32 scores = q_f k_f^T through the residual epilogue on a zeroed buffer (gate = 1)
+    B200_CHECK_CUDA(cudaMemsetAsync(c.ws.scores, 0, static_cast<size_t>(hw) * hw * 4, stream));
+    GemmArgs sc{};
+    sc.A = c.ws.q + off; sc.W = c.ws.k + off; sc.M = hw; sc.N = hw; sc.K = C0; sc.bf16 = c.bf16; sc.epilogue = B200_EPI_GATE_RESIDUAL;
+    sc.resid = c.ws.scores; sc.gate = c.ws.ones; sc.gate_batch_stride = 0; sc.rows_per_batch = hw;
+    B200_TRY(launch_gemm(sc, stream));
+    B200_TRY(launch_softmax_rows(c.ws.scores, c.ws.p16, hw, hw, scale, c.bf16, stream));
+    B200_TRY(gemm16(c, c.ws.p16, c.ws.vt, nullptr, hw, C0, hw, o + off, nullptr));
+  }
+  B200_TRY(gemm16(c, o, a.o_w16, a.o_b, n_img * hw, C0, C0, xg, x));   // + residual
+  *out_idx = fr[0];
   return B200_OK;
 }
 
@@ -453,6 +552,7 @@ int vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w,
   B200_TRY(check_arch());
   VaeCtx c{};
   c.d = d; c.n_img = n_img; c.bf16 = d->dtype == B200_BF16; c.stream = stream; c.frames = num_frames;
+  c.groups = d->groups; c.eps = d->eps; c.temporal_eps = d->temporal_eps;
   vae_carve(d, n_img, h, w, workspace, &c.ws);
   B200_REQUIRE(c.ws.bytes <= workspace_bytes, B200_ERR_WORKSPACE, "vae: workspace too small: need %zu bytes, got %zu", c.ws.bytes, workspace_bytes);
   const int C0 = d->up_channels[0];
@@ -464,31 +564,8 @@ int vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w,
   // mid block: resnet, single-head attention over the h*w positions, resnet
   B200_TRY(resnet(c, d->mid[0], xi, h, w, &xi));
   {
-    int fr[3], nf = 0;
-    for (int i = 0; i < 4; ++i) if (i != xi) fr[nf++] = i;
-    uint8_t* x = c.ws.buf[xi];
-    uint8_t* xg = c.ws.buf[fr[0]];
-    uint8_t* o = c.ws.buf[fr[1]];
-    B200_TRY(launch_gn(x, c.ws.part, d->attn_gn_g, d->attn_gn_b, xg, n_img, hw, C0, d->groups, d->eps, 0, c.bf16, stream));
-    B200_TRY(gemm16(c, xg, d->attn_q_w16, d->attn_q_b, n_img * hw, C0, C0, c.ws.q, nullptr));
-    B200_TRY(gemm16(c, xg, d->attn_k_w16, d->attn_k_b, n_img * hw, C0, C0, c.ws.k, nullptr));
-    B200_TRY(launch_fill(c.ws.ones, 1.0f, hw, stream));
-    const float scale = 1.0f / sqrtf(static_cast<float>(C0));
-    for (int f = 0; f < n_img; ++f) {
-      const size_t off = static_cast<size_t>(f) * hw * C0 * 2;
-      // V^T [C0, hw] = Wv [C0, C0] . xg_f^T  (bias of v is folded into the output projection bias by the packer)
-      B200_TRY(gemm16(c, d->attn_v_w16, xg + off, nullptr, C0, hw, C0, c.ws.vt, nullptr));
-      // fp32 scores = q_f k_f^T through the residual epilogue on a zeroed buffer (gate = 1)
-      B200_CHECK_CUDA(cudaMemsetAsync(c.ws.scores, 0, static_cast<size_t>(hw) * hw * 4, stream));
-      GemmArgs s{};
-      s.A = c.ws.q + off; s.W = c.ws.k + off; s.M = hw; s.N = hw; s.K = C0; s.bf16 = c.bf16; s.epilogue = B200_EPI_GATE_RESIDUAL;
-      s.resid = c.ws.scores; s.gate = c.ws.ones; s.gate_batch_stride = 0; s.rows_per_batch = hw;
-      B200_TRY(launch_gemm(s, stream));
-      B200_TRY(launch_softmax_rows(c.ws.scores, c.ws.p16, hw, hw, scale, c.bf16, stream));
-      B200_TRY(gemm16(c, c.ws.p16, c.ws.vt, nullptr, hw, C0, hw, o + off, nullptr));
-    }
-    B200_TRY(gemm16(c, o, d->attn_o_w16, d->attn_o_b, n_img * hw, C0, C0, xg, x));   // + residual
-    xi = fr[0];
+    const MidAttn at{d->attn_gn_g, d->attn_gn_b, d->attn_q_w16, d->attn_q_b, d->attn_k_w16, d->attn_k_b, d->attn_v_w16, d->attn_o_w16, d->attn_o_b};
+    B200_TRY(mid_attention(c, at, C0, xi, h, w, &xi));
   }
   B200_TRY(resnet(c, d->mid[1], xi, h, w, &xi));
 
@@ -524,6 +601,96 @@ int vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w,
   return B200_OK;
 }
 
+// ====================================================================================================== encode
+// AutoencoderKL.encode (train.py:206-211: vae.encode(x).latent_dist): Encoder = conv_in, n_down DownEncoderBlock2D (2 resnets,
+// stride-2 conv except the last), mid block (resnet, attention, resnet), GroupNorm + SiLU, conv_out -> quant_conv -> moments.
+int enc_ok(const B200VaeEncoder* e, int n_img, int h, int w) {
+  B200_REQUIRE(e && n_img > 0 && h > 0 && w > 0, B200_ERR_SHAPE, "vae encode: bad arguments");
+  B200_REQUIRE(e->n_down >= 1 && e->n_down <= 4 && e->in_channels <= 8 && e->latent_channels >= 1 && e->latent_channels <= 4,
+               B200_ERR_UNSUPPORTED, "vae encode: topology not built (n_down %d, in %d, latent %d)", e->n_down, e->in_channels, e->latent_channels);
+  for (int b = 0; b < e->n_down; ++b) B200_REQUIRE(e->down_channels[b] % 64 == 0, B200_ERR_UNSUPPORTED, "vae encode: channels %d not a multiple of 64", e->down_channels[b]);
+  const int f = 1 << (e->n_down - 1);
+  B200_REQUIRE(h % f == 0 && w % f == 0, B200_ERR_SHAPE, "vae encode: %dx%d not divisible by %d", h, w, f);
+  for (int b = 0, ch = h, cw = w; b < e->n_down; ++b, ch /= 2, cw /= 2)
+    B200_REQUIRE((ch * cw) % 128 == 0 && (cw >= 128 ? cw % 128 == 0 : 128 % cw == 0) && ch % (cw >= 128 ? 1 : 128 / cw) == 0, B200_ERR_UNSUPPORTED,
+                 "vae encode: the %dx%d feature map cannot be tiled by 128-pixel patches", ch, cw);
+  B200_REQUIRE(e->dtype == B200_FP16 || e->dtype == B200_BF16, B200_ERR_DTYPE, "vae encode: dtype");
+  return B200_OK;
+}
+
+void enc_carve(const B200VaeEncoder* e, int n_img, int h, int w, void* base, VaeWs* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += up1k(bytes);
+    return p;
+  };
+  size_t act = 0;
+  for (int b = 0, ch = h, cw = w, cin = e->down_channels[0]; b < e->n_down; ++b, ch /= 2, cw /= 2) {
+    const int co = e->down_channels[b];
+    const size_t here = static_cast<size_t>(n_img) * ch * cw * static_cast<size_t>(cin > co ? cin : co) * 2;
+    if (here > act) act = here;
+    cin = co;
+  }
+  for (int i = 0; i < 4; ++i) ws->buf[i] = take(act);
+  const int f = 1 << (e->n_down - 1);
+  const size_t hw = static_cast<size_t>(h / f) * (w / f), C0 = e->down_channels[e->n_down - 1];
+  ws->q = take(static_cast<size_t>(n_img) * hw * C0 * 2);
+  ws->k = take(static_cast<size_t>(n_img) * hw * C0 * 2);
+  ws->vt = take(C0 * hw * 2);
+  ws->p16 = take(hw * hw * 2);
+  ws->scores = reinterpret_cast<float*>(take(hw * hw * 4));
+  ws->ones = reinterpret_cast<float*>(take(hw * 4));
+  ws->part = reinterpret_cast<float*>(take(static_cast<size_t>(n_img) * e->groups * 2 * 4));
+  ws->bytes = off;
+}
+
+int vae_encode(const B200VaeEncoder* e, const float* x, int n_img, int h, int w, float* moments, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream) {
+  B200_TRY(enc_ok(e, n_img, h, w));
+  B200_REQUIRE(x && moments && workspace && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, B200_ERR_ALIGN, "vae encode: bad pointers");
+  B200_TRY(check_arch());
+  VaeCtx c{};
+  c.d = nullptr; c.n_img = n_img; c.bf16 = e->dtype == B200_BF16; c.stream = stream; c.frames = 0;
+  c.groups = e->groups; c.eps = e->eps; c.temporal_eps = e->eps;
+  enc_carve(e, n_img, h, w, workspace, &c.ws);
+  B200_REQUIRE(c.ws.bytes <= workspace_bytes, B200_ERR_WORKSPACE, "vae encode: workspace too small: need %zu bytes, got %zu", c.ws.bytes, workspace_bytes);
+  int xi = 0, ch = h, cw = w;
+  B200_TRY(launch_conv_in(x, nullptr, nullptr, e->conv_in_w, e->conv_in_b, c.ws.buf[xi], n_img, e->in_channels, h, w, e->down_channels[0], c.bf16, stream));
+  for (int b = 0; b < e->n_down; ++b) {
+    for (int r = 0; r < 2; ++r) B200_TRY(resnet(c, e->down[b * 2 + r], xi, ch, cw, &xi));
+    if (b + 1 < e->n_down) {
+      const int co = e->down_channels[b];
+      int fr[3], nf = 0;
+      for (int i = 0; i < 4; ++i) if (i != xi) fr[nf++] = i;
+      B200_TRY(launch_space_to_depth(c.ws.buf[xi], c.ws.buf[fr[0]], n_img, ch, cw, co, stream));
+      ch /= 2; cw /= 2;
+      GemmArgs a{};
+      a.A = c.ws.buf[fr[0]]; a.W = e->down_w16[b]; a.bias = e->down_b[b]; a.M = n_img * ch * cw; a.N = co; a.K = 4 * 4 * co; a.bf16 = c.bf16;
+      a.epilogue = B200_EPI_BIAS; a.out16 = c.ws.buf[fr[1]];
+      a.conv_taps = 4; a.conv_n = n_img; a.conv_h = ch; a.conv_w = cw; a.conv_c = 4 * co;
+      for (int t = 0; t < 9; ++t) { a.conv_dx[t] = t < 4 ? (t & 1) : 0; a.conv_dy[t] = t < 4 ? (t >> 1) : 0; a.conv_dz[t] = 0; }
+      B200_TRY(launch_gemm(a, stream));
+      xi = fr[1];
+    }
+  }
+  const int C0 = e->down_channels[e->n_down - 1];
+  B200_TRY(resnet(c, e->mid[0], xi, ch, cw, &xi));
+  {
+    const MidAttn at{e->attn_gn_g, e->attn_gn_b, e->attn_q_w16, e->attn_q_b, e->attn_k_w16, e->attn_k_b, e->attn_v_w16, e->attn_o_w16, e->attn_o_b};
+    B200_TRY(mid_attention(c, at, C0, xi, ch, cw, &xi));
+  }
+  B200_TRY(resnet(c, e->mid[1], xi, ch, cw, &xi));
+  {
+    int fr[3], nf = 0;
+    for (int i = 0; i < 4; ++i) if (i != xi) fr[nf++] = i;
+    B200_TRY(launch_gn(c.ws.buf[xi], c.ws.part, e->norm_out_g, e->norm_out_b, c.ws.buf[fr[0]], n_img, ch * cw, C0, e->groups, e->eps, 1, c.bf16, stream));
+    B200_TRY(conv3x3(c, c.ws.buf[fr[0]], e->conv_out_w16, e->conv_out_b, c.ws.buf[fr[1]], ch, cw, C0, 32, nullptr));
+    B200_TRY(launch_moments(c.ws.buf[fr[1]], e->quant_w, e->quant_b, moments, n_img, 2 * e->latent_channels, ch * cw, c.bf16, stream));
+  }
+  return B200_OK;
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -539,6 +706,18 @@ B200_API size_t b200_vae_workspace_bytes(const B200VaeDecoder* d, int n_img, int
 B200_API int b200_vae_decode(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, float* out, void* workspace,
                              size_t workspace_bytes, void* stream) {
   return b200::vae_decode(d, z, n_img, h, w, 0, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+B200_API size_t b200_vae_encode_workspace_bytes(const B200VaeEncoder* e, int n_img, int h, int w) {
+  if (b200::enc_ok(e, n_img, h, w) != B200_OK) return 0;
+  b200::VaeWs ws;
+  b200::enc_carve(e, n_img, h, w, nullptr, &ws);
+  return ws.bytes;
+}
+
+B200_API int b200_vae_encode(const B200VaeEncoder* e, const float* x, int n_img, int h, int w, float* moments, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return b200::vae_encode(e, x, n_img, h, w, moments, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 B200_API int b200_vae_decode_temporal(const B200VaeDecoder* d, const float* z, int n_img, int h, int w, int num_frames, float* out,

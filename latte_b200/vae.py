@@ -1,9 +1,9 @@
 """`AutoencoderKL` — the decode half of the SD-VAE the reference samplers call once after the loop
 (`vae.decode(samples / 0.18215).sample`, sample/sample.py:114, sample_ddp.py:167, pipeline_latte.py:758,771), backed by
-TMA implicit-GEMM convolutions on the tcgen05 GEMM kernel (`b200_vae_decode`).  Parameter names follow the diffusers
-0.24.0 `AutoencoderKL` state dict (decoder.* and post_quant_conv.*; encoder keys in a checkpoint are ignored), so
-`vae/diffusion_pytorch_model.safetensors` loads unchanged.  **Parity unpinned** (diffusers absent offline).  No CPU path;
-`encode` is not built (training data path)."""
+TMA implicit-GEMM convolutions on the tcgen05 GEMM kernel (`b200_vae_decode`), and the encode half train.py calls on every
+batch (`vae.encode(x).latent_dist.sample()`, train.py:206-211; `b200_vae_encode`).  Parameter names
+follow the diffusers 0.24.0 `AutoencoderKL` state dict (encoder.*, quant_conv.*, post_quant_conv.*, decoder.*), so
+`vae/diffusion_pytorch_model.safetensors` loads unchanged.  **Parity unpinned** (diffusers absent offline).  No CPU path."""
 from __future__ import annotations
 
 import ctypes as C
@@ -80,6 +80,72 @@ class DecoderOutput(SimpleNamespace):
     pass
 
 
+class AutoencoderKLOutput(SimpleNamespace):
+    pass
+
+
+class _Downsampler(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)     # diffusers Downsample2D(padding=0): F.pad (0,1,0,1) first
+
+
+class _DownBlock(nn.Module):
+    def __init__(self, cin, cout, n, groups, add_downsample):
+        super().__init__()
+        self.resnets = nn.ModuleList([_Resnet(cin if i == 0 else cout, cout, groups) for i in range(n)])
+        if add_downsample:
+            self.downsamplers = nn.ModuleList([_Downsampler(cout)])
+
+
+class _Encoder(nn.Module):
+    """diffusers 0.24.0 `Encoder` parameter layout (encoder.conv_in, down_blocks.i.resnets.j, downsamplers.0.conv, mid_block,
+    conv_norm_out, conv_out with 2 * latent_channels outputs)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        ch, g = tuple(cfg.block_out_channels), cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.in_channels, ch[0], 3, padding=1)
+        blocks, cin = [], ch[0]
+        for i, co in enumerate(ch):
+            blocks.append(_DownBlock(cin, co, cfg.layers_per_block, g, i + 1 < len(ch)))
+            cin = co
+        self.down_blocks = nn.ModuleList(blocks)
+        self.mid_block = _Mid(ch[-1], g)
+        self.conv_norm_out = nn.GroupNorm(g, ch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[-1], 2 * cfg.latent_channels, 3, padding=1)
+
+
+class DiagonalGaussianDistribution:
+    """diffusers.models.vae.DiagonalGaussianDistribution on the (n, 2L, h, w) moments: mean | logvar, logvar clamped to
+    [-30, 20]; `sample()` = mean + std * randn (train.py:210), `mode()` = mean."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self):
+        return self.mean
+
+    def kl(self, other=None):
+        if self.deterministic:
+            return torch.zeros(self.mean.shape[0], device=self.mean.device)
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0 - self.logvar + other.logvar,
+                               dim=[1, 2, 3])
+
+
 # ---- AutoencoderKLTemporalDecoder containers (diffusers 0.24.0 names) --------------------------------------------
 class _TemporalResnet(nn.Module):
     def __init__(self, c, groups):
@@ -147,12 +213,15 @@ class AutoencoderKL(DeviceCacheMixin, nn.Module):
         if self._temporal:
             self.decoder = _TemporalDecoder(self.config)     # no post_quant_conv in the SVD decoder
         else:
+            self.encoder = _Encoder(self.config)
+            self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
             self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
             self.decoder = _Decoder(self.config)
         self.compute_dtype = torch.float16
         self._packed = None
         self._packed_key = None
         self._workspace = None
+        self._packed_enc = None
 
     @property
     def dtype(self):
@@ -171,11 +240,121 @@ class AutoencoderKL(DeviceCacheMixin, nn.Module):
         else:
             sd = torch.load(os.path.join(root, "diffusion_pytorch_model.bin"), map_location="cpu")
         own = model.state_dict()
-        model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)   # encoder / quant_conv keys are not used by decode
+        # the SVD temporal decoder checkpoint also carries the image encoder; this class keeps only what its decode uses
+        missing = [k for k in own if k not in sd and not k.startswith(("encoder.", "quant_conv."))]
+        if missing:
+            raise RuntimeError(f"checkpoint {st} lacks {missing[:4]} ...")
+        model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
         return model.to(torch_dtype) if torch_dtype is not None else model
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("AutoencoderKL.encode (training data path) is not built")
+    # ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _pack_encoder(self):
+        enc = self.encoder
+        ver = sum(p._version for p in enc.parameters()) + sum(p._version for p in self.quant_conv.parameters())
+        w0 = enc.conv_in.weight
+        key = (ver, w0.data_ptr(), w0.device, w0.dtype, self.compute_dtype)
+        if self._packed_enc is not None and self._packed_enc[2] == key:
+            return self._packed_enc
+        dev, c = w0.device, self.config
+        od = w0.dtype if w0.dtype in (torch.float16, torch.bfloat16) else self.compute_dtype
+        keep = []
+
+        def f32(t):
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def t16(t):
+            t = t.to(device=dev, dtype=od).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        conv16 = lambda wt: t16(wt.detach().permute(0, 2, 3, 1).reshape(wt.shape[0], -1))      # noqa: E731  OIHW -> [O][tap][I]
+        lin16 = lambda wt: t16(wt.detach().reshape(wt.shape[0], -1))                           # noqa: E731
+
+        def down16(wt):
+            """Conv2d(C, C, 3, stride 2) after F.pad (0,1,0,1) -> 2x2-tap conv over the space-to-depth input: input pixel (2y+dy,
+            2x+dx) is phase (dy & 1, dx & 1) at offset (dy >> 1, dx >> 1); [O][tap = oy*2+ox][phase = py*2+px][I], zeros elsewhere."""
+            O, I = wt.shape[:2]
+            out = torch.zeros(O, 2, 2, 2, 2, I, dtype=torch.float32, device=wt.device)     # [O][oy][ox][py][px][I]
+            w = wt.detach().float()
+            for dy in range(3):
+                for dx in range(3):
+                    out[:, dy >> 1, dx >> 1, dy & 1, dx & 1, :] = w[:, :, dy, dx]
+            return t16(out.reshape(O, -1))
+
+        def resnet(r):
+            s = _lib.VaeResnet()
+            s.gn1_g, s.gn1_b, s.conv1_w16, s.conv1_b = f32(r.norm1.weight), f32(r.norm1.bias), conv16(r.conv1.weight), f32(r.conv1.bias)
+            s.gn2_g, s.gn2_b, s.conv2_w16, s.conv2_b = f32(r.norm2.weight), f32(r.norm2.bias), conv16(r.conv2.weight), f32(r.conv2.bias)
+            s.cin, s.cout = r.conv1.weight.shape[1], r.conv1.weight.shape[0]
+            if hasattr(r, "conv_shortcut"):
+                s.short_w16, s.short_b = lin16(r.conv_shortcut.weight), f32(r.conv_shortcut.bias)
+            else:
+                s.short_w16, s.short_b = None, None
+            return s
+
+        e = _lib.VaeEncoder()
+        ch = tuple(c.block_out_channels)
+        e.in_channels, e.n_down, e.groups, e.latent_channels = c.in_channels, len(ch), c.norm_num_groups, c.latent_channels
+        for i in range(4):
+            e.down_channels[i] = ch[i] if i < len(ch) else 0
+        e.dtype = _lib.BF16 if od == torch.bfloat16 else _lib.FP16
+        e.eps = 1e-6
+        e.conv_in_w, e.conv_in_b = f32(enc.conv_in.weight), f32(enc.conv_in.bias)
+        for b, blk in enumerate(enc.down_blocks):
+            for r in range(2):
+                e.down[b * 2 + r] = resnet(blk.resnets[r])
+            if hasattr(blk, "downsamplers"):
+                e.down_w16[b], e.down_b[b] = down16(blk.downsamplers[0].conv.weight), f32(blk.downsamplers[0].conv.bias)
+        e.mid[0], e.mid[1] = resnet(enc.mid_block.resnets[0]), resnet(enc.mid_block.resnets[1])
+        at = enc.mid_block.attentions[0]
+        e.attn_gn_g, e.attn_gn_b = f32(at.group_norm.weight), f32(at.group_norm.bias)
+        e.attn_q_w16, e.attn_q_b = lin16(at.to_q.weight), f32(at.to_q.bias)
+        e.attn_k_w16, e.attn_k_b = lin16(at.to_k.weight), f32(at.to_k.bias)
+        e.attn_v_w16, e.attn_o_w16 = lin16(at.to_v.weight), lin16(at.to_out[0].weight)
+        e.attn_o_b = f32(at.to_out[0].bias.detach().float() + at.to_out[0].weight.detach().float() @ at.to_v.bias.detach().float())
+        e.norm_out_g, e.norm_out_b = f32(enc.conv_norm_out.weight), f32(enc.conv_norm_out.bias)
+        M = 2 * c.latent_channels
+        wo = torch.zeros(32, *enc.conv_out.weight.shape[1:], dtype=torch.float32, device=dev)
+        wo[:M] = enc.conv_out.weight.detach().float()
+        bo = torch.zeros(32, dtype=torch.float32, device=dev)
+        bo[:M] = enc.conv_out.bias.detach().float()
+        e.conv_out_w16, e.conv_out_b = conv16(wo), f32(bo)
+        e.quant_w, e.quant_b = f32(self.quant_conv.weight.reshape(M, M)), f32(self.quant_conv.bias)
+        self._packed_enc = (e, keep, key)
+        return self._packed_enc
+
+    def encode(self, x, return_dict=True):
+        """x (n, 3, H, W) in [-1, 1] -> AutoencoderKLOutput(latent_dist=DiagonalGaussianDistribution) -- the call train.py:206-211
+        makes on every batch (`vae.encode(x).latent_dist.sample().mul_(0.18215)`).  The moments (n, 2L, H/8, W/8) come from
+        `b200_vae_encode`; the reparameterised sample stays a torch expression on that small tensor (its RNG is the caller's)."""
+        if self._temporal:
+            raise NotImplementedError("AutoencoderKLTemporalDecoder.encode is outside the built path (the pipelines only decode with it)")
+        if not x.is_cuda:
+            raise RuntimeError("latte_b200.AutoencoderKL runs on CUDA (sm_100a) only; there is no CPU fallback")
+        lib = _lib.load()
+        dev = x.device
+        n, ci, h, w = x.shape
+        f = 2 ** (len(self.config.block_out_channels) - 1)
+        with torch.cuda.device(dev):
+            e, _, _ = self._pack_encoder()
+            xf = x.detach().to(torch.float32).contiguous()
+            moments = torch.empty(n, 2 * self.config.latent_channels, h // f, w // f, dtype=torch.float32, device=dev)
+            need = lib.b200_vae_encode_workspace_bytes(C.byref(e), n, h, w)
+            if need == 0:
+                raise RuntimeError("latte_b200: unsupported VAE encode configuration: " + _lib.last_error())
+            ws = self._workspace
+            if ws is None or ws.numel() < need + 1024 or ws.device != dev:
+                ws = self._workspace = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            rc = lib.b200_vae_encode(C.byref(e), xf.data_ptr(), n, h, w, moments.data_ptr(), base, need,
+                                     torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "b200_vae_encode")
+        pd = self.dtype
+        dist = DiagonalGaussianDistribution(moments if pd == torch.float32 else moments.to(pd))
+        return AutoencoderKLOutput(latent_dist=dist) if return_dict else (dist,)
 
     # ---------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -1,4 +1,4 @@
-"""CPU oracle for AutoencoderKL.decode — TEST INFRASTRUCTURE, NOT PRODUCT CODE.  **Parity unpinned.**
+"""CPU oracle for AutoencoderKL.decode / .encode — TEST INFRASTRUCTURE, NOT PRODUCT CODE.  **Parity unpinned.**
 
 The reference calls `vae.decode(z).sample` (sample/sample.py:114, sample/sample_ddp.py:167,
 sample/pipeline_latte.py:758,771) on diffusers' `AutoencoderKL` (diffusers==0.24.0, environment.yml:13), which is
@@ -20,6 +20,7 @@ import torch.nn.functional as F
 @dataclass(frozen=True)
 class VaeConfig:
     latent_channels: int = 4
+    in_channels: int = 3
     out_channels: int = 3
     block_out_channels: tuple = (128, 256, 512, 512)
     layers_per_block: int = 2
@@ -64,10 +65,41 @@ def state_dict_spec(cfg: VaeConfig):
     return spec
 
 
+def encoder_state_dict_spec(cfg: VaeConfig):
+    """diffusers 0.24.0 `Encoder` + `quant_conv` keys: conv_in, DownEncoderBlock2D x n (layers_per_block
+    resnets, Downsample2D conv on all but the last), UNetMidBlock2D, conv_norm_out, conv_out (2 * latent channels)."""
+    ch = cfg.block_out_channels
+    spec = [("encoder.conv_in.weight", (ch[0], cfg.in_channels, 3, 3)), ("encoder.conv_in.bias", (ch[0],))]
+    cin = ch[0]
+    for b, co in enumerate(ch):
+        for r in range(cfg.layers_per_block):
+            spec += _resnet_spec(f"encoder.down_blocks.{b}.resnets.{r}", cin if r == 0 else co, co)
+        if b + 1 < len(ch):
+            spec += [(f"encoder.down_blocks.{b}.downsamplers.0.conv.weight", (co, co, 3, 3)), (f"encoder.down_blocks.{b}.downsamplers.0.conv.bias", (co,))]
+        cin = co
+    C0 = ch[-1]
+    spec += _resnet_spec("encoder.mid_block.resnets.0", C0, C0)
+    a = "encoder.mid_block.attentions.0"
+    spec += [(f"{a}.group_norm.weight", (C0,)), (f"{a}.group_norm.bias", (C0,))]
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        spec += [(f"{a}.{n}.weight", (C0, C0)), (f"{a}.{n}.bias", (C0,))]
+    spec += _resnet_spec("encoder.mid_block.resnets.1", C0, C0)
+    M = 2 * cfg.latent_channels
+    spec += [("encoder.conv_norm_out.weight", (C0,)), ("encoder.conv_norm_out.bias", (C0,)),
+             ("encoder.conv_out.weight", (M, C0, 3, 3)), ("encoder.conv_out.bias", (M,)),
+             ("quant_conv.weight", (M, M, 1, 1)), ("quant_conv.bias", (M,))]
+    return spec
+
+
 def make_weights(cfg: VaeConfig, seed: int = 0):
+    """Decoder keys first (drawn exactly as before the encoder was added, so existing expectations keep their numbers), then the
+    encoder + quant_conv keys from a second generator."""
     g = torch.Generator().manual_seed(seed)
+    g_enc = torch.Generator().manual_seed(seed + 7919)
     sd = {}
-    for name, shape in state_dict_spec(cfg):
+    for name, shape in state_dict_spec(cfg) + encoder_state_dict_spec(cfg):
+        if name.startswith(("encoder.", "quant_conv.")):
+            g = g_enc
         if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("norm.weight") or name.endswith("norm_out.weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif name.endswith(".bias"):
@@ -97,6 +129,26 @@ def mid_attention(sd, p, x, groups):
     a = torch.softmax(q @ k.transpose(1, 2) * c ** -0.5, dim=-1)
     o = F.linear(a @ v, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
     return o.transpose(1, 2).reshape(n, c, h, w) + r
+
+
+def vae_encode(sd, cfg: VaeConfig, x):
+    """x (n, 3, H, W) -> moments (n, 2 * latent_channels, H/8, W/8) = quant_conv(Encoder(x)): mean | logvar of the
+    DiagonalGaussianDistribution that train.py:206-211 samples.  Downsample2D(padding=0) = F.pad (0, 1, 0, 1) + Conv2d stride 2."""
+    G = cfg.norm_num_groups
+    ch = cfg.block_out_channels
+    h = F.conv2d(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    for b in range(len(ch)):
+        for r in range(cfg.layers_per_block):
+            h = resnet(sd, f"encoder.down_blocks.{b}.resnets.{r}", h, G)
+        if b + 1 < len(ch):
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0.0)
+            h = F.conv2d(h, sd[f"encoder.down_blocks.{b}.downsamplers.0.conv.weight"], sd[f"encoder.down_blocks.{b}.downsamplers.0.conv.bias"], stride=2)
+    h = resnet(sd, "encoder.mid_block.resnets.0", h, G)
+    h = mid_attention(sd, "encoder.mid_block.attentions.0", h, G)
+    h = resnet(sd, "encoder.mid_block.resnets.1", h, G)
+    h = F.silu(F.group_norm(h, G, sd["encoder.conv_norm_out.weight"], sd["encoder.conv_norm_out.bias"], eps=1e-6))
+    h = F.conv2d(h, sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
 
 
 def vae_decode(sd, cfg: VaeConfig, z):

@@ -42,7 +42,7 @@ def test_surface():
     assert vae.config.scaling_factor == 0.18215 and vae.config.block_out_channels == (64, 128, 128)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         vae.decode(torch.zeros(1, 4, 16, 16))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         vae.encode(torch.zeros(1, 3, 64, 64))
     vae = vae.cuda().half()
     out = vae.decode(torch.randn(2, 4, 16, 16, device="cuda").half(), num_frames=2).sample   # kwargs like the temporal decoder call
@@ -70,3 +70,49 @@ def test_temporal_decoder_matches_oracle(case):
     assert err.max().item() < 3e-2 and err.mean().item() < 3e-3, f"max {err.max().item():.3e} mean {err.mean().item():.3e}"
     with pytest.raises(RuntimeError, match="ONE clip"):
         vae.decode(z.cuda(), num_frames=n // 2)
+
+
+@pytest.mark.parametrize("case", [
+    ((64, 128, 128), 16, 2, 128, 128),       # 3 blocks: 128x128 -> 32x32 latent (two stride-2 convs, W = 128 and packed-row tiles)
+    ((64, 64, 128, 128), 16, 3, 128, 128),   # 4 blocks -> 16x16 latent
+    ((128, 256, 512, 512), 32, 1, 256, 256), # the SD-VAE topology at train.py's 256x256 frames
+])
+def test_encode_matches_oracle(case):
+    """AutoencoderKL.encode(x).latent_dist (train.py:206-211): moments = quant_conv(Encoder(x)) against the CPU oracle
+    restatement (PARITY UNPINNED, like decode); the stride-2 convolutions run as space-to-depth + 2x2-tap implicit GEMMs."""
+    from latte_b200 import AutoencoderKL
+    from oracle import vae_oracle as V
+    block_out, groups, n, h, w = case
+    cfg = V.VaeConfig(block_out_channels=block_out, norm_num_groups=groups)
+    sd = V.make_weights(cfg, 9)
+    g = torch.Generator().manual_seed(10)
+    x = torch.rand(n, 3, h, w, generator=g) * 2 - 1
+    vae = AutoencoderKL(block_out_channels=block_out, norm_num_groups=groups)
+    vae.load_state_dict(sd, strict=True)
+    vae = vae.cuda().eval()
+    with torch.no_grad():
+        dist = vae.encode(x.cuda()).latent_dist
+        ref = V.vae_encode(sd, cfg, x)
+    f = 2 ** (len(block_out) - 1)
+    got = dist.parameters.cpu()
+    assert got.shape == ref.shape == (n, 8, h // f, w // f)
+    err = (got - ref).abs()
+    assert err.max().item() < 3e-2 and err.mean().item() < 3e-3, f"max {err.max():.3e} mean {err.mean():.3e} (|ref| max {ref.abs().max():.2f})"
+    # DiagonalGaussianDistribution surface: mean | clamped logvar, reparameterised sample with the caller's generator
+    assert torch.equal(dist.mean, dist.parameters[:, :4]) and torch.equal(dist.mode(), dist.mean)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    s1 = dist.sample(generator=gen)
+    gen.manual_seed(1)
+    noise = torch.randn(dist.mean.shape, generator=gen, device="cuda")
+    assert torch.allclose(s1, dist.mean + dist.std * noise)
+    assert dist.kl().shape == (n,)
+
+
+def test_encode_then_decode_shapes():
+    from latte_b200 import AutoencoderKL
+    vae = AutoencoderKL(block_out_channels=(64, 128, 128), norm_num_groups=16).cuda().half()
+    x = torch.rand(2, 3, 128, 128, device="cuda").half() * 2 - 1
+    z = vae.encode(x).latent_dist.sample().mul_(0.18215)             # train.py:210
+    assert z.dtype == torch.float16 and z.shape == (2, 4, 32, 32)
+    out = vae.decode(z / 0.18215).sample
+    assert out.shape == (2, 3, 128, 128) and torch.isfinite(out).all()
