@@ -113,7 +113,73 @@ def sampler():
     print("sampler ddim 8 steps: finite", bool(torch.isfinite(out).all()), flush=True)
 
 
+def train():
+    """One training step of the tiny64 model (every kernel of csrc/train.cu, dgrad / wgrad in the GEMM's MN-major modes, the
+    multi-tensor passes) checked against the reference's golden gradients."""
+    import numpy as np
+    from latte_b200 import utils as U
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, "tests", "golden", "train_tiny64.npz"))
+    cfg = O.make_config("Latte-tiny64/2", input_size=16, num_frames=8)
+    m = Latte(input_size=16, hidden_size=128, depth=2, num_heads=2, num_frames=8, num_classes=101, extras=2)
+    m.load_state_dict(O.make_weights(cfg, 21), strict=True)
+    m = m.to(dev).train()
+    m.y_embedder.dropout_prob = 0.0
+    from latte_b200.diffusion import create_diffusion
+    d = create_diffusion(timestep_respacing="")
+    x0, noise = torch.from_numpy(gold["x0"]).to(dev), torch.from_numpy(gold["noise"]).to(dev)
+    t, y = torch.from_numpy(gold["t"]).to(dev), torch.from_numpy(gold["y"]).to(dev)
+    loss = d.training_losses(m, x0, t, dict(y=y), noise=noise)["loss"].mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    named = dict(m.named_parameters())
+    worst = max(abs(named[str(k)].grad.double().norm().item() - w) / w for k, w in zip(gold["grad_names"], gold["grad_norms"]))
+    print("train tiny64 step: loss", loss.item(), "golden", float(gold["loss"]), "max err of grad norms (relative)", worst, flush=True)
+    ema = Latte(input_size=16, hidden_size=128, depth=2, num_heads=2, num_frames=8, num_classes=101, extras=2).to(dev)
+    n = U.clip_grad_norm_(m.parameters(), 1.0)
+    U.update_ema(ema, m, 0.99)
+    torch.cuda.synchronize()
+    print("clip / ema: finite", bool(torch.isfinite(n)), flush=True)
+
+
+def train72():
+    """head_dim 72 kernels of the attention backward (spatial 64-token tiles, temporal warp kernel) and the transposing fallbacks."""
+    from latte_b200.train_ops import NativeOps
+    ops_ = NativeOps(torch.bfloat16)
+    g = torch.Generator().manual_seed(4)
+    for (b, f, n, h, hd, temporal) in [(1, 2, 128, 2, 72, False), (1, 16, 64, 3, 72, True), (1, 8, 64, 2, 64, True)]:
+        T, D = b * f * n, h * hd
+        qkv = torch.randn(T, 3 * D, generator=g).to(dev).bfloat16()
+        do = torch.randn(T, D, generator=g).to(dev).bfloat16()
+        o = ops_.attention(qkv, b, f, n, h, temporal)
+        dq = ops_.attention_bwd(qkv, o, do, b, f, n, h, temporal)
+        torch.cuda.synchronize()
+        print(f"attn_bwd {'temporal' if temporal else 'spatial'} hd {hd}: finite", bool(torch.isfinite(dq.float()).all()), flush=True)
+    dy = torch.randn(512, 192, generator=g).to(dev).bfloat16()
+    x = torch.randn(512, 576, generator=g).to(dev).bfloat16()
+    w = torch.randn(192, 576, generator=g).to(dev).bfloat16()
+    gw = ops_.wgrad(torch.zeros(192, 576, device=dev), dy, x)             # n_in = 576: transposing fallback
+    gx = ops_.dgrad(dy, w)
+    torch.cuda.synchronize()
+    print("fallback wgrad / dgrad: max err", (gw - dy.float().t() @ x.float()).abs().max().item(), (gx.float() - dy.float() @ w.float()).abs().max().item(), flush=True)
+
+
+def vae_enc():
+    from latte_b200 import AutoencoderKL
+    from oracle import vae_oracle as V
+    cfg = V.VaeConfig(block_out_channels=(64, 128, 128), norm_num_groups=16)
+    sd = V.make_weights(cfg, 9)
+    vae = AutoencoderKL(block_out_channels=(64, 128, 128), norm_num_groups=16)
+    vae.load_state_dict(sd, strict=True)
+    vae = vae.to(dev).eval()
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    with torch.no_grad():
+        got = vae.encode(x.to(dev)).latent_dist.parameters.cpu()
+    print("vae encode: max err", (got - V.vae_encode(sd, cfg, x)).abs().max().item(), flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["latte", "gemm", "attn", "t2v", "vae", "sampler"]
+    which = sys.argv[1:] or ["latte", "gemm", "attn", "t2v", "vae", "sampler", "train", "train72", "vae_enc"]
     for w in which:
-        {"latte": latte, "gemm": gemm, "attn": attn, "t2v": t2v, "vae": vae, "sampler": sampler}[w]()
+        {"latte": latte, "gemm": gemm, "attn": attn, "t2v": t2v, "vae": vae, "sampler": sampler, "train": train, "train72": train72,
+         "vae_enc": vae_enc}[w]()
