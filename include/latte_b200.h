@@ -41,7 +41,9 @@ enum {
   B200_ERR_UNSUPPORTED = -7
 };
 enum { B200_FP16 = 0, B200_BF16 = 1 };
-enum { B200_EPI_BIAS = 0, B200_EPI_BIAS_GELU = 1, B200_EPI_GATE_RESIDUAL = 2, B200_EPI_BIAS_ADD16 = 3, B200_EPI_BIAS_MUL16 = 4 };
+enum { B200_EPI_BIAS = 0, B200_EPI_BIAS_GELU = 1, B200_EPI_GATE_RESIDUAL = 2, B200_EPI_BIAS_ADD16 = 3, B200_EPI_BIAS_MUL16 = 4,
+       B200_EPI_BIAS_GELU_BOTH = 5,   /* training fc1: out16 = acc + bias (kept for the backward), aux16 (written) = gelu_tanh(out16) */
+       B200_EPI_MUL_GELUGRAD16 = 6 }; /* training dgrad of fc2: out16 = acc * gelu_tanh'(aux16), aux16 = fc1's pre-activation (read)  */
 
 /* Model geometry: the ctor arguments of reference `Latte` (models/latte.py:208-223). */
 typedef struct B200LatteShape {
@@ -361,8 +363,14 @@ B200_API int b200_ln_modulate(const float* x, const float* shift, const float* s
 B200_API int b200_wgrad(const void* dy16, const void* x16, const float* col_scale, float* dW, int rows, int n_out, int n_in,
                         int dtype, void* sk_flags, void* stream);
 /* dX16[rows, n_in] = dY16[rows, n_out] . W16[n_out, n_in] -- the input gradient of Y = X W^T with the weight in its nn.Linear
- * [out, in] layout (MN-major W operand: no transposed weight copy).  n_out % 64 == 0, n_in % 128 == 0.                     */
-B200_API int b200_dgrad(const void* dy16, const void* w16, void* dx16, int rows, int n_out, int n_in, int dtype, void* stream);
+ * [out, in] layout (MN-major W operand: no transposed weight copy).  n_out % 64 == 0, n_in % 128 == 0.
+ * gelu_u16 != NULL: X = gelu_tanh(U) and the result is the gradient w.r.t. U: dX * gelu_tanh'(U[rows, n_in]), fused in the epilogue
+ * (the backward of timm Mlp's act between fc1 and fc2, latte.py:169-171).                                                     */
+B200_API int b200_dgrad(const void* dy16, const void* w16, const void* gelu_u16, void* dx16, int rows, int n_out, int n_in, int dtype,
+                        void* stream);
+/* Training-mode fc1: u16 = A W^T + bias (kept for the backward) and a16 = gelu_tanh(u16) from the same epilogue.              */
+B200_API int b200_linear_gelu_both(const void* A, const void* W, const float* bias, int M, int N, int K, int dtype, void* u16, void* a16,
+                                   void* stream);
 /* out16[cols, rows] = in16[rows, cols]^T (operands of shapes b200_wgrad / b200_dgrad do not take).                          */
 B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream);
 /* fp32 master parameter [rows, cols] -> 16-bit copy and (out16_t != NULL) its transpose [cols, rows], one read.           */
@@ -445,6 +453,15 @@ B200_API int b200_sampler_step(const B200SamplerTables* tables, int method, int 
                                const float* x, const void* model_out, int model_out_dtype, const float* noise, int batch,
                                int frames, int channels, int hw, float* x_prev, float* pred_xstart, float* mean,
                                float* log_variance, void* stream);
+
+/* GaussianDiffusion.training_losses (gaussian_diffusion.py:719-795; LossType.MSE + LEARNED_RANGE, the objective train.py:221
+ * uses) in one pass: sums[0][b] = sum over the sample of (noise - eps)^2, sums[1][b] = sum of the variational-bound term in
+ * NATS (KL to the true posterior, decoder NLL where t[b] == 0; the mean is frozen: it gets no gradient from this term), and, if
+ * dmo != NULL, the gradient of [mean_flat(mse) | mean_flat(vb) / ln 2] with respect to model_out: channels [0, C) of every frame
+ * hold d mse / d eps, channels [C, 2C) hold d vb / d var_values.  x0, xt, noise (B,F,C,H,W) fp32; model_out, dmo (B,F,2C,H,W) fp32;
+ * t (B,) int64 chain indices; sums 2*B floats (overwritten).                                                                  */
+B200_API int b200_training_loss(const B200SamplerTables* tables, const int64_t* t, const float* x0, const float* xt, const float* noise,
+                                const float* model_out, int batch, int frames, int channels, int hw, float* sums, float* dmo, void* stream);
 
 /* Host-only introspection (no GPU touched): the work schedule b200_linear would use on a device with `num_sms` SMs --
  * chosen tile width, number of CTA pairs, whether the last waves are split along K (stream-K, residual epilogue), and

@@ -522,6 +522,12 @@ B200_API int b200_sampler_step(const B200SamplerTables* tables, int method, int 
                                    log_variance, static_cast<cudaStream_t>(stream));
 }
 
+B200_API int b200_training_loss(const B200SamplerTables* tables, const int64_t* t, const float* x0, const float* xt, const float* noise,
+                                const float* model_out, int batch, int frames, int channels, int hw, float* sums, float* dmo, void* stream) {
+  return b200::launch_training_loss(tables, reinterpret_cast<const long long*>(t), x0, xt, noise, model_out, batch, frames, channels, hw,
+                                    sums, dmo, static_cast<cudaStream_t>(stream));
+}
+
 B200_API int b200_gemm_schedule(int M, int N, int K, int epilogue, int block_n, int num_sms, int* block_n_out, int* pairs_out,
                                 int* streamk_out, int32_t* segments, int max_segments) {
   return b200::gemm_schedule(M, N, K, epilogue, block_n, num_sms, block_n_out, pairs_out, streamk_out, segments, max_segments);
@@ -670,11 +676,21 @@ B200_API int b200_wgrad(const void* dy16, const void* x16, const float* col_scal
   a.sk_flags = static_cast<unsigned long long*>(sk_flags);
   return b200::launch_gemm(a, static_cast<cudaStream_t>(stream));
 }
-B200_API int b200_dgrad(const void* dy16, const void* w16, void* dx16, int rows, int n_out, int n_in, int dtype, void* stream) {
+B200_API int b200_dgrad(const void* dy16, const void* w16, const void* gelu_u16, void* dx16, int rows, int n_out, int n_in, int dtype,
+                        void* stream) {
   B200_DT(dtype);
   b200::GemmArgs a{};
-  a.A = dy16; a.W = w16; a.M = rows; a.N = n_in; a.K = n_out; a.bf16 = dtype == B200_BF16; a.epilogue = B200_EPI_BIAS;
-  a.out16 = dx16; a.mn_major = 2;
+  a.A = dy16; a.W = w16; a.M = rows; a.N = n_in; a.K = n_out; a.bf16 = dtype == B200_BF16;
+  a.epilogue = gelu_u16 ? B200_EPI_MUL_GELUGRAD16 : B200_EPI_BIAS;
+  a.add16 = gelu_u16; a.out16 = dx16; a.mn_major = 2;
+  return b200::launch_gemm(a, static_cast<cudaStream_t>(stream));
+}
+B200_API int b200_linear_gelu_both(const void* A, const void* W, const float* bias, int M, int N, int K, int dtype, void* u16, void* a16,
+                                   void* stream) {
+  B200_DT(dtype);
+  b200::GemmArgs a{};
+  a.A = A; a.W = W; a.bias = bias; a.M = M; a.N = N; a.K = K; a.bf16 = dtype == B200_BF16; a.epilogue = B200_EPI_BIAS_GELU_BOTH;
+  a.out16 = u16; a.out16b = a16; a.w_const = 1;
   return b200::launch_gemm(a, static_cast<cudaStream_t>(stream));
 }
 B200_API int b200_transpose16(const void* in16, void* out16, int rows, int cols, void* stream) {

@@ -104,7 +104,8 @@ struct GemmArgs {
   int mn_major;         // bit 0: A is stored [K, M]; bit 1: W is stored [K, N] (N % 128 == 0).  3 = wgrad (dW[M, N] += dY[K, M]^T X[K, N]),
                         // 2 = dgrad (dX[M, N] = dY[M, K] W[K, N] with the weight in its nn.Linear [out, in] layout)
   unsigned long long* sk_flags;  // B200_GEMM_SK_FLAGS zeroed u64 (caller's workspace) or nullptr: enables ordered stream-K
-  const void* add16;    // EPI_BIAS_ADD16: [M, N] 16-bit tensor added to the result (resnet shortcut)
+  const void* add16;    // EPI_BIAS_ADD16: [M, N] 16-bit tensor added to the result (resnet shortcut); EPI_BIAS_MUL16 / EPI_MUL_GELUGRAD16: the factor
+  void* out16b;         // EPI_BIAS_GELU_BOTH: [M, N] 16-bit second output = gelu_tanh(out16)
   // implicit-GEMM convolution (conv_taps > 0): A is an NHWC activation [conv_n, conv_h, conv_w, conv_c] (16-bit), M =
   // conv_n*conv_h*conv_w output pixels, K = conv_taps * conv_c with W laid out [N][tap][c]; tap t reads the input pixel
   // shifted by (conv_dx[t], conv_dy[t]) with zero padding (TMA out-of-bounds fill).
@@ -200,6 +201,8 @@ int launch_sampler_step(const B200SamplerTables* tab, int method, int clip_denoi
                         const float* x, const void* model_out, int model_out_dtype, const float* noise, int batch,
                         int frames, int channels, int hw, float* x_prev, float* pred_xstart, float* mean,
                         float* log_variance, cudaStream_t stream);
+int launch_training_loss(const B200SamplerTables* tab, const long long* t, const float* x0, const float* xt, const float* noise,
+                         const float* model_out, int batch, int frames, int channels, int hw, float* sums, float* dmo, cudaStream_t stream);
 int launch_time_conv(const float* x, const float* w, const float* b, float* y, int frames, int c, int hw, cudaStream_t stream);
 
 }  // namespace b200

@@ -75,6 +75,7 @@ struct GemmDev {
   const float* row_add;
   int row_add_div, row_add_period;
   const uint16_t* add16;
+  uint16_t* out16b;    // EPI_BIAS_GELU_BOTH: second output, gelu(out16)
   // implicit-GEMM convolution: see GemmArgs
   int conv_taps, conv_cblk, conv_h, conv_w, conv_bw, conv_bh;
   int conv_dx[9], conv_dy[9], conv_dz[9];
@@ -152,6 +153,16 @@ struct TileSched {
     return true;
   }
 };
+
+// d/dx of the tanh-form GELU with the same one-MUFU tanh
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k0 * fmaf(k1 * x2, x, x)));
+  const float sech2 = fmaf(-t, t, 1.0f);
+  return fmaf(0.5f * x * sech2, k0 * fmaf(3.0f * k1, x2, 1.0f), fmaf(0.5f, t, 0.5f));
+}
 
 __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh(u)),  u = sqrt(2/pi) (x + 0.044715 x^3).  ONE MUFU op per element (tanh.approx, rel. error 2^-11,
@@ -534,6 +545,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   val.z = pack2<BF16>(a2.x * r2.x, a2.y * r2.y);
                   val.w = pack2<BF16>(a3.x * r3.x, a3.y * r3.y);
                 }
+                if constexpr (EPI == B200_EPI_MUL_GELUGRAD16) {   // training, dgrad of fc2: du = da * gelu'(u), u (fc1's pre-activation) read back in 16 bits
+                  const uint4 rs = __ldg(reinterpret_cast<const uint4*>(p.add16 + static_cast<size_t>(row) * p.N + col));
+                  const float2 a0 = unpack2<BF16>(val.x), a1 = unpack2<BF16>(val.y), a2 = unpack2<BF16>(val.z), a3 = unpack2<BF16>(val.w);
+                  const float2 r0 = unpack2<BF16>(rs.x), r1 = unpack2<BF16>(rs.y), r2 = unpack2<BF16>(rs.z), r3 = unpack2<BF16>(rs.w);
+                  val.x = pack2<BF16>(a0.x * gelu_tanh_grad(r0.x), a0.y * gelu_tanh_grad(r0.y));
+                  val.y = pack2<BF16>(a1.x * gelu_tanh_grad(r1.x), a1.y * gelu_tanh_grad(r1.y));
+                  val.z = pack2<BF16>(a2.x * gelu_tanh_grad(r2.x), a2.y * gelu_tanh_grad(r2.y));
+                  val.w = pack2<BF16>(a3.x * gelu_tanh_grad(r3.x), a3.y * gelu_tanh_grad(r3.y));
+                }
+                if constexpr (EPI == B200_EPI_BIAS_GELU_BOTH) {   // training, fc1: keep the pre-activation u (out16) AND write gelu(u) (out16b)
+                  const float2 a0 = unpack2<BF16>(val.x), a1 = unpack2<BF16>(val.y), a2 = unpack2<BF16>(val.z), a3 = unpack2<BF16>(val.w);
+                  uint4 gl;
+                  gl.x = pack2<BF16>(gelu_tanh(a0.x), gelu_tanh(a0.y));
+                  gl.y = pack2<BF16>(gelu_tanh(a1.x), gelu_tanh(a1.y));
+                  gl.z = pack2<BF16>(gelu_tanh(a2.x), gelu_tanh(a2.y));
+                  gl.w = pack2<BF16>(gelu_tanh(a3.x), gelu_tanh(a3.y));
+                  *reinterpret_cast<uint4*>(p.out16b + static_cast<size_t>(row) * p.N + col) = gl;
+                }
                 if constexpr (EPI == B200_EPI_BIAS_ADD16) {   // + shortcut, both already rounded to 16 bits like the reference
                   const uint4 rs = __ldg(reinterpret_cast<const uint4*>(p.add16 + static_cast<size_t>(row) * p.N + col));
                   const float2 a0 = unpack2<BF16>(val.x), a1 = unpack2<BF16>(val.y), a2 = unpack2<BF16>(val.z), a3 = unpack2<BF16>(val.w);
@@ -583,6 +612,8 @@ int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     case B200_EPI_GATE_RESIDUAL: return launch_one<BN, B200_EPI_GATE_RESIDUAL, BF16>(tmA, tmB, tmX, p, grid, s);
     case B200_EPI_BIAS_ADD16: return launch_one<BN, B200_EPI_BIAS_ADD16, BF16>(tmA, tmB, tmX, p, grid, s);
     case B200_EPI_BIAS_MUL16: return launch_one<BN, B200_EPI_BIAS_MUL16, BF16>(tmA, tmB, tmX, p, grid, s);
+    case B200_EPI_BIAS_GELU_BOTH: return launch_one<BN, B200_EPI_BIAS_GELU_BOTH, BF16>(tmA, tmB, tmX, p, grid, s);
+    case B200_EPI_MUL_GELUGRAD16: return launch_one<BN, B200_EPI_MUL_GELUGRAD16, BF16>(tmA, tmB, tmX, p, grid, s);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return B200_ERR_UNSUPPORTED;
@@ -674,10 +705,14 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   B200_REQUIRE(a.K % BK == 0, B200_ERR_SHAPE, "gemm: K=%d must be a multiple of %d", a.K, BK);
   B200_REQUIRE(a.N % 32 == 0, B200_ERR_SHAPE, "gemm: N=%d must be a multiple of 32", a.N);
   B200_REQUIRE(a.epilogue == B200_EPI_BIAS || a.epilogue == B200_EPI_BIAS_GELU || a.epilogue == B200_EPI_GATE_RESIDUAL ||
-                   a.epilogue == B200_EPI_BIAS_ADD16 || a.epilogue == B200_EPI_BIAS_MUL16,
+                   a.epilogue == B200_EPI_BIAS_ADD16 || a.epilogue == B200_EPI_BIAS_MUL16 || a.epilogue == B200_EPI_BIAS_GELU_BOTH ||
+                   a.epilogue == B200_EPI_MUL_GELUGRAD16,
                B200_ERR_UNSUPPORTED, "gemm: unknown epilogue %d", a.epilogue);
-  B200_REQUIRE((a.epilogue != B200_EPI_BIAS_ADD16 && a.epilogue != B200_EPI_BIAS_MUL16) || (a.add16 && (reinterpret_cast<uintptr_t>(a.add16) & 15) == 0), B200_ERR_ALIGN,
-               "gemm: add16 tensor missing or unaligned");
+  B200_REQUIRE((a.epilogue != B200_EPI_BIAS_ADD16 && a.epilogue != B200_EPI_BIAS_MUL16 && a.epilogue != B200_EPI_MUL_GELUGRAD16) ||
+                   (a.add16 && (reinterpret_cast<uintptr_t>(a.add16) & 15) == 0), B200_ERR_ALIGN, "gemm: add16 tensor missing or unaligned");
+  B200_REQUIRE(a.epilogue != B200_EPI_BIAS_GELU_BOTH || (a.out16b && (reinterpret_cast<uintptr_t>(a.out16b) & 15) == 0), B200_ERR_ALIGN,
+               "gemm: second output missing or unaligned");
+  B200_REQUIRE((a.epilogue != B200_EPI_BIAS_GELU_BOTH && a.epilogue != B200_EPI_MUL_GELUGRAD16) || a.N % 8 == 0, B200_ERR_SHAPE, "gemm: N %% 8");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
                B200_ERR_ALIGN, "gemm: A and W must be 16-byte aligned");
   const bool resid = a.epilogue == B200_EPI_GATE_RESIDUAL;
@@ -771,6 +806,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.row_add_div = a.row_add_div > 0 ? a.row_add_div : 1;
   p.row_add_period = a.row_add_period > 0 ? a.row_add_period : 1;
   p.add16 = static_cast<const uint16_t*>(a.add16);
+  p.out16b = static_cast<uint16_t*>(a.out16b);
   p.conv_taps = a.conv_taps;
   p.conv_cblk = a.conv_taps > 0 ? a.conv_c / BK : 0;
   p.conv_h = a.conv_h; p.conv_w = a.conv_w; p.conv_bw = conv_bw; p.conv_bh = conv_bh;

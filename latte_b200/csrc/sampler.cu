@@ -127,6 +127,86 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerDev p) {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ training objective
+// GaussianDiffusion.training_losses for LossType.MSE + LEARNED_RANGE (gaussian_diffusion.py:719-795; vb term :686-716,
+// diffusion_utils.py:10-88) as ONE pass over (x_0, x_t, noise, model output): per-sample sums of the squared error and of the
+// variational-bound term (KL to the true posterior in bits, discretised decoder NLL at t == 0), AND the gradient of both with
+// respect to the model output -- eps channels get d mse, the variance channels get d vb (the mean is frozen there, :757-765).
+// The reference issues ~80 elementwise launches for this (forward + autograd) on 65 k elements per video.
+struct LossDev {
+  const float *x0, *xt, *noise, *mo;
+  const long long* t;
+  const float *recip, *recipm1, *coef1, *coef2, *min_log, *max_log;   // schedule tables (fp32 copies of the float64 arrays)
+  float* dmo;                                                          // same layout as mo, or nullptr
+  float* sums;                                                         // [2][B]: sum of squared error, sum of vb (nats)
+  long long per_sample;                                                // F * C * HW
+  int C, HW, batch;
+};
+
+__device__ __forceinline__ float approx_cdf(float z, float* dz) {      // diffusion_utils.py:40-45 and its derivative
+  const float k = 0.7978845608028654f;
+  const float th = tanhf(k * (z + 0.044715f * z * z * z));
+  *dz = 0.5f * (1.0f - th * th) * k * (1.0f + 3.0f * 0.044715f * z * z);
+  return 0.5f * (1.0f + th);
+}
+
+__global__ void __launch_bounds__(256) training_loss_kernel(const LossDev p) {
+  const int b = blockIdx.y;
+  const long long chw = static_cast<long long>(p.C) * p.HW;
+  const long long t = p.t[b];
+  const float A = p.recip[t], Bc = p.recipm1[t], c1 = p.coef1[t], c2 = p.coef2[t], mn = p.min_log[t], mx = p.max_log[t];
+  const float inv_n = 1.0f / static_cast<float>(p.per_sample);
+  float s_mse = 0.f, s_vb = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < p.per_sample;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = i / chw, cp = i - f * chw;
+    const long long xi = static_cast<long long>(b) * p.per_sample + i;
+    const long long mi = (static_cast<long long>(b) * (p.per_sample / chw) + f) * 2 * chw + cp;   // eps; var values at + chw
+    const float x0 = p.x0[xi], xt = p.xt[xi], nz = p.noise[xi], eps = p.mo[mi], v = p.mo[mi + chw];
+    const float d = nz - eps;
+    s_mse += d * d;
+    const float frac = 0.5f * (v + 1.0f);
+    const float lv = frac * mx + (1.0f - frac) * mn;
+    const float mean = c1 * (A * xt - Bc * eps) + c2 * xt;
+    float term, dterm_dlv;
+    if (t != 0) {
+      const float tm = c1 * x0 + c2 * xt;
+      const float e1 = __expf(mn - lv), dm = tm - mean, e2 = dm * dm * __expf(-lv);
+      term = 0.5f * (-1.0f + lv - mn + e1 + e2);
+      dterm_dlv = 0.5f * (1.0f - e1 - e2);
+    } else {
+      const float cen = x0 - mean, inv_std = __expf(-0.5f * lv);
+      const float za = inv_std * (cen + 1.0f / 255.0f), zb = inv_std * (cen - 1.0f / 255.0f);
+      float da, db;
+      const float ca = approx_cdf(za, &da), cb = approx_cdf(zb, &db);
+      float arg, darg;                       // log_probs = log(max(arg, 1e-12)); z scales with inv_std: dz/dlv = -z/2
+      if (x0 < -0.999f) { arg = ca; darg = da * (-0.5f * za); }
+      else if (x0 > 0.999f) { arg = 1.0f - cb; darg = -db * (-0.5f * zb); }
+      else { arg = ca - cb; darg = da * (-0.5f * za) - db * (-0.5f * zb); }
+      const bool live = arg > 1e-12f;
+      term = -__logf(live ? arg : 1e-12f);
+      dterm_dlv = live ? -darg / arg : 0.f;
+    }
+    s_vb += term;
+    if (p.dmo != nullptr) {
+      p.dmo[mi] = -2.0f * d * inv_n;
+      p.dmo[mi + chw] = dterm_dlv * 0.5f * (mx - mn) * inv_n * 1.4426950408889634f;   // / ln 2: bits
+    }
+  }
+  __shared__ float red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s_mse += __shfl_xor_sync(0xffffffffu, s_mse, o);
+    s_vb += __shfl_xor_sync(0xffffffffu, s_vb, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_mse; red[1][threadIdx.x >> 5] = s_vb; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float tsum = 0.f;
+    for (int w = 0; w < 8; ++w) tsum += red[threadIdx.x][w];
+    atomicAdd(p.sums + threadIdx.x * p.batch + b, tsum);
+  }
+}
+
 int launch_sampler_step(const B200SamplerTables* tab, int method, int clip_denoised, const long long* t,
                         const float* x, const void* model_out, int model_out_dtype, const float* noise, int batch,
                         int frames, int channels, int hw, float* x_prev, float* pred_xstart, float* mean,
@@ -160,6 +240,28 @@ int launch_sampler_step(const B200SamplerTables* tab, int method, int clip_denoi
     case 1: sampler_step_kernel<1><<<blocks, 256, 0, stream>>>(p); break;
     default: sampler_step_kernel<2><<<blocks, 256, 0, stream>>>(p); break;
   }
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_training_loss(const B200SamplerTables* tab, const long long* t, const float* x0, const float* xt, const float* noise,
+                         const float* model_out, int batch, int frames, int channels, int hw, float* sums, float* dmo, cudaStream_t stream) {
+  B200_REQUIRE(tab && t && x0 && xt && noise && model_out && sums, B200_ERR_SHAPE, "training_loss: NULL argument");
+  B200_REQUIRE(batch > 0 && frames > 0 && channels > 0 && hw > 0, B200_ERR_SHAPE, "training_loss: bad shape");
+  B200_REQUIRE(tab->sqrt_recip_alphas_cumprod && tab->sqrt_recipm1_alphas_cumprod && tab->posterior_mean_coef1 &&
+                   tab->posterior_mean_coef2 && tab->posterior_log_variance_clipped && tab->log_betas,
+               B200_ERR_SHAPE, "training_loss: a schedule table is NULL");
+  LossDev p;
+  p.x0 = x0; p.xt = xt; p.noise = noise; p.mo = model_out; p.t = t;
+  p.recip = tab->sqrt_recip_alphas_cumprod; p.recipm1 = tab->sqrt_recipm1_alphas_cumprod; p.coef1 = tab->posterior_mean_coef1;
+  p.coef2 = tab->posterior_mean_coef2; p.min_log = tab->posterior_log_variance_clipped; p.max_log = tab->log_betas;
+  p.dmo = dmo; p.sums = sums;
+  p.per_sample = static_cast<long long>(frames) * channels * hw;
+  p.C = channels; p.HW = hw; p.batch = batch;
+  B200_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * batch, stream));
+  long long bx = (p.per_sample + 255) / 256;
+  if (bx > 64) bx = 64;
+  training_loss_kernel<<<dim3(static_cast<unsigned>(bx), batch), 256, 0, stream>>>(p);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -270,10 +270,25 @@ class SpacedDiffusion:
         """LossType.MSE with LEARNED_RANGE variance (gaussian_diffusion.py:719-795, the only objective create_diffusion builds):
         loss = mean((noise - eps)^2) + L_vb(eps.detach(), var_values), with L_vb = KL(q(x_{t-1}|x_t,x_0) || p) in bits and the
         discretised decoder NLL at t == 0 (:686-716; diffusion_utils.py:10-88).  The model is called with the ORIGINAL timestep
-        (respace.py:125-130).  Elementwise fp32 torch ops on (B, F, C, h, w) -- 65 k elements per video -- with autograd; the
-        denoiser underneath is latte_b200.Latte's native forward/backward (latte_b200/training.py)."""
+        (respace.py:125-130).  On CUDA the terms and their gradient with respect to the model output come from ONE kernel
+        (`b200_training_loss`, csrc/sampler.cu) behind an autograd node -- the reference spends ~80 elementwise launches here;
+        on CPU tensors (tests, toy models) the same expressions run as torch ops with autograd."""
         if noise is None:
             noise = torch.randn_like(x_start)
+        if x_start.is_cuda and x_start.dim() == 5:
+            x_t = self.q_sample(x_start.float(), t, noise.float())
+            mo = self._call_model(model, x_t, t, model_kwargs)
+            if isinstance(mo, tuple):
+                mo = mo[0]
+            Cc = x_t.shape[2]
+            if tuple(mo.shape) != (x_t.shape[0], x_t.shape[1], 2 * Cc, *x_t.shape[3:]):
+                raise ValueError(f"model output {tuple(mo.shape)} is not the learn_sigma layout of x {tuple(x_t.shape)}")
+            mse, vb = _FusedLoss.apply(self, mo.float(), x_start.float(), x_t, noise.float(), t)
+            return {"loss": mse + vb, "mse": mse, "vb": vb}
+        return self._training_losses_torch(model, x_start, t, model_kwargs, noise)
+
+    def _training_losses_torch(self, model, x_start, t, model_kwargs, noise):
+        """The same objective as elementwise torch ops (CPU tensors / non-video shapes); the fused kernel is tested against it."""
         nd = x_start.dim()
         x_t = self.q_sample(x_start, t, noise)
         mo = self._call_model(model, x_t, t, model_kwargs)
@@ -308,6 +323,42 @@ class SpacedDiffusion:
         vb = torch.where(t.to(kl.device) == 0, nll, kl)
         mse = flat((noise - eps) ** 2)
         return {"loss": mse + vb, "mse": mse, "vb": vb}
+
+
+class _FusedLoss(torch.autograd.Function):
+    """(mse, vb) per sample from `b200_training_loss`, with d mse / d eps and d vb / d var_values kept for the backward."""
+
+    @staticmethod
+    def forward(ctx, diff, mo, x0, x_t, noise, t):
+        B, F, C2 = mo.shape[:3]
+        Cc = C2 // 2
+        hw = int(np.prod(mo.shape[3:]))
+        dev = mo.device
+        mo, x0, x_t, noise = mo.contiguous(), x0.contiguous(), x_t.contiguous(), noise.contiguous()
+        tt = t.to(device=dev, dtype=torch.int64).contiguous()
+        tab = diff._state(dev, B)[0]
+        sums = torch.empty(2, B, dtype=torch.float32, device=dev)
+        need_grad = ctx.needs_input_grad[1]
+        dmo = torch.empty_like(mo) if need_grad else None
+        with torch.cuda.device(dev):
+            rc = _lib.load().b200_training_loss(C.byref(tab), tt.data_ptr(), x0.data_ptr(), x_t.data_ptr(), noise.data_ptr(), mo.data_ptr(),
+                                                B, F, Cc, hw, sums.data_ptr(), dmo.data_ptr() if need_grad else None,
+                                                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "b200_training_loss")
+        n = float(F * Cc * hw)
+        ctx.dmo, ctx.Cc = dmo, Cc
+        return sums[0] / n, sums[1] / (n * float(np.log(2.0)))
+
+    @staticmethod
+    def backward(ctx, g_mse, g_vb):
+        dmo, Cc = ctx.dmo, ctx.Cc
+        if dmo is None:
+            return (None,) * 6
+        ctx.dmo = None
+        shape = (-1, 1, 1, 1, 1)
+        dmo[:, :, :Cc].mul_(g_mse.reshape(shape))
+        dmo[:, :, Cc:].mul_(g_vb.reshape(shape))
+        return None, dmo, None, None, None, None
 
 
 def create_diffusion(timestep_respacing, noise_schedule="linear", use_kl=False, sigma_small=False, predict_xstart=False,

@@ -60,19 +60,38 @@ class NativeOps:
             return dW32
         return self.linear_accum(dW32, self.transpose(dy), self.transpose(x))
 
-    def dgrad(self, dy, w):
-        """dx [rows, n_in] = dy [rows, n_out] @ w [n_out, n_in] with the weight in its nn.Linear layout (MN-major W operand)."""
-        self._cuda(dy, w)
+    def dgrad(self, dy, w, gelu_u=None):
+        """dx [rows, n_in] = dy [rows, n_out] @ w [n_out, n_in] with the weight in its nn.Linear layout (MN-major W operand);
+        with `gelu_u` the epilogue multiplies by gelu_tanh'(gelu_u) (the backward through the Mlp activation)."""
+        self._cuda(dy, w, gelu_u)
         rows, n_out = dy.shape
         n_in = w.shape[1]
         if n_in % 128 == 0 and n_out % 64 == 0:
-            assert dy.is_contiguous() and w.is_contiguous() and dy.dtype == w.dtype
+            assert dy.is_contiguous() and w.is_contiguous() and dy.dtype == w.dtype and (gelu_u is None or gelu_u.is_contiguous())
             dx = torch.empty(rows, n_in, dtype=dy.dtype, device=dy.device)
             with torch.cuda.device(dy.device):
-                rc = _lib.load().b200_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), rows, n_out, n_in, self.dt, _s(dy))
+                rc = _lib.load().b200_dgrad(dy.data_ptr(), w.data_ptr(), gelu_u.data_ptr() if gelu_u is not None else None, dx.data_ptr(),
+                                            rows, n_out, n_in, self.dt, _s(dy))
             _lib.check(rc, "b200_dgrad")
             return dx
-        return self.linear(dy, self.transpose(w))
+        dx = self.linear(dy, self.transpose(w))
+        if gelu_u is None:
+            return dx
+        return self.gelu_bwd(dx, gelu_u, torch.zeros(n_in, dtype=torch.float32, device=dy.device))
+
+    def linear_gelu_both(self, a, w, bias):
+        """(u, gelu_tanh(u)) with u = a @ w^T + bias, both from one GEMM epilogue (training-mode fc1)."""
+        self._cuda(a, w, bias)
+        assert a.is_contiguous() and w.is_contiguous() and a.dtype == w.dtype
+        M, K = a.shape
+        N = w.shape[0]
+        u = torch.empty(M, N, dtype=a.dtype, device=a.device)
+        act = torch.empty(M, N, dtype=a.dtype, device=a.device)
+        with torch.cuda.device(a.device):
+            rc = _lib.load().b200_linear_gelu_both(a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, M, N, K, self.dt,
+                                                   u.data_ptr(), act.data_ptr(), _s(a))
+        _lib.check(rc, "b200_linear_gelu_both")
+        return u, act
 
     def attention(self, qkv, B, Fr, N, H, temporal):
         return ops.attention(qkv, B, Fr, N, H, temporal)

@@ -144,8 +144,7 @@ class TrainEngine:
             m1 = ops.linear(o, wp[0], wp[1])
             xm = ops.gate_residual(xs, m1, g1, rpb)
             h2 = ops.ln_modulate(xm, sh2, sc2, rpb)
-            u = ops.linear(h2, w1[0], w1[1])
-            a = ops.gelu(u)
+            u, a = ops.linear_gelu_both(h2, w1[0], w1[1])
             m2 = ops.linear(a, w2[0], w2[1])
             xo = ops.gate_residual(xm, m2, g2, rpb, row_add=temp if i == 0 else None, tokens=N)
             S["blocks"].append((xs, h1, qkv, o, m1, xm, h2, u, a, m2))
@@ -214,9 +213,9 @@ class TrainEngine:
             dm2 = ops.gate_bwd(dx, m2, g2, rpb, dg2, G[p + "mlp.fc2.bias"])
             G[p + "mlp.fc2.weight"] = wgrad(dm2, a)
             del a
-            da = ops.dgrad(dm2, w2[0])
-            du = ops.gelu_bwd(da, u, G[p + "mlp.fc1.bias"])
-            del da, dm2
+            du = ops.dgrad(dm2, w2[0], gelu_u=u)           # dgrad of fc2 with gelu'(u) in its epilogue
+            ops.colsum(du, G[p + "mlp.fc1.bias"])
+            del dm2
             G[p + "mlp.fc1.weight"] = wgrad(du, h2)
             dh2 = ops.dgrad(du, w1[0])
             del du

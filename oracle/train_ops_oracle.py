@@ -46,9 +46,16 @@ class TorchOps:
         out32 += r
         return out32
 
-    def dgrad(self, dy, w):
-        """dx [rows, n_in] = dy [rows, n_out] @ w [n_out, n_in]."""
-        return (dy.float() @ w.float()).to(self.dtype)
+    def dgrad(self, dy, w, gelu_u=None):
+        """dx [rows, n_in] = dy [rows, n_out] @ w [n_out, n_in]; with gelu_u: times gelu_tanh'(gelu_u) (the rounded dx, like the kernel)."""
+        dx = (dy.float() @ w.float()).to(self.dtype)
+        if gelu_u is None:
+            return dx
+        return self.gelu_bwd(dx, gelu_u, torch.zeros(w.shape[1], dtype=torch.float32, device=dy.device))
+
+    def linear_gelu_both(self, a, w, bias):
+        u = self.linear(a, w, bias)
+        return u, self.gelu(u)
 
     def wgrad(self, dW32, dy, x):
         """dW [n_out, n_in] += dy [rows, n_out]^T @ x [rows, n_in]."""

@@ -190,6 +190,50 @@ def test_adaln_gradients(dev, dt):
     _close(nat.ada_dsc(dmod, w), ref.ada_dsc(dmod, w), 2e-5, "ada_dsc")
 
 
+@pytest.mark.parametrize("dt", DTS)
+def test_fused_gelu_epilogues(dev, dt):
+    """Training-mode fc1 (u and gelu(u) from one epilogue) and the dgrad of fc2 with gelu'(u) in its epilogue."""
+    nat, ref = _ops(dt)
+    g = torch.Generator().manual_seed(12)
+    a = torch.randn(2048, 384, generator=g).to(dev).to(dt)
+    w = (torch.randn(1536, 384, generator=g) / 384 ** 0.5).to(dev).to(dt)
+    b = torch.randn(1536, generator=g).to(dev)
+    u, act = nat.linear_gelu_both(a, w, b)
+    u_r, act_r = ref.linear_gelu_both(a, w, b)
+    _close(u, u_r, EPS[dt], "fc1 pre-activation")
+    _close(act, ref.gelu(u), EPS[dt], "gelu of the kernel's own u")
+    _close(act, act_r, 2 * EPS[dt], "gelu(u)")
+    dy = torch.randn(2048, 384, generator=g).to(dev).to(dt)
+    w2 = (torch.randn(384, 1536, generator=g) / 384 ** 0.5).to(dev).to(dt)
+    _close(nat.dgrad(dy, w2, gelu_u=u), ref.dgrad(dy, w2, gelu_u=u), 2 * EPS[dt], "dgrad * gelu'(u)")
+
+
+def test_fused_training_loss_matches_torch_expressions(dev):
+    """`b200_training_loss` (values and gradient w.r.t. the model output) against the module's own elementwise torch version, with
+    a t == 0 sample (decoder NLL branch) and x_0 values outside [-0.999, 0.999] (the clamped CDF branches)."""
+    from latte_b200.diffusion import create_diffusion
+    d = create_diffusion(timestep_respacing="")
+    g = torch.Generator().manual_seed(13)
+    B, Fr, Cc, H = 4, 3, 4, 8
+    x0 = (torch.randn(B, Fr, Cc, H, H, generator=g) * 0.8).to(dev)
+    x0[0, 0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -0.9995, 0.9995], device=dev)
+    noise = torch.randn(B, Fr, Cc, H, H, generator=g).to(dev)
+    t = torch.tensor([0, 1, 500, 999], device=dev)
+    mo0 = torch.randn(B, Fr, 2 * Cc, H, H, generator=g).to(dev)
+    outs = []
+    for fused in (True, False):
+        mo = mo0.clone().requires_grad_(True)
+        model = lambda x, tt, **kw: mo          # noqa: E731
+        terms = d.training_losses(model, x0, t, None, noise) if fused else d._training_losses_torch(model, x0, t, None, noise)
+        w = torch.tensor([1.0, 0.5, 2.0, 1.5], device=dev)
+        ((terms["loss"] * w).sum() + 0.3 * terms["mse"].sum() + 0.7 * (terms["vb"] * w).sum()).backward()
+        outs.append((terms, mo.grad.clone()))
+    (tf, gf), (tt_, gt) = outs
+    for k in ("loss", "mse", "vb"):
+        assert torch.allclose(tf[k], tt_[k], rtol=2e-4, atol=1e-6), (k, tf[k], tt_[k])
+    assert torch.allclose(gf, gt, rtol=2e-3, atol=1e-7), (gf - gt).abs().max()
+
+
 def _golden_model(golden_dir, dev):
     from latte_b200 import Latte
     from oracle import latte_oracle as O

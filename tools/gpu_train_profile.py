@@ -32,7 +32,7 @@ def wrap(name, fn):
         return r
     return inner
 for n in ("ln_modulate", "linear", "linear_accum", "attention", "gate_residual", "gelu", "gate_bwd", "gelu_bwd", "ln_modulate_bwd",
-          "attention_bwd", "wgrad", "dgrad", "cast_into", "colsum", "transpose", "cast", "to_operand", "ada_outer", "ada_dsc"):
+          "attention_bwd", "wgrad", "dgrad", "cast_into", "linear_gelu_both", "colsum", "transpose", "cast", "to_operand", "ada_outer", "ada_dsc"):
     setattr(ops, n, wrap(n, getattr(ops, n)))
 x = torch.randn(B, 16, 4, 32, 32, device=dev)
 t = torch.randint(0, 1000, (B,), device=dev)
