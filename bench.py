@@ -334,11 +334,17 @@ def run_train_leg(args, dev, world, rank, barrier, sharding, steps=5, local_batc
     from latte_b200 import Latte_models
     from latte_b200.diffusion import create_diffusion
     torch.manual_seed(1234 + rank)
-    model = Latte_models[args.model](input_size=32, num_classes=101, num_frames=16, learn_sigma=True, extras=2).to(dev)
+    try:
+        with torch.device(dev):                             # parameters are created and initialised on the GPU (674 M of them)
+            model = Latte_models[args.model](input_size=32, num_classes=101, num_frames=16, learn_sigma=True, extras=2)
+    except Exception:  # noqa: BLE001  (a torch build without device-context factories): build on the host, then move
+        model = Latte_models[args.model](input_size=32, num_classes=101, num_frames=16, learn_sigma=True, extras=2).to(dev)
+    assert model.pos_embed.device == dev
     with torch.no_grad():
-        for p in model.parameters():                      # adaLN-Zero / final layer start at zero: give every parameter a gradient
-            if p.requires_grad and float(p.abs().max()) == 0.0:
-                p.normal_(0, 0.02)
+        zero_init = [b.adaLN_modulation[1] for b in model.blocks] + [model.final_layer.adaLN_modulation[1], model.final_layer.linear]
+        for lin in zero_init:                              # adaLN-Zero / final layer start at zero: give every parameter a gradient
+            lin.weight.normal_(0, 0.02)
+            lin.bias.normal_(0, 0.02)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()} if world == 1 else None
     model.train()
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if world > 1 else model
