@@ -395,6 +395,11 @@ B200_API int b200_cast16(const float* in, void* out16, int64_t n, int dtype, voi
  * (latte.py:357-358).                                                                                                     */
 B200_API int b200_gate_residual(const float* x, const void* m16, const float* gate, int64_t gate_batch_stride, int rows_per_batch,
                                 const float* row_add, int tokens, int frames, float* out, int rows, int dim, int dtype, void* stream);
+/* b200_gate_residual followed by b200_ln_modulate of its result, in one pass: x_out as above AND h16 = LayerNorm(x_out) * (1 +
+ * scale[b]) + shift[b] (the next GEMM's operand; latte.py:179-180 across the two halves of a block / consecutive blocks).         */
+B200_API int b200_gate_residual_ln(const float* x, const void* m16, const float* gate, int64_t gate_batch_stride, const float* shift,
+                                   const float* scale, int64_t mod_batch_stride, int rows_per_batch, const float* row_add, int tokens, int frames,
+                                   float* x_out, void* h16, int rows, int dim, int dtype, void* stream);
 /* a16 = gelu_tanh(u16) (timm Mlp act, latte.py:169).                                                                      */
 B200_API int b200_gelu(const void* u16, void* a16, int64_t n, int dtype, void* stream);
 /* du16 = da16 * gelu_tanh'(u16); dbias[dim] (fp32) += column sums of du = fc1.bias gradient.  (Every reduction output of the

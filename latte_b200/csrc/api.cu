@@ -719,6 +719,13 @@ B200_API int b200_gate_residual(const float* x, const void* m16, const float* ga
   return b200::launch_gate_residual(x, m16, gate, gate_batch_stride, rows_per_batch, row_add, tokens, frames, out, rows, dim,
                                     dtype == B200_BF16, static_cast<cudaStream_t>(stream));
 }
+B200_API int b200_gate_residual_ln(const float* x, const void* m16, const float* gate, int64_t gate_batch_stride, const float* shift,
+                                   const float* scale, int64_t mod_batch_stride, int rows_per_batch, const float* row_add, int tokens, int frames,
+                                   float* x_out, void* h16, int rows, int dim, int dtype, void* stream) {
+  B200_DT(dtype);
+  return b200::launch_gate_residual_ln(x, m16, gate, gate_batch_stride, shift, scale, mod_batch_stride, rows_per_batch, row_add, tokens, frames,
+                                       x_out, h16, rows, dim, dtype == B200_BF16, static_cast<cudaStream_t>(stream));
+}
 B200_API int b200_gelu(const void* u16, void* a16, int64_t n, int dtype, void* stream) {
   B200_DT(dtype);
   return b200::launch_gelu_fwd(u16, a16, n, dtype == B200_BF16, static_cast<cudaStream_t>(stream));

@@ -175,6 +175,9 @@ int launch_multi_tensor(const void* table, int n_entries, long long total_chunks
 int launch_cast_transpose(const float* in, void* out16, void* out16_t, int rows, int cols, int bf16, cudaStream_t stream);
 int launch_gate_residual(const float* x, const void* m16, const float* gate, long long gate_bs, int rows_per_batch,
                          const float* row_add, int tokens, int frames, float* out, int rows, int dim, int bf16, cudaStream_t stream);
+int launch_gate_residual_ln(const float* x, const void* m16, const float* gate, long long gate_bs, const float* shift, const float* scale,
+                            long long mod_bs, int rows_per_batch, const float* row_add, int tokens, int frames, float* x_out, void* h16,
+                            int rows, int dim, int bf16, cudaStream_t stream);
 int launch_gelu_fwd(const void* u16, void* a16, long long n, int bf16, cudaStream_t stream);
 int launch_gelu_bwd(const void* da16, const void* u16, void* du16, float* dbias, int rows, int dim, int bf16, cudaStream_t stream);
 int launch_gate_bwd(const float* dx, const void* m16, const float* gate, long long gate_bs, int rows_per_batch, void* dm16,

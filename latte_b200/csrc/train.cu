@@ -228,6 +228,72 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const float* __restr
   }
 }
 
+// gate_residual + the LayerNorm-modulate that always follows it, in one pass: x_out = x + gate[b] * m (+ row_add), written for the
+// backward, and h = LN(x_out) * (1 + scale[b]) + shift[b] as the next GEMM's 16-bit operand -- the row never leaves registers
+// between the two (saves re-reading the 94 MB stream per pair at local batch 5).  One warp per row, rows dealt round-robin.
+template <bool BF16, int NV>
+__global__ void __launch_bounds__(128) gate_residual_ln_kernel(const float* __restrict__ x, const uint16_t* __restrict__ m,
+                                                               const float* __restrict__ gate, long long gate_bs,
+                                                               const float* __restrict__ shift, const float* __restrict__ scale, long long mod_bs,
+                                                               int rpb, const float* __restrict__ row_add, int tokens, int frames,
+                                                               float* __restrict__ x_out, uint16_t* __restrict__ h, int rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  const int nv = dim >> 2;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const float inv_d = 1.0f / static_cast<float>(dim);
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const int b = row / rpb;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
+    const uint2* mr = reinterpret_cast<const uint2*>(m + static_cast<size_t>(row) * dim);
+    const float4* g4 = reinterpret_cast<const float4*>(gate + b * gate_bs);
+    const float4* ra = row_add ? reinterpret_cast<const float4*>(row_add + static_cast<size_t>((row / tokens) % frames) * dim) : nullptr;
+    float4 v[NV];
+    uint2 mv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) { v[i] = xr[idx]; mv[i] = mr[idx]; }
+    }
+    float s = 0.f;
+    float4* xo = reinterpret_cast<float4*>(x_out + static_cast<size_t>(row) * dim);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        const float4 g = __ldg(g4 + idx);
+        const float2 m0 = unpack2<BF16>(mv[i].x), m1 = unpack2<BF16>(mv[i].y);
+        v[i].x = fmaf(g.x, m0.x, v[i].x); v[i].y = fmaf(g.y, m0.y, v[i].y); v[i].z = fmaf(g.z, m1.x, v[i].z); v[i].w = fmaf(g.w, m1.y, v[i].w);
+        if (ra) { const float4 a = __ldg(ra + idx); v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
+        xo[idx] = v[i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nv) {
+        const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + bb * bb) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + 1e-6f);
+    const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_bs);
+    const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_bs);
+    uint2* hr = reinterpret_cast<uint2*>(h + static_cast<size_t>(row) * dim);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) {
+        const float4 a = __ldg(sh + idx), c = __ldg(sc + idx);
+        const float y0 = fmaf((v[i].x - mean) * rstd, 1.0f + c.x, a.x), y1 = fmaf((v[i].y - mean) * rstd, 1.0f + c.y, a.y);
+        const float y2 = fmaf((v[i].z - mean) * rstd, 1.0f + c.z, a.z), y3 = fmaf((v[i].w - mean) * rstd, 1.0f + c.w, a.w);
+        hr[idx] = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GELU (tanh form)
 // one MUFU op per element (tanh.approx, relative error 2^-11 -- below the 16-bit rounding of the result), as in the GEMM's
 // GELU epilogue: with libm's tanhf the backward pass was ALU-bound (~60 instructions per element on 94 M elements per call)
@@ -1221,6 +1287,41 @@ int launch_gate_residual(const float* x, const void* m16, const float* gate, lon
   else gate_residual_kernel<false><<<blocks, 256, 0, stream>>>(x, m, gate, gate_bs, rows_per_batch, row_add, tokens, frames, out, rows, dim);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
+}
+
+template <bool BF16, int NV>
+static int grl_launch(cudaStream_t stream, const float* x, const uint16_t* m, const float* gate, long long gate_bs, const float* shift,
+                      const float* scale, long long mod_bs, int rpb, const float* row_add, int tokens, int frames, float* x_out, uint16_t* h,
+                      int rows, int dim) {
+  const int blocks = rows / 4 < 148 * 8 ? (rows + 3) / 4 : 148 * 8;
+  gate_residual_ln_kernel<BF16, NV><<<blocks, 128, 0, stream>>>(x, m, gate, gate_bs, shift, scale, mod_bs, rpb, row_add, tokens, frames, x_out, h, rows, dim);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_gate_residual_ln(const float* x, const void* m16, const float* gate, long long gate_bs, const float* shift, const float* scale,
+                            long long mod_bs, int rows_per_batch, const float* row_add, int tokens, int frames, float* x_out, void* h16,
+                            int rows, int dim, int bf16, cudaStream_t stream) {
+  B200_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 12 * 128 && rows_per_batch > 0 && gate_bs % 4 == 0 && mod_bs % 4 == 0, B200_ERR_SHAPE,
+               "gate_residual_ln: bad shape");
+  B200_REQUIRE(row_add == nullptr || (tokens > 0 && frames > 0), B200_ERR_SHAPE, "gate_residual_ln: row_add needs tokens and frames");
+  B200_REQUIRE(ALIGNED16(x) && ALIGNED16(gate) && ALIGNED16(shift) && ALIGNED16(scale) && ALIGNED16(x_out) && (reinterpret_cast<uintptr_t>(m16) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(h16) & 7) == 0 && (row_add == nullptr || ALIGNED16(row_add)), B200_ERR_ALIGN, "gate_residual_ln: misaligned pointer");
+  const uint16_t* m = static_cast<const uint16_t*>(m16);
+  uint16_t* h = static_cast<uint16_t*>(h16);
+  const int nvmax = (dim / 4 + 31) / 32;
+#define GRL(BF, NVV) return grl_launch<BF, NVV>(stream, x, m, gate, gate_bs, shift, scale, mod_bs, rows_per_batch, row_add, tokens, frames, x_out, h, rows, dim)
+  if (bf16) {
+    if (nvmax <= 3) GRL(true, 3);
+    if (nvmax <= 6) GRL(true, 6);
+    if (nvmax <= 9) GRL(true, 9);
+    GRL(true, 12);
+  }
+  if (nvmax <= 3) GRL(false, 3);
+  if (nvmax <= 6) GRL(false, 6);
+  if (nvmax <= 9) GRL(false, 9);
+  GRL(false, 12);
+#undef GRL
 }
 
 int launch_gelu_fwd(const void* u16, void* a16, long long n, int bf16, cudaStream_t stream) {

@@ -108,6 +108,20 @@ class NativeOps:
         _lib.check(rc, "b200_gate_residual")
         return out
 
+    def gate_residual_ln(self, x, m, gate, shift, scale, rpb, row_add=None, tokens=1):
+        """(x_out, h) = (x + gate * m (+ row_add), LN-modulate(x_out)) in one pass."""
+        self._cuda(x, m, gate, shift, scale, row_add)
+        assert x.dtype == torch.float32 and x.is_contiguous() and m.is_contiguous() and shift.stride(0) == scale.stride(0)
+        out = torch.empty_like(x)
+        h = torch.empty(x.shape, dtype=self.dtype, device=x.device)
+        frames = row_add.shape[0] if row_add is not None else 0
+        with torch.cuda.device(x.device):
+            rc = _lib.load().b200_gate_residual_ln(x.data_ptr(), m.data_ptr(), gate.data_ptr(), gate.stride(0), shift.data_ptr(), scale.data_ptr(),
+                                                   shift.stride(0), rpb, row_add.data_ptr() if row_add is not None else None, tokens, frames,
+                                                   out.data_ptr(), h.data_ptr(), x.shape[0], x.shape[1], self.dt, _s(x))
+        _lib.check(rc, "b200_gate_residual_ln")
+        return out, h
+
     def gelu(self, u):
         self._cuda(u)
         a = torch.empty_like(u)

@@ -95,6 +95,10 @@ class TorchOps:
             out = out.view(B, Fr, tokens, -1) + row_add.float()[None, :, None]
         return out.reshape(x.shape).contiguous()
 
+    def gate_residual_ln(self, x, m, gate, shift, scale, rpb, row_add=None, tokens=1):
+        out = self.gate_residual(x, m, gate, rpb, row_add=row_add, tokens=tokens)
+        return out, self.ln_modulate(out, shift, scale, rpb)
+
     def gelu(self, u):
         return F.gelu(u.float(), approximate="tanh").to(self.dtype)
 

@@ -120,6 +120,13 @@ def test_elementwise_forward_ops(dev, dt):
            1e-6, "gate_residual+temp")
     u = (torch.randn(T, 4 * D, generator=g) * 2).to(dev).to(dt)
     _close(nat.gelu(u), ref.gelu(u), EPS[dt], "gelu")
+    # the residual update and the LayerNorm-modulate that follows it, fused
+    shift, scale = mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D]
+    for kw in (dict(), dict(row_add=temp, tokens=N)):
+        xo, h = nat.gate_residual_ln(x, m, gate, shift, scale, rpb, **kw)
+        xo_r, h_r = ref.gate_residual_ln(x, m, gate, shift, scale, rpb, **kw)
+        _close(xo, xo_r, 1e-6, "gate_residual_ln x_out")
+        _close(h, h_r, EPS[dt], "gate_residual_ln h")
 
 
 @pytest.mark.parametrize("dt", DTS)
