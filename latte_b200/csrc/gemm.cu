@@ -740,6 +740,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (block_n == 0) {
       block_n = pick_block_n(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL, sms);
       if (block_n == 192) block_n = (a.N % 256 == 0 || a.N > 1024) ? 256 : 128;     // W chunks are 64 wide per CTA: 128 or 256 only
+      // weight gradients: 256-wide tiles throughout -- the cost model's 128 for small outputs (proj: 1152 x 1152) measured slower
+      // once the tiles are split along K anyway (88.5 vs 75.4 us); B200_WGRAD_BN=128|256 forces a width for A/B runs
+      static const int wgrad_bn = env_int("B200_WGRAD_BN", 0);
+      if (a.mn_major == 3) block_n = (wgrad_bn == 128 || wgrad_bn == 256) ? wgrad_bn : (a.N >= 256 ? 256 : block_n);
     }
   }
   const GemmPlan plan = plan_gemm(a.M, a.N, a.K, a.epilogue == B200_EPI_GATE_RESIDUAL, block_n, sms, a.mn_major == 3);
