@@ -80,7 +80,7 @@ def test_wgrad_reads_untransposed_operands(dev, dt):
     nat, ref = _ops(dt)
     g = torch.Generator().manual_seed(7)
     for rows, n_out, n_in in [(2048, 32, 1152), (4096, 1152, 128), (1536, 384, 128), (8192, 3456, 1152), (20480, 1152, 4608),
-                              (4096, 512, 256), (2048, 1152, 576)]:
+                              (4096, 512, 256), (2048, 1152, 576), (20480, 1152, 1152), (4096, 1152, 1152)]:   # last two: 25 tiles of 256 cut into 3 K-segments each
         dy = torch.randn(rows, n_out, generator=g).to(dev).to(dt)
         x = torch.randn(rows, n_in, generator=g).to(dev).to(dt)
         base = torch.randn(n_out, n_in, generator=g).to(dev)
