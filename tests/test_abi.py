@@ -84,3 +84,13 @@ def test_workspace_size_formula(lib):
     s.heads = 16
     s.patch = 4
     assert lib.b200_latte_workspace_bytes(C.byref(s), 2) == 0 and "patch" in _lib.last_error()
+
+
+def test_every_export_is_documented():
+    """INTEGRATION.md section 1 maps each exported symbol to the reference code it replaces; the header declares all of them."""
+    from latte_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    hdr = open(os.path.join(root, "include", "latte_b200.h")).read()
+    assert [n for n in _lib.EXPORTS if n not in doc] == []
+    assert [n for n in _lib.EXPORTS if n not in hdr] == []
