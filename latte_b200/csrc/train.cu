@@ -1467,6 +1467,7 @@ int launch_attention_bwd(const void* qkv, const void* o, const void* d_o, void* 
   B200_REQUIRE(head_dim == 64 || head_dim == 72, B200_ERR_UNSUPPORTED, "attention_bwd: head_dim %d not built (64, 72)", head_dim);
   B200_REQUIRE(stats != nullptr && ALIGNED16(stats), B200_ERR_ALIGN, "attention_bwd: stats workspace missing");
   const int nseq = batch * frames;
+  B200_REQUIRE(nseq <= 65535 && heads <= 65535, B200_ERR_UNSUPPORTED, "attention_bwd: batch * frames = %d sequences exceed the grid's z extent", nseq);
   float* lse = stats;
   float* delta = stats + static_cast<size_t>(nseq) * heads * tokens;
   if (head_dim == 72) {
