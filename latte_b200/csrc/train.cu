@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const float* __restr
 // gate_residual + the LayerNorm-modulate that always follows it, in one pass: x_out = x + gate[b] * m (+ row_add), written for the
 // backward, and h = LN(x_out) * (1 + scale[b]) + shift[b] as the next GEMM's 16-bit operand -- the row never leaves registers
 // between the two (saves re-reading the 94 MB stream per pair at local batch 5).  One warp per row, rows dealt round-robin.
-template <bool BF16, int NV>
-__global__ void __launch_bounds__(128) gate_residual_ln_kernel(const float* __restrict__ x, const uint16_t* __restrict__ m,
+template <bool BF16, int NV, int MINB>
+__global__ void __launch_bounds__(128, MINB) gate_residual_ln_kernel(const float* __restrict__ x, const uint16_t* __restrict__ m,
                                                                const float* __restrict__ gate, long long gate_bs,
                                                                const float* __restrict__ shift, const float* __restrict__ scale, long long mod_bs,
                                                                int rpb, const float* __restrict__ row_add, int tokens, int frames,
@@ -1293,8 +1293,10 @@ template <bool BF16, int NV>
 static int grl_launch(cudaStream_t stream, const float* x, const uint16_t* m, const float* gate, long long gate_bs, const float* shift,
                       const float* scale, long long mod_bs, int rpb, const float* row_add, int tokens, int frames, float* x_out, uint16_t* h,
                       int rows, int dim) {
+  static const int minb = env_int("B200_GRL_MINB", 5);     // A/B switch: register cap (5 blocks of 4 warps per SM: 96 registers) vs none (134)
   const int blocks = rows / 4 < 148 * 8 ? (rows + 3) / 4 : 148 * 8;
-  gate_residual_ln_kernel<BF16, NV><<<blocks, 128, 0, stream>>>(x, m, gate, gate_bs, shift, scale, mod_bs, rpb, row_add, tokens, frames, x_out, h, rows, dim);
+  if (minb >= 5) gate_residual_ln_kernel<BF16, NV, 5><<<blocks, 128, 0, stream>>>(x, m, gate, gate_bs, shift, scale, mod_bs, rpb, row_add, tokens, frames, x_out, h, rows, dim);
+  else gate_residual_ln_kernel<BF16, NV, 1><<<blocks, 128, 0, stream>>>(x, m, gate, gate_bs, shift, scale, mod_bs, rpb, row_add, tokens, frames, x_out, h, rows, dim);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
