@@ -77,3 +77,25 @@ def test_backward_is_single_use(golden_dir):
         assert "backward called twice" in str(e)
     else:
         raise AssertionError("second backward over freed activations must raise")
+
+
+def test_engine_with_16bit_operands_on_cpu(golden_dir):
+    """The same orchestration with bf16 operand rounding at every point where the CUDA backend rounds (operand casts, GEMM /
+    attention / LayerNorm outputs): gradients stay within bf16 noise of the reference's fp32 ones -- i.e. no reduction or
+    accumulation in the engine runs in 16 bits by accident."""
+    g, cfg, sd, m = _setup(golden_dir)
+    m.eval()
+    d = create_diffusion(timestep_respacing="")
+    x0, noise = torch.from_numpy(g["x0"]), torch.from_numpy(g["noise"])
+    t, y = torch.from_numpy(g["t"]), torch.from_numpy(g["y"])
+    ops = TorchOps(torch.bfloat16)
+    terms = d.training_losses(lambda x, tt, y: training.train_forward(m, ops, torch.bfloat16, x, training.conditioning(m, tt, y)),
+                              x0, t, dict(y=y), noise=noise)
+    loss = terms["loss"].mean()
+    assert abs(loss.item() - float(g["loss"])) < 2e-2 * abs(float(g["loss"]))
+    loss.backward()
+    named = dict(m.named_parameters())
+    for k, want in zip([str(n) for n in g["grad_names"]], g["grad_norms"]):
+        assert named[k].grad.dtype == torch.float32
+        got = named[k].grad.double().norm().item()
+        assert abs(got - want) <= 8e-2 * want, (k, got, want)
