@@ -474,6 +474,10 @@ B200_API int b200_training_loss(const B200SamplerTables* tables, const int64_t* 
  * is the total count, negative on error).  The CPU tests check coverage and the ordering invariant on it.            */
 B200_API int b200_gemm_schedule(int M, int N, int K, int epilogue, int block_n, int num_sms, int* block_n_out, int* pairs_out,
                                 int* streamk_out, int32_t* segments, int max_segments);
+/* The same for b200_wgrad(rows, n_out, n_in): a [n_out, n_in] output under a contraction over `rows`.  Outputs with fewer tiles
+ * than CTA pairs are cut into several K-segments per tile, executed by consecutive pairs and added in k order.               */
+B200_API int b200_wgrad_schedule(int rows, int n_out, int n_in, int num_sms, int* block_n_out, int* pairs_out, int* streamk_out,
+                                 int32_t* segments, int max_segments);
 
 /* Measurement hook (bench.py roofline): while enabled, b200_latte_forward brackets every kernel launch with
  * CUDA events on the launching stream.  b200_profile_collect waits for them and returns, per class

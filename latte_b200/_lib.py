@@ -145,6 +145,8 @@ EXPORTS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_training_loss": (C.c_int, [C.POINTER(SamplerTables), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200_wgrad_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int32), C.c_int]),
     "b200_gemm_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_int32), C.c_int]),
     # training-step passes (csrc/train.cu)

@@ -528,6 +528,11 @@ B200_API int b200_training_loss(const B200SamplerTables* tables, const int64_t* 
                                     sums, dmo, static_cast<cudaStream_t>(stream));
 }
 
+B200_API int b200_wgrad_schedule(int rows, int n_out, int n_in, int num_sms, int* block_n_out, int* pairs_out, int* streamk_out,
+                                 int32_t* segments, int max_segments) {
+  return b200::gemm_schedule(n_out, n_in, rows, B200_EPI_GATE_RESIDUAL, 0, num_sms, block_n_out, pairs_out, streamk_out, segments, max_segments, 1);
+}
+
 B200_API int b200_gemm_schedule(int M, int N, int K, int epilogue, int block_n, int num_sms, int* block_n_out, int* pairs_out,
                                 int* streamk_out, int32_t* segments, int max_segments) {
   return b200::gemm_schedule(M, N, K, epilogue, block_n, num_sms, block_n_out, pairs_out, streamk_out, segments, max_segments);

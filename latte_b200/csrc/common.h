@@ -199,7 +199,7 @@ int launch_conv_in(const float* z, const float* pq_w, const float* pq_b, const f
 int launch_softmax_rows(const float* s, void* p, int rows, int n, float scale, int bf16, cudaStream_t stream);
 int launch_to_nchw(const void* x, float* y, int n_img, int c, int cpad, int hw, int bf16, cudaStream_t stream);
 int gemm_schedule(int M, int N, int K, int epilogue, int block_n, int sms, int* bn_out, int* pairs_out, int* streamk_out,
-                  int* segments, int max_segments);
+                  int* segments, int max_segments, int wgrad = 0);
 int launch_sampler_step(const B200SamplerTables* tab, int method, int clip_denoised, const long long* t,
                         const float* x, const void* model_out, int model_out_dtype, const float* noise, int batch,
                         int frames, int channels, int hw, float* x_prev, float* pred_xstart, float* mean,

@@ -679,10 +679,15 @@ GemmPlan plan_gemm(int M, int N, int K, bool resid, int block_n, int sms, bool s
 }  // namespace
 
 int gemm_schedule(int M, int N, int K, int epilogue, int block_n, int sms, int* bn_out, int* pairs_out, int* streamk_out,
-                  int* segments, int max_segments) {
+                  int* segments, int max_segments, int wgrad) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0 && sms >= 2, B200_ERR_SHAPE, "gemm_schedule: bad arguments");
   B200_REQUIRE(block_n == 0 || block_n == 128 || block_n == 192 || block_n == 256, B200_ERR_UNSUPPORTED, "gemm_schedule: block_n %d", block_n);
-  const GemmPlan g = plan_gemm(M, N, K, epilogue == B200_EPI_GATE_RESIDUAL, block_n, sms);
+  if (wgrad && block_n == 0) {               // the tile-width rule launch_gemm applies to weight gradients (mn_major == 3)
+    block_n = pick_block_n(M, N, K, true, sms);
+    if (block_n == 192) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+    if (N >= 256) block_n = 256;
+  }
+  const GemmPlan g = plan_gemm(M, N, K, epilogue == B200_EPI_GATE_RESIDUAL, block_n, sms, wgrad != 0);
   if (bn_out) *bn_out = g.bn;
   if (pairs_out) *pairs_out = g.pairs;
   if (streamk_out) *streamk_out = g.streamk;
